@@ -1,0 +1,126 @@
+"""ctypes binding of libb2splat.so (include/b2splat.h).
+
+There is NO fallback: if the library is missing or fails to load, importing the
+render path raises.  Build it with `python 3dgaussian_b200/build.py`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb2splat.so")
+
+MODE_WSUM, MODE_SORTED = 0, 1
+STYLE_TORCH, STYLE_NATIVE = 0, 1
+ACT_SCALES_SOFTPLUS, ACT_OPACITY_SIGMOID, ACT_COLORS_SIGMOID = 1, 2, 4
+TILE = 16
+
+EXPORTS = [
+    "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_version", "b2s_state_bytes", "b2s_workspace_bytes",
+    "b2s_count_pairs", "b2s_forward", "b2s_backward", "b2s_state_info", "b2s_render_rgba8",
+    "b2s_render_rgba8_host", "b2s_dump_bins", "b2s_sort_tmp_bytes", "b2s_sort_pairs", "b2s_fit_loss",
+    "b2s_adam_step",
+]
+
+
+class Params(C.Structure):
+    """struct b2s_params -- mirrors gr::RenderParams (reference include/gr/gaussian_types.h:24-46)."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("view", C.c_float * 16), ("proj", C.c_float * 16), ("background", C.c_float * 3),
+        ("enable_depth_sort", C.c_int32), ("depth_slices", C.c_int32), ("force_cpu", C.c_int32),
+        ("style", C.c_int32), ("cutoff_sigma", C.c_float), ("sh_coeffs", C.c_int32),
+        ("sort_depth", C.c_int32), ("act_flags", C.c_int32), ("exact_bbox", C.c_int32),
+    ]
+
+
+class B2SError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2SError(f"{LIB_PATH} not built (run `python 3dgaussian_b200/build.py`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+        PP = C.POINTER(Params)
+        L.b2s_create.restype = vp
+        L.b2s_create.argtypes = [i32]
+        L.b2s_destroy.restype = None
+        L.b2s_destroy.argtypes = [vp]
+        L.b2s_last_error.restype = C.c_char_p
+        L.b2s_version.restype = C.c_char_p
+        L.b2s_state_bytes.restype = sz
+        L.b2s_state_bytes.argtypes = [i32, i32, i32, i64]
+        L.b2s_workspace_bytes.restype = sz
+        L.b2s_workspace_bytes.argtypes = [i32, i32, i32, i64]
+        L.b2s_count_pairs.restype = i32
+        L.b2s_count_pairs.argtypes = [vp, PP, vp, vp, vp, i32, C.POINTER(i64), vp, sz, vp]
+        L.b2s_forward.restype = i32
+        L.b2s_forward.argtypes = [vp, PP, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, vp, sz, vp]
+        L.b2s_backward.restype = i32
+        L.b2s_backward.argtypes = [vp, PP, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, i32, vp]
+        L.b2s_state_info.restype = i32
+        L.b2s_state_info.argtypes = [vp, vp, i32, i32, i32, i64, C.POINTER(i64), vp]
+        L.b2s_render_rgba8.restype = i32
+        L.b2s_render_rgba8.argtypes = [vp, PP, vp, vp, vp, vp, i32, i64, vp, vp, sz, vp]
+        L.b2s_render_rgba8_host.restype = i32
+        L.b2s_render_rgba8_host.argtypes = [vp, PP, vp, vp, vp, vp, i32, vp]
+        L.b2s_dump_bins.restype = i32
+        L.b2s_dump_bins.argtypes = [vp, PP, vp, vp, vp, i32, i64] + [vp] * 13 + [vp, sz, vp]
+        L.b2s_sort_tmp_bytes.restype = sz
+        L.b2s_sort_tmp_bytes.argtypes = [i64]
+        L.b2s_sort_pairs.restype = i32
+        L.b2s_sort_pairs.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, sz, vp]
+        L.b2s_fit_loss.restype = i32
+        L.b2s_fit_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp, vp]
+        L.b2s_adam_step.restype = i32
+        L.b2s_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    i64, i64, C.c_float, i64, i64, C.c_float, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B2SError(f"libb2splat error {rc}: {lib().b2s_last_error().decode()}")
+
+
+_ctx = {}
+
+
+def ctx(device_index: int):
+    """One b2s_ctx per device per process."""
+    if device_index not in _ctx:
+        h = lib().b2s_create(device_index)
+        if not h:
+            raise B2SError(lib().b2s_last_error().decode())
+        _ctx[device_index] = h
+    return _ctx[device_index]
+
+
+def make_params(width, height, view, proj, background=(0.0, 0.0, 0.0), mode=MODE_WSUM, style=STYLE_TORCH,
+                cutoff_sigma=5.0, sh_coeffs=1, sort_depth=0, act_flags=0, exact_bbox=0) -> Params:
+    """view/proj: 16 floats row-major (any iterable)."""
+    p = Params()
+    p.width, p.height = int(width), int(height)
+    p.view[:] = [float(x) for x in view]
+    p.proj[:] = [float(x) for x in proj]
+    p.background[:] = [float(x) for x in background]
+    p.enable_depth_sort = int(mode)
+    p.depth_slices = 32
+    p.force_cpu = 0
+    p.style = int(style)
+    p.cutoff_sigma = float(cutoff_sigma)
+    p.sh_coeffs = int(sh_coeffs)
+    p.sort_depth = int(sort_depth)
+    p.act_flags = int(act_flags)
+    p.exact_bbox = int(exact_bbox)
+    return p

@@ -1,0 +1,496 @@
+// extern "C" entry points of libb2splat.so -- see include/b2splat.h for the contract.
+// Replaces the reference's dispatch + binding layer (src/renderer_dispatch.cpp:5-21,
+// src/bindings.cpp:27-100) and the host wrapper of src/renderer.cu:272-408.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b2s {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// inverse of a row-major 4x4 (Gauss-Jordan, double) -> camera centre inv(V)[:3,3]
+static bool camera_centre(const float* v, float* cam) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      a[r][c] = v[4 * r + c];
+      a[r][4 + c] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 4; ++r)
+      if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+    if (fabs(a[piv][col]) < 1e-30) return false;
+    if (piv != col)
+      for (int c = 0; c < 8; ++c) { const double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+    const double d = 1.0 / a[col][col];
+    for (int c = 0; c < 8; ++c) a[col][c] *= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != col) {
+        const double f = a[r][col];
+        if (f != 0.0)
+          for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+      }
+  }
+  for (int r = 0; r < 3; ++r) cam[r] = (float)a[r][7];
+  return true;
+}
+
+static int make_view(const b2s_params* p, ViewParams* vp) {
+  if (p == nullptr) { set_error("params is NULL"); return B2S_ERR_INVALID; }
+  if (p->force_cpu != 0) { set_error("force_cpu is not supported: this library has no CPU path"); return B2S_ERR_UNSUPPORTED; }
+  if (p->width <= 0 || p->height <= 0 || p->width > 32767 || p->height > 32767) {
+    set_error("bad image size %dx%d", p->width, p->height);
+    return B2S_ERR_INVALID;
+  }
+  if (!(p->cutoff_sigma > 0.0f)) { set_error("cutoff_sigma must be > 0"); return B2S_ERR_INVALID; }
+  memcpy(vp->view, p->view, sizeof(float) * 16);
+  memcpy(vp->proj, p->proj, sizeof(float) * 16);
+  memcpy(vp->bg, p->background, sizeof(float) * 3);
+  vp->cam[0] = vp->cam[1] = vp->cam[2] = 0.0f;
+  if (p->sh_coeffs > 1 && !camera_centre(p->view, vp->cam)) { set_error("view matrix is singular"); return B2S_ERR_INVALID; }
+  vp->k = p->cutoff_sigma;
+  vp->width = p->width;
+  vp->height = p->height;
+  vp->wm1 = (float)(p->width - 1);
+  vp->hm1 = (float)(p->height - 1);
+  vp->wf = (float)p->width;
+  vp->hf = (float)p->height;
+  vp->fx = fabsf(p->proj[0]);
+  vp->fy = fabsf(p->proj[5]);
+  vp->tiles_x = (p->width + TILE - 1) / TILE;
+  vp->tiles_y = (p->height + TILE - 1) / TILE;
+  vp->n_tiles = vp->tiles_x * vp->tiles_y;
+  vp->style = p->style;
+  vp->sh = p->sh_coeffs > 0 ? p->sh_coeffs : 1;
+  vp->act = p->act_flags;
+  vp->mode = p->enable_depth_sort ? B2S_MODE_SORTED : B2S_MODE_WSUM;
+  vp->exact_bbox = (p->exact_bbox || vp->mode == B2S_MODE_SORTED) ? 1 : 0;
+  return B2S_OK;
+}
+
+static int tile_bits(int n_tiles) {
+  int b = 1;
+  while ((1 << b) < n_tiles) ++b;
+  return b;
+}
+
+struct Bufs {  // resolved pointers into state / workspace
+  Counters* counters;
+  float4* rec;
+  int2* ranges;
+  int* vals;
+  float* acc;
+  uint2* rect;
+  uint32_t* dbits;
+  int* cnt;
+  long long* bsum;
+  unsigned long long *keysA, *keysB;
+  int* valsB;
+  int *hist, *hsum;
+  float* gacc;
+};
+
+static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
+  Bufs b;
+  memset(&b, 0, sizeof(b));
+  if (state != nullptr) {
+    const StateLayout S = state_layout(n, w, h, mp);
+    char* s = (char*)state;
+    b.counters = (Counters*)(s + S.counters);
+    b.rec = (float4*)(s + S.rec);
+    b.ranges = (int2*)(s + S.ranges);
+    b.vals = (int*)(s + S.vals);
+    b.acc = (float*)(s + S.acc);
+  }
+  if (ws != nullptr) {
+    const WorkLayout L = work_layout(n, w, h, mp);
+    char* q = (char*)ws;
+    b.rect = (uint2*)(q + L.rect);
+    b.dbits = (uint32_t*)(q + L.dbits);
+    b.cnt = (int*)(q + L.cnt);
+    b.bsum = (long long*)(q + L.bsum);
+    b.keysA = (unsigned long long*)(q + L.keysA);
+    b.keysB = (unsigned long long*)(q + L.keysB);
+    b.valsB = (int*)(q + L.valsB);
+    b.hist = (int*)(q + L.hist);
+    b.hsum = (int*)(q + L.hsum);
+    b.gacc = (float*)(q + L.gacc);
+  }
+  return b;
+}
+
+// projection -> count -> scan -> emit -> sort -> ranges.  On return the sorted Gaussian ids are
+// in B.vals (state) and the sorted keys in *keys_sorted.
+static int run_binning(const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
+                       const float* colors, const float* opac, int n, int64_t max_pairs, const Bufs& B,
+                       float* dbg, int* dbg_bbox, unsigned long long** keys_sorted,
+                       unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
+  int rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+  if (rc != B2S_OK) return rc;
+  const int begin_bit = p->sort_depth ? 0 : 32;
+  const int end_bit = 32 + tile_bits(vp.n_tiles);
+  const int passes = sort_passes(begin_bit, end_bit);
+  // choose the ping-pong so that the sorted values land in the state buffer
+  unsigned long long* kA = B.keysA;
+  unsigned long long* kB = B.keysB;
+  int* vA = (passes % 2 == 0) ? B.vals : B.valsB;
+  int* vB = (passes % 2 == 0) ? B.valsB : B.vals;
+  rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
+  if (rc != B2S_OK) return rc;
+  if (keys_unsorted_copy != nullptr)
+    B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, kA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
+  if (vals_unsorted_copy != nullptr)
+    B2S_CUDA_TRY(cudaMemcpyAsync(vals_unsorted_copy, vA, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, st));
+  int in_b = 0;
+  rc = launch_sort(kA, vA, kB, vB, max_pairs, &B.counters->kept, begin_bit, end_bit, B.hist, B.hsum, &in_b, st);
+  if (rc != B2S_OK) return rc;
+  unsigned long long* ks = in_b ? kB : kA;
+  rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
+  if (rc != B2S_OK) return rc;
+  if (keys_sorted != nullptr) *keys_sorted = ks;
+  return B2S_OK;
+}
+
+static int check_sizes(int n, int w, int h, int64_t mp, size_t state_bytes, bool need_state, size_t ws_bytes) {
+  if (n < 0 || mp < 0 || mp > 0x7fffffffLL) { set_error("bad n=%d or max_pairs=%lld", n, (long long)mp); return B2S_ERR_INVALID; }
+  if (need_state && state_bytes < state_layout(n, w, h, mp).total) {
+    set_error("state buffer too small: %zu < %zu", state_bytes, state_layout(n, w, h, mp).total);
+    return B2S_ERR_WORKSPACE;
+  }
+  if (ws_bytes < work_layout(n, w, h, mp).total) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, work_layout(n, w, h, mp).total);
+    return B2S_ERR_WORKSPACE;
+  }
+  return B2S_OK;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+struct b2s_ctx {
+  int device;
+  // grow-only cache used by b2s_render_rgba8_host only
+  void* host_dev = nullptr;
+  size_t host_dev_bytes = 0;
+};
+
+extern "C" {
+
+const char* b2s_last_error(void) { return g_err; }
+const char* b2s_version(void) { return "b2splat 0.1 (sm_100a)"; }
+
+b2s_ctx* b2s_create(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    set_error("b2s_create: CUDA device %d not available (%d devices)", device, count);
+    return nullptr;
+  }
+  b2s_ctx* c = new b2s_ctx();
+  c->device = device;
+  return c;
+}
+
+void b2s_destroy(b2s_ctx* ctx) {
+  if (ctx == nullptr) return;
+  if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
+  delete ctx;
+}
+
+size_t b2s_state_bytes(int n, int width, int height, int64_t max_pairs) {
+  return state_layout(n, width, height, max_pairs).total;
+}
+size_t b2s_workspace_bytes(int n, int width, int height, int64_t max_pairs) {
+  return work_layout(n, width, height, max_pairs).total;
+}
+
+int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                    const float* opacities, int n, int64_t* total_host, void* workspace, size_t ws_bytes,
+                    void* stream) {
+  if (ctx == nullptr || total_host == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  *total_host = 0;
+  if (n == 0) return B2S_OK;
+  rc = check_sizes(n, p->width, p->height, 0, 0, false, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(nullptr, workspace, n, p->width, p->height, 0);
+  // the counters live in the (otherwise unused) head of the histogram scratch
+  Counters* counters = (Counters*)B.hist;
+  rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, B.rect, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
+  if (rc != B2S_OK) return rc;
+  rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, st);
+  if (rc != B2S_OK) return rc;
+  Counters h;
+  B2S_CUDA_TRY(cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_TRY(cudaStreamSynchronize(st));
+  *total_host = h.needed;
+  return B2S_OK;
+}
+
+int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* colors,
+                const float* opacities, int n, int64_t max_pairs, float* out_rgb, float* out_alpha,
+                float* out_depth, void* state, size_t state_bytes, void* workspace, size_t ws_bytes, void* stream) {
+  if (ctx == nullptr || out_rgb == nullptr || state == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  rc = check_sizes(n, p->width, p->height, max_pairs, state_bytes, true, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(state, workspace, n, p->width, p->height, max_pairs);
+  rc = run_binning(vp, p, means, scales, colors, opacities, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode == B2S_MODE_SORTED)
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, nullptr, st);
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, out_depth, B.acc, nullptr, st);
+}
+
+int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* colors,
+                 const float* opacities, int n, int64_t max_pairs, const float* g_rgb, const float* g_alpha,
+                 const float* g_depth, const void* state, void* workspace, size_t ws_bytes, float* grad_means,
+                 float* grad_scales, float* grad_colors, float* grad_opacities, int accumulate, void* stream) {
+  if (ctx == nullptr || g_rgb == nullptr || state == nullptr || workspace == nullptr || grad_means == nullptr ||
+      grad_scales == nullptr || grad_opacities == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode != B2S_MODE_WSUM || vp.exact_bbox || vp.style != B2S_STYLE_TORCH) {
+    set_error("backward is implemented for the weighted-sum torch-style mode only");
+    return B2S_ERR_UNSUPPORTED;
+  }
+  rc = check_sizes(n, p->width, p->height, max_pairs, 0, false, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  if (n == 0) return B2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
+  B2S_CUDA_TRY(cudaMemsetAsync(B.gacc, 0, (size_t)n * GACC_F * sizeof(float), st));
+  rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.acc, g_rgb, g_alpha, g_depth, B.gacc, st);
+  if (rc != B2S_OK) return rc;
+  return launch_preprocess_bwd(vp, means, scales, colors, opacities, n, B.gacc, grad_means, grad_scales,
+                               grad_colors, grad_opacities, accumulate, st);
+}
+
+int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,
+                   int64_t* info_host, void* stream) {
+  if (ctx == nullptr || state == nullptr || info_host == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  const StateLayout S = state_layout(n, width, height, max_pairs);
+  Counters h;
+  cudaStream_t st = (cudaStream_t)stream;
+  B2S_CUDA_TRY(cudaMemcpyAsync(&h, (const char*)state + S.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_TRY(cudaStreamSynchronize(st));
+  info_host[0] = h.needed;
+  info_host[1] = h.kept;
+  info_host[2] = h.overflow;
+  return B2S_OK;
+}
+
+// The RGBA8 paths keep their "state" inside the workspace: workspace = [work | state].
+static int render_rgba8_impl(const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
+                             const float* colors, const float* opac, int n, int64_t max_pairs, uint8_t* out_rgba,
+                             void* workspace, size_t ws_bytes, cudaStream_t st) {
+  const size_t wbytes = work_layout(n, p->width, p->height, max_pairs).total;
+  const size_t sbytes = state_layout(n, p->width, p->height, max_pairs).total;
+  if (ws_bytes < wbytes + sbytes) {
+    set_error("rgba8 workspace too small: %zu < %zu", ws_bytes, wbytes + sbytes);
+    return B2S_ERR_WORKSPACE;
+  }
+  Bufs B = resolve((char*)workspace + wbytes, workspace, n, p->width, p->height, max_pairs);
+  int rc = run_binning(vp, p, means, scales, colors, opac, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode == B2S_MODE_SORTED)
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, out_rgba, st);
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, nullptr, nullptr, out_rgba, st);
+}
+
+int b2s_render_rgba8(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                     const float* colors, const float* opacities, int n, int64_t max_pairs, uint8_t* out_rgba,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  if (ctx == nullptr || out_rgba == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (n < 0 || max_pairs < 0 || max_pairs > 0x7fffffffLL) { set_error("bad n or max_pairs"); return B2S_ERR_INVALID; }
+  return render_rgba8_impl(vp, p, means, scales, colors, opacities, n, max_pairs, out_rgba, workspace, ws_bytes,
+                           (cudaStream_t)stream);
+}
+
+// Host-pointer entry: same argument meaning as gr::render_gaussians (include/gr/renderer.h:33-39).
+// Like the reference's CUDA wrapper (src/renderer.cu:361-405) it uploads the four arrays, renders
+// and downloads the image synchronously; unlike it, it sizes the pair buffers exactly (one count
+// pass) and keeps a per-ctx grow-only device arena instead of a function-local static.
+int b2s_render_rgba8_host(b2s_ctx* ctx, const b2s_params* p, const float* means_host, const float* scales_host,
+                          const float* colors_host, const float* opacities_host, int n, uint8_t* out_rgba_host) {
+  if (ctx == nullptr || out_rgba_host == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (vp.sh != 1) { set_error("the native entry takes (N,3) colours only (src/bindings.cpp:50)"); return B2S_ERR_INVALID; }
+  const size_t pixels = (size_t)p->width * p->height;
+  if (n <= 0) {   // src/renderer.cu:279-281
+    memset(out_rgba_host, 0, pixels * 4);
+    return B2S_OK;
+  }
+  B2S_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = 0;
+  const size_t in_bytes = align_up((size_t)n * 12) * 3 + align_up((size_t)n * 4);
+  const size_t out_bytes = align_up(pixels * 4);
+  auto ensure = [&](size_t bytes) -> int {
+    if (bytes <= ctx->host_dev_bytes) return B2S_OK;
+    if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
+    ctx->host_dev = nullptr;
+    ctx->host_dev_bytes = 0;
+    B2S_CUDA_TRY(cudaMalloc(&ctx->host_dev, bytes));
+    ctx->host_dev_bytes = bytes;
+    return B2S_OK;
+  };
+  // pass 1: upload + count
+  const size_t count_ws = work_layout(n, p->width, p->height, 0).total;
+  rc = ensure(in_bytes + out_bytes + count_ws);
+  if (rc != B2S_OK) return rc;
+  auto carve = [&](float** m, float** s, float** c, float** o, uint8_t** img, char** ws) {
+    char* base = (char*)ctx->host_dev;
+    *m = (float*)base; base += align_up((size_t)n * 12);
+    *s = (float*)base; base += align_up((size_t)n * 12);
+    *c = (float*)base; base += align_up((size_t)n * 12);
+    *o = (float*)base; base += align_up((size_t)n * 4);
+    *img = (uint8_t*)base; base += out_bytes;
+    *ws = base;
+  };
+  float *dm, *ds, *dc, *dop;
+  uint8_t* dimg;
+  char* ws;
+  carve(&dm, &ds, &dc, &dop, &dimg, &ws);
+  B2S_CUDA_TRY(cudaMemcpyAsync(dm, means_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  B2S_CUDA_TRY(cudaMemcpyAsync(ds, scales_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  B2S_CUDA_TRY(cudaMemcpyAsync(dop, opacities_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  int64_t total = 0;
+  rc = b2s_count_pairs(ctx, p, dm, ds, dop, n, &total, ws, count_ws, st);
+  if (rc != B2S_OK) return rc;
+  if (total > 0x7fffffffLL) { set_error("too many (Gaussian,tile) pairs: %lld", (long long)total); return B2S_ERR_OVERFLOW; }
+  // pass 2: render with exact capacity
+  const size_t need = work_layout(n, p->width, p->height, total).total + state_layout(n, p->width, p->height, total).total;
+  if (in_bytes + out_bytes + need > ctx->host_dev_bytes) {
+    rc = ensure((in_bytes + out_bytes + need) * 5 / 4);
+    if (rc != B2S_OK) return rc;
+    carve(&dm, &ds, &dc, &dop, &dimg, &ws);
+    B2S_CUDA_TRY(cudaMemcpyAsync(dm, means_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    B2S_CUDA_TRY(cudaMemcpyAsync(ds, scales_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    B2S_CUDA_TRY(cudaMemcpyAsync(dop, opacities_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  B2S_CUDA_TRY(cudaMemcpyAsync(dc, colors_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  rc = render_rgba8_impl(vp, p, dm, ds, dc, dop, n, total, dimg, ws, need, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA_TRY(cudaMemcpyAsync(out_rgba_host, dimg, pixels * 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_TRY(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
+int b2s_dump_bins(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* opacities,
+                  int n, int64_t max_pairs, float* px, float* py, float* sx, float* sy, float* zabs, int32_t* bbox,
+                  int32_t* cnt, uint64_t* keys_unsorted, int32_t* vals_unsorted, uint64_t* keys_sorted,
+                  int32_t* vals_sorted, int32_t* ranges, int64_t* total, void* workspace, size_t ws_bytes, void* stream) {
+  if (ctx == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  const size_t wbytes = work_layout(n, p->width, p->height, max_pairs).total;
+  const size_t sbytes = state_layout(n, p->width, p->height, max_pairs).total;
+  const size_t dbg_bytes = align_up((size_t)(n > 0 ? n : 1) * 5 * 4);
+  if (ws_bytes < wbytes + sbytes + dbg_bytes) {
+    set_error("dump_bins workspace too small: %zu < %zu", ws_bytes, wbytes + sbytes + dbg_bytes);
+    return B2S_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve((char*)workspace + wbytes, workspace, n, p->width, p->height, max_pairs);
+  float* dbg = (float*)((char*)workspace + wbytes + sbytes);
+  unsigned long long* ks = nullptr;
+  rc = run_binning(vp, p, means, scales, nullptr, opacities, n, max_pairs, B, dbg, bbox, &ks,
+                   (unsigned long long*)keys_unsorted, vals_unsorted, st);
+  if (rc != B2S_OK) return rc;
+  const size_t nb = (size_t)n * 4;
+  if (n > 0) {
+    if (px) B2S_CUDA_TRY(cudaMemcpyAsync(px, dbg, nb, cudaMemcpyDeviceToDevice, st));
+    if (py) B2S_CUDA_TRY(cudaMemcpyAsync(py, dbg + n, nb, cudaMemcpyDeviceToDevice, st));
+    if (sx) B2S_CUDA_TRY(cudaMemcpyAsync(sx, dbg + 2 * (size_t)n, nb, cudaMemcpyDeviceToDevice, st));
+    if (sy) B2S_CUDA_TRY(cudaMemcpyAsync(sy, dbg + 3 * (size_t)n, nb, cudaMemcpyDeviceToDevice, st));
+    if (zabs) B2S_CUDA_TRY(cudaMemcpyAsync(zabs, dbg + 4 * (size_t)n, nb, cudaMemcpyDeviceToDevice, st));
+    if (cnt) B2S_CUDA_TRY(cudaMemcpyAsync(cnt, B.cnt, nb, cudaMemcpyDeviceToDevice, st));
+  }
+  if (max_pairs > 0) {
+    if (keys_sorted) B2S_CUDA_TRY(cudaMemcpyAsync(keys_sorted, ks, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
+    if (vals_sorted) B2S_CUDA_TRY(cudaMemcpyAsync(vals_sorted, B.vals, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (ranges) B2S_CUDA_TRY(cudaMemcpyAsync(ranges, B.ranges, (size_t)vp.n_tiles * 8, cudaMemcpyDeviceToDevice, st));
+  if (total) B2S_CUDA_TRY(cudaMemcpyAsync(total, &B.counters->needed, 8, cudaMemcpyDeviceToDevice, st));
+  return B2S_OK;
+}
+
+size_t b2s_sort_tmp_bytes(int64_t m) {
+  const size_t mp = (size_t)(m > 0 ? m : 1);
+  const size_t nb = (mp + SORT_KPB - 1) / SORT_KPB;
+  return align_up(mp * 8) * 2 + align_up(mp * 4) * 2 + align_up(nb * 256 * 4) +
+         align_up(((nb * 256 + 4095) / 4096 + 1) * 4) + 256;
+}
+
+int b2s_sort_pairs(b2s_ctx* ctx, const uint64_t* keys_in, const int32_t* vals_in, uint64_t* keys_out,
+                   int32_t* vals_out, int64_t m, int begin_bit, int end_bit, void* tmp, size_t tmp_bytes,
+                   void* stream) {
+  if (ctx == nullptr || tmp == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (m < 0 || m > 0x7fffffffLL || begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) { set_error("bad sort arguments"); return B2S_ERR_INVALID; }
+  if (tmp_bytes < b2s_sort_tmp_bytes(m)) { set_error("sort tmp too small"); return B2S_ERR_WORKSPACE; }
+  if (m == 0) return B2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t mp = (size_t)m;
+  const size_t nb = (mp + SORT_KPB - 1) / SORT_KPB;
+  char* q = (char*)tmp;
+  unsigned long long* kA = (unsigned long long*)q; q += align_up(mp * 8);
+  unsigned long long* kB = (unsigned long long*)q; q += align_up(mp * 8);
+  int* vA = (int*)q; q += align_up(mp * 4);
+  int* vB = (int*)q; q += align_up(mp * 4);
+  int* hist = (int*)q; q += align_up(nb * 256 * 4);
+  int* hsum = (int*)q; q += align_up(((nb * 256 + 4095) / 4096 + 1) * 4);
+  int* count_dev = (int*)q;
+  const int mi = (int)m;
+  B2S_CUDA_TRY(cudaMemcpyAsync(count_dev, &mi, 4, cudaMemcpyHostToDevice, st));
+  B2S_CUDA_TRY(cudaMemcpyAsync(kA, keys_in, mp * 8, cudaMemcpyDeviceToDevice, st));
+  B2S_CUDA_TRY(cudaMemcpyAsync(vA, vals_in, mp * 4, cudaMemcpyDeviceToDevice, st));
+  int in_b = 0;
+  int rc = launch_sort(kA, vA, kB, vB, m, count_dev, begin_bit, end_bit, hist, hsum, &in_b, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA_TRY(cudaMemcpyAsync(keys_out, in_b ? kB : kA, mp * 8, cudaMemcpyDeviceToDevice, st));
+  B2S_CUDA_TRY(cudaMemcpyAsync(vals_out, in_b ? vB : vA, mp * 4, cudaMemcpyDeviceToDevice, st));
+  return B2S_OK;
+}
+
+int b2s_fit_loss(b2s_ctx* ctx, const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
+                 int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum, void* stream) {
+  if (ctx == nullptr || rgb == nullptr || tgt == nullptr || g_rgb == nullptr || loss_accum == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (mask != nullptr && (alpha == nullptr || g_alpha == nullptr)) { set_error("mask given without alpha/g_alpha"); return B2S_ERR_INVALID; }
+  return launch_fit_loss(rgb, alpha, tgt, mask, width, height, w_sil, scale, g_rgb, g_alpha, loss_accum, (cudaStream_t)stream);
+}
+
+int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t count, int step,
+                  float lr, float beta1, float beta2, float eps, int64_t scales_begin, int64_t scales_end,
+                  float reg_scale, int64_t opac_begin, int64_t opac_end, float reg_opacity, void* stream) {
+  if (ctx == nullptr || params == nullptr || grads == nullptr || m == nullptr || v == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (step < 1) { set_error("Adam step is 1-based"); return B2S_ERR_INVALID; }
+  return launch_adam(params, grads, m, v, count, step, lr, beta1, beta2, eps, scales_begin, scales_end, reg_scale,
+                     opac_begin, opac_end, reg_opacity, (cudaStream_t)stream);
+}
+
+}  // extern "C"

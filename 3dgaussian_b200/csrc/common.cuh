@@ -1,0 +1,224 @@
+// Shared device/host definitions for libb2splat (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2splat.h"
+
+namespace b2s {
+
+constexpr int TILE = B2S_TILE;        // 16x16 pixel tiles
+constexpr int TILE_PIX = TILE * TILE;
+constexpr int REC_F4 = 3;             // per-Gaussian blend record: 3 x float4 = 48 B
+constexpr int GACC_F = 12;            // per-Gaussian backward accumulator: 12 floats = 48 B
+
+// Per-view constants handed to every kernel by value.
+struct ViewParams {
+  float view[16];
+  float proj[16];
+  float cam[3];     // inv(view)[:3,3]  (torch_renderer.py:81-83)
+  float bg[3];
+  float k;          // cutoff in sigmas
+  float wm1, hm1;   // float(W-1), float(H-1)
+  float wf, hf;     // float(W), float(H)
+  float fx, fy;     // |P00|, |P11|
+  int width, height, tiles_x, tiles_y, n_tiles;
+  int style, sh, act, exact_bbox, mode;
+};
+
+// One Gaussian after projection.  Every quantity that feeds an integer (bbox, tile rect,
+// depth key) is computed with explicitly rounded, non-contracted fp32 ops in exactly the
+// order of oracle/bins_oracle.c so that GPU and CPU agree bit for bit.
+struct Proj {
+  float px, py, sx, sy, zabs, zcam;
+  float w, wsafe, ndcx, ndcy;   // for the backward chain
+  float ax, ay;                 // unclamped sigmas
+  int xmin, ymin, xmax, ymax;   // pixel bbox (inclusive)
+  bool ok;
+};
+
+__device__ __forceinline__ float dot4_lr(const float* m, float a, float b, float c, float d) {
+  float t = __fmul_rn(m[0], a);
+  t = __fadd_rn(t, __fmul_rn(m[1], b));
+  t = __fadd_rn(t, __fmul_rn(m[2], c));
+  t = __fadd_rn(t, __fmul_rn(m[3], d));
+  return t;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// torch.nn.functional.softplus (beta=1, threshold=20)
+__device__ __forceinline__ float softplusf_acc(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ Proj project_gaussian(const ViewParams& vp, float mx, float my, float mz,
+                                                 float s0, float s1, float op) {
+  Proj r;
+  float cam[4], clip[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) cam[q] = dot4_lr(vp.view + 4 * q, mx, my, mz, 1.0f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) clip[q] = dot4_lr(vp.proj + 4 * q, cam[0], cam[1], cam[2], cam[3]);
+  const float w = clip[3];
+  float nx, ny, nz, ssx, ssy;
+  bool ok;
+  if (vp.style == B2S_STYLE_TORCH) {
+    const float ws = (fabsf(w) < 1e-8f) ? 1.0f : w;
+    nx = __fdiv_rn(clip[0], ws);
+    ny = __fdiv_rn(clip[1], ws);
+    nz = __fdiv_rn(clip[2], ws);
+    ok = (nz >= -1.0f) && (nz <= 1.0f) && (w != 0.0f);
+    r.zabs = fmaxf(fabsf(cam[2]), 1e-6f);
+    ssx = fabsf(s0);
+    ssy = fabsf(s1);
+    ok = ok && (op > 0.0f);
+    r.wsafe = ws;
+  } else {
+    const float iw = __fdiv_rn(1.0f, (w == 0.0f) ? 1.0f : w);
+    nx = __fmul_rn(clip[0], iw);
+    ny = __fmul_rn(clip[1], iw);
+    nz = __fmul_rn(clip[2], iw);
+    ok = (w != 0.0f) && !(nz < -1.0f || nz > 1.0f) && (nz == nz);
+    r.zabs = __fadd_rn(fabsf(cam[2]), 1e-6f);
+    ssx = s0;
+    ssy = s1;
+    ok = ok && (op >= 1e-5f);
+    r.wsafe = (w == 0.0f) ? 1.0f : w;
+  }
+  r.w = w;
+  r.ndcx = nx;
+  r.ndcy = ny;
+  r.zcam = cam[2];
+  r.px = __fmul_rn(__fadd_rn(__fmul_rn(nx, 0.5f), 0.5f), vp.wm1);
+  r.py = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(__fmul_rn(ny, 0.5f), 0.5f)), vp.hm1);
+  r.ax = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(ssx, 0.5f), vp.wf), vp.fx), r.zabs);
+  r.ay = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(ssy, 0.5f), vp.hf), vp.fy), r.zabs);
+  r.sx = fmaxf(r.ax, 1.0f);
+  r.sy = fmaxf(r.ay, 1.0f);
+  const float rx = __fmul_rn(vp.k, r.sx), ry = __fmul_rn(vp.k, r.sy);
+  const float lox = floorf(__fsub_rn(r.px, rx)), hix = ceilf(__fadd_rn(r.px, rx));
+  const float loy = floorf(__fsub_rn(r.py, ry)), hiy = ceilf(__fadd_rn(r.py, ry));
+  ok = ok && (hix >= 0.0f) && (lox <= vp.wm1) && (hiy >= 0.0f) && (loy <= vp.hm1);
+  r.ok = ok;
+  if (ok) {
+    r.xmin = (int)fmaxf(lox, 0.0f);
+    r.xmax = (int)fminf(hix, vp.wm1);
+    r.ymin = (int)fmaxf(loy, 0.0f);
+    r.ymax = (int)fminf(hiy, vp.hm1);
+  } else {
+    r.xmin = r.ymin = 0;
+    r.xmax = r.ymax = -1;
+  }
+  return r;
+}
+
+// ascending key order == descending camera z; same as b2o_depth_bits (oracle/bins_oracle.c)
+__device__ __forceinline__ uint32_t depth_bits(float zcam) {
+  uint32_t u = __float_as_uint(zcam);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- state / workspace layout (all offsets 256-B aligned) -------------------------------
+struct StateLayout {
+  size_t rec, ranges, vals, acc, counters, total;
+};
+struct WorkLayout {
+  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, total;
+};
+constexpr int SORT_KPB = 4096;   // keys per radix block
+constexpr int PRE_BLOCK = 256;   // Gaussians per preprocess block
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+inline StateLayout state_layout(int n, int width, int height, int64_t max_pairs) {
+  StateLayout L;
+  const int tiles = ((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
+  size_t o = 0;
+  L.counters = o; o += align_up(64);
+  L.rec = o;      o += align_up((size_t)(n > 0 ? n : 1) * REC_F4 * 16);
+  L.ranges = o;   o += align_up((size_t)tiles * 8);
+  L.vals = o;     o += align_up((size_t)(max_pairs > 0 ? max_pairs : 1) * 4);
+  L.acc = o;      o += align_up((size_t)width * height * 5 * 4);
+  L.total = o;
+  return L;
+}
+
+inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
+  WorkLayout L;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  const size_t mp = (size_t)(max_pairs > 0 ? max_pairs : 1);
+  const size_t nb_pre = (nn + PRE_BLOCK - 1) / PRE_BLOCK;
+  const size_t nb_sort = (mp + SORT_KPB - 1) / SORT_KPB;
+  size_t o = 0;
+  L.rect = o;  o += align_up(nn * 8);
+  L.dbits = o; o += align_up(nn * 4);
+  L.cnt = o;   o += align_up(nn * 4);
+  L.bsum = o;  o += align_up((nb_pre + 1) * 8);
+  L.keysA = o; o += align_up(mp * 8);
+  L.keysB = o; o += align_up(mp * 8);
+  L.valsB = o; o += align_up(mp * 4);
+  L.hist = o;  o += align_up(nb_sort * 256 * 4);
+  L.hsum = o;  o += align_up(((nb_sort * 256 + 4095) / 4096 + 1) * 4);
+  L.gacc = o;  o += align_up(nn * GACC_F * 4);
+  L.total = o;
+  return L;
+}
+
+// counters block at the head of the state buffer
+struct Counters {
+  long long needed;   // pairs the view produces
+  int kept;           // pairs actually emitted (<= max_pairs)
+  int overflow;       // 1 if needed > max_pairs
+};
+
+// ---- host-side error plumbing ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define B2S_CUDA_TRY(expr)                                                               \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      b2s::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return B2S_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+#define B2S_LAUNCH_CHECK() B2S_CUDA_TRY(cudaGetLastError())
+
+// ---- kernel launchers (defined in the .cu files) ------------------------------------------
+int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
+                      const float* opac, int n, float4* rec, uint2* rect, uint32_t* dbits, int* cnt,
+                      long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/, int* dbg_bbox,
+                      cudaStream_t st);
+int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const uint32_t* dbits,
+               const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
+               cudaStream_t st);
+// sorts (keysA, valsA) on key bits [begin_bit,end_bit); returns via *result_in_B where the result lives
+int launch_sort(unsigned long long* keysA, int* valsA, unsigned long long* keysB, int* valsB, int64_t cap,
+                const int* count_dev, int begin_bit, int end_bit, int* hist, int* hsum, int* result_in_B,
+                cudaStream_t st);
+inline int sort_passes(int begin_bit, int end_bit) { return end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0; }
+int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t cap, int n_tiles, int2* ranges,
+                  cudaStream_t st);
+int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
+                          float* out_rgb, float* out_alpha, float* out_depth, float* acc, uint8_t* out_rgba,
+                          cudaStream_t st);
+int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
+                            float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
+int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
+                          const float* acc, const float* g_rgb, const float* g_alpha, const float* g_depth,
+                          float* gacc, cudaStream_t st);
+int launch_preprocess_bwd(const ViewParams& vp, const float* means, const float* scales, const float* colors,
+                          const float* opac, int n, const float* gacc, float* g_means, float* g_scales,
+                          float* g_colors, float* g_opac, int accumulate, cudaStream_t st);
+int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
+                    int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum,
+                    cudaStream_t st);
+int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,
+                float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
+                float reg_op, cudaStream_t st);
+
+}  // namespace b2s

@@ -1,0 +1,93 @@
+// Fit-loop kernels: per-view L1 losses with their image-space gradients, and the fused
+// Adam step (+ regulariser gradients).  Reference semantics:
+//   python/fit_multiview_stub.py:292-308 (loss), :262,311 (torch.optim.Adam defaults).
+// Both are HBM-bound streaming kernels: loss 24..40 B/pixel, Adam 28 B/element.
+#include "common.cuh"
+
+namespace b2s {
+
+__device__ __forceinline__ float signf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+__global__ void __launch_bounds__(256)
+fit_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ alpha, const float* __restrict__ tgt,
+                const float* __restrict__ mask, int hw, float w_sil, float scale, float* __restrict__ g_rgb,
+                float* __restrict__ g_alpha, float* __restrict__ loss_accum) {
+  const float inv3 = 1.0f / (3.0f * (float)hw), inv1 = 1.0f / (float)hw;
+  float local = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = rgb[3 * (size_t)p + c] - tgt[3 * (size_t)p + c];
+      local += fabsf(d) * inv3;
+      g_rgb[3 * (size_t)p + c] = scale * inv3 * signf(d);
+    }
+    if (mask != nullptr) {
+      const float d = alpha[p] - mask[p];
+      local += w_sil * fabsf(d) * inv1;
+      g_alpha[p] = scale * w_sil * inv1 * signf(d);
+    }
+  }
+  __shared__ float ws[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += ws[q];
+    atomicAdd(loss_accum, scale * t);
+  }
+}
+
+int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
+                    int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum,
+                    cudaStream_t st) {
+  const int hw = width * height;
+  if (hw <= 0) return B2S_OK;
+  int blocks = (hw + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fit_loss_kernel<<<blocks, 256, 0, st>>>(rgb, alpha, tgt, mask, hw, w_sil, scale, g_rgb, g_alpha, loss_accum);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+// p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)    (torch.optim.Adam, single-tensor form)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long count, float b1, float b2, float eps, float step_size, float inv_sqrt_bc2, long long sb,
+            long long se, float reg_s, long long ob, long long oe, float reg_o) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    float pi = p[i], gi = g[i];
+    if (i >= sb && i < se) gi += reg_s * sigmoidf_acc(pi);                       // d softplus = sigmoid
+    if (i >= ob && i < oe) { const float s = sigmoidf_acc(pi); gi += reg_o * s * (1.0f - s); }
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,
+                float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
+                float reg_op, cudaStream_t st) {
+  if (count <= 0) return B2S_OK;
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float rs = (se > sb) ? reg_scale / (float)(se - sb) : 0.f;
+  const float ro = (oe > ob) ? reg_op / (float)(oe - ob) : 0.f;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, m, v, (long long)count, b1, b2, eps, step_size,
+                                            inv_sqrt_bc2, (long long)sb, (long long)se, rs, (long long)ob,
+                                            (long long)oe, ro);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+}  // namespace b2s

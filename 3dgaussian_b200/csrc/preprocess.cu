@@ -1,0 +1,375 @@
+// Per-Gaussian kernels: projection + sigma + colour/SH + bbox + tile count (forward) and the
+// chain rule back to means / scales / opacities / colours (backward).
+//
+// Replaces: _project / sigma / _eval_colors of the reference
+//   python/torch_renderer.py:57-106,143-150   and the per-thread prologue of
+//   src/renderer.cu:41-84 (AoS stride-3 loads, no culling of work).
+// HBM-bound: algorithmic bytes per Gaussian*view = 28 + 12*sh (read) + 48+16 (write).
+#include "common.cuh"
+
+namespace b2s {
+
+__device__ __forceinline__ float act_scale(const ViewParams& vp, float raw) {
+  return (vp.act & B2S_ACT_SCALES_SOFTPLUS) ? softplusf_acc(raw) + 1e-3f : raw;
+}
+__device__ __forceinline__ float act_opac(const ViewParams& vp, float raw) {
+  return (vp.act & B2S_ACT_OPACITY_SIGMOID) ? sigmoidf_acc(raw) : raw;
+}
+
+// Basis of the colour model: k=0..3 is the reference's [1, d.x, d.y, d.z]
+// (torch_renderer.py:98-103); k=4..15 are standard real-SH band 2/3 polynomials (extension).
+__device__ __forceinline__ void sh_basis(float x, float y, float z, int K, float* b) {
+  b[0] = 1.0f; b[1] = x; b[2] = y; b[3] = z;
+  if (K > 4) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = 1.0925484305920792f * xy;
+    b[5] = -1.0925484305920792f * yz;
+    b[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    b[7] = -1.0925484305920792f * xz;
+    b[8] = 0.5462742152960396f * (xx - yy);
+    if (K > 9) {
+      b[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
+      b[10] = 2.890611442640554f * xy * z;
+      b[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
+      b[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+      b[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
+      b[14] = 1.445305721320277f * z * (xx - yy);
+      b[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+    }
+  }
+}
+
+// d basis_k / d (x,y,z)
+__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, int K, float* bx, float* by, float* bz) {
+  bx[0] = by[0] = bz[0] = 0.0f;
+  bx[1] = 1.0f; by[1] = 0.0f; bz[1] = 0.0f;
+  bx[2] = 0.0f; by[2] = 1.0f; bz[2] = 0.0f;
+  bx[3] = 0.0f; by[3] = 0.0f; bz[3] = 1.0f;
+  if (K > 4) {
+    const float c0 = 1.0925484305920792f, c2 = 0.31539156525252005f, c4 = 0.5462742152960396f;
+    bx[4] = c0 * y;          by[4] = c0 * x;          bz[4] = 0.0f;
+    bx[5] = 0.0f;            by[5] = -c0 * z;         bz[5] = -c0 * y;
+    bx[6] = -2.0f * c2 * x;  by[6] = -2.0f * c2 * y;  bz[6] = 4.0f * c2 * z;
+    bx[7] = -c0 * z;         by[7] = 0.0f;            bz[7] = -c0 * x;
+    bx[8] = 2.0f * c4 * x;   by[8] = -2.0f * c4 * y;  bz[8] = 0.0f;
+    if (K > 9) {
+      const float xx = x * x, yy = y * y, zz = z * z;
+      const float d0 = -0.5900435899266435f, d1 = 2.890611442640554f, d2 = -0.4570457994644658f,
+                  d3 = 0.3731763325901154f, d5 = 1.445305721320277f;
+      // b9 = d0*y*(3xx-yy)
+      bx[9] = d0 * 6.0f * x * y;  by[9] = d0 * (3.0f * xx - 3.0f * yy);  bz[9] = 0.0f;
+      // b10 = d1*x*y*z
+      bx[10] = d1 * y * z;  by[10] = d1 * x * z;  bz[10] = d1 * x * y;
+      // b11 = d2*y*(4zz-xx-yy)
+      bx[11] = d2 * (-2.0f * x * y);  by[11] = d2 * (4.0f * zz - xx - 3.0f * yy);  bz[11] = d2 * 8.0f * y * z;
+      // b12 = d3*z*(2zz-3xx-3yy)
+      bx[12] = d3 * (-6.0f * x * z);  by[12] = d3 * (-6.0f * y * z);  bz[12] = d3 * (6.0f * zz - 3.0f * xx - 3.0f * yy);
+      // b13 = d2*x*(4zz-xx-yy)
+      bx[13] = d2 * (4.0f * zz - 3.0f * xx - yy);  by[13] = d2 * (-2.0f * x * y);  bz[13] = d2 * 8.0f * x * z;
+      // b14 = d5*z*(xx-yy)
+      bx[14] = d5 * 2.0f * x * z;  by[14] = d5 * (-2.0f * y * z);  bz[14] = d5 * (xx - yy);
+      // b15 = d0*x*(xx-3yy)
+      bx[15] = d0 * (3.0f * xx - 3.0f * yy);  by[15] = d0 * (-6.0f * x * y);  bz[15] = 0.0f;
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void load_coeffs(const float* __restrict__ colors, int i, float* c) {
+  // (N,K,3) row-major: 3K contiguous floats per Gaussian; 12K bytes is a multiple of 16 when K%4==0
+  if constexpr ((K * 3) % 4 == 0) {
+    const float4* p = reinterpret_cast<const float4*>(colors + (size_t)i * K * 3);
+#pragma unroll
+    for (int q = 0; q < K * 3 / 4; ++q) {
+      const float4 v = __ldg(p + q);
+      c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < K * 3; ++q) c[q] = __ldg(colors + (size_t)i * K * 3 + q);
+  }
+}
+
+// raw (pre-clamp) colour + the unit direction used by the SH model
+template <int K>
+__device__ __forceinline__ void eval_color(const ViewParams& vp, const float* c, float mx, float my, float mz,
+                                           float* rgb_raw, float* dir, float* rinv) {
+  if constexpr (K == 1) {
+    rgb_raw[0] = c[0]; rgb_raw[1] = c[1]; rgb_raw[2] = c[2];
+    if (vp.act & B2S_ACT_COLORS_SIGMOID) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) rgb_raw[q] = sigmoidf_acc(rgb_raw[q]);
+    }
+    dir[0] = dir[1] = dir[2] = 0.0f;
+    *rinv = 0.0f;
+  } else {
+    const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
+    const float r = sqrtf(vx * vx + vy * vy + vz * vz);
+    const float inv = 1.0f / (r + 1e-8f);
+    dir[0] = vx * inv; dir[1] = vy * inv; dir[2] = vz * inv;
+    *rinv = inv;
+    float b[16];
+    sh_basis(dir[0], dir[1], dir[2], K, b);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      r0 = fmaf(b[k], c[3 * k], r0);
+      r1 = fmaf(b[k], c[3 * k + 1], r1);
+      r2 = fmaf(b[k], c[3 * k + 2], r2);
+    }
+    rgb_raw[0] = r0; rgb_raw[1] = r1; rgb_raw[2] = r2;
+  }
+}
+
+constexpr float NEG_HALF_LOG2E = -0.72134752044448170368f;  // -0.5 * log2(e)
+
+// Forward: one thread per Gaussian.  Writes the 48-byte blend record
+//   rec[3i+0] = {px, py, qx, qy}    qx = -0.5*log2(e)/sx^2  (so w = 2^(qx dx^2 + qy dy^2 + lop))
+//   rec[3i+1] = {r, g, b, lop}      lop = log2(op)  (style NATIVE keeps op itself, see blend_sorted)
+//   rec[3i+2] = {zabs, bbox x (min|max<<16), bbox y, unused}
+// plus the tile rect / depth bits / tile count consumed by the binning kernels, and the
+// per-block sum of tile counts (first level of the exclusive scan).
+template <int K>
+__global__ void __launch_bounds__(PRE_BLOCK)
+preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const float* __restrict__ scales,
+                  const float* __restrict__ colors, const float* __restrict__ opac, int n,
+                  float4* __restrict__ rec, uint2* __restrict__ rect, uint32_t* __restrict__ dbits,
+                  int* __restrict__ cnt, long long* __restrict__ bsum, float* __restrict__ dbg,
+                  int* __restrict__ dbg_bbox) {
+  const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
+  int my_cnt = 0;
+  if (i < n) {
+    const float mx = __ldg(means + 3 * (size_t)i), my = __ldg(means + 3 * (size_t)i + 1),
+                mz = __ldg(means + 3 * (size_t)i + 2);
+    const float s0 = act_scale(vp, __ldg(scales + 3 * (size_t)i)), s1 = act_scale(vp, __ldg(scales + 3 * (size_t)i + 1));
+    const float op = act_opac(vp, __ldg(opac + i));
+    const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+    uint2 rc = make_uint2(0u, 0u);
+    if (pr.ok) {
+      const int tx0 = pr.xmin / TILE, tx1 = pr.xmax / TILE, ty0 = pr.ymin / TILE, ty1 = pr.ymax / TILE;
+      my_cnt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+      rc = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+    }
+    rect[i] = rc;
+    dbits[i] = depth_bits(pr.zcam);
+    cnt[i] = my_cnt;
+    if (rec != nullptr) {
+      float4 a, b, c;
+      if (pr.ok) {
+        float craw[3], dir[3], rinv;
+        if (colors != nullptr) {
+          float coef[K * 3];
+          load_coeffs<K>(colors, i, coef);
+          eval_color<K>(vp, coef, mx, my, mz, craw, dir, &rinv);
+        } else {
+          craw[0] = craw[1] = craw[2] = 0.0f;
+        }
+        a.x = pr.px; a.y = pr.py;
+        a.z = NEG_HALF_LOG2E / (pr.sx * pr.sx);
+        a.w = NEG_HALF_LOG2E / (pr.sy * pr.sy);
+        b.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
+        b.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
+        b.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
+        b.w = (vp.style == B2S_STYLE_TORCH) ? log2f(op) : op;
+        c.x = pr.zabs;
+        c.y = __int_as_float(pr.xmin | (pr.xmax << 16));
+        c.z = __int_as_float(pr.ymin | (pr.ymax << 16));
+        c.w = 0.0f;
+      } else {
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        b = make_float4(0.f, 0.f, 0.f, (vp.style == B2S_STYLE_TORCH) ? -INFINITY : 0.0f);
+        c = make_float4(0.f, __int_as_float(0), __int_as_float(0), 0.f);
+      }
+      rec[3 * (size_t)i] = a;
+      rec[3 * (size_t)i + 1] = b;
+      rec[3 * (size_t)i + 2] = c;
+    }
+    if (dbg != nullptr) {
+      dbg[i] = pr.px; dbg[(size_t)n + i] = pr.py; dbg[2 * (size_t)n + i] = pr.sx;
+      dbg[3 * (size_t)n + i] = pr.sy; dbg[4 * (size_t)n + i] = pr.zabs;
+    }
+    if (dbg_bbox != nullptr) {
+      dbg_bbox[4 * (size_t)i] = pr.xmin; dbg_bbox[4 * (size_t)i + 1] = pr.ymin;
+      dbg_bbox[4 * (size_t)i + 2] = pr.xmax; dbg_bbox[4 * (size_t)i + 3] = pr.ymax;
+    }
+  }
+  // block sum of tile counts -> bsum[block]
+  __shared__ int wsum[PRE_BLOCK / 32];
+  int s = my_cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+#pragma unroll
+    for (int q = 0; q < PRE_BLOCK / 32; ++q) t += wsum[q];
+    bsum[blockIdx.x] = t;
+  }
+}
+
+int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
+                      const float* opac, int n, float4* rec, uint2* rect, uint32_t* dbits, int* cnt,
+                      long long* bsum, float* dbg, int* dbg_bbox, cudaStream_t st) {
+  if (n <= 0) return B2S_OK;
+  const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
+#define B2S_PRE(KK) preprocess_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, rec, rect, dbits, cnt, bsum, dbg, dbg_bbox)
+  switch (vp.sh) {
+    case 1: B2S_PRE(1); break;
+    case 4: B2S_PRE(4); break;
+    case 9: B2S_PRE(9); break;
+    case 16: B2S_PRE(16); break;
+    default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", vp.sh); return B2S_ERR_INVALID;
+  }
+#undef B2S_PRE
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+// Backward: one thread per Gaussian.  gacc[12i..] = {dR,dG,dB,dZ, S,Sx,Sxx,Sy, Syy,-,-,-} from the
+// blend backward, where S = sum w*t, Sx = sum w*t*dx, Sxx = sum w*t*dx^2 (same for y).
+// Chain rule of SURVEY Appendix A / autograd of torch_renderer.py:57-104,143-150.
+template <int K>
+__global__ void __launch_bounds__(PRE_BLOCK)
+preprocess_bwd_kernel(const ViewParams vp, const float* __restrict__ means, const float* __restrict__ scales,
+                      const float* __restrict__ colors, const float* __restrict__ opac, int n,
+                      const float4* __restrict__ gacc, float* __restrict__ g_means, float* __restrict__ g_scales,
+                      float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
+  const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const float mx = __ldg(means + 3 * (size_t)i), my = __ldg(means + 3 * (size_t)i + 1),
+              mz = __ldg(means + 3 * (size_t)i + 2);
+  const float raw_s0 = __ldg(scales + 3 * (size_t)i), raw_s1 = __ldg(scales + 3 * (size_t)i + 1);
+  const float raw_op = __ldg(opac + i);
+  const float s0 = act_scale(vp, raw_s0), s1 = act_scale(vp, raw_s1), op = act_opac(vp, raw_op);
+  const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+
+  float gm[3] = {0.f, 0.f, 0.f}, gs0 = 0.f, gs1 = 0.f, gop = 0.f;
+  float gcoef[K * 3];
+#pragma unroll
+  for (int q = 0; q < K * 3; ++q) gcoef[q] = 0.0f;
+
+  if (pr.ok) {
+    const float4 g0 = gacc[3 * (size_t)i], g1 = gacc[3 * (size_t)i + 1], g2 = gacc[3 * (size_t)i + 2];
+    const float dC[3] = {g0.x, g0.y, g0.z};
+    float dZ = g0.w;
+    const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
+
+    // opacity: w = op * E  =>  dL/dop = S / op
+    gop = S / op;
+    if (vp.act & B2S_ACT_OPACITY_SIGMOID) gop *= op * (1.0f - op);
+
+    // position / sigma
+    const float isx2 = 1.0f / (pr.sx * pr.sx), isy2 = 1.0f / (pr.sy * pr.sy);
+    const float dpx = Sx * isx2, dpy = Sy * isy2;
+    const float dsx = Sxx * isx2 / pr.sx, dsy = Syy * isy2 / pr.sy;
+    if (pr.ax >= 1.0f) {   // clamp_min(1) passes the gradient on [1, inf)
+      const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s0 > 0.f) - (s0 < 0.f)) : 1.0f;
+      gs0 = dsx * sgn * (0.5f * vp.wf * vp.fx / pr.zabs);
+      dZ -= dsx * pr.ax / pr.zabs;
+    }
+    if (pr.ay >= 1.0f) {
+      const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s1 > 0.f) - (s1 < 0.f)) : 1.0f;
+      gs1 = dsy * sgn * (0.5f * vp.hf * vp.fy / pr.zabs);
+      dZ -= dsy * pr.ay / pr.zabs;
+    }
+    if (vp.act & B2S_ACT_SCALES_SOFTPLUS) {
+      gs0 *= sigmoidf_acc(raw_s0);
+      gs1 *= sigmoidf_acc(raw_s1);
+    }
+    // zabs = max(|cam.z|, 1e-6)
+    float dcam[4] = {0.f, 0.f, 0.f, 0.f};
+    if (fabsf(pr.zcam) >= 1e-6f) dcam[2] = dZ * ((pr.zcam > 0.f) ? 1.0f : -1.0f);
+    // px,py -> ndc -> clip
+    const float dnx = dpx * 0.5f * vp.wm1, dny = -dpy * 0.5f * vp.hm1;
+    float dclip[4];
+    dclip[0] = dnx / pr.wsafe;
+    dclip[1] = dny / pr.wsafe;
+    dclip[2] = 0.0f;
+    dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) / pr.wsafe;
+    // clip = P cam ; cam = V [m,1]
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) dcam[c] = fmaf(vp.proj[4 * r + c], dclip[r], dcam[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) gm[c] = fmaf(vp.view[4 * r + c], dcam[r], gm[c]);
+
+    // colour
+    if (colors != nullptr) {
+      float coef[K * 3], craw[3], dir[3], rinv;
+      load_coeffs<K>(colors, i, coef);
+      eval_color<K>(vp, coef, mx, my, mz, craw, dir, &rinv);
+      float dc[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) dc[q] = (craw[q] >= 0.0f && craw[q] <= 1.0f) ? dC[q] : 0.0f;
+      if constexpr (K == 1) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          gcoef[q] = (vp.act & B2S_ACT_COLORS_SIGMOID) ? dc[q] * craw[q] * (1.0f - craw[q]) : dc[q];
+      } else {
+        float b[16], bx[16], by[16], bz[16];
+        sh_basis(dir[0], dir[1], dir[2], K, b);
+        sh_basis_grad(dir[0], dir[1], dir[2], K, bx, by, bz);
+        float dd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float s = coef[3 * k] * dc[0] + coef[3 * k + 1] * dc[1] + coef[3 * k + 2] * dc[2];
+          gcoef[3 * k] = b[k] * dc[0];
+          gcoef[3 * k + 1] = b[k] * dc[1];
+          gcoef[3 * k + 2] = b[k] * dc[2];
+          dd[0] = fmaf(bx[k], s, dd[0]);
+          dd[1] = fmaf(by[k], s, dd[1]);
+          dd[2] = fmaf(bz[k], s, dd[2]);
+        }
+        // d = v/(r+eps), v = cam - m :  dv = dd/(r+eps) - v (v.dd) / (r (r+eps)^2) ; dm = -dv
+        const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
+        const float r = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float vdd = vx * dd[0] + vy * dd[1] + vz * dd[2];
+        const float k2 = (r > 0.0f) ? vdd * rinv * rinv / r : 0.0f;
+        gm[0] -= dd[0] * rinv - vx * k2;
+        gm[1] -= dd[1] * rinv - vy * k2;
+        gm[2] -= dd[2] * rinv - vz * k2;
+      }
+    }
+  }
+  if (accumulate) {
+    g_means[3 * (size_t)i] += gm[0]; g_means[3 * (size_t)i + 1] += gm[1]; g_means[3 * (size_t)i + 2] += gm[2];
+    g_scales[3 * (size_t)i] += gs0; g_scales[3 * (size_t)i + 1] += gs1;
+    g_opac[i] += gop;
+    if (g_colors != nullptr) {
+#pragma unroll
+      for (int q = 0; q < K * 3; ++q) g_colors[(size_t)i * K * 3 + q] += gcoef[q];
+    }
+  } else {
+    g_means[3 * (size_t)i] = gm[0]; g_means[3 * (size_t)i + 1] = gm[1]; g_means[3 * (size_t)i + 2] = gm[2];
+    g_scales[3 * (size_t)i] = gs0; g_scales[3 * (size_t)i + 1] = gs1; g_scales[3 * (size_t)i + 2] = 0.0f;
+    g_opac[i] = gop;
+    if (g_colors != nullptr) {
+#pragma unroll
+      for (int q = 0; q < K * 3; ++q) g_colors[(size_t)i * K * 3 + q] = gcoef[q];
+    }
+  }
+}
+
+int launch_preprocess_bwd(const ViewParams& vp, const float* means, const float* scales, const float* colors,
+                          const float* opac, int n, const float* gacc, float* g_means, float* g_scales,
+                          float* g_colors, float* g_opac, int accumulate, cudaStream_t st) {
+  if (n <= 0) return B2S_OK;
+  const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
+#define B2S_PREB(KK) preprocess_bwd_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, reinterpret_cast<const float4*>(gacc), g_means, g_scales, g_colors, g_opac, accumulate)
+  switch (vp.sh) {
+    case 1: B2S_PREB(1); break;
+    case 4: B2S_PREB(4); break;
+    case 9: B2S_PREB(9); break;
+    case 16: B2S_PREB(16); break;
+    default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", vp.sh); return B2S_ERR_INVALID;
+  }
+#undef B2S_PREB
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+}  // namespace b2s

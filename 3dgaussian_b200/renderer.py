@@ -1,0 +1,378 @@
+"""Host side of the render path: the reference's Python render API on top of libb2splat.
+
+Mirrors /root/reference/python/torch_renderer.py (names, signatures, defaults, return
+structure, exceptions): Camera :10-13, perspective :24-32, look_at :35-54,
+render_gaussians_torch :109-203 -- and the pybind entry of src/bindings.cpp:27-100
+(`render_gaussians`, numpy in / uint8 (H,W,4) out).
+
+PyTorch supplies device memory, streams and autograd plumbing only; all arithmetic of the
+render path runs in the hand-written CUDA kernels of csrc/ through the C ABI.  CUDA tensors
+only: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+@dataclass
+class Camera:
+    view: torch.Tensor  # (4,4) float32
+    proj: torch.Tensor  # (4,4) float32
+
+
+def get_default_device() -> torch.device:
+    """The reference picks cpu on Linux even with CUDA (python/device_utils.py:8-13); this
+    path only exists on CUDA, so it returns the current CUDA device and fails loudly
+    otherwise."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("3dgaussian_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def perspective(fovy_deg: float, aspect: float, znear: float, zfar: float, device=None) -> torch.Tensor:
+    f = 1.0 / torch.tan(torch.tensor(fovy_deg, device=device) * torch.pi / 180.0 * 0.5)
+    m = torch.zeros((4, 4), dtype=torch.float32, device=device)
+    m[0, 0] = f / aspect
+    m[1, 1] = f
+    m[2, 2] = (zfar + znear) / (znear - zfar)
+    m[2, 3] = (2.0 * zfar * znear) / (znear - zfar)
+    m[3, 2] = -1.0
+    return m
+
+
+def look_at(eye: torch.Tensor, target: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    eye, target, up = (t.to(dtype=torch.float32) for t in (eye, target, up))
+    fwd = target - eye
+    fwd = fwd / (torch.linalg.norm(fwd) + 1e-8)
+    upn = up / (torch.linalg.norm(up) + 1e-8)
+    side = torch.linalg.cross(fwd, upn)
+    side = side / (torch.linalg.norm(side) + 1e-8)
+    up2 = torch.linalg.cross(side, fwd)
+    rot = torch.eye(4, dtype=torch.float32, device=eye.device)
+    rot[0, :3], rot[1, :3], rot[2, :3] = side, up2, -fwd
+    trans = torch.eye(4, dtype=torch.float32, device=eye.device)
+    trans[:3, 3] = -eye
+    return rot @ trans
+
+
+# ------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _host_matrix(t) -> list:
+    if isinstance(t, torch.Tensor):
+        return t.detach().to(device="cpu", dtype=torch.float32).reshape(-1).tolist()
+    return np.asarray(t, dtype=np.float32).reshape(-1).tolist()
+
+
+def _camera_host(camera) -> tuple:
+    """Host copies of view/proj, cached on the camera object (keyed by tensor identity and
+    version counter, so in-place edits invalidate it) to avoid a D2H sync per call."""
+    v, p = camera.view, camera.proj
+    key = (id(v), getattr(v, "_version", 0), id(p), getattr(p, "_version", 0))
+    cached = getattr(camera, "_b2s_host", None)
+    if cached is not None and cached[0] == key and cached[1] is v and cached[2] is p:
+        return cached[3], cached[4]
+    hv, hp = _host_matrix(v), _host_matrix(p)
+    if len(hv) != 16 or len(hp) != 16:
+        raise ValueError("camera.view and camera.proj must be (4,4)")
+    try:
+        camera._b2s_host = (key, v, p, hv, hp)
+    except Exception:
+        pass
+    return hv, hp
+
+
+def _sh_coeffs(colors: torch.Tensor) -> int:
+    if colors.ndim == 2 and colors.shape[1] == 3:
+        return 1
+    if colors.ndim == 3 and colors.shape[2] == 3 and colors.shape[1] in (4, 9, 16):
+        return int(colors.shape[1])
+    raise ValueError("colors must be (N,3) or SH coeffs (N,4,3)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def count_pairs(params: capi.Params, means, scales, opac) -> int:
+    n = means.shape[0]
+    dev = means.device
+    ws_bytes = capi.lib().b2s_workspace_bytes(n, params.width, params.height, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    total = C.c_int64(0)
+    capi.check(capi.lib().b2s_count_pairs(capi.ctx(dev.index), C.byref(params), _ptr(means), _ptr(scales),
+                                          _ptr(opac), n, C.byref(total), _ptr(ws), ws_bytes, _stream()))
+    return int(total.value)
+
+
+class _RenderFn(torch.autograd.Function):
+    """forward -> b2s_forward, backward -> b2s_backward.  Saves the compact per-view state
+    (48 B/Gaussian records, sorted ids, tile ranges, 5 floats/pixel), not O(N*H*W)."""
+
+    @staticmethod
+    def forward(ctx, means, scales, colors, opacities, params, want_aux):
+        dev = means.device
+        n = means.shape[0]
+        m32, s32, c32, o32 = _f32c(means), _f32c(scales), _f32c(colors), _f32c(opacities)
+        L = capi.lib()
+        W, H = params.width, params.height
+        with torch.cuda.device(dev):
+            total = count_pairs(params, m32, s32, o32)
+            if total > 0x7FFFFFFF:
+                raise capi.B2SError(f"view needs {total} (Gaussian,tile) pairs; limit is 2^31-1")
+            state_bytes = L.b2s_state_bytes(n, W, H, total)
+            ws_bytes = L.b2s_workspace_bytes(n, W, H, total)
+            state = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+            depth = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+            capi.check(L.b2s_forward(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(c32),
+                                     _ptr(o32), n, total, _ptr(rgb), _ptr(alpha), _ptr(depth), _ptr(state),
+                                     state_bytes, _ptr(ws), ws_bytes, _stream()))
+        ctx.params = params
+        ctx.total = total
+        ctx.in_dtypes = (means.dtype, scales.dtype, colors.dtype, opacities.dtype)
+        ctx.colors_shape = tuple(colors.shape)
+        ctx.save_for_backward(m32, s32, c32, o32, state)
+        ctx.set_materialize_grads(False)
+        if want_aux:
+            return rgb, alpha, depth
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha=None, g_depth=None):
+        m32, s32, c32, o32, state = ctx.saved_tensors
+        dev = m32.device
+        n = m32.shape[0]
+        params, total = ctx.params, ctx.total
+        L = capi.lib()
+        W, H = params.width, params.height
+        with torch.cuda.device(dev):
+            if g_rgb is None:
+                g_rgb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+            g_rgb = _f32c(g_rgb)
+            g_alpha = None if g_alpha is None else _f32c(g_alpha)
+            g_depth = None if g_depth is None else _f32c(g_depth)
+            ws_bytes = L.b2s_workspace_bytes(n, W, H, total)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gm = torch.empty_like(m32)
+            gs = torch.empty_like(s32)
+            gc = torch.empty_like(c32)
+            go = torch.empty_like(o32)
+            capi.check(L.b2s_backward(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(c32),
+                                      _ptr(o32), n, total, _ptr(g_rgb), _ptr(g_alpha), _ptr(g_depth),
+                                      _ptr(state), _ptr(ws), ws_bytes, _ptr(gm), _ptr(gs), _ptr(gc), _ptr(go),
+                                      0, _stream()))
+        dm, ds, dc, do = ctx.in_dtypes
+        return gm.to(dm), gs.to(ds), gc.to(dc), go.to(do), None, None
+
+
+def _default_cutoff(return_aux: bool) -> float:
+    env = os.environ.get("B2S_CUTOFF_SIGMA")
+    if env:
+        return float(env)
+    # the reference has no cutoff.  k=5 keeps RGB/alpha within 1e-5 of it; the
+    # depth output (and its gradient) needs k=7 because depth = D/(W+1e-6) amplifies the tails.
+    return 7.0 if return_aux else 5.0
+
+
+def render_gaussians_torch(
+    means: torch.Tensor,      # (N,3) float32
+    scales: torch.Tensor,     # (N,3) float32
+    colors: torch.Tensor,     # (N,3) or SH coeffs (N,4,3)
+    opacities: torch.Tensor,  # (N,)  float32
+    camera: Camera,
+    width: int,
+    height: int,
+    background: Optional[torch.Tensor] = None,  # (3,)
+    max_gaussians: int = 10000,
+    chunk_size: int = 256,
+    return_aux: bool = False,
+    *,
+    cutoff_sigma: Optional[float] = None,
+    sort_depth: bool = False,
+):
+    """Drop-in for the reference's differentiable renderer (python/torch_renderer.py:109-203).
+
+    Same arguments, defaults, outputs ((H,W,3) or ((H,W,3),(H,W),(H,W)) with return_aux),
+    exceptions and quirks (n == 0 returns a bare zeros image, :135-136; n > max_gaussians
+    raises ValueError, :137-138).  `chunk_size` is accepted and ignored.  Keyword-only
+    extras: `cutoff_sigma` (bbox radius in sigmas; default 5, or 7 with return_aux) and
+    `sort_depth` (also radix-sort the depth half of the 64-bit keys).
+    """
+    if means.ndim != 2 or means.shape[1] != 3:
+        raise ValueError("means must be (N,3)")
+    if not means.is_cuda:
+        raise RuntimeError("3dgaussian_b200.render_gaussians_torch needs CUDA tensors (no CPU fallback)")
+    dev = means.device
+    n = means.shape[0]
+    if n == 0:
+        return torch.zeros((height, width, 3), dtype=torch.float32, device=dev)
+    if n > max_gaussians:
+        raise ValueError(f"N={n} too large for torch reference renderer. Increase max_gaussians or downsample.")
+    sh = _sh_coeffs(colors)
+    if background is None:
+        bg = [0.0, 0.0, 0.0]
+    elif isinstance(background, torch.Tensor):
+        bg = background.detach().to(device="cpu", dtype=torch.float32).reshape(-1).tolist()
+    else:
+        bg = [float(v) for v in background]
+    view, proj = _camera_host(camera)
+    k = _default_cutoff(return_aux) if cutoff_sigma is None else float(cutoff_sigma)
+    params = capi.make_params(width, height, view, proj, bg, mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
+                              cutoff_sigma=k, sh_coeffs=sh, sort_depth=int(sort_depth))
+    scales = scales.to(dev)
+    colors = colors.to(dev)
+    opacities = opacities.to(dev)
+    return _RenderFn.apply(means, scales, colors, opacities, params, bool(return_aux))
+
+
+# ------------------------------------------------------------------------------------------
+def render_rgba8(means, scales, colors, opacities, view, proj, width, height, background=(0.0, 0.0, 0.0),
+                 enable_depth_sort: int = 1, cutoff_sigma: float = 3.0, max_pairs: Optional[int] = None,
+                 out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """Device-resident RGBA8 frame: the gr::render_gaussians equivalent (reference
+    include/gr/renderer.h:33-39) with the arrays already in HBM.  Returns uint8 (H,W,4)."""
+    dev = means.device
+    if not means.is_cuda:
+        raise RuntimeError("render_rgba8 needs CUDA tensors (no CPU fallback)")
+    n = means.shape[0]
+    m32, s32, c32, o32 = _f32c(means), _f32c(scales), _f32c(colors), _f32c(opacities)
+    params = capi.make_params(width, height, _host_matrix(view), _host_matrix(proj), background,
+                              mode=capi.MODE_SORTED if enable_depth_sort else capi.MODE_WSUM,
+                              style=capi.STYLE_NATIVE, cutoff_sigma=cutoff_sigma, sh_coeffs=1,
+                              sort_depth=1 if enable_depth_sort else 0, exact_bbox=1)
+    L = capi.lib()
+    with torch.cuda.device(dev):
+        if max_pairs is None:
+            max_pairs = count_pairs(params, m32, s32, o32)
+        need = L.b2s_workspace_bytes(n, width, height, max_pairs) + L.b2s_state_bytes(n, width, height, max_pairs)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((height, width, 4), dtype=torch.uint8, device=dev)
+        capi.check(L.b2s_render_rgba8(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(c32),
+                                      _ptr(o32), n, max_pairs, _ptr(out), _ptr(workspace), workspace.numel(),
+                                      _stream()))
+    return out
+
+
+def _require_f32c(arr, name):
+    if not isinstance(arr, np.ndarray):
+        raise RuntimeError(f"{name} must be a numpy array")
+    if arr.dtype.kind != "f" or arr.dtype.itemsize != 4:
+        raise RuntimeError(f"{name} must be float32")
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise RuntimeError(f"{name} must be C-contiguous")
+
+
+def render_gaussians(means, scales, colors, opacities, width=800, height=600, view=None, proj=None,
+                     background=None, *, enable_depth_sort: int = 0, device: int = 0):
+    """Same call as the reference's pybind module `gaussian_renderer.render_gaussians`
+    (src/bindings.cpp:29-100): float32 C-contiguous numpy in, uint8 (H,W,4) out,
+    RuntimeError on malformed input.  Host buffers in and out through b2s_render_rgba8_host."""
+    for a, nm in ((means, "means"), (scales, "scales"), (colors, "colors"), (opacities, "opacities"),
+                  (view, "view"), (proj, "proj")):
+        _require_f32c(a, nm)
+    if means.ndim != 2 or means.shape[1] != 3:
+        raise RuntimeError("means must be (N,3)")
+    if scales.ndim != 2 or scales.shape[1] != 3:
+        raise RuntimeError("scales must be (N,3)")
+    if colors.ndim != 2 or colors.shape[1] != 3:
+        raise RuntimeError("colors must be (N,3)")
+    if opacities.ndim != 1:
+        raise RuntimeError("opacities must be (N,)")
+    if view.shape != (4, 4):
+        raise RuntimeError("view must be (4,4)")
+    if proj.shape != (4, 4):
+        raise RuntimeError("proj must be (4,4)")
+    if background is None:
+        bg = np.zeros(3, np.float32)
+    else:
+        bg = background
+        _require_f32c(bg, "background")
+        if bg.ndim != 1 or bg.shape[0] != 3:
+            raise RuntimeError("background must be (3,)")
+    n = means.shape[0]
+    if scales.shape[0] != n or colors.shape[0] != n or opacities.shape[0] != n:
+        raise RuntimeError("means/scales/colors/opacities must have matching N")
+    params = capi.make_params(width, height, view.reshape(-1), proj.reshape(-1), bg,
+                              mode=capi.MODE_SORTED if enable_depth_sort else capi.MODE_WSUM,
+                              style=capi.STYLE_NATIVE, cutoff_sigma=3.0, sh_coeffs=1,
+                              sort_depth=1 if enable_depth_sort else 0, exact_bbox=1)
+    out = np.empty((height, width, 4), np.uint8)
+    vp = C.c_void_p
+    capi.check(capi.lib().b2s_render_rgba8_host(capi.ctx(device), C.byref(params), vp(means.ctypes.data),
+                                                vp(scales.ctypes.data), vp(colors.ctypes.data),
+                                                vp(opacities.ctypes.data), n, vp(out.ctypes.data)))
+    return out
+
+
+def dump_bins(means, scales, opacities, view, proj, width, height, cutoff_sigma=5.0, style=capi.STYLE_TORCH,
+              sort_depth=1):
+    """Test hook over b2s_dump_bins: returns the integer pipeline's intermediates as CPU numpy."""
+    dev = means.device
+    n = means.shape[0]
+    m32, s32, o32 = _f32c(means), _f32c(scales), _f32c(opacities)
+    params = capi.make_params(width, height, _host_matrix(view), _host_matrix(proj), (0, 0, 0),
+                              style=style, cutoff_sigma=cutoff_sigma, sort_depth=sort_depth)
+    L = capi.lib()
+    with torch.cuda.device(dev):
+        total = count_pairs(params, m32, s32, o32)
+        mp = max(total, 1)
+        tiles = ((width + 15) // 16) * ((height + 15) // 16)
+        need = (L.b2s_workspace_bytes(n, width, height, mp) + L.b2s_state_bytes(n, width, height, mp) +
+                (max(n, 1) * 20 + 512))
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        f = lambda: torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        px, py, sx, sy, zabs = f(), f(), f(), f(), f()
+        bbox = torch.zeros((max(n, 1), 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        ku = torch.zeros(mp, dtype=torch.int64, device=dev)
+        vu = torch.zeros(mp, dtype=torch.int32, device=dev)
+        ks = torch.zeros(mp, dtype=torch.int64, device=dev)
+        vs = torch.zeros(mp, dtype=torch.int32, device=dev)
+        ranges = torch.zeros((tiles, 2), dtype=torch.int32, device=dev)
+        tot = torch.zeros(1, dtype=torch.int64, device=dev)
+        capi.check(L.b2s_dump_bins(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(o32), n, mp,
+                                   _ptr(px), _ptr(py), _ptr(sx), _ptr(sy), _ptr(zabs), _ptr(bbox), _ptr(cnt),
+                                   _ptr(ku), _ptr(vu), _ptr(ks), _ptr(vs), _ptr(ranges), _ptr(tot), _ptr(ws),
+                                   ws.numel(), _stream()))
+        torch.cuda.synchronize(dev)
+    t = int(tot.item())
+    assert t == total
+    u64 = lambda a: a[:t].cpu().numpy().view(np.uint64)
+    return dict(px=px[:n].cpu().numpy(), py=py[:n].cpu().numpy(), sx=sx[:n].cpu().numpy(),
+                sy=sy[:n].cpu().numpy(), zabs=zabs[:n].cpu().numpy(), bbox=bbox[:n].cpu().numpy(),
+                cnt=cnt[:n].cpu().numpy(), total=t, keys_unsorted=u64(ku), vals_unsorted=vu[:t].cpu().numpy(),
+                keys=u64(ks), vals=vs[:t].cpu().numpy(), ranges=ranges.cpu().numpy())
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, begin_bit=0, end_bit=64):
+    """Test/bench hook over b2s_sort_pairs (keys int64 viewed as uint64, vals int32)."""
+    dev = keys.device
+    m = keys.numel()
+    L = capi.lib()
+    with torch.cuda.device(dev):
+        tmp_bytes = L.b2s_sort_tmp_bytes(m)
+        tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+        ko = torch.empty_like(keys)
+        vo = torch.empty_like(vals)
+        capi.check(L.b2s_sort_pairs(capi.ctx(dev.index), _ptr(keys), _ptr(vals), _ptr(ko), _ptr(vo), m,
+                                    begin_bit, end_bit, _ptr(tmp), tmp_bytes, _stream()))
+    return ko, vo

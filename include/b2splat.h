@@ -1,0 +1,167 @@
+/* b2splat -- C-ABI of the B200-native Gaussian-splatting rasterizer (libb2splat.so).
+ *
+ * This header is the drop-in boundary for the render path of Kirkice/3DGaussian.
+ * It replaces, for that path only:
+ *   - the native entry   gr::render_gaussians          (reference include/gr/renderer.h:33-39,
+ *                                                        src/renderer_dispatch.cpp:5-21)
+ *   - the pybind module  gaussian_renderer             (reference src/bindings.cpp:27-100)
+ *   - and it is what a torch.autograd.Function binds to stand in for
+ *     render_gaussians_torch                           (reference python/torch_renderer.py:109-203)
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
+ *     name ends in _host; nothing is allocated or freed inside the hot calls except by
+ *     b2s_render_rgba8_host, which keeps a grow-only device cache in the ctx (the role of
+ *     the reference's static DeviceBuffers, src/renderer.cu:287-349);
+ *   - work is enqueued on the caller's CUDA stream (pass the raw cudaStream_t as void*);
+ *     no implicit synchronisation unless documented;
+ *   - return value 0 = success, negative = error; the message is available from
+ *     b2s_last_error() (thread-local).  Nothing throws across the ABI.  There is no CPU
+ *     fallback: params.force_cpu != 0 is rejected with B2S_ERR_UNSUPPORTED.
+ *   - matrices are 4x4 row-major float, column-vector convention (p_cam = view * [m,1]),
+ *     exactly as RenderParams (reference include/gr/gaussian_types.h:24-46).
+ */
+#ifndef B2SPLAT_H_
+#define B2SPLAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_ERR_INVALID -1      /* bad argument */
+#define B2S_ERR_CUDA -2         /* CUDA runtime error, see b2s_last_error */
+#define B2S_ERR_UNSUPPORTED -3  /* e.g. force_cpu, unsupported tile size */
+#define B2S_ERR_WORKSPACE -4    /* workspace / state buffer too small */
+#define B2S_ERR_OVERFLOW -5     /* more (Gaussian,tile) pairs than max_pairs (only from syncing calls) */
+
+#define B2S_TILE 16             /* pixels per tile edge */
+
+/* blend modes (reference include/gr/gaussian_types.h:30-34 `enable_depth_sort`) */
+#define B2S_MODE_WSUM 0         /* order-independent weighted sum (torch_renderer.py, renderer_cpu.cpp mode 0) */
+#define B2S_MODE_SORTED 1       /* depth-sorted front-to-back "over" (renderer_cpu.cpp:125-217) */
+
+/* arithmetic style of the per-Gaussian projection */
+#define B2S_STYLE_TORCH 0       /* python/torch_renderer.py:57-78,147-150 (|s|, max(|z|,1e-6), divide by w_safe, op clamp_min 0) */
+#define B2S_STYLE_NATIVE 1      /* src/renderer_cpu.cpp:166-200 (signed s, |z|+1e-6, multiply by 1/w, skip a<1e-5) */
+
+/* activation flags: parameters are passed raw and activated inside the preprocess kernel
+ * (python/fit_multiview_stub.py:268-275) */
+#define B2S_ACT_SCALES_SOFTPLUS 1   /* scales = softplus(raw) + 1e-3 */
+#define B2S_ACT_OPACITY_SIGMOID 2   /* opacities = sigmoid(raw) */
+#define B2S_ACT_COLORS_SIGMOID 4    /* colors = sigmoid(raw), (N,3) colours only */
+
+typedef struct b2s_ctx b2s_ctx;
+
+/* Mirrors gr::RenderParams field for field, then the knobs the reference hard-codes. */
+typedef struct b2s_params {
+  int32_t width;
+  int32_t height;
+  float view[16];
+  float proj[16];
+  float background[3];
+  int32_t enable_depth_sort; /* B2S_MODE_* */
+  int32_t depth_slices;      /* accepted and ignored: sorting is exact, not sliced (src/renderer.cu:106-189) */
+  int32_t force_cpu;         /* must be 0 */
+  /* ---- extensions (the reference hard-codes these) ---- */
+  int32_t style;             /* B2S_STYLE_* */
+  float cutoff_sigma;        /* bbox half-size in sigmas; reference C++ uses 3 (renderer_cpu.cpp:96-97) */
+  int32_t sh_coeffs;         /* colour floats per Gaussian / 3: 1 (RGB), 4 (reference "SH"), 9, 16 */
+  int32_t sort_depth;        /* 1: radix-sort the full 64-bit tile|depth key; 0: tile bits only (stable) */
+  int32_t act_flags;         /* B2S_ACT_* */
+  int32_t exact_bbox;        /* 1: a Gaussian only touches pixels inside its bbox (renderer_cpu.cpp:202-203) */
+} b2s_params;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+b2s_ctx* b2s_create(int device);
+void b2s_destroy(b2s_ctx* ctx);
+const char* b2s_last_error(void);
+const char* b2s_version(void);
+
+/* ---- sizes ------------------------------------------------------------------------------ */
+/* bytes of the per-view state saved by b2s_forward for b2s_backward */
+size_t b2s_state_bytes(int n, int width, int height, int64_t max_pairs);
+/* bytes of transient scratch needed by any call below */
+size_t b2s_workspace_bytes(int n, int width, int height, int64_t max_pairs);
+
+/* Number of (Gaussian,tile) pairs this view produces.  Runs the projection + count and
+ * SYNCHRONISES the stream to return the total on the host. */
+int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                    const float* opacities, int n, int64_t* total_host, void* workspace,
+                    size_t ws_bytes, void* stream);
+
+/* ---- differentiable render (stands in for render_gaussians_torch) --------------------- */
+/* out_rgb (H,W,3), out_alpha (H,W), out_depth (H,W) float32; alpha/depth may be NULL.
+ * colors: (N,3) or (N,sh_coeffs,3).  If the view needs more than max_pairs pairs the extra
+ * ones are dropped and state's overflow counter is set (query with b2s_state_info). */
+int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                const float* colors, const float* opacities, int n, int64_t max_pairs,
+                float* out_rgb, float* out_alpha, float* out_depth, void* state, size_t state_bytes,
+                void* workspace, size_t ws_bytes, void* stream);
+
+/* Gradients of sum(out_rgb*g_rgb + out_alpha*g_alpha + out_depth*g_depth) wrt the inputs.
+ * g_alpha / g_depth may be NULL (treated as zeros).  accumulate != 0: grads are added to
+ * the output buffers, else overwritten.  grad_scales is (N,3) with column 2 == 0. */
+int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                 const float* colors, const float* opacities, int n, int64_t max_pairs,
+                 const float* g_rgb, const float* g_alpha, const float* g_depth, const void* state,
+                 void* workspace, size_t ws_bytes, float* grad_means, float* grad_scales,
+                 float* grad_colors, float* grad_opacities, int accumulate, void* stream);
+
+/* info_host[0] = pairs needed, [1] = pairs kept, [2] = overflow flag.  Synchronises. */
+int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,
+                   int64_t* info_host, void* stream);
+
+/* ---- RGBA8 frame (stands in for gr::render_gaussians) --------------------------------- */
+/* device-resident inputs, device output (H,W,4) uint8 */
+int b2s_render_rgba8(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                     const float* colors, const float* opacities, int n, int64_t max_pairs,
+                     uint8_t* out_rgba, void* workspace, size_t ws_bytes, void* stream);
+/* HOST pointers in and out, same argument meaning as gr::render_gaussians; synchronous. */
+int b2s_render_rgba8_host(b2s_ctx* ctx, const b2s_params* p, const float* means_host,
+                          const float* scales_host, const float* colors_host,
+                          const float* opacities_host, int n, uint8_t* out_rgba_host);
+
+/* ---- binning dump (bit-exact tests) ------------------------------------------------------ */
+/* Runs projection -> count -> scan -> key emit -> radix sort -> tile ranges and copies the
+ * intermediate results into caller buffers (any may be NULL):
+ *   px,py,sx,sy,zabs: float[n]; bbox: int32[4n]; cnt: int32[n];
+ *   keys_unsorted/keys_sorted: uint64[max_pairs]; vals_unsorted/vals_sorted: int32[max_pairs];
+ *   ranges: int32[2*tiles]; total: int64[1] (device). */
+int b2s_dump_bins(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
+                  const float* opacities, int n, int64_t max_pairs, float* px, float* py, float* sx,
+                  float* sy, float* zabs, int32_t* bbox, int32_t* cnt, uint64_t* keys_unsorted,
+                  int32_t* vals_unsorted, uint64_t* keys_sorted, int32_t* vals_sorted, int32_t* ranges,
+                  int64_t* total, void* workspace, size_t ws_bytes, void* stream);
+
+/* Stand-alone stable LSD radix sort of (uint64 key, int32 value) pairs on key bits
+ * [begin_bit, end_bit); result in keys_out/vals_out.  tmp: b2s_sort_tmp_bytes(m). */
+size_t b2s_sort_tmp_bytes(int64_t m);
+int b2s_sort_pairs(b2s_ctx* ctx, const uint64_t* keys_in, const int32_t* vals_in, uint64_t* keys_out,
+                   int32_t* vals_out, int64_t m, int begin_bit, int end_bit, void* tmp, size_t tmp_bytes,
+                   void* stream);
+
+/* ---- fit-loop kernels (python/fit_multiview_stub.py:292-311) --------------------------- */
+/* Per-view loss  mean|rgb-tgt| + w_sil*mean|alpha-mask|  and its gradient wrt rgb/alpha,
+ * scaled by `scale` (1/V).  mask/g_alpha may be NULL.  Adds the loss value to *loss_accum. */
+int b2s_fit_loss(b2s_ctx* ctx, const float* rgb, const float* alpha, const float* tgt,
+                 const float* mask, int width, int height, float w_sil, float scale,
+                 float* g_rgb, float* g_alpha, float* loss_accum, void* stream);
+
+/* torch.optim.Adam step (defaults beta=(0.9,0.999), eps=1e-8, no weight decay) over a flat
+ * parameter buffer; step is 1-based.  Optional fused regulariser gradients of
+ *   reg_opacity*mean(sigmoid(op_raw)) + reg_scale*mean(softplus(scales_raw)+1e-3)
+ * (fit_multiview_stub.py:307) for the element ranges [scales_begin,scales_end),
+ * [opac_begin,opac_end) of the flat buffer (pass empty ranges to disable). */
+int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t count,
+                  int step, float lr, float beta1, float beta2, float eps, int64_t scales_begin,
+                  int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
+                  float reg_opacity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SPLAT_H_ */

@@ -1,0 +1,283 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C ABI vs the CPU oracles
+and the golden vectors of the unmodified reference.
+
+Tolerances (BASELINE.json north_star): keys / sort order / tile ranges bit-exact; images
+max-abs <= 1e-4; gradients relative L2 <= 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from conftest import golden_names, load_golden, rel_l2
+from gpu_util import camera, dev, pkg, to_dev
+from oracle import cpu as ocpu
+from oracle import r1_oracle as r1
+
+pytestmark = pytest.mark.gpu
+
+R1 = golden_names("r1_")
+R2 = golden_names("r2_")
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def _render(g, return_aux=True, **kw):
+    r = pkg("renderer")
+    m, s, c, o, bg = to_dev(g["means"], g["scales"], g["colors"], g["opac"], g["bg"])
+    cam = camera(g["view"], g["proj"])
+    return r.render_gaussians_torch(m, s, c, o, cam, int(g["width"]), int(g["height"]), background=bg,
+                                    max_gaussians=10 ** 7, return_aux=return_aux, **kw)
+
+
+# ---------------------------------------------------------------- integer pipeline ---------
+def _check_bins(means, scales, opac, view, proj, W, H, k, style, sort_depth):
+    r = pkg("renderer")
+    m, s, o = to_dev(means, scales, opac)
+    got = r.dump_bins(m, s, o, view, proj, W, H, cutoff_sigma=k, style=style, sort_depth=sort_depth)
+    ref = ocpu.bin_gaussians(means, scales, opac, view, proj, W, H, k=k, style=style,
+                             begin_bit=0 if sort_depth else 32)
+    assert got["total"] == ref["total"]
+    for key in ("px", "py", "sx", "sy", "zabs"):
+        assert np.array_equal(got[key].view(np.uint32), ref[key].view(np.uint32)), key   # bit-exact floats
+    on = ref["cnt"] > 0
+    assert np.array_equal(got["cnt"], ref["cnt"])
+    assert np.array_equal(got["bbox"][on], ref["bbox"][on])
+    assert np.array_equal(got["keys_unsorted"], ref["keys_unsorted"])
+    assert np.array_equal(got["vals_unsorted"], ref["vals_unsorted"])
+    assert np.array_equal(got["keys"], ref["keys"])
+    assert np.array_equal(got["vals"], ref["vals"])
+    assert np.array_equal(got["ranges"], ref["ranges"])
+    return got
+
+
+@pytest.mark.parametrize("name", R1)
+@pytest.mark.parametrize("sort_depth", [0, 1])
+def test_bins_bit_exact_golden_scenes(name, sort_depth):
+    g = load_golden(name)
+    _check_bins(g["means"], g["scales"], g["opac"], g["view"], g["proj"], int(g["width"]), int(g["height"]),
+                5.0, 0, sort_depth)
+
+
+@pytest.mark.parametrize("style,k", [(0, 5.0), (0, 7.0), (1, 3.0)])
+@pytest.mark.parametrize("n,W,H", [(1, 16, 16), (257, 33, 17), (5000, 320, 200), (200000, 960, 540)])
+def test_bins_bit_exact_random(style, k, n, W, H):
+    means, scales, colors, opac = scenes.make_scene(100 + n, n, s_lo=0.004, s_hi=0.05, edge_cases=n >= 16)
+    view, proj = scenes.orbit_camera(3, 7, W, H)
+    _check_bins(means, scales, opac, view, proj, W, H, k, style, 1)
+
+
+def test_bins_all_culled_and_empty_tiles():
+    means, scales, colors, opac = scenes.make_scene(5, 64)
+    means[:, 2] += 50.0                      # everything behind the camera
+    view, proj = scenes.orbit_camera(0, 1, 64, 48)
+    got = _check_bins(means, scales, opac, view, proj, 64, 48, 5.0, 0, 1)
+    assert got["total"] == 0 and not got["ranges"].any()
+
+
+@pytest.mark.parametrize("m", [1, 31, 4096, 4097, 1 << 20])
+@pytest.mark.parametrize("bits", [(0, 64), (32, 45), (0, 45), (8, 20)])
+def test_radix_sort_matches_stable_sort(m, bits):
+    r = pkg("renderer")
+    rng = np.random.RandomState(m)
+    keys = rng.randint(0, 2 ** 63 - 1, size=m, dtype=np.int64).view(np.uint64)
+    keys[rng.rand(m) < 0.3] &= np.uint64(0xFFFF_0000_FFFF_0000)     # many ties
+    vals = np.arange(m, dtype=np.int32)
+    k_d, v_d = to_dev(keys.view(np.int64), vals)
+    ko, vo = r.sort_pairs(k_d, v_d, bits[0], bits[1])
+    field = (keys >> np.uint64(bits[0])) & np.uint64((1 << (bits[1] - bits[0])) - 1)
+    order = np.argsort(field, kind="stable")
+    assert np.array_equal(vo.cpu().numpy(), vals[order])
+    assert np.array_equal(ko.cpu().numpy().view(np.uint64), keys[order])
+
+
+# ---------------------------------------------------------------- images --------------------
+@pytest.mark.parametrize("name", R1)
+def test_image_matches_reference_golden(name):
+    g = load_golden(name)
+    rgb, alpha, depth = _render(g, True)            # aux => k = 7
+    assert np.abs(rgb.cpu().numpy() - g["rgb"]).max() <= IMG_TOL
+    assert np.abs(alpha.cpu().numpy() - g["alpha"]).max() <= IMG_TOL
+    m = g["alpha"] > 1e-2                           # depth is ill-conditioned where W ~ 0
+    assert np.abs(depth.cpu().numpy() - g["depth"])[m].max() <= 1e-3
+    rgb5 = _render(g, False)                        # no aux => k = 5
+    assert np.abs(rgb5.cpu().numpy() - g["rgb"]).max() <= IMG_TOL
+
+
+@pytest.mark.parametrize("sh", [1, 4, 9, 16])
+def test_image_matches_oracle_larger(sh):
+    n, W, H = 3000, 160, 120
+    means, scales, colors, opac = scenes.make_scene(40 + sh, n, sh=sh, s_lo=0.01, s_hi=0.08)
+    view, proj = scenes.orbit_camera(2, 5, W, H)
+    bg = np.array([0.1, 0.0, 0.2], np.float32)
+    t = lambda a: torch.from_numpy(a)
+    ref = r1.render_r1(t(means), t(scales), t(colors), t(opac), t(view), t(proj), W, H, background=t(bg))
+    g = dict(means=means, scales=scales, colors=colors, opac=opac, view=view, proj=proj, bg=bg, width=W, height=H)
+    rgb, alpha, depth = _render(g, True)
+    assert np.abs(rgb.cpu().numpy() - ref[0].numpy()).max() <= IMG_TOL
+    assert np.abs(alpha.cpu().numpy() - ref[1].numpy()).max() <= IMG_TOL
+    m = ref[1].numpy() > 1e-2
+    assert np.abs(depth.cpu().numpy() - ref[2].numpy())[m].max() <= 1e-3
+
+
+# ---------------------------------------------------------------- gradients -----------------
+def _grads(g, use_depth, **kw):
+    r = pkg("renderer")
+    m, s, c, o, bg = to_dev(g["means"], g["scales"], g["colors"], g["opac"], g["bg"])
+    leaves = [x.requires_grad_(True) for x in (m, s, c, o)]
+    cam = camera(g["view"], g["proj"])
+    rgb, alpha, depth = r.render_gaussians_torch(*leaves, cam, int(g["width"]), int(g["height"]), background=bg,
+                                                 max_gaussians=10 ** 7, return_aux=True, **kw)
+    g_rgb, g_alpha, g_depth = to_dev(g["g_rgb"], g["g_alpha"], g["g_depth"])
+    loss = (rgb * g_rgb).sum() + (alpha * g_alpha).sum()
+    if use_depth:
+        loss = loss + (depth * g_depth).sum()
+    loss.backward()
+    return [x.grad.cpu().numpy() for x in leaves]
+
+
+@pytest.mark.parametrize("name", R1)
+@pytest.mark.parametrize("tag", ["nodepth", "depth"])
+def test_gradients_match_reference_autograd(name, tag):
+    g = load_golden(name)
+    got = _grads(g, tag == "depth")
+    for arr, key in zip(got, ("means", "scales", "colors", "opac")):
+        assert rel_l2(arr, g[f"grad_{key}_{tag}"]) <= GRAD_TOL, key
+    assert not got[1][:, 2].any()                   # scales[:,2] never receives a gradient
+
+
+@pytest.mark.parametrize("sh", [1, 4, 9, 16])
+def test_gradients_match_oracle_fp64(sh):
+    n, W, H = 1200, 96, 80
+    means, scales, colors, opac = scenes.make_scene(60 + sh, n, sh=sh, s_lo=0.01, s_hi=0.1)
+    view, proj = scenes.orbit_camera(1, 6, W, H)
+    rng = np.random.RandomState(7)
+    g = dict(means=means, scales=scales, colors=colors, opac=opac, view=view, proj=proj,
+             bg=np.array([0.2, 0.1, 0.0], np.float32), width=W, height=H,
+             g_rgb=rng.randn(H, W, 3).astype(np.float32), g_alpha=rng.randn(H, W).astype(np.float32),
+             g_depth=(0.1 * rng.randn(H, W)).astype(np.float32))
+    dt = torch.float64
+    t = lambda a: torch.from_numpy(a).to(dt)
+    leaves = [t(g[k]).requires_grad_(True) for k in ("means", "scales", "colors", "opac")]
+    rgb, alpha, depth = r1.render_r1(*leaves, t(view), t(proj), W, H, background=t(g["bg"]))
+    loss = (rgb * t(g["g_rgb"])).sum() + (alpha * t(g["g_alpha"])).sum() + (depth * t(g["g_depth"])).sum()
+    loss.backward()
+    got = _grads(g, True)
+    for arr, leaf, key in zip(got, leaves, ("means", "scales", "colors", "opac")):
+        assert rel_l2(arr, leaf.grad.numpy()) <= GRAD_TOL, key
+
+
+# ---------------------------------------------------------------- native RGBA8 --------------
+@pytest.mark.parametrize("name", R2)
+@pytest.mark.parametrize("depth_sort", [1, 0])
+def test_rgba8_matches_reference_cpu_renderer(name, depth_sort):
+    g = load_golden(name)
+    r = pkg("renderer")
+    want = g["rgba_sorted" if depth_sort else "rgba_wsum"].astype(np.int32)
+    # device-resident entry
+    m, s, c, o = to_dev(g["means"], g["scales"], g["colors"], g["opac"])
+    img = r.render_rgba8(m, s, c, o, g["view"], g["proj"], int(g["width"]), int(g["height"]), g["bg"],
+                         enable_depth_sort=depth_sort).cpu().numpy().astype(np.int32)
+    assert np.abs(img - want).max() <= 1
+    assert (img == want).mean() >= 0.99
+    # host-pointer entry (the gr::render_gaussians / pybind signature)
+    img2 = r.render_gaussians(g["means"], g["scales"], g["colors"], g["opac"], int(g["width"]), int(g["height"]),
+                              g["view"], g["proj"], g["bg"], enable_depth_sort=depth_sort).astype(np.int32)
+    assert np.array_equal(img2, img)
+    assert (img2[..., 3] == 255).all()
+
+
+def test_rgba8_vs_compiled_reference_medium():
+    if not ocpu.have_r2ref():
+        pytest.skip("oracle/_ref/libr2ref.so not available")
+    r = pkg("renderer")
+    n, W, H = 50000, 480, 270
+    means, scales, colors, opac = scenes.make_scene(77, n, s_lo=0.004, s_hi=0.03)
+    view, proj = scenes.orbit_camera(0, 1, W, H)
+    bg = np.array([0.02, 0.02, 0.02], np.float32)
+    for ds in (1, 0):
+        want = ocpu.r2_render(means, scales, colors, opac, view, proj, W, H, bg, depth_sort=ds).astype(np.int32)
+        got = r.render_gaussians(means, scales, colors, opac, W, H, view, proj, bg, enable_depth_sort=ds).astype(np.int32)
+        assert np.abs(got - want).max() <= 1
+        assert (got == want).mean() >= 0.99
+
+
+# ---------------------------------------------------------------- drop-in behaviour ---------
+def test_dropin_quirks():
+    r = pkg("renderer")
+    d = dev()
+    cam = camera(*scenes.orbit_camera(0, 4, 32, 24))
+    z = lambda *s: torch.zeros(*s, device=d)
+    out = r.render_gaussians_torch(z(0, 3), z(0, 3), z(0, 3), z(0), cam, 32, 24, return_aux=True)
+    assert isinstance(out, torch.Tensor) and out.shape == (24, 32, 3) and not out.any()   # torch_renderer.py:135-136
+    with pytest.raises(ValueError):
+        r.render_gaussians_torch(z(11, 3), z(11, 3), z(11, 3), z(11), cam, 32, 24, max_gaussians=10)
+    with pytest.raises(ValueError):
+        r.render_gaussians_torch(z(5, 2), z(5, 3), z(5, 3), z(5), cam, 32, 24)
+    with pytest.raises(ValueError):
+        r.render_gaussians_torch(z(5, 3), z(5, 3), z(5, 5, 3), z(5), cam, 32, 24)
+    with pytest.raises(RuntimeError):
+        c = torch.zeros(5, 3)
+        r.render_gaussians_torch(c, c, c, torch.zeros(5), cam, 32, 24)
+    with pytest.raises(RuntimeError):
+        r.render_gaussians(np.zeros((4, 3)), np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32),
+                           np.zeros(4, np.float32), 8, 8, np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32))
+
+
+def test_permutation_invariance_and_cutoff_consistency_full_hd():
+    """Size-independent properties at a size the dense oracle cannot reach."""
+    r = pkg("renderer")
+    n, W, H = 300000, 1920, 1080
+    means, scales, colors, opac = scenes.make_scene(9, n, s_lo=0.004, s_hi=0.02)
+    view, proj = scenes.orbit_camera(5, 64, W, H)
+    cam = camera(view, proj)
+    m, s, c, o = to_dev(means, scales, colors, opac)
+    a = r.render_gaussians_torch(m, s, c, o, cam, W, H, max_gaussians=n)
+    perm = torch.randperm(n, device=dev())
+    b = r.render_gaussians_torch(m[perm], s[perm], c[perm], o[perm], cam, W, H, max_gaussians=n)
+    assert (a - b).abs().max().item() <= 2e-5
+    c7 = r.render_gaussians_torch(m, s, c, o, cam, W, H, max_gaussians=n, cutoff_sigma=7.0)
+    assert (a - c7).abs().max().item() <= IMG_TOL
+    d = r.render_gaussians_torch(m, s, c, o, cam, W, H, max_gaussians=n, sort_depth=True)
+    assert (a - d).abs().max().item() <= 2e-5
+
+
+# ---------------------------------------------------------------- fit-loop kernels ----------
+def test_adam_matches_torch():
+    import ctypes as C
+    capi = pkg("capi")
+    d = dev()
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device=d)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=0.02)
+    p, m, v = p0.clone(), torch.zeros(n, device=d), torch.zeros(n, device=d)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(1, 8):
+        g = torch.randn(n, device=d)
+        ref_p.grad = g.clone()
+        opt.step()
+        capi.check(capi.lib().b2s_adam_step(capi.ctx(0), p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, step,
+                                            0.02, 0.9, 0.999, 1e-8, 0, 0, 0.0, 0, 0, 0.0, st))
+        assert torch.allclose(p, ref_p.detach(), rtol=2e-5, atol=2e-6)
+
+
+def test_fit_loss_matches_torch():
+    import ctypes as C
+    capi = pkg("capi")
+    d = dev()
+    torch.manual_seed(1)
+    H, W = 77, 130
+    rgb = torch.rand(H, W, 3, device=d, requires_grad=True)
+    alpha = torch.rand(H, W, device=d, requires_grad=True)
+    tgt, mask = torch.rand(H, W, 3, device=d), (torch.rand(H, W, device=d) > 0.5).float()
+    loss = r1.fit_loss(rgb, alpha, None, tgt, mask, None, silhouette_weight=0.2) * 0.25
+    loss.backward()
+    g_rgb, g_alpha, acc = torch.empty_like(rgb), torch.empty_like(alpha), torch.zeros(1, device=d)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(capi.lib().b2s_fit_loss(capi.ctx(0), rgb.data_ptr(), alpha.data_ptr(), tgt.data_ptr(), mask.data_ptr(), W, H,
+                                       0.2, 0.25, g_rgb.data_ptr(), g_alpha.data_ptr(), acc.data_ptr(), st))
+    assert abs(acc.item() - loss.item()) <= 1e-5
+    assert torch.allclose(g_rgb, rgb.grad, atol=1e-9)
+    assert torch.allclose(g_alpha, alpha.grad, atol=1e-9)
