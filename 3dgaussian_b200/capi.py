@@ -21,7 +21,7 @@ EXPORTS = [
     "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_version", "b2s_state_bytes", "b2s_workspace_bytes",
     "b2s_count_pairs", "b2s_forward", "b2s_backward", "b2s_state_info", "b2s_render_rgba8",
     "b2s_render_rgba8_host", "b2s_dump_bins", "b2s_sort_tmp_bytes", "b2s_sort_pairs", "b2s_fit_loss",
-    "b2s_adam_step",
+    "b2s_adam_step", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
 ]
 
 
@@ -84,8 +84,30 @@ def lib() -> C.CDLL:
         L.b2s_adam_step.restype = i32
         L.b2s_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
                                     i64, i64, C.c_float, i64, i64, C.c_float, vp]
+        L.b2s_launch_count.restype = i64
+        L.b2s_launch_count.argtypes = []
+        L.b2s_num_stages.restype = i32
+        L.b2s_stage_name.restype = C.c_char_p
+        L.b2s_stage_name.argtypes = [i32]
+        L.b2s_timing_enable.restype = i32
+        L.b2s_timing_enable.argtypes = [vp, i32]
+        L.b2s_timing_read.restype = i32
+        L.b2s_timing_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i64)]
         _lib = L
     return _lib
+
+
+def timing_enable(device_index: int, on: bool) -> None:
+    check(lib().b2s_timing_enable(ctx(device_index), 1 if on else 0))
+
+
+def timing_read(device_index: int) -> dict:
+    """{stage name: (milliseconds, spans)} accumulated since the last read."""
+    ns = lib().b2s_num_stages()
+    ms = (C.c_float * ns)()
+    cnt = (C.c_int64 * ns)()
+    check(lib().b2s_timing_read(ctx(device_index), ms, cnt))
+    return {lib().b2s_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(ns)}
 
 
 def check(rc: int) -> None:

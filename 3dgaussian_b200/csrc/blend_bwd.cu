@@ -79,12 +79,16 @@ blend_wsum_bwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
       b = __ldg(rec + 3 * (size_t)id + 1);
       z = __ldg(reinterpret_cast<const float*>(rec + 3 * (size_t)id + 2));
     }
+    // op == 0 (log2 op = -inf): the forward weight is 0 but torch's clamp_min(0) still passes
+    // dL/dop = sum E*t at 0, so sweep with E instead of w and keep only S.
+    const bool zero_op = (b.w == -INFINITY);
+    const float lop = zero_op ? 0.0f : b.w;
     const float dx0 = x0 - a.x;
     float ex[TILE], colS[TILE];
 #pragma unroll
     for (int c = 0; c < TILE; ++c) {
       const float dx = dx0 + (float)c;
-      ex[c] = fmaf(a.z * dx, dx, b.w);   // qx dx^2 + log2(op)
+      ex[c] = fmaf(a.z * dx, dx, lop);   // qx dx^2 + log2(op)
       colS[c] = 0.f;
     }
     float dR = 0.f, dG = 0.f, dB = 0.f, dZ = 0.f, S = 0.f, Sy = 0.f, Syy = 0.f;
@@ -130,6 +134,7 @@ blend_wsum_bwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
       Sx += cd;
       Sxx = fmaf(cd, dx, Sxx);
     }
+    if (zero_op) dR = dG = dB = dZ = Sx = Sxx = Sy = Syy = 0.0f;
     if (active) {
       float* dst = gacc + (size_t)id * GACC_F;
       red_add_v4(dst, dR, dG, dB, dZ);

@@ -3,14 +3,46 @@
 // src/bindings.cpp:27-100) and the host wrapper of src/renderer.cu:272-408.
 #include <math.h>
 #include <stdarg.h>
+#include <atomic>
+#include <vector>
 #include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
 
+struct b2s_ctx {
+  int device;
+  // grow-only cache used by b2s_render_rgba8_host only
+  void* host_dev = nullptr;
+  size_t host_dev_bytes = 0;
+  // optional per-stage event timing
+  bool timing = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+};
+
 namespace b2s {
 
 static thread_local char g_err[512] = "";
+
+struct StageTimer {   // RAII: records an event pair around one stage when ctx->timing is on
+  b2s_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  StageTimer(b2s_ctx* ctx, int stage, cudaStream_t s) : c(ctx), st(s) {
+    if (c == nullptr || !c->timing) { c = nullptr; return; }
+    cudaEvent_t e[2];
+    for (int i = 0; i < 2; ++i) {
+      if (!c->pool.empty()) { e[i] = c->pool.back(); c->pool.pop_back(); }
+      else if (cudaEventCreate(&e[i]) != cudaSuccess) { c = nullptr; return; }
+    }
+    cudaEventRecord(e[0], st);
+    b = e[1];
+    c->spans.push_back({stage, e[0], e[1]});
+  }
+  ~StageTimer() { if (c != nullptr) cudaEventRecord(b, st); }
+};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,6 +50,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // inverse of a row-major 4x4 (Gauss-Jordan, double) -> camera centre inv(V)[:3,3]
 static bool camera_centre(const float* v, float* cam) {
@@ -133,11 +168,15 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
 
 // projection -> count -> scan -> emit -> sort -> ranges.  On return the sorted Gaussian ids are
 // in B.vals (state) and the sorted keys in *keys_sorted.
-static int run_binning(const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
+static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
                        const float* colors, const float* opac, int n, int64_t max_pairs, const Bufs& B,
                        float* dbg, int* dbg_bbox, unsigned long long** keys_sorted,
                        unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
-  int rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+  int rc;
+  {
+    StageTimer t(ctx, ST_PREPROCESS, st);
+    rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+  }
   if (rc != B2S_OK) return rc;
   const int begin_bit = p->sort_depth ? 0 : 32;
   const int end_bit = 32 + tile_bits(vp.n_tiles);
@@ -147,17 +186,26 @@ static int run_binning(const ViewParams& vp, const b2s_params* p, const float* m
   unsigned long long* kB = B.keysB;
   int* vA = (passes % 2 == 0) ? B.vals : B.valsB;
   int* vB = (passes % 2 == 0) ? B.valsB : B.vals;
-  rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
+  {
+    StageTimer t(ctx, ST_BIN, st);
+    rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
+  }
   if (rc != B2S_OK) return rc;
   if (keys_unsorted_copy != nullptr)
     B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, kA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
   if (vals_unsorted_copy != nullptr)
     B2S_CUDA_TRY(cudaMemcpyAsync(vals_unsorted_copy, vA, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, st));
   int in_b = 0;
-  rc = launch_sort(kA, vA, kB, vB, max_pairs, &B.counters->kept, begin_bit, end_bit, B.hist, B.hsum, &in_b, st);
+  {
+    StageTimer t(ctx, ST_SORT, st);
+    rc = launch_sort(kA, vA, kB, vB, max_pairs, &B.counters->kept, begin_bit, end_bit, B.hist, B.hsum, &in_b, st);
+  }
   if (rc != B2S_OK) return rc;
   unsigned long long* ks = in_b ? kB : kA;
-  rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
+  {
+    StageTimer t(ctx, ST_RANGES, st);
+    rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
+  }
   if (rc != B2S_OK) return rc;
   if (keys_sorted != nullptr) *keys_sorted = ks;
   return B2S_OK;
@@ -180,13 +228,6 @@ static int check_sizes(int n, int w, int h, int64_t mp, size_t state_bytes, bool
 
 using namespace b2s;
 
-struct b2s_ctx {
-  int device;
-  // grow-only cache used by b2s_render_rgba8_host only
-  void* host_dev = nullptr;
-  size_t host_dev_bytes = 0;
-};
-
 extern "C" {
 
 const char* b2s_last_error(void) { return g_err; }
@@ -206,6 +247,8 @@ b2s_ctx* b2s_create(int device) {
 void b2s_destroy(b2s_ctx* ctx) {
   if (ctx == nullptr) return;
   if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
+  for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto& e : ctx->pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -253,8 +296,9 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
   if (rc != B2S_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(state, workspace, n, p->width, p->height, max_pairs);
-  rc = run_binning(vp, p, means, scales, colors, opacities, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  rc = run_binning(ctx, vp, p, means, scales, colors, opacities, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, nullptr, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, out_depth, B.acc, nullptr, st);
@@ -278,9 +322,13 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   if (n == 0) return B2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
-  B2S_CUDA_TRY(cudaMemsetAsync(B.gacc, 0, (size_t)n * GACC_F * sizeof(float), st));
-  rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.acc, g_rgb, g_alpha, g_depth, B.gacc, st);
+  {
+    StageTimer t(ctx, ST_BLEND_BWD, st);
+    B2S_CUDA_TRY(cudaMemsetAsync(B.gacc, 0, (size_t)n * GACC_F * sizeof(float), st));
+    rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.acc, g_rgb, g_alpha, g_depth, B.gacc, st);
+  }
   if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_PREPROCESS_BWD, st);
   return launch_preprocess_bwd(vp, means, scales, colors, opacities, n, B.gacc, grad_means, grad_scales,
                                grad_colors, grad_opacities, accumulate, st);
 }
@@ -300,7 +348,7 @@ int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height
 }
 
 // The RGBA8 paths keep their "state" inside the workspace: workspace = [work | state].
-static int render_rgba8_impl(const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
+static int render_rgba8_impl(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
                              const float* colors, const float* opac, int n, int64_t max_pairs, uint8_t* out_rgba,
                              void* workspace, size_t ws_bytes, cudaStream_t st) {
   const size_t wbytes = work_layout(n, p->width, p->height, max_pairs).total;
@@ -310,8 +358,9 @@ static int render_rgba8_impl(const ViewParams& vp, const b2s_params* p, const fl
     return B2S_ERR_WORKSPACE;
   }
   Bufs B = resolve((char*)workspace + wbytes, workspace, n, p->width, p->height, max_pairs);
-  int rc = run_binning(vp, p, means, scales, colors, opac, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  int rc = run_binning(ctx, vp, p, means, scales, colors, opac, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, out_rgba, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, nullptr, nullptr, out_rgba, st);
@@ -325,7 +374,7 @@ int b2s_render_rgba8(b2s_ctx* ctx, const b2s_params* p, const float* means, cons
   int rc = make_view(p, &vp);
   if (rc != B2S_OK) return rc;
   if (n < 0 || max_pairs < 0 || max_pairs > 0x7fffffffLL) { set_error("bad n or max_pairs"); return B2S_ERR_INVALID; }
-  return render_rgba8_impl(vp, p, means, scales, colors, opacities, n, max_pairs, out_rgba, workspace, ws_bytes,
+  return render_rgba8_impl(ctx, vp, p, means, scales, colors, opacities, n, max_pairs, out_rgba, workspace, ws_bytes,
                            (cudaStream_t)stream);
 }
 
@@ -393,7 +442,7 @@ int b2s_render_rgba8_host(b2s_ctx* ctx, const b2s_params* p, const float* means_
     B2S_CUDA_TRY(cudaMemcpyAsync(dop, opacities_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
   B2S_CUDA_TRY(cudaMemcpyAsync(dc, colors_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
-  rc = render_rgba8_impl(vp, p, dm, ds, dc, dop, n, total, dimg, ws, need, st);
+  rc = render_rgba8_impl(ctx, vp, p, dm, ds, dc, dop, n, total, dimg, ws, need, st);
   if (rc != B2S_OK) return rc;
   B2S_CUDA_TRY(cudaMemcpyAsync(out_rgba_host, dimg, pixels * 4, cudaMemcpyDeviceToHost, st));
   B2S_CUDA_TRY(cudaStreamSynchronize(st));
@@ -419,7 +468,7 @@ int b2s_dump_bins(b2s_ctx* ctx, const b2s_params* p, const float* means, const f
   Bufs B = resolve((char*)workspace + wbytes, workspace, n, p->width, p->height, max_pairs);
   float* dbg = (float*)((char*)workspace + wbytes + sbytes);
   unsigned long long* ks = nullptr;
-  rc = run_binning(vp, p, means, scales, nullptr, opacities, n, max_pairs, B, dbg, bbox, &ks,
+  rc = run_binning(ctx, vp, p, means, scales, nullptr, opacities, n, max_pairs, B, dbg, bbox, &ks,
                    (unsigned long long*)keys_unsorted, vals_unsorted, st);
   if (rc != B2S_OK) return rc;
   const size_t nb = (size_t)n * 4;
@@ -481,6 +530,7 @@ int b2s_fit_loss(b2s_ctx* ctx, const float* rgb, const float* alpha, const float
                  int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum, void* stream) {
   if (ctx == nullptr || rgb == nullptr || tgt == nullptr || g_rgb == nullptr || loss_accum == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   if (mask != nullptr && (alpha == nullptr || g_alpha == nullptr)) { set_error("mask given without alpha/g_alpha"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_LOSS, (cudaStream_t)stream);
   return launch_fit_loss(rgb, alpha, tgt, mask, width, height, w_sil, scale, g_rgb, g_alpha, loss_accum, (cudaStream_t)stream);
 }
 
@@ -489,8 +539,38 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
                   float reg_scale, int64_t opac_begin, int64_t opac_end, float reg_opacity, void* stream) {
   if (ctx == nullptr || params == nullptr || grads == nullptr || m == nullptr || v == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   if (step < 1) { set_error("Adam step is 1-based"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_ADAM, (cudaStream_t)stream);
   return launch_adam(params, grads, m, v, count, step, lr, beta1, beta2, eps, scales_begin, scales_end, reg_scale,
                      opac_begin, opac_end, reg_opacity, (cudaStream_t)stream);
+}
+
+int64_t b2s_launch_count(void) { return (int64_t)g_launches.load(); }
+int b2s_num_stages(void) { return ST_COUNT; }
+const char* b2s_stage_name(int stage) {
+  static const char* names[ST_COUNT] = {"preprocess", "bin", "sort", "ranges", "blend_fwd", "loss",
+                                        "blend_bwd", "preprocess_bwd", "adam"};
+  return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
+}
+int b2s_timing_enable(b2s_ctx* ctx, int on) {
+  if (ctx == nullptr) { set_error("NULL ctx"); return B2S_ERR_INVALID; }
+  ctx->timing = on != 0;
+  return B2S_OK;
+}
+int b2s_timing_read(b2s_ctx* ctx, float* ms_per_stage, int64_t* spans_per_stage) {
+  if (ctx == nullptr || ms_per_stage == nullptr || spans_per_stage == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  for (int s = 0; s < ST_COUNT; ++s) { ms_per_stage[s] = 0.f; spans_per_stage[s] = 0; }
+  if (!ctx->spans.empty()) B2S_CUDA_TRY(cudaEventSynchronize(ctx->spans.back().b));
+  for (auto& sp : ctx->spans) {
+    float ms = 0.f;
+    B2S_CUDA_TRY(cudaEventSynchronize(sp.b));
+    B2S_CUDA_TRY(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    ms_per_stage[sp.stage] += ms;
+    spans_per_stage[sp.stage] += 1;
+    ctx->pool.push_back(sp.a);
+    ctx->pool.push_back(sp.b);
+  }
+  ctx->spans.clear();
+  return B2S_OK;
 }
 
 }  // extern "C"

@@ -69,7 +69,7 @@ __device__ __forceinline__ Proj project_gaussian(const ViewParams& vp, float mx,
     r.zabs = fmaxf(fabsf(cam[2]), 1e-6f);
     ssx = fabsf(s0);
     ssy = fabsf(s1);
-    ok = ok && (op > 0.0f);
+    ok = ok && (op >= 0.0f);   // op == 0 stays: weight 0, but clamp_min(0) passes dL/dop at 0
     r.wsafe = ws;
   } else {
     const float iw = __fdiv_rn(1.0f, (w == 0.0f) ? 1.0f : w);
@@ -186,7 +186,15 @@ void set_error(const char* fmt, ...);
       return B2S_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
-#define B2S_LAUNCH_CHECK() B2S_CUDA_TRY(cudaGetLastError())
+void count_launch();
+#define B2S_LAUNCH_CHECK()             \
+  do {                                 \
+    b2s::count_launch();               \
+    B2S_CUDA_TRY(cudaGetLastError());  \
+  } while (0)
+
+// pipeline stages, for the optional CUDA-event timing of b2s_timing_*
+enum Stage { ST_PREPROCESS = 0, ST_BIN, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_LOSS, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_ADAM, ST_COUNT };
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------
 int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,

@@ -256,7 +256,7 @@ preprocess_bwd_kernel(const ViewParams vp, const float* __restrict__ means, cons
     const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
 
     // opacity: w = op * E  =>  dL/dop = S / op
-    gop = S / op;
+    gop = (op > 0.0f) ? S / op : S;   // at op == 0 the blend backward accumulated sum E*t directly
     if (vp.act & B2S_ACT_OPACITY_SIGMOID) gop *= op * (1.0f - op);
 
     // position / sigma

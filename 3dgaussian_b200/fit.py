@@ -1,0 +1,221 @@
+"""On-device multi-view fit loop (the hot loop of the reference's
+python/fit_multiview_stub.py:265-311 without the per-view Python autograd graph).
+
+One FitDriver per process / GPU.  Parameters, gradients and Adam state are flat fp32
+buffers laid out [means 3N | scales_raw 3N | opacities_raw N | colours C*N]; activations
+(softplus+1e-3, sigmoid; fit_multiview_stub.py:268-275) are applied inside the preprocess
+kernels, the per-view loss (mean|pred-tgt| + w_sil*mean|alpha-mask|, :292-297) and the Adam
+step with the regulariser gradients (:307-311) are fused kernels of libb2splat.
+
+Multi-GPU (torch.distributed, NCCL): parameters are replicated, view i belongs to rank
+i % world; every rank accumulates the gradients of its views into the flat buffer, ONE
+all-reduce (sum) combines them, then every rank runs the identical Adam step, so the
+replicas stay bit-identical without a broadcast.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import capi
+from .renderer import _ptr, _stream, count_pairs
+
+
+def local_views(num_views: int, rank: int, world: int) -> List[int]:
+    """Round-robin view sharding: orbit neighbours (similar cost) land on different ranks."""
+    return [i for i in range(num_views) if i % world == rank]
+
+
+class FitDriver:
+    def __init__(self, n: int, sh_coeffs: int, width: int, height: int,
+                 cameras: Sequence[Tuple[Sequence[float], Sequence[float]]], device: torch.device,
+                 lr: float = 0.02, silhouette_weight: float = 0.2, reg_opacity: float = 1e-3,
+                 reg_scale: float = 1e-3, cutoff_sigma: float = 5.0, background=(0.0, 0.0, 0.0),
+                 rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25):
+        if device.type != "cuda":
+            raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
+        self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
+        self.dev = device
+        self.lr, self.w_sil = float(lr), float(silhouette_weight)
+        self.reg_op, self.reg_scale = float(reg_opacity), float(reg_scale)
+        self.rank, self.world, self.pg = rank, world, process_group
+        self.num_views = len(cameras)
+        self.views = local_views(self.num_views, rank, world)
+        act = capi.ACT_SCALES_SOFTPLUS | capi.ACT_OPACITY_SIGMOID | (capi.ACT_COLORS_SIGMOID if self.sh == 1 else 0)
+        self.params_c = {i: capi.make_params(width, height, cameras[i][0], cameras[i][1], background,
+                                             mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
+                                             cutoff_sigma=cutoff_sigma, sh_coeffs=self.sh, sort_depth=0,
+                                             act_flags=act) for i in self.views}
+        c = 3 * self.sh
+        self.o_means, self.o_scales, self.o_opac, self.o_colors = 0, 3 * n, 6 * n, 7 * n
+        self.count = (7 + c) * n
+        z = lambda: torch.zeros(self.count, dtype=torch.float32, device=device)
+        self.p, self.g, self.m, self.v = z(), z(), z(), z()
+        self.step_no = 0
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=device)
+        self.rgb = torch.empty((height, width, 3), dtype=torch.float32, device=device)
+        self.alpha = torch.empty((height, width), dtype=torch.float32, device=device)
+        self.g_rgb = torch.empty_like(self.rgb)
+        self.g_alpha = torch.empty_like(self.alpha)
+        self.pair_slack = pair_slack
+        self.max_pairs = 0
+        self.state = self.ws = None
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.targets: dict = {}
+        self.masks: dict = {}
+        self._copy_stream = None
+        self._stage = None
+
+    # ---- parameter views -------------------------------------------------------------------
+    def means(self): return self.p[self.o_means:self.o_scales].view(self.n, 3)
+    def scales_raw(self): return self.p[self.o_scales:self.o_opac].view(self.n, 3)
+    def opacities_raw(self): return self.p[self.o_opac:self.o_colors]
+    def colors_raw(self):
+        t = self.p[self.o_colors:]
+        return t.view(self.n, 3) if self.sh == 1 else t.view(self.n, self.sh, 3)
+
+    def set_params(self, means, scales_raw, opacities_raw, colors_raw):
+        with torch.no_grad():
+            self.means().copy_(means)
+            self.scales_raw().copy_(scales_raw)
+            self.opacities_raw().copy_(opacities_raw)
+            self.colors_raw().copy_(colors_raw)
+        self.m.zero_(); self.v.zero_()
+        self.step_no = 0
+
+    def _pp(self, off):  # raw device pointer into a flat buffer
+        return C.c_void_p(self.p.data_ptr() + 4 * off)
+
+    def _gp(self, off):
+        return C.c_void_p(self.g.data_ptr() + 4 * off)
+
+    # ---- capacity ----------------------------------------------------------------------------
+    def plan(self, extra_slack: float = 1.0):
+        """Sizes the pair buffers from the current parameters (one count pass per local view;
+        synchronises).  Called once up front and again if a step reports an overflow."""
+        worst = 0
+        with torch.cuda.device(self.dev):
+            sc = torch.nn.functional.softplus(self.scales_raw()) + 1e-3
+            op = torch.sigmoid(self.opacities_raw())
+            for i in self.views:
+                pc = capi.make_params(self.W, self.H, list(self.params_c[i].view), list(self.params_c[i].proj),
+                                      (0, 0, 0), cutoff_sigma=self.params_c[i].cutoff_sigma)
+                worst = max(worst, count_pairs(pc, self.means().contiguous(), sc.contiguous(), op.contiguous()))
+            self.max_pairs = max(int(worst * self.pair_slack * extra_slack) + 4096, 4096)
+            L = capi.lib()
+            self.state_bytes = L.b2s_state_bytes(self.n, self.W, self.H, self.max_pairs)
+            self.ws_bytes = L.b2s_workspace_bytes(self.n, self.W, self.H, self.max_pairs)
+            self.state = torch.empty(self.state_bytes, dtype=torch.uint8, device=self.dev)
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+            self._counters = self.state[:16].view(torch.int32)   # needed(lo,hi), kept, overflow
+        return worst
+
+    # ---- targets -------------------------------------------------------------------------------
+    def set_targets(self, targets: dict, masks: Optional[dict] = None):
+        """Device-resident targets {view index: (H,W,3) float32} (+ masks {(H,W)})."""
+        self.targets, self.masks = dict(targets), dict(masks or {})
+
+    def render_view(self, i: int, out_rgb=None, out_alpha=None):
+        """Forward only (used to synthesise targets)."""
+        if self.state is None:
+            self.plan()
+        out_rgb = self.rgb if out_rgb is None else out_rgb
+        out_alpha = self.alpha if out_alpha is None else out_alpha
+        with torch.cuda.device(self.dev):
+            capi.check(capi.lib().b2s_forward(
+                capi.ctx(self.dev.index), C.byref(self.params_c[i]), self._pp(self.o_means), self._pp(self.o_scales),
+                self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, _ptr(out_rgb), _ptr(out_alpha),
+                None, _ptr(self.state), self.state_bytes, _ptr(self.ws), self.ws_bytes, _stream()))
+        return out_rgb, out_alpha
+
+    # ---- one fit iteration -------------------------------------------------------------------
+    def _view_fwd_bwd(self, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor]):
+        L, ctx, st = capi.lib(), capi.ctx(self.dev.index), _stream()
+        pc = C.byref(self.params_c[i])
+        capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
+                                 self._pp(self.o_opac), self.n, self.max_pairs, _ptr(self.rgb), _ptr(self.alpha), None,
+                                 _ptr(self.state), self.state_bytes, _ptr(self.ws), self.ws_bytes, st))
+        self.overflow += self._counters[3]
+        capi.check(L.b2s_fit_loss(ctx, _ptr(self.rgb), _ptr(self.alpha), _ptr(tgt), _ptr(mask), self.W, self.H,
+                                  self.w_sil, 1.0 / self.num_views, _ptr(self.g_rgb),
+                                  _ptr(self.g_alpha) if mask is not None else None, _ptr(self.loss_dev), st))
+        capi.check(L.b2s_backward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
+                                  self._pp(self.o_opac), self.n, self.max_pairs, _ptr(self.g_rgb),
+                                  _ptr(self.g_alpha) if mask is not None else None, None, _ptr(self.state),
+                                  _ptr(self.ws), self.ws_bytes, self._gp(self.o_means), self._gp(self.o_scales),
+                                  self._gp(self.o_colors), self._gp(self.o_opac), 1, st))
+
+    def _finish_step(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.g, group=self.pg)
+            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+        self.step_no += 1
+        capi.check(capi.lib().b2s_adam_step(
+            capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
+            self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_opac, self.reg_scale, self.o_opac, self.o_colors,
+            self.reg_op, _stream()))
+
+    def step(self):
+        """fwd + bwd over this rank's views (device-resident targets) + all-reduce + Adam.
+        Returns the device scalar holding sum_i loss_i / V (without the regulariser)."""
+        if self.state is None:
+            self.plan()
+        with torch.cuda.device(self.dev):
+            self.g.zero_()
+            self.loss_dev.zero_()
+            for i in self.views:
+                self._view_fwd_bwd(i, self.targets[i], self.masks.get(i))
+            self._finish_step()
+        return self.loss_dev
+
+    def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None) -> float:
+        """Same iteration fed from PINNED HOST buffers: every view's target (and mask) is copied
+        host->device inside the step (double-buffered on a side stream so the copy of view k+1
+        overlaps the kernels of view k) and the loss is read back to the host at the end."""
+        if self.state is None:
+            self.plan()
+        with torch.cuda.device(self.dev):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.dev)
+                self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(2)]
+                self._ev_ready = [torch.cuda.Event() for _ in range(2)]
+                self._ev_free = [torch.cuda.Event() for _ in range(2)]
+            main = torch.cuda.current_stream()
+            self.g.zero_()
+            self.loss_dev.zero_()
+            use_mask = host_masks is not None
+
+            def issue(k):
+                slot = k % 2
+                i = self.views[k]
+                with torch.cuda.stream(self._copy_stream):
+                    if k >= 2:
+                        self._copy_stream.wait_event(self._ev_free[slot])
+                    self._stage[slot][0].copy_(host_targets[i], non_blocking=True)
+                    if use_mask:
+                        self._stage[slot][1].copy_(host_masks[i], non_blocking=True)
+                    self._ev_ready[slot].record(self._copy_stream)
+
+            if self.views:
+                issue(0)
+            for k, i in enumerate(self.views):
+                if k + 1 < len(self.views):
+                    issue(k + 1)
+                slot = k % 2
+                main.wait_event(self._ev_ready[slot])
+                self._view_fwd_bwd(i, self._stage[slot][0], self._stage[slot][1] if use_mask else None)
+                self._ev_free[slot].record(main)
+            self._finish_step()
+            return float(self.loss_dev.item())
+
+    def check_overflow(self) -> bool:
+        """True if any view since the last call needed more pairs than the buffers hold."""
+        v = int(self.overflow.item())
+        self.overflow.zero_()
+        return v != 0
+
+    def launches_per_step(self) -> int:
+        """Kernels of ours launched by one step on this rank (counted by the library)."""
+        return -1

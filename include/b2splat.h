@@ -161,6 +161,18 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
                   int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
                   float reg_opacity, void* stream);
 
+/* ---- instrumentation -------------------------------------------------------------------- */
+/* number of kernels this library has launched in this process (all contexts) */
+int64_t b2s_launch_count(void);
+/* Per-stage CUDA-event timing.  While enabled, every stage launched through `ctx` is
+ * bracketed by events on the caller's stream.  b2s_timing_read synchronises on the last
+ * event, adds up elapsed milliseconds and launch counts per stage (arrays of
+ * b2s_num_stages() entries) and clears the log. */
+int b2s_num_stages(void);
+const char* b2s_stage_name(int stage);
+int b2s_timing_enable(b2s_ctx* ctx, int on);
+int b2s_timing_read(b2s_ctx* ctx, float* ms_per_stage, int64_t* spans_per_stage);
+
 #ifdef __cplusplus
 }
 #endif

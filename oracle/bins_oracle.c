@@ -67,7 +67,7 @@ int64_t b2o_project(const float* means, const float* scales, const float* opac,
       ok = (nz >= -1.0f) && (nz <= 1.0f) && (w != 0.0f);
       zabs = fmaxf(fabsf(cam[2]), 1e-6f);
       ssx = fabsf(scales[3 * i]); ssy = fabsf(scales[3 * i + 1]);
-      ok = ok && (opac[i] > 0.0f);            /* clamp_min(0): weight is exactly 0 */
+      ok = ok && (opac[i] >= 0.0f);           /* clamp_min(0): op<0 has weight 0 and gradient 0; op==0 keeps dL/dop */
     } else {                     /* renderer_cpu.cpp:172-181 */
       const float iw = 1.0f / ((w == 0.0f) ? 1.0f : w);
       nx = clip[0] * iw; ny = clip[1] * iw; nz = clip[2] * iw;
