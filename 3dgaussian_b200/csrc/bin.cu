@@ -100,6 +100,63 @@ int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect
   return B2S_OK;
 }
 
+// Work-unit table: tile t gets max(1, ceil(count_t / SEG)) units (an empty tile keeps one so
+// that its background pixels are written).  unit_start[t] = exclusive prefix, unit_start[n_tiles]
+// = number of units; units[u] = (tile, segment).  One block: n_tiles is a few thousand.
+__global__ void __launch_bounds__(1024)
+units_kernel(const int2* __restrict__ ranges, int n_tiles, int unit_cap, int* __restrict__ unit_start,
+             int2* __restrict__ units) {
+  __shared__ int wtot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    int v = 0;
+    if (t < n_tiles) {
+      const int2 rg = ranges[t];
+      const int c = rg.y - rg.x;
+      v = c > 0 ? (c + SEG - 1) / SEG : 1;
+    }
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int s = wtot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      wtot[lane] = s;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (wid > 0 ? wtot[wid - 1] : 0) + (x - v);
+    if (t < n_tiles) {
+      unit_start[t] = excl;
+      for (int s = 0; s < v; ++s)
+        if (excl + s < unit_cap) units[excl + s] = make_int2(t, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wtot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) unit_start[n_tiles] = carry_s < unit_cap ? carry_s : unit_cap;
+}
+
+int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st) {
+  units_kernel<<<1, 1024, 0, st>>>(ranges, n_tiles, (int)unit_cap, unit_start, units);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 // ranges[t] = [start, end) of tile t in the sorted list; (0,0) for empty tiles (memset before).
 __global__ void ranges_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ count_dev,
                               int2* __restrict__ ranges) {

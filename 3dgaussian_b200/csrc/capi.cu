@@ -135,11 +135,17 @@ struct Bufs {  // resolved pointers into state / workspace
   int* valsB;
   int *hist, *hsum;
   float* gacc;
+  int* unit_start;
+  int2* units;
+  float* partial;
+  float* gbuf;
+  int64_t unit_cap;
 };
 
 static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
   Bufs b;
   memset(&b, 0, sizeof(b));
+  b.unit_cap = max_units(w, h, mp);
   if (state != nullptr) {
     const StateLayout S = state_layout(n, w, h, mp);
     char* s = (char*)state;
@@ -148,6 +154,8 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.ranges = (int2*)(s + S.ranges);
     b.vals = (int*)(s + S.vals);
     b.acc = (float*)(s + S.acc);
+    b.unit_start = (int*)(s + S.unit_start);
+    b.units = (int2*)(s + S.units);
   }
   if (ws != nullptr) {
     const WorkLayout L = work_layout(n, w, h, mp);
@@ -162,6 +170,8 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.hist = (int*)(q + L.hist);
     b.hsum = (int*)(q + L.hsum);
     b.gacc = (float*)(q + L.gacc);
+    b.partial = (float*)(q + L.partial);
+    b.gbuf = (float*)(q + L.gbuf);
   }
   return b;
 }
@@ -205,6 +215,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   {
     StageTimer t(ctx, ST_RANGES, st);
     rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
+    if (rc == B2S_OK) rc = launch_units(B.ranges, vp.n_tiles, B.unit_cap, B.unit_start, B.units, st);
   }
   if (rc != B2S_OK) return rc;
   if (keys_sorted != nullptr) *keys_sorted = ks;
@@ -301,7 +312,8 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, nullptr, st);
-  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, out_depth, B.acc, nullptr, st);
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, out_rgb,
+                               out_alpha, out_depth, B.acc, nullptr, st);
 }
 
 int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* colors,
@@ -325,7 +337,8 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   {
     StageTimer t(ctx, ST_BLEND_BWD, st);
     B2S_CUDA_TRY(cudaMemsetAsync(B.gacc, 0, (size_t)n * GACC_F * sizeof(float), st));
-    rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.acc, g_rgb, g_alpha, g_depth, B.gacc, st);
+    rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
+                               g_depth, B.gbuf, B.gacc, st);
   }
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_PREPROCESS_BWD, st);
@@ -363,7 +376,8 @@ static int render_rgba8_impl(b2s_ctx* ctx, const ViewParams& vp, const b2s_param
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, out_rgba, st);
-  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, nullptr, nullptr, out_rgba, st);
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, nullptr,
+                               nullptr, nullptr, nullptr, out_rgba, st);
 }
 
 int b2s_render_rgba8(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,

@@ -125,11 +125,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // ---- state / workspace layout (all offsets 256-B aligned) -------------------------------
 struct StateLayout {
-  size_t rec, ranges, vals, acc, counters, total;
+  size_t rec, ranges, vals, acc, counters, unit_start, units, total;
 };
 struct WorkLayout {
-  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, total;
+  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, total;
 };
+// A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
+// list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
+// to ~5000 Gaussians; one CTA per tile left the SMs idle a third of the time).
+constexpr int SEG = 256;
+inline int64_t max_units(int width, int height, int64_t max_pairs) {
+  const int64_t tiles = (int64_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
+  return (max_pairs > 0 ? max_pairs : 0) / SEG + tiles;   // sum_t max(1, ceil(c_t/SEG)) <= P1/SEG + tiles
+}
 constexpr int SORT_KPB = 4096;   // keys per radix block
 constexpr int PRE_BLOCK = 256;   // Gaussians per preprocess block
 
@@ -144,6 +152,8 @@ inline StateLayout state_layout(int n, int width, int height, int64_t max_pairs)
   L.ranges = o;   o += align_up((size_t)tiles * 8);
   L.vals = o;     o += align_up((size_t)(max_pairs > 0 ? max_pairs : 1) * 4);
   L.acc = o;      o += align_up((size_t)width * height * 5 * 4);
+  L.unit_start = o; o += align_up((size_t)(tiles + 1) * 4);
+  L.units = o;    o += align_up((size_t)max_units(width, height, max_pairs) * 8);
   L.total = o;
   return L;
 }
@@ -165,6 +175,9 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   L.hist = o;  o += align_up(nb_sort * 256 * 4);
   L.hsum = o;  o += align_up(((nb_sort * 256 + 4095) / 4096 + 1) * 4);
   L.gacc = o;  o += align_up(nn * GACC_F * 4);
+  const size_t tiles = (size_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
+  L.partial = o; o += align_up((size_t)max_units(width, height, max_pairs) * 5 * TILE_PIX * 4);
+  L.gbuf = o;  o += align_up(tiles * TILE_PIX * 20);   // float4 g + float gD per pixel, tile-major
   L.total = o;
   return L;
 }
@@ -211,13 +224,16 @@ int launch_sort(unsigned long long* keysA, int* valsA, unsigned long long* keysB
 inline int sort_passes(int begin_bit, int end_bit) { return end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0; }
 int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t cap, int n_tiles, int2* ranges,
                   cudaStream_t st);
+int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
 int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
+                          const int* unit_start, const int2* units, int64_t unit_cap, float* partial,
                           float* out_rgb, float* out_alpha, float* out_depth, float* acc, uint8_t* out_rgba,
                           cudaStream_t st);
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                             float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                          const float* acc, const float* g_rgb, const float* g_alpha, const float* g_depth,
+                          const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
+                          const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,
                           float* gacc, cudaStream_t st);
 int launch_preprocess_bwd(const ViewParams& vp, const float* means, const float* scales, const float* colors,
                           const float* opac, int n, const float* gacc, float* g_means, float* g_scales,

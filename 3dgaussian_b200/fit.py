@@ -49,8 +49,13 @@ class FitDriver:
                                              cutoff_sigma=cutoff_sigma, sh_coeffs=self.sh, sort_depth=0,
                                              act_flags=act) for i in self.views}
         c = 3 * self.sh
-        self.o_means, self.o_scales, self.o_opac, self.o_colors = 0, 3 * n, 6 * n, 7 * n
-        self.count = (7 + c) * n
+        # segment starts are padded to 64 floats (256 B): the kernels read colours with 16-byte loads
+        al = lambda x: (x + 63) // 64 * 64
+        self.o_means = 0
+        self.o_scales = al(3 * n)
+        self.o_opac = self.o_scales + al(3 * n)
+        self.o_colors = self.o_opac + al(n)
+        self.count = self.o_colors + al(c * n)
         z = lambda: torch.zeros(self.count, dtype=torch.float32, device=device)
         self.p, self.g, self.m, self.v = z(), z(), z(), z()
         self.step_no = 0
@@ -69,12 +74,19 @@ class FitDriver:
         self._stage = None
 
     # ---- parameter views -------------------------------------------------------------------
-    def means(self): return self.p[self.o_means:self.o_scales].view(self.n, 3)
-    def scales_raw(self): return self.p[self.o_scales:self.o_opac].view(self.n, 3)
-    def opacities_raw(self): return self.p[self.o_opac:self.o_colors]
+    def _seg(self, buf, off, numel): return buf[off:off + numel]
+    def means(self): return self._seg(self.p, self.o_means, 3 * self.n).view(self.n, 3)
+    def scales_raw(self): return self._seg(self.p, self.o_scales, 3 * self.n).view(self.n, 3)
+    def opacities_raw(self): return self._seg(self.p, self.o_opac, self.n)
     def colors_raw(self):
-        t = self.p[self.o_colors:]
+        t = self._seg(self.p, self.o_colors, 3 * self.sh * self.n)
         return t.view(self.n, 3) if self.sh == 1 else t.view(self.n, self.sh, 3)
+
+    def grad_views(self):
+        """(means, scales_raw, opacities_raw, colours) views of the flat gradient buffer."""
+        n = self.n
+        return (self._seg(self.g, self.o_means, 3 * n), self._seg(self.g, self.o_scales, 3 * n),
+                self._seg(self.g, self.o_opac, n), self._seg(self.g, self.o_colors, 3 * self.sh * n))
 
     def set_params(self, means, scales_raw, opacities_raw, colors_raw):
         with torch.no_grad():
@@ -154,8 +166,8 @@ class FitDriver:
         self.step_no += 1
         capi.check(capi.lib().b2s_adam_step(
             capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
-            self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_opac, self.reg_scale, self.o_opac, self.o_colors,
-            self.reg_op, _stream()))
+            self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_scales + 3 * self.n, self.reg_scale, self.o_opac,
+            self.o_opac + self.n, self.reg_op, _stream()))
 
     def step(self):
         """fwd + bwd over this rank's views (device-resident targets) + all-reduce + Adam.
@@ -215,7 +227,3 @@ class FitDriver:
         v = int(self.overflow.item())
         self.overflow.zero_()
         return v != 0
-
-    def launches_per_step(self) -> int:
-        """Kernels of ours launched by one step on this rank (counted by the library)."""
-        return -1

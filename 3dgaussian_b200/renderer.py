@@ -105,7 +105,10 @@ def _sh_coeffs(colors: torch.Tensor) -> int:
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
-    return t.detach().to(dtype=torch.float32).contiguous()
+    t = t.detach().to(dtype=torch.float32).contiguous()
+    if t.data_ptr() % 16 != 0:      # the kernels use 16-byte loads; an offset view can be misaligned
+        t = t.clone()
+    return t
 
 
 def count_pairs(params: capi.Params, means, scales, opac) -> int:

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _setup(sh, n=200, V=3, W=48, H=32, seed=5):
+def _setup(sh, n=203, V=3, W=48, H=32, seed=5):
     means, scales, colors, opac = scenes.make_scene(seed, n, sh=sh, s_lo=0.03, s_hi=0.15)
     rng = np.random.RandomState(seed)
     scales_raw = np.log(np.expm1(np.maximum(scales - 1e-3, 1e-4))).astype(np.float32)
@@ -72,10 +72,11 @@ def test_fit_step_gradients_and_adam_match_oracle(sh):
     data.backward()
     ref_g = torch.cat([l.grad.reshape(-1) for l in leaves]).numpy()
     assert abs(float(loss_dev.item()) - float(data)) <= 1e-5
-    got_g = d.g.cpu().numpy()
     n = S["n"]
-    for name, a, b in (("means", 0, 3 * n), ("scales", 3 * n, 6 * n), ("opac", 6 * n, 7 * n), ("colors", 7 * n, None)):
-        assert rel_l2(got_g[a:b], ref_g[a:b]) <= 1e-3, name
+    got = [v.cpu().numpy() for v in d.grad_views()]
+    for name, gv, (a, b) in zip(("means", "scales", "opac", "colors"), got,
+                                ((0, 3 * n), (3 * n, 6 * n), (6 * n, 7 * n), (7 * n, None))):
+        assert rel_l2(gv, ref_g[a:b]) <= 1e-3, name
     # Adam with the regulariser gradients == torch Adam on the full loss
     leaves2 = [torch.nn.Parameter(torch.from_numpy(S[k]).to(dt)) for k in ("means", "scales_raw", "op_raw", "col_raw")]
     opt = torch.optim.Adam(leaves2, lr=0.02)
@@ -83,8 +84,10 @@ def test_fit_step_gradients_and_adam_match_oracle(sh):
     full2.backward()
     opt.step()
     ref_p = torch.cat([l.detach().reshape(-1) for l in leaves2]).numpy()
-    step = d.p.cpu().numpy() - p0.cpu().numpy()
-    ref_step = ref_p - p0.cpu().numpy().astype(np.float64)
+    flat = lambda drv, buf: torch.cat([drv._seg(buf, o, k) for o, k in ((drv.o_means, 3 * n), (drv.o_scales, 3 * n),
+                                      (drv.o_opac, n), (drv.o_colors, 3 * S["sh"] * n))]).cpu().numpy()
+    step = flat(d, d.p) - flat(d, p0)
+    ref_step = ref_p - flat(d, p0).astype(np.float64)
     # first Adam step is lr*sign(g) wherever |g| >> eps: compare where the reference gradient is not tiny
     assert np.abs(step - ref_step).max() <= 2e-3
     assert rel_l2(step, ref_step) <= 2e-2
