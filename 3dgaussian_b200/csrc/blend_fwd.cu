@@ -5,13 +5,14 @@
 //   WSUM  : A += w c ; W += w ; D += w z ; out = clamp((bg+A)/(1+W))   torch_renderer.py:181-202
 //   SORTED: front-to-back "over" with per-pixel alpha state           renderer_cpu.cpp:196-215,241-257
 //
-// WSUM schedule (v2): the work unit is (tile, segment of <= SEG Gaussians); ONE WARP owns a unit
-// and every lane owns 8 pixels (a column of 8 rows), so a Gaussian record is read from shared
-// memory once per 256 pixel-pairs and the x-term of the exponent is shared by the 8 rows.  The
-// unit's records are gathered with cp.async into a per-warp 3-stage ring (no block barriers).
-// Because the weighted sum is order independent, a tile whose list spans several units is
-// summed from per-unit partial accumulators by finalize_kernel (fixed order: deterministic).
-// Bound: FP32 issue + MUFU.EX2 -- 8 FP32 + 1 ex2 per pixel-pair (+1 FFMA with depth).
+// WSUM schedule (v3): the work unit is (tile, segment of <= SEG Gaussians); ONE WARP owns a unit
+// and every lane owns 8 pixels (a column of 8 rows).  The unit's records are gathered with
+// cp.async into a per-warp 3-stage ring (no block barriers).  The weight of the reference's
+// axis-aligned Gaussians is separable, so the 32 lanes compute the tile's 16 column + 16 row
+// factors (1 MUFU.EX2 per lane per Gaussian) and each pixel-pair costs 5 FP32 ops issued as
+// packed f32x2 instructions.  Because the weighted sum is order independent, a tile whose list
+// spans several units is summed from per-unit partial accumulators by finalize_kernel (fixed
+// order: deterministic).  Bound: FP32 pipe, ~5.5 lane-cycles per evaluated pixel-pair.
 #include "common.cuh"
 
 namespace b2s {
@@ -56,14 +57,22 @@ constexpr int FW_STAGES = 3;
 constexpr int FW_ROWS = 8;      // pixels per lane
 
 struct FwStage {
-  float4 a[FW_CHUNK];
-  float4 b[FW_CHUNK];
-  float4 c[FW_CHUNK];
+  float4 a[FW_CHUNK];   // x record  {px, qx, lop|op, bbox x}
+  float4 b[FW_CHUNK];   // y record  {py, qy, 0|1,    bbox y}
+  float4 c[FW_CHUNK];   // {r, g, b, zabs}
 };
 
-// EXACT=false : w = 2^(qx dx^2 + qy dy^2 + log2 op) on every pixel of the tile
-// EXACT=true  : w = op * 2^(...), only inside the Gaussian's pixel bbox and if w >= 1e-5
-//               (renderer_cpu.cpp:107-113 -- the native weighted-sum mode)
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
+// The weight is separable (axis-aligned Gaussians): w(x,y) = fx(x) * fy(y) with
+//   fx = 2^(qx dx^2 + log2 op),  fy = 2^(qy dy^2).
+// Per Gaussian the 32 lanes compute the 16 column factors and the 16 row factors of the tile --
+// ONE MUFU.EX2 per lane instead of one per pixel -- exchange them through 128 B of shared
+// memory, and every pixel-pair then costs FMUL + FADD + 3 FFMA, issued as packed f32x2
+// instructions (FFMA2/FADD2/FMUL2: half the issue slots on sm_100).
+// EXACT=false : every pixel of the tile is evaluated
+// EXACT=true  : fx/fy are zero outside the Gaussian's pixel bbox and w < 1e-5 is dropped
+//               (renderer_cpu.cpp:107-113 -- the native weighted-sum mode; records hold op, not log2 op)
 template <bool DEPTH, bool EXACT>
 __global__ void __launch_bounds__(FW_WARPS * 32)
 blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
@@ -72,6 +81,7 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
                       float* __restrict__ out_alpha, float* __restrict__ out_depth, float* __restrict__ acc,
                       uint8_t* __restrict__ out_rgba) {
   __shared__ __align__(16) FwStage ring[FW_WARPS][FW_STAGES];
+  __shared__ __align__(16) float fac[FW_WARPS][2][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * FW_WARPS + warp;
   if (u >= unit_start[vp.n_tiles]) return;           // warps are independent: no block barrier below
@@ -84,12 +94,14 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
   const int cx = lane & 15, half = lane >> 4;
   const int xi = tx * TILE + cx, yi0 = ty * TILE + half * FW_ROWS;
-  const float x = xi + 0.5f, y0 = yi0 + 0.5f;
+  // lanes 0..15 own column factors, lanes 16..31 own row factors
+  const int ci = half ? (ty * TILE + cx) : xi;
+  const float coord = ci + 0.5f;
   FwStage* my = ring[warp];
 
-  float R[FW_ROWS], G[FW_ROWS], B[FW_ROWS], W[FW_ROWS], D[FW_ROWS];
+  float2 W2[FW_ROWS / 2], R2[FW_ROWS / 2], G2[FW_ROWS / 2], B2[FW_ROWS / 2], D2[FW_ROWS / 2];
 #pragma unroll
-  for (int r = 0; r < FW_ROWS; ++r) R[r] = G[r] = B[r] = W[r] = D[r] = 0.f;
+  for (int r = 0; r < FW_ROWS / 2; ++r) W2[r] = R2[r] = G2[r] = B2[r] = D2[r] = make_float2(0.f, 0.f);
 
   const int nchunks = (n + FW_CHUNK - 1) / FW_CHUNK;
   auto issue = [&](int c) {
@@ -116,47 +128,55 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
     const int cnt = min(FW_CHUNK, n - c * FW_CHUNK);
 #pragma unroll 2
     for (int j = 0; j < cnt; ++j) {
-      const float4 a = s.a[j];
-      const float4 b = s.b[j];
-      const float dx = x - a.x;
-      const float dy0 = y0 - a.y;
-      float zz = 0.f;
-      if (DEPTH) zz = s.c[j].x;
+      // ---- separable factor of this lane (a and b are 512 B apart: one LDS.128, two addresses)
+      const float4 h = *(reinterpret_cast<const float4*>(&s.a[j]) + half * FW_CHUNK);
+      const float d = coord - h.x;
+      float f;
       if constexpr (!EXACT) {
-        const float tx2 = fmaf(a.z * dx, dx, b.w);
-#pragma unroll
-        for (int r = 0; r < FW_ROWS; ++r) {
-          const float dy = dy0 + (float)r;
-          const float w = ex2_approx(fmaf(a.w * dy, dy, tx2));
-          W[r] += w;
-          R[r] = fmaf(w, b.x, R[r]);
-          G[r] = fmaf(w, b.y, G[r]);
-          B[r] = fmaf(w, b.z, B[r]);
-          if (DEPTH) D[r] = fmaf(w, zz, D[r]);
-        }
+        f = ex2_approx(fmaf(h.y * d, d, h.z));
       } else {
-        const float4 cc = s.c[j];
-        const float tx2 = a.z * dx * dx;
-        const int bx = __float_as_int(cc.y), by = __float_as_int(cc.z);
-        const bool inx = (xi >= (bx & 0xffff)) && (xi <= (bx >> 16));
-        const int ymin = by & 0xffff, ymax = by >> 16;
+        f = h.z * ex2_approx(h.y * d * d);
+        const int bb = __float_as_int(h.w);
+        f = (ci >= (bb & 0xffff) && ci <= (bb >> 16)) ? f : 0.0f;
+      }
+      float* fb = fac[warp][j & 1];
+      fb[lane] = f;
+      __syncwarp();
+      const float wx = fb[cx];
+      const float4 wya = *reinterpret_cast<const float4*>(fb + 16 + half * FW_ROWS);
+      const float4 wyb = *reinterpret_cast<const float4*>(fb + 20 + half * FW_ROWS);
+      const float4 col = s.c[j];
+      float2 w2[FW_ROWS / 2];
+      w2[0] = __fmul2_rn(bcast2(wx), make_float2(wya.x, wya.y));
+      w2[1] = __fmul2_rn(bcast2(wx), make_float2(wya.z, wya.w));
+      w2[2] = __fmul2_rn(bcast2(wx), make_float2(wyb.x, wyb.y));
+      w2[3] = __fmul2_rn(bcast2(wx), make_float2(wyb.z, wyb.w));
 #pragma unroll
-        for (int r = 0; r < FW_ROWS; ++r) {
-          const float dy = dy0 + (float)r;
-          float w = b.w * ex2_approx(fmaf(a.w * dy, dy, tx2));
-          w = (inx && (yi0 + r) >= ymin && (yi0 + r) <= ymax && w >= 1e-5f) ? w : 0.0f;
-          W[r] += w;
-          R[r] = fmaf(w, b.x, R[r]);
-          G[r] = fmaf(w, b.y, G[r]);
-          B[r] = fmaf(w, b.z, B[r]);
-          if (DEPTH) D[r] = fmaf(w, zz, D[r]);
+      for (int r = 0; r < FW_ROWS / 2; ++r) {
+        if constexpr (EXACT) {
+          w2[r].x = (w2[r].x >= 1e-5f) ? w2[r].x : 0.0f;
+          w2[r].y = (w2[r].y >= 1e-5f) ? w2[r].y : 0.0f;
         }
+        W2[r] = __fadd2_rn(W2[r], w2[r]);
+        R2[r] = __ffma2_rn(w2[r], bcast2(col.x), R2[r]);
+        G2[r] = __ffma2_rn(w2[r], bcast2(col.y), G2[r]);
+        B2[r] = __ffma2_rn(w2[r], bcast2(col.z), B2[r]);
+        if (DEPTH) D2[r] = __ffma2_rn(w2[r], bcast2(col.w), D2[r]);
       }
     }
     __syncwarp();
   }
   cp_async_wait<0>();
 
+  float R[FW_ROWS], G[FW_ROWS], B[FW_ROWS], W[FW_ROWS], D[FW_ROWS];
+#pragma unroll
+  for (int r = 0; r < FW_ROWS / 2; ++r) {
+    R[2 * r] = R2[r].x; R[2 * r + 1] = R2[r].y;
+    G[2 * r] = G2[r].x; G[2 * r + 1] = G2[r].y;
+    B[2 * r] = B2[r].x; B[2 * r + 1] = B2[r].y;
+    W[2 * r] = W2[r].x; W[2 * r + 1] = W2[r].y;
+    D[2 * r] = D2[r].x; D[2 * r + 1] = D2[r].y;
+  }
   const size_t hw = (size_t)vp.width * vp.height;
   if (nseg <= 1) {
     if (xi < vp.width) {
@@ -283,17 +303,17 @@ blend_sorted_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, con
       const float4 a = s.a[j];
       const float4 b = s.b[j];
       const float4 cc = s.c[j];
-      const float dx = x - a.x, dy = y - a.y;
-      float al = b.w * ex2_approx(fmaf(a.w * dy, dy, a.z * dx * dx));
-      const int bx = __float_as_int(cc.y), by = __float_as_int(cc.z);
+      const float dx = x - a.x, dy = y - b.x;     // a = x record, b = y record, cc = colour
+      float al = a.z * ex2_approx(fmaf(b.y * dy, dy, a.y * dx * dx));
+      const int bx = __float_as_int(a.w), by = __float_as_int(b.w);
       const bool in = (xi >= (bx & 0xffff)) && (xi <= (bx >> 16)) && (yi >= (by & 0xffff)) && (yi <= (by >> 16));
       if (in && al >= 1e-5f) {
         al = fminf(al, 1.0f);
         const float contrib = (1.0f - A) * al;
         if (contrib > 0.0f) {
-          C0 = fmaf(contrib, b.x, C0);
-          C1 = fmaf(contrib, b.y, C1);
-          C2 = fmaf(contrib, b.z, C2);
+          C0 = fmaf(contrib, cc.x, C0);
+          C1 = fmaf(contrib, cc.y, C1);
+          C2 = fmaf(contrib, cc.z, C2);
           A += contrib;
         }
       }

@@ -124,9 +124,10 @@ __device__ __forceinline__ void eval_color(const ViewParams& vp, const float* c,
 constexpr float NEG_HALF_LOG2E = -0.72134752044448170368f;  // -0.5 * log2(e)
 
 // Forward: one thread per Gaussian.  Writes the 48-byte blend record
-//   rec[3i+0] = {px, py, qx, qy}    qx = -0.5*log2(e)/sx^2  (so w = 2^(qx dx^2 + qy dy^2 + lop))
-//   rec[3i+1] = {r, g, b, lop}      lop = log2(op)  (style NATIVE keeps op itself, see blend_sorted)
-//   rec[3i+2] = {zabs, bbox x (min|max<<16), bbox y, unused}
+//   rec[3i+0] = {px, qx, lop, bbox x (min|max<<16)}   qx = -0.5*log2(e)/sx^2, lop = log2(op)
+//   rec[3i+1] = {py, qy, 0,   bbox y (min|max<<16)}   so  w = 2^(qx dx^2 + lop) * 2^(qy dy^2)
+//   rec[3i+2] = {r, g, b, zabs}
+//   (exact_bbox mode keeps op and 1 in the third slots: w = op*2^(qx dx^2) * 1*2^(qy dy^2))
 // plus the tile rect / depth bits / tile count consumed by the binning kernels, and the
 // per-block sum of tile counts (first level of the exclusive scan).
 template <int K>
@@ -164,21 +165,25 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
         } else {
           craw[0] = craw[1] = craw[2] = 0.0f;
         }
-        a.x = pr.px; a.y = pr.py;
-        a.z = NEG_HALF_LOG2E / (pr.sx * pr.sx);
-        a.w = NEG_HALF_LOG2E / (pr.sy * pr.sy);
-        b.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
-        b.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
-        b.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
-        b.w = (vp.style == B2S_STYLE_TORCH) ? log2f(op) : op;
-        c.x = pr.zabs;
-        c.y = __int_as_float(pr.xmin | (pr.xmax << 16));
-        c.z = __int_as_float(pr.ymin | (pr.ymax << 16));
-        c.w = 0.0f;
+        // The reference's Gaussians are axis aligned, so the weight is separable:
+        //   w(x,y) = [op * exp(-dx^2/2sx^2)] * [exp(-dy^2/2sy^2)]  -- one x record, one y record.
+        const bool lg = (vp.exact_bbox == 0);        // log-domain opacity unless the native exact mode
+        a.x = pr.px;
+        a.y = NEG_HALF_LOG2E / (pr.sx * pr.sx);
+        a.z = lg ? log2f(op) : op;
+        a.w = __int_as_float(pr.xmin | (pr.xmax << 16));
+        b.x = pr.py;
+        b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
+        b.z = lg ? 0.0f : 1.0f;
+        b.w = __int_as_float(pr.ymin | (pr.ymax << 16));
+        c.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
+        c.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
+        c.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
+        c.w = pr.zabs;
       } else {
-        a = make_float4(0.f, 0.f, 0.f, 0.f);
-        b = make_float4(0.f, 0.f, 0.f, (vp.style == B2S_STYLE_TORCH) ? -INFINITY : 0.0f);
-        c = make_float4(0.f, __int_as_float(0), __int_as_float(0), 0.f);
+        a = make_float4(0.f, 0.f, (vp.exact_bbox == 0) ? -INFINITY : 0.0f, __int_as_float(0));
+        b = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        c = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       rec[3 * (size_t)i] = a;
       rec[3 * (size_t)i + 1] = b;
