@@ -139,6 +139,8 @@ struct Bufs {  // resolved pointers into state / workspace
   int2* units;
   float* partial;
   float* gbuf;
+  int* cs_table;
+  int* cs_total;
   int64_t unit_cap;
 };
 
@@ -172,6 +174,8 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.gacc = (float*)(q + L.gacc);
     b.partial = (float*)(q + L.partial);
     b.gbuf = (float*)(q + L.gbuf);
+    b.cs_table = (int*)(q + L.cs_table);
+    b.cs_total = (int*)(q + L.cs_total);
   }
   return b;
 }
@@ -191,7 +195,32 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   const int begin_bit = p->sort_depth ? 0 : 32;
   const int end_bit = 32 + tile_bits(vp.n_tiles);
   const int passes = sort_passes(begin_bit, end_bit);
-  // choose the ping-pong so that the sorted values land in the state buffer
+  if (!p->sort_depth && counting_sort_fits(vp.n_tiles)) {
+    // order inside a tile is irrelevant: group with one counting pass + one scatter pass
+    {
+      StageTimer t(ctx, ST_BIN, st);
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+                                B.unit_start, B.units, B.vals, 0, st);
+    }
+    if (rc != B2S_OK) return rc;
+    if (keys_unsorted_copy != nullptr || vals_unsorted_copy != nullptr) {   // dump hook only: the emit order
+      Counters* scratch = (Counters*)B.hist;
+      rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, st);
+      if (rc != B2S_OK) return rc;
+      if (keys_unsorted_copy != nullptr)
+        B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, B.keysA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
+      if (vals_unsorted_copy != nullptr)
+        B2S_CUDA_TRY(cudaMemcpyAsync(vals_unsorted_copy, B.valsB, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    {
+      StageTimer t(ctx, ST_SORT, st);
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+                                B.unit_start, B.units, B.vals, 1, st);
+    }
+    if (rc != B2S_OK) return rc;
+    if (keys_sorted != nullptr) *keys_sorted = nullptr;   // this path has no keys
+    return B2S_OK;
+  }
   unsigned long long* kA = B.keysA;
   unsigned long long* kB = B.keysB;
   int* vA = (passes % 2 == 0) ? B.vals : B.valsB;
@@ -342,8 +371,55 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   }
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_PREPROCESS_BWD, st);
-  return launch_preprocess_bwd(vp, means, scales, colors, opacities, n, B.gacc, grad_means, grad_scales,
-                               grad_colors, grad_opacities, accumulate, st);
+  return launch_preprocess_bwd(&vp, nullptr, 1, vp.sh, means, scales, colors, opacities, n, B.gacc, grad_means,
+                               grad_scales, grad_colors, grad_opacities, accumulate, st);
+}
+
+size_t b2s_view_block_bytes(void) { return sizeof(ViewParams); }
+
+int b2s_pack_views(const b2s_params* params, int num_views, void* out_host) {
+  if (params == nullptr || out_host == nullptr || num_views < 0) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams* out = (ViewParams*)out_host;
+  for (int v = 0; v < num_views; ++v) {
+    const int rc = make_view(&params[v], &out[v]);
+    if (rc != B2S_OK) return rc;
+  }
+  return B2S_OK;
+}
+
+int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* g_rgb,
+                       const float* g_alpha, const float* g_depth, const void* state, void* workspace, size_t ws_bytes,
+                       float* gacc_out, void* stream) {
+  if (ctx == nullptr || g_rgb == nullptr || state == nullptr || workspace == nullptr || gacc_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode != B2S_MODE_WSUM || vp.exact_bbox || vp.style != B2S_STYLE_TORCH) {
+    set_error("backward is implemented for the weighted-sum torch-style mode only");
+    return B2S_ERR_UNSUPPORTED;
+  }
+  rc = check_sizes(n, p->width, p->height, max_pairs, 0, false, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  if (n == 0) return B2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
+  StageTimer t(ctx, ST_BLEND_BWD, st);
+  B2S_CUDA_TRY(cudaMemsetAsync(gacc_out, 0, (size_t)n * GACC_F * sizeof(float), st));
+  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
+                               g_depth, B.gbuf, gacc_out, st);
+}
+
+int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                        const float* scales, const float* colors, const float* opacities, int n, const float* gacc_all,
+                        float* grad_means, float* grad_scales, float* grad_colors, float* grad_opacities,
+                        int accumulate, void* stream) {
+  if (ctx == nullptr || views_dev == nullptr || gacc_all == nullptr || grad_means == nullptr || grad_scales == nullptr ||
+      grad_opacities == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (n < 0 || num_views < 0) { set_error("bad n or num_views"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_PREPROCESS_BWD, (cudaStream_t)stream);
+  return launch_preprocess_bwd(nullptr, (const ViewParams*)views_dev, num_views, sh_coeffs > 0 ? sh_coeffs : 1, means,
+                               scales, colors, opacities, n, gacc_all, grad_means, grad_scales, grad_colors,
+                               grad_opacities, accumulate, (cudaStream_t)stream);
 }
 
 int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,
@@ -495,7 +571,8 @@ int b2s_dump_bins(b2s_ctx* ctx, const b2s_params* p, const float* means, const f
     if (cnt) B2S_CUDA_TRY(cudaMemcpyAsync(cnt, B.cnt, nb, cudaMemcpyDeviceToDevice, st));
   }
   if (max_pairs > 0) {
-    if (keys_sorted) B2S_CUDA_TRY(cudaMemcpyAsync(keys_sorted, ks, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
+    if (keys_sorted && ks) B2S_CUDA_TRY(cudaMemcpyAsync(keys_sorted, ks, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
+    if (keys_sorted && !ks) B2S_CUDA_TRY(cudaMemsetAsync(keys_sorted, 0, (size_t)max_pairs * 8, st));   // counting path: no keys
     if (vals_sorted) B2S_CUDA_TRY(cudaMemcpyAsync(vals_sorted, B.vals, (size_t)max_pairs * 4, cudaMemcpyDeviceToDevice, st));
   }
   if (ranges) B2S_CUDA_TRY(cudaMemcpyAsync(ranges, B.ranges, (size_t)vp.n_tiles * 8, cudaMemcpyDeviceToDevice, st));

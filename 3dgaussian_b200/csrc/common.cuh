@@ -128,7 +128,7 @@ struct StateLayout {
   size_t rec, ranges, vals, acc, counters, unit_start, units, total;
 };
 struct WorkLayout {
-  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, total;
+  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
 };
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
@@ -139,6 +139,8 @@ inline int64_t max_units(int width, int height, int64_t max_pairs) {
   return (max_pairs > 0 ? max_pairs : 0) / SEG + tiles;   // sum_t max(1, ceil(c_t/SEG)) <= P1/SEG + tiles
 }
 constexpr int SORT_KPB = 4096;   // keys per radix block
+constexpr int CS_NB = 296;       // counting-sort blocks: 2 per SM (148 SMs)
+constexpr size_t CS_MAX_SMEM = 200 * 1024;   // per-block tile histogram (4 B per tile) must fit
 constexpr int PRE_BLOCK = 256;   // Gaussians per preprocess block
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -178,6 +180,8 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   const size_t tiles = (size_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
   L.partial = o; o += align_up((size_t)max_units(width, height, max_pairs) * 5 * TILE_PIX * 4);
   L.gbuf = o;  o += align_up(tiles * TILE_PIX * 20);   // float4 g + float gD per pixel, tile-major
+  L.cs_table = o; o += align_up((size_t)CS_NB * tiles * 4);
+  L.cs_total = o; o += align_up(tiles * 4);
   L.total = o;
   return L;
 }
@@ -224,6 +228,11 @@ int launch_sort(unsigned long long* keysA, int* valsA, unsigned long long* keysB
 inline int sort_passes(int begin_bit, int end_bit) { return end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0; }
 int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t cap, int n_tiles, int2* ranges,
                   cudaStream_t st);
+// tile-major counting sort (bin.cu): stage 0 = histogram + scans (ranges, units, counters), stage 1 = scatter
+bool counting_sort_fits(int n_tiles);
+int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, int* table, int* total,
+                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int* vals,
+                         int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
 int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, int64_t unit_cap, float* partial,
@@ -235,9 +244,12 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
                           const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
                           const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,
                           float* gacc, cudaStream_t st);
-int launch_preprocess_bwd(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                          const float* opac, int n, const float* gacc, float* g_means, float* g_scales,
-                          float* g_colors, float* g_opac, int accumulate, cudaStream_t st);
+// single != null: one view passed by value (views_dev must be null, num_views 1, gacc = n x 12 floats);
+// else views_dev[num_views] in device memory and gacc = num_views x n x 12 floats.
+int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,
+                          const float* means, const float* scales, const float* colors, const float* opac, int n,
+                          const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
+                          int accumulate, cudaStream_t st);
 int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
                     int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum,
                     cudaStream_t st);

@@ -5,6 +5,8 @@
 //   python/torch_renderer.py:57-106,143-150   and the per-thread prologue of
 //   src/renderer.cu:41-84 (AoS stride-3 loads, no culling of work).
 // HBM-bound: algorithmic bytes per Gaussian*view = 28 + 12*sh (read) + 48+16 (write).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -145,7 +147,7 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
     const float s0 = act_scale(vp, __ldg(scales + 3 * (size_t)i)), s1 = act_scale(vp, __ldg(scales + 3 * (size_t)i + 1));
     const float op = act_opac(vp, __ldg(opac + i));
     const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
-    uint2 rc = make_uint2(0u, 0u);
+    uint2 rc = make_uint2(1u, 0u);   // empty tile rect (tx1 < tx0) for culled Gaussians
     if (pr.ok) {
       const int tx0 = pr.xmin / TILE, tx1 = pr.xmax / TILE, ty0 = pr.ymin / TILE, ty1 = pr.ymax / TILE;
       my_cnt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
@@ -231,146 +233,255 @@ int launch_preprocess(const ViewParams& vp, const float* means, const float* sca
   return B2S_OK;
 }
 
-// Backward: one thread per Gaussian.  gacc[12i..] = {dR,dG,dB,dZ, S,Sx,Sxx,Sy, Syy,-,-,-} from the
-// blend backward, where S = sum w*t, Sx = sum w*t*dx, Sxx = sum w*t*dx^2 (same for y).
+// Backward chain rule, for ONE OR MANY views in a single pass over the parameters.
+//   gacc[v][12i..] = {dR,dG,dB,dZ, S,Sx,Sxx,Sy, Syy,-,-,-} from the blend backward of view v, where
+//   S = sum w*t, Sx = sum w*t*dx, Sxx = sum w*t*dx^2 (same for y).
 // Chain rule of SURVEY Appendix A / autograd of torch_renderer.py:57-104,143-150.
-template <int K>
+//
+// The fit loop used to run this once per view and read-modify-write the whole gradient buffer
+// (28+12K floats... 220 B at K=16) every time: 64 views x 0.7 GB.  Here the per-view results stay
+// compact (48 B per Gaussian per view) and one launch folds all views: each Gaussian's gradients
+// are accumulated in registers over the view loop and written once.
+// LPG lanes share a Gaussian: lane `sub` owns SH coefficients [sub*KL, sub*KL+KL), so a warp reads
+// and writes the (N,K,3) arrays as contiguous 16-byte pieces (coalesced), and the few cross-lane
+// sums (raw colour, d colour / d direction) are quad shuffles.
+constexpr int BWD_VIEWS_SMEM = 32;   // views staged in shared memory per chunk
+
+template <int K, int LPG>
 __global__ void __launch_bounds__(PRE_BLOCK)
-preprocess_bwd_kernel(const ViewParams vp, const float* __restrict__ means, const float* __restrict__ scales,
+preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ views, int num_views,
+                      const float* __restrict__ means, const float* __restrict__ scales,
                       const float* __restrict__ colors, const float* __restrict__ opac, int n,
                       const float4* __restrict__ gacc, float* __restrict__ g_means, float* __restrict__ g_scales,
                       float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
-  const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
-  if (i >= n) return;
-  const float mx = __ldg(means + 3 * (size_t)i), my = __ldg(means + 3 * (size_t)i + 1),
-              mz = __ldg(means + 3 * (size_t)i + 2);
-  const float raw_s0 = __ldg(scales + 3 * (size_t)i), raw_s1 = __ldg(scales + 3 * (size_t)i + 1);
-  const float raw_op = __ldg(opac + i);
-  const float s0 = act_scale(vp, raw_s0), s1 = act_scale(vp, raw_s1), op = act_opac(vp, raw_op);
-  const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+  constexpr int KL = K / LPG;       // SH coefficients per lane
+  constexpr int CL = KL * 3;        // colour floats per lane
+  static_assert(K % LPG == 0 && (LPG == 1 || (CL % 4) == 0), "lane split must keep 16-byte pieces");
+  __shared__ ViewParams sv[BWD_VIEWS_SMEM];
+  const int gidx = blockIdx.x * PRE_BLOCK + threadIdx.x;
+  const int i = gidx / LPG, sub = gidx % LPG;
+  const bool live = i < n;
+  const int ii = live ? i : 0;
+
+  const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
+              mz = __ldg(means + 3 * (size_t)ii + 2);
+  const float raw_s0 = __ldg(scales + 3 * (size_t)ii), raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
+  const float raw_op = __ldg(opac + ii);
+  float coef[CL];
+  if (colors != nullptr) {
+    const float* cp = colors + (size_t)ii * K * 3 + sub * CL;
+    if constexpr (CL % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < CL / 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cp) + q);
+        coef[4 * q] = v.x; coef[4 * q + 1] = v.y; coef[4 * q + 2] = v.z; coef[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CL; ++q) coef[q] = __ldg(cp + q);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < CL; ++q) coef[q] = 0.0f;
+  }
 
   float gm[3] = {0.f, 0.f, 0.f}, gs0 = 0.f, gs1 = 0.f, gop = 0.f;
-  float gcoef[K * 3];
+  float gcoef[CL];
 #pragma unroll
-  for (int q = 0; q < K * 3; ++q) gcoef[q] = 0.0f;
+  for (int q = 0; q < CL; ++q) gcoef[q] = 0.0f;
 
-  if (pr.ok) {
-    const float4 g0 = gacc[3 * (size_t)i], g1 = gacc[3 * (size_t)i + 1], g2 = gacc[3 * (size_t)i + 2];
-    const float dC[3] = {g0.x, g0.y, g0.z};
-    float dZ = g0.w;
-    const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
-
-    // opacity: w = op * E  =>  dL/dop = S / op
-    gop = (op > 0.0f) ? S / op : S;   // at op == 0 the blend backward accumulated sum E*t directly
-    if (vp.act & B2S_ACT_OPACITY_SIGMOID) gop *= op * (1.0f - op);
-
-    // position / sigma
-    const float isx2 = 1.0f / (pr.sx * pr.sx), isy2 = 1.0f / (pr.sy * pr.sy);
-    const float dpx = Sx * isx2, dpy = Sy * isy2;
-    const float dsx = Sxx * isx2 / pr.sx, dsy = Syy * isy2 / pr.sy;
-    if (pr.ax >= 1.0f) {   // clamp_min(1) passes the gradient on [1, inf)
-      const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s0 > 0.f) - (s0 < 0.f)) : 1.0f;
-      gs0 = dsx * sgn * (0.5f * vp.wf * vp.fx / pr.zabs);
-      dZ -= dsx * pr.ax / pr.zabs;
+  for (int vbase = 0; vbase < num_views; vbase += BWD_VIEWS_SMEM) {
+    const int vcount = min(BWD_VIEWS_SMEM, num_views - vbase);
+    if (views != nullptr) {
+      __syncthreads();
+      const int words = vcount * (int)(sizeof(ViewParams) / 4);
+      const int* src = reinterpret_cast<const int*>(views + vbase);
+      int* dst = reinterpret_cast<int*>(sv);
+      for (int q = threadIdx.x; q < words; q += PRE_BLOCK) dst[q] = src[q];
+      __syncthreads();
     }
-    if (pr.ay >= 1.0f) {
-      const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s1 > 0.f) - (s1 < 0.f)) : 1.0f;
-      gs1 = dsy * sgn * (0.5f * vp.hf * vp.fy / pr.zabs);
-      dZ -= dsy * pr.ay / pr.zabs;
-    }
-    if (vp.act & B2S_ACT_SCALES_SOFTPLUS) {
-      gs0 *= sigmoidf_acc(raw_s0);
-      gs1 *= sigmoidf_acc(raw_s1);
-    }
-    // zabs = max(|cam.z|, 1e-6)
-    float dcam[4] = {0.f, 0.f, 0.f, 0.f};
-    if (fabsf(pr.zcam) >= 1e-6f) dcam[2] = dZ * ((pr.zcam > 0.f) ? 1.0f : -1.0f);
-    // px,py -> ndc -> clip
-    const float dnx = dpx * 0.5f * vp.wm1, dny = -dpy * 0.5f * vp.hm1;
-    float dclip[4];
-    dclip[0] = dnx / pr.wsafe;
-    dclip[1] = dny / pr.wsafe;
-    dclip[2] = 0.0f;
-    dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) / pr.wsafe;
-    // clip = P cam ; cam = V [m,1]
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) dcam[c] = fmaf(vp.proj[4 * r + c], dclip[r], dcam[c]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) gm[c] = fmaf(vp.view[4 * r + c], dcam[r], gm[c]);
+    for (int vl = 0; vl < vcount; ++vl) {
+      const ViewParams& vp = (views != nullptr) ? sv[vl] : single;
+      const float4* ga = gacc + ((size_t)(vbase + vl) * n + ii) * 3;
+      const float4 g0 = __ldg(ga), g1 = __ldg(ga + 1), g2 = __ldg(ga + 2);
+      const float s0 = act_scale(vp, raw_s0), s1 = act_scale(vp, raw_s1), op = act_opac(vp, raw_op);
+      const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+      const bool ok = pr.ok;      // culled in this view: its gacc row is all zeros (no `continue`: the
+                                  // colour block below holds warp shuffles that every lane must reach)
+      const float dC[3] = {g0.x, g0.y, g0.z};
+      float dZ = g0.w;
+      const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
 
-    // colour
-    if (colors != nullptr) {
-      float coef[K * 3], craw[3], dir[3], rinv;
-      load_coeffs<K>(colors, i, coef);
-      eval_color<K>(vp, coef, mx, my, mz, craw, dir, &rinv);
-      float dc[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) dc[q] = (craw[q] >= 0.0f && craw[q] <= 1.0f) ? dC[q] : 0.0f;
-      if constexpr (K == 1) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          gcoef[q] = (vp.act & B2S_ACT_COLORS_SIGMOID) ? dc[q] * craw[q] * (1.0f - craw[q]) : dc[q];
-      } else {
-        float b[16], bx[16], by[16], bz[16];
-        sh_basis(dir[0], dir[1], dir[2], K, b);
-        sh_basis_grad(dir[0], dir[1], dir[2], K, bx, by, bz);
-        float dd[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const float s = coef[3 * k] * dc[0] + coef[3 * k + 1] * dc[1] + coef[3 * k + 2] * dc[2];
-          gcoef[3 * k] = b[k] * dc[0];
-          gcoef[3 * k + 1] = b[k] * dc[1];
-          gcoef[3 * k + 2] = b[k] * dc[2];
-          dd[0] = fmaf(bx[k], s, dd[0]);
-          dd[1] = fmaf(by[k], s, dd[1]);
-          dd[2] = fmaf(bz[k], s, dd[2]);
+      if (ok) {
+        // opacity: w = op * E  =>  dL/dop = S / op
+        float go = (op > 0.0f) ? S / op : S;   // at op == 0 the blend backward accumulated sum E*t directly
+        if (vp.act & B2S_ACT_OPACITY_SIGMOID) go *= op * (1.0f - op);
+        gop += go;
+
+        // position / sigma
+        const float isx2 = 1.0f / (pr.sx * pr.sx), isy2 = 1.0f / (pr.sy * pr.sy);
+        const float dpx = Sx * isx2, dpy = Sy * isy2;
+        const float dsx = Sxx * isx2 / pr.sx, dsy = Syy * isy2 / pr.sy;
+        if (pr.ax >= 1.0f) {   // clamp_min(1) passes the gradient on [1, inf)
+          const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s0 > 0.f) - (s0 < 0.f)) : 1.0f;
+          float t = dsx * sgn * (0.5f * vp.wf * vp.fx / pr.zabs);
+          if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s0);
+          gs0 += t;
+          dZ -= dsx * pr.ax / pr.zabs;
         }
-        // d = v/(r+eps), v = cam - m :  dv = dd/(r+eps) - v (v.dd) / (r (r+eps)^2) ; dm = -dv
-        const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
-        const float r = sqrtf(vx * vx + vy * vy + vz * vz);
-        const float vdd = vx * dd[0] + vy * dd[1] + vz * dd[2];
-        const float k2 = (r > 0.0f) ? vdd * rinv * rinv / r : 0.0f;
-        gm[0] -= dd[0] * rinv - vx * k2;
-        gm[1] -= dd[1] * rinv - vy * k2;
-        gm[2] -= dd[2] * rinv - vz * k2;
+        if (pr.ay >= 1.0f) {
+          const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s1 > 0.f) - (s1 < 0.f)) : 1.0f;
+          float t = dsy * sgn * (0.5f * vp.hf * vp.fy / pr.zabs);
+          if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s1);
+          gs1 += t;
+          dZ -= dsy * pr.ay / pr.zabs;
+        }
+        // zabs = max(|cam.z|, 1e-6)
+        float dcam[4] = {0.f, 0.f, 0.f, 0.f};
+        if (fabsf(pr.zcam) >= 1e-6f) dcam[2] = dZ * ((pr.zcam > 0.f) ? 1.0f : -1.0f);
+        // px,py -> ndc -> clip
+        const float dnx = dpx * 0.5f * vp.wm1, dny = -dpy * 0.5f * vp.hm1;
+        float dclip[4];
+        dclip[0] = dnx / pr.wsafe;
+        dclip[1] = dny / pr.wsafe;
+        dclip[2] = 0.0f;
+        dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) / pr.wsafe;
+        // clip = P cam ; cam = V [m,1]
+  #pragma unroll
+        for (int c = 0; c < 4; ++c)
+  #pragma unroll
+          for (int r = 0; r < 4; ++r) dcam[c] = fmaf(vp.proj[4 * r + c], dclip[r], dcam[c]);
+  #pragma unroll
+        for (int c = 0; c < 3; ++c)
+  #pragma unroll
+          for (int r = 0; r < 4; ++r) gm[c] = fmaf(vp.view[4 * r + c], dcam[r], gm[c]);
+
+      }
+      // colour
+      if (colors != nullptr) {
+        if constexpr (K == 1) {
+          if (!ok) continue;
+          float craw[3] = {coef[0], coef[1], coef[2]};
+          if (vp.act & B2S_ACT_COLORS_SIGMOID) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) craw[q] = sigmoidf_acc(craw[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float dc = (craw[q] >= 0.0f && craw[q] <= 1.0f) ? dC[q] : 0.0f;
+            gcoef[q] += (vp.act & B2S_ACT_COLORS_SIGMOID) ? dc * craw[q] * (1.0f - craw[q]) : dc;
+          }
+        } else {
+          const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
+          const float r = sqrtf(vx * vx + vy * vy + vz * vz);
+          const float rinv = 1.0f / (r + 1e-8f);
+          const float dx = vx * rinv, dy = vy * rinv, dz = vz * rinv;
+          float b[16], bx[16], by[16], bz[16];
+          sh_basis(dx, dy, dz, K, b);
+          sh_basis_grad(dx, dy, dz, K, bx, by, bz);
+          // this lane's KL basis functions (static register indexing: select, do not index by `sub`)
+          float lb[KL], lbx[KL], lby[KL], lbz[KL];
+#pragma unroll
+          for (int j = 0; j < KL; ++j) {
+            lb[j] = b[j]; lbx[j] = bx[j]; lby[j] = by[j]; lbz[j] = bz[j];
+#pragma unroll
+            for (int s2 = 1; s2 < LPG; ++s2) {
+              if (sub == s2) { lb[j] = b[s2 * KL + j]; lbx[j] = bx[s2 * KL + j]; lby[j] = by[s2 * KL + j]; lbz[j] = bz[s2 * KL + j]; }
+            }
+          }
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < KL; ++j) {
+            c0 = fmaf(lb[j], coef[3 * j], c0);
+            c1 = fmaf(lb[j], coef[3 * j + 1], c1);
+            c2 = fmaf(lb[j], coef[3 * j + 2], c2);
+          }
+#pragma unroll
+          for (int o = 1; o < LPG; o <<= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+          }
+          const float dc0 = (ok && c0 >= 0.0f && c0 <= 1.0f) ? dC[0] : 0.0f;
+          const float dc1 = (ok && c1 >= 0.0f && c1 <= 1.0f) ? dC[1] : 0.0f;
+          const float dc2 = (ok && c2 >= 0.0f && c2 <= 1.0f) ? dC[2] : 0.0f;
+          float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < KL; ++j) {
+            const float s = coef[3 * j] * dc0 + coef[3 * j + 1] * dc1 + coef[3 * j + 2] * dc2;
+            gcoef[3 * j] = fmaf(lb[j], dc0, gcoef[3 * j]);
+            gcoef[3 * j + 1] = fmaf(lb[j], dc1, gcoef[3 * j + 1]);
+            gcoef[3 * j + 2] = fmaf(lb[j], dc2, gcoef[3 * j + 2]);
+            dd0 = fmaf(lbx[j], s, dd0);
+            dd1 = fmaf(lby[j], s, dd1);
+            dd2 = fmaf(lbz[j], s, dd2);
+          }
+#pragma unroll
+          for (int o = 1; o < LPG; o <<= 1) {
+            dd0 += __shfl_xor_sync(0xffffffffu, dd0, o);
+            dd1 += __shfl_xor_sync(0xffffffffu, dd1, o);
+            dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);
+          }
+          // d = v/(r+eps), v = cam - m :  dv = dd/(r+eps) - v (v.dd) / (r (r+eps)^2) ; dm = -dv
+          const float vdd = vx * dd0 + vy * dd1 + vz * dd2;
+          const float k2 = (r > 0.0f) ? vdd * rinv * rinv / r : 0.0f;
+          if (ok) {
+            gm[0] -= dd0 * rinv - vx * k2;
+            gm[1] -= dd1 * rinv - vy * k2;
+            gm[2] -= dd2 * rinv - vz * k2;
+          }
+        }
       }
     }
   }
-  if (accumulate) {
-    g_means[3 * (size_t)i] += gm[0]; g_means[3 * (size_t)i + 1] += gm[1]; g_means[3 * (size_t)i + 2] += gm[2];
-    g_scales[3 * (size_t)i] += gs0; g_scales[3 * (size_t)i + 1] += gs1;
-    g_opac[i] += gop;
-    if (g_colors != nullptr) {
-#pragma unroll
-      for (int q = 0; q < K * 3; ++q) g_colors[(size_t)i * K * 3 + q] += gcoef[q];
+  if (!live) return;
+  if (sub == 0) {
+    if (accumulate) {
+      g_means[3 * (size_t)i] += gm[0]; g_means[3 * (size_t)i + 1] += gm[1]; g_means[3 * (size_t)i + 2] += gm[2];
+      g_scales[3 * (size_t)i] += gs0; g_scales[3 * (size_t)i + 1] += gs1;
+      g_opac[i] += gop;
+    } else {
+      g_means[3 * (size_t)i] = gm[0]; g_means[3 * (size_t)i + 1] = gm[1]; g_means[3 * (size_t)i + 2] = gm[2];
+      g_scales[3 * (size_t)i] = gs0; g_scales[3 * (size_t)i + 1] = gs1; g_scales[3 * (size_t)i + 2] = 0.0f;
+      g_opac[i] = gop;
     }
-  } else {
-    g_means[3 * (size_t)i] = gm[0]; g_means[3 * (size_t)i + 1] = gm[1]; g_means[3 * (size_t)i + 2] = gm[2];
-    g_scales[3 * (size_t)i] = gs0; g_scales[3 * (size_t)i + 1] = gs1; g_scales[3 * (size_t)i + 2] = 0.0f;
-    g_opac[i] = gop;
-    if (g_colors != nullptr) {
+  }
+  if (g_colors != nullptr) {
+    float* gp = g_colors + (size_t)i * K * 3 + sub * CL;
+    if constexpr (CL % 4 == 0) {
 #pragma unroll
-      for (int q = 0; q < K * 3; ++q) g_colors[(size_t)i * K * 3 + q] = gcoef[q];
+      for (int q = 0; q < CL / 4; ++q) {
+        float4 v = make_float4(gcoef[4 * q], gcoef[4 * q + 1], gcoef[4 * q + 2], gcoef[4 * q + 3]);
+        if (accumulate) {
+          const float4 o = reinterpret_cast<const float4*>(gp)[q];
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        reinterpret_cast<float4*>(gp)[q] = v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CL; ++q) gp[q] = accumulate ? gp[q] + gcoef[q] : gcoef[q];
     }
   }
 }
 
-int launch_preprocess_bwd(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                          const float* opac, int n, const float* gacc, float* g_means, float* g_scales,
-                          float* g_colors, float* g_opac, int accumulate, cudaStream_t st) {
-  if (n <= 0) return B2S_OK;
-  const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
-#define B2S_PREB(KK) preprocess_bwd_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, reinterpret_cast<const float4*>(gacc), g_means, g_scales, g_colors, g_opac, accumulate)
-  switch (vp.sh) {
-    case 1: B2S_PREB(1); break;
-    case 4: B2S_PREB(4); break;
-    case 9: B2S_PREB(9); break;
-    case 16: B2S_PREB(16); break;
-    default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", vp.sh); return B2S_ERR_INVALID;
+int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,
+                          const float* means, const float* scales, const float* colors, const float* opac, int n,
+                          const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
+                          int accumulate, cudaStream_t st) {
+  if (n <= 0 || num_views <= 0) return B2S_OK;
+  ViewParams one;
+  if (single != nullptr) one = *single; else memset(&one, 0, sizeof(one));
+#define B2S_PREB(KK, LL)                                                                                              \
+  preprocess_bwd_kernel<KK, LL><<<(int)(((size_t)n * LL + PRE_BLOCK - 1) / PRE_BLOCK), PRE_BLOCK, 0, st>>>(           \
+      one, views_dev, num_views, means, scales, colors, opac, n, reinterpret_cast<const float4*>(gacc), g_means,      \
+      g_scales, g_colors, g_opac, accumulate)
+  switch (sh) {
+    case 1: B2S_PREB(1, 1); break;
+    case 4: B2S_PREB(4, 1); break;
+    case 9: B2S_PREB(9, 1); break;
+    case 16: B2S_PREB(16, 4); break;
+    default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", sh); return B2S_ERR_INVALID;
   }
 #undef B2S_PREB
   B2S_LAUNCH_CHECK();

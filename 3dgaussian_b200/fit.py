@@ -70,6 +70,16 @@ class FitDriver:
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self.targets: dict = {}
         self.masks: dict = {}
+        # per-view constant blocks for the multi-view chain rule, uploaded once (cameras are fixed)
+        L = capi.lib()
+        vb = L.b2s_view_block_bytes()
+        nv = len(self.views)
+        arr = (capi.Params * max(nv, 1))(*[self.params_c[i] for i in self.views])
+        host = (C.c_uint8 * (vb * max(nv, 1)))()
+        capi.check(L.b2s_pack_views(arr, nv, host))
+        self.views_dev = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(device)
+        # compact per-view blend-backward sums: (local views, n, 12) floats = 48 B per Gaussian per view
+        self.gacc = torch.empty((max(nv, 1), max(self.n, 1), 12), dtype=torch.float32, device=device)
         self._copy_stream = None
         self._stage = None
 
@@ -143,7 +153,7 @@ class FitDriver:
         return out_rgb, out_alpha
 
     # ---- one fit iteration -------------------------------------------------------------------
-    def _view_fwd_bwd(self, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor]):
+    def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor]):
         L, ctx, st = capi.lib(), capi.ctx(self.dev.index), _stream()
         pc = C.byref(self.params_c[i])
         capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
@@ -153,13 +163,20 @@ class FitDriver:
         capi.check(L.b2s_fit_loss(ctx, _ptr(self.rgb), _ptr(self.alpha), _ptr(tgt), _ptr(mask), self.W, self.H,
                                   self.w_sil, 1.0 / self.num_views, _ptr(self.g_rgb),
                                   _ptr(self.g_alpha) if mask is not None else None, _ptr(self.loss_dev), st))
-        capi.check(L.b2s_backward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
-                                  self._pp(self.o_opac), self.n, self.max_pairs, _ptr(self.g_rgb),
-                                  _ptr(self.g_alpha) if mask is not None else None, None, _ptr(self.state),
-                                  _ptr(self.ws), self.ws_bytes, self._gp(self.o_means), self._gp(self.o_scales),
-                                  self._gp(self.o_colors), self._gp(self.o_opac), 1, st))
+        capi.check(L.b2s_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(self.g_rgb),
+                                        _ptr(self.g_alpha) if mask is not None else None, None, _ptr(self.state),
+                                        _ptr(self.ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
 
     def _finish_step(self):
+        # chain rule over ALL local views in one pass: gradients written once (no per-view read-modify-write)
+        if self.views:
+            capi.check(capi.lib().b2s_backward_params(
+                capi.ctx(self.dev.index), _ptr(self.views_dev), len(self.views), self.sh, self._pp(self.o_means),
+                self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n, _ptr(self.gacc),
+                self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_colors), self._gp(self.o_opac), 0,
+                _stream()))
+        else:
+            self.g.zero_()
         if self.world > 1:
             torch.distributed.all_reduce(self.g, group=self.pg)
             torch.distributed.all_reduce(self.loss_dev, group=self.pg)
@@ -175,10 +192,9 @@ class FitDriver:
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            self.g.zero_()
             self.loss_dev.zero_()
-            for i in self.views:
-                self._view_fwd_bwd(i, self.targets[i], self.masks.get(i))
+            for k, i in enumerate(self.views):
+                self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i))
             self._finish_step()
         return self.loss_dev
 
@@ -195,7 +211,6 @@ class FitDriver:
                 self._ev_ready = [torch.cuda.Event() for _ in range(2)]
                 self._ev_free = [torch.cuda.Event() for _ in range(2)]
             main = torch.cuda.current_stream()
-            self.g.zero_()
             self.loss_dev.zero_()
             use_mask = host_masks is not None
 
@@ -217,7 +232,7 @@ class FitDriver:
                     issue(k + 1)
                 slot = k % 2
                 main.wait_event(self._ev_ready[slot])
-                self._view_fwd_bwd(i, self._stage[slot][0], self._stage[slot][1] if use_mask else None)
+                self._view_fwd_bwd(k, i, self._stage[slot][0], self._stage[slot][1] if use_mask else None)
                 self._ev_free[slot].record(main)
             self._finish_step()
             return float(self.loss_dev.item())

@@ -111,6 +111,25 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
                  void* workspace, size_t ws_bytes, float* grad_means, float* grad_scales,
                  float* grad_colors, float* grad_opacities, int accumulate, void* stream);
 
+/* ---- multi-view backward (the fit loop) --------------------------------------------------
+ * b2s_backward = b2s_backward_blend (per view) + b2s_backward_params (chain rule).  The fit loop
+ * calls the first once per view into slot v of a (num_views, n, 12) float buffer and the second
+ * ONCE per iteration: every Gaussian's gradients are accumulated over all views in registers
+ * and written once, instead of a read-modify-write of the whole gradient buffer per view. */
+size_t b2s_view_block_bytes(void);
+/* Converts num_views parameter blocks into the kernels' per-view constant blocks
+ * (out_host: num_views * b2s_view_block_bytes() bytes of HOST memory; upload it once). */
+int b2s_pack_views(const b2s_params* params, int num_views, void* out_host);
+/* Blend backward of one view: gacc_out (n,12) float = per-Gaussian partial sums (overwritten). */
+int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* g_rgb,
+                       const float* g_alpha, const float* g_depth, const void* state, void* workspace,
+                       size_t ws_bytes, float* gacc_out, void* stream);
+/* Chain rule over all views: views_dev = device copy of the b2s_pack_views block. */
+int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                        const float* scales, const float* colors, const float* opacities, int n,
+                        const float* gacc_all, float* grad_means, float* grad_scales, float* grad_colors,
+                        float* grad_opacities, int accumulate, void* stream);
+
 /* info_host[0] = pairs needed, [1] = pairs kept, [2] = overflow flag.  Synchronises. */
 int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,
                    int64_t* info_host, void* stream);
