@@ -20,6 +20,9 @@
 //   dColour = sum_r fy[r] * sum_c fx[c] gA(r,c)          S = sum_r fy[r] * sum_c fx[c] T(r,c)
 //   column sums (for d/dpx, d/dsx): colS[c] = fx[c] * sum_r fy[r] T(r,c)
 // => 8 FFMA per pixel-pair, issued as 4 packed f32x2 instructions + 1 LDS.128 per 4 pairs/channel.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -66,6 +69,88 @@ gbuf_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __r
   dst[2 * TILE_PIX] = g.z;
   dst[3 * TILE_PIX] = g.w;
   if (DEPTH) dst[4 * TILE_PIX] = gd;
+}
+
+// ---- per-pixel g-buffer, emitted directly as tensor-core B fragments (v5) -------------------------
+// Same per-pixel numbers as gbuf_kernel, but stored for blend_wsum_bwd_mma_kernel: every plane value
+// is scaled by the tile's power of two 2^sG (so that max|G| lands in [2^11, 2^12)), split into
+// fp16 hi + fp16 lo (22 significant bits together) and written at the position the consumer's
+// lane/register expects for the two operand orientations:
+//   B1: N = row, K = column   (U = G . fx)        B2: N = column, K = row   (V = fy . G)
+// m16n8k16 B fragment: lane (g = lane/4, t = lane%4) holds b0 = {K=2t, 2t+1}, b1 = {K=2t+8, 2t+9} at N = g.
+// Register index = ((ch*2 + h)*2 + part)*2 + slot, h = N/8, part = hi|lo, slot = K/8; B2 follows B1.
+// Layout in memory: [tile][register/4][lane] uint4  -> the consumer's loads are coalesced LDG.128.
+// tile_scale[tile] = 2^-(sG + 16): undoes 2^sG and the 2^8 applied to each of fx, fy ... see the consumer.
+template <bool DEPTH>
+__global__ void __launch_bounds__(TILE_PIX)
+gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __restrict__ g_rgb,
+                 const float* __restrict__ g_alpha, const float* __restrict__ g_depth, uint32_t* __restrict__ frag,
+                 float* __restrict__ tile_scale) {
+  constexpr int CH = DEPTH ? 5 : 4;
+  constexpr int NREG = CH * 16;
+  __shared__ float wmax[TILE_PIX / 32];
+  const int tile = blockIdx.x, q = threadIdx.x;
+  const int r = q >> 4, c = q & 15;
+  const int xi = (tile % vp.tiles_x) * TILE + c, yi = (tile / vp.tiles_x) * TILE + r;
+  const size_t hw = (size_t)vp.width * vp.height;
+  float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (xi < vp.width && yi < vp.height) {
+    const size_t p = (size_t)yi * vp.width + xi;
+    const float A0 = acc[p], A1 = acc[hw + p], A2 = acc[2 * hw + p], W = acc[3 * hw + p];
+    const float inv = 1.0f / (1.0f + W);
+    const float o0 = (vp.bg[0] + A0) * inv, o1 = (vp.bg[1] + A1) * inv, o2 = (vp.bg[2] + A2) * inv;
+    v[0] = (o0 >= 0.f && o0 <= 1.f) ? g_rgb[3 * p] * inv : 0.f;
+    v[1] = (o1 >= 0.f && o1 <= 1.f) ? g_rgb[3 * p + 1] * inv : 0.f;
+    v[2] = (o2 >= 0.f && o2 <= 1.f) ? g_rgb[3 * p + 2] * inv : 0.f;
+    v[3] = -(v[0] * o0 + v[1] * o1 + v[2] * o2);
+    if (g_alpha != nullptr) v[3] = fmaf(g_alpha[p], inv * inv, v[3]);
+    if (DEPTH) {
+      const float D = acc[4 * hw + p];
+      const float iw = 1.0f / (W + 1e-6f);
+      const float gdep = (D * iw >= 0.f) ? g_depth[p] : 0.f;
+      v[4] = gdep * iw;
+      v[3] = fmaf(-gdep * D, iw * iw, v[3]);
+    }
+  }
+  float m = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) m = fmaxf(m, fabsf(v[ch]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((q & 31) == 0) wmax[q >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+#pragma unroll
+  for (int w = 0; w < TILE_PIX / 32; ++w) m = fmaxf(m, wmax[w]);
+  int sG = 0;
+  if (m > 0.f && m < INFINITY) {
+    int e;
+    frexpf(m, &e);                 // 2^(e-1) <= m < 2^e
+    sG = min(max(12 - e, -60), 60);
+  }
+  const float scale = ldexpf(1.0f, sG);
+  if (q == 0) tile_scale[tile] = ldexpf(1.0f, -(sG + 16));
+  __half* out = reinterpret_cast<__half*>(frag) + (size_t)tile * NREG * 32 * 2;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    const float x = v[ch] * scale;
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      const __half val = part ? lo : hi;
+      {   // B1: N = row r, K = column c
+        const int h = r >> 3, g = r & 7, slot = c >> 3, t = (c & 7) >> 1, half = c & 1;
+        const int reg = ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
+        out[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+      }
+      {   // B2: N = column c, K = row r
+        const int h = c >> 3, g = c & 7, slot = r >> 3, t = (r & 7) >> 1, half = r & 1;
+        const int reg = CH * 8 + ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
+        out[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+      }
+    }
+  }
 }
 
 // ---- TMA bulk copy helpers (global -> shared, completion on an mbarrier) ------------------------
@@ -223,19 +308,295 @@ blend_wsum_bwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
   }
 }
 
+// ---- v5: the separable sums as small GEMMs on the tensor cores -----------------------------------
+// With w(r,c) = op fy[r] fx[c] the per-Gaussian sums of one tile are two matrix products over the
+// 16x16 g-buffer planes G_ch (ch = gA.r, gA.g, gA.b, gW [, gD]):
+//   U_ch[i][r] = sum_c fx_i[c] G_ch[r][c]      (contract the columns)
+//   V_ch[i][c] = sum_r fy_i[r] G_ch[r][c]      (contract the rows)
+// followed by O(16) FP32 work per Gaussian:
+//   dColour_ch = sum_r fy[r] U_ch[r];  rowT[r] = colour . U[r] + U_W[r];  S,Sy,Syy = sum_r fy[r] dy^k rowT[r]
+//   colT[c] = colour . V[c] + V_W[c];  Sx,Sxx = sum_c fx[c] dx^k colT[c]
+// i.e. 2 x 16 x 16 x CH MACs per (Gaussian,tile) on the tensor pipe (mma.sync m16n8k16, FP32
+// accumulate: K = 16 is exactly the tile edge) + ~70 FP32 ops, instead of 8 FP32 FMAs for each of
+// the 256 pixels.
+// Precision (gradients are held to relative L2 <= 1e-3 by north_star):
+//   * the factors fx, fy enter as single fp16 (2^-11): their rounding is common to all planes, so it
+//     commutes with the per-Gaussian plane combination colour.G + G_W and stays a 2^-11-relative
+//     perturbation of each term;
+//   * the planes enter as fp16 hi + fp16 lo (2 MMAs): rounding them independently (as the first
+//     TF32 version did) is amplified by the cancellation inside colour.G + G_W = gA.(colour - out) and
+//     measured 1.2e-3..2.4e-3 on the scale gradients; with hi + lo the planes carry 22 bits.
+//   * range: planes are pre-scaled per tile by a power of two (gbuf_frag_kernel), factors by 2^8
+//     (added to the exponent of ex2, free); opacity is applied in FP32 afterwards.
+//
+// One warp owns a work unit (tile, <= SEG Gaussians) and processes 16 Gaussians per step with
+// M = Gaussians.  Lane (g = lane/4, t = lane%4) owns Gaussians g and g+8 of the step and the pixel
+// coordinates idx(q) = 8*(q/2) + 2t + (q%2), q = 0..3, on both axes: the K slots of the A fragment a
+// lane builds (its 4 fx / 4 fy values per Gaussian) are exactly the N slots (rows / columns) it
+// receives back in the accumulator fragment.  The tile's planes live in registers as B fragments
+// for the whole unit.  Records are staged per warp with cp.async, ids one stage ahead.
+constexpr int BM_WARPS = 4;
+constexpr int BM_STAGE = 32;      // Gaussians per cp.async stage = 2 MMA steps
+constexpr int BM_STAGES = 3;
+
+struct BmStage {
+  float4 a[BM_STAGE];   // {px, qx, log2 op, bbox x}
+  float4 b[BM_STAGE];   // {py, qy, 0, bbox y}
+  float4 c[BM_STAGE];   // {r, g, b, zabs}
+  int id[BM_STAGE];
+};
+
+__device__ __forceinline__ void cp_async16_b(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_b() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_b() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {   // {K even, K odd} -> f16x2
+  const __half2 h = __floats2half2_rn(lo_k, hi_k);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// D (16x8, fp32) = A (16x16 f16, row) * B (16x8 f16, col) + C
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(BM_WARPS * 32)
+blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                          const int2* __restrict__ units, const uint4* __restrict__ frag,
+                          const float* __restrict__ tile_scale, float* __restrict__ gacc) {
+  constexpr int CH = DEPTH ? 5 : 4;
+  constexpr int NREG = CH * 16;
+  __shared__ __align__(16) BmStage ring[BM_WARPS][BM_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * BM_WARPS + warp;
+  if (u >= unit_start[vp.n_tiles]) return;             // warps are independent: no block barrier below
+  const int2 ud = units[u];
+  const int tile = ud.x;
+  const int2 rg = ranges[tile];
+  const int start = rg.x + ud.y * SEG;
+  const int n = min(SEG, rg.y - start);
+  if (n <= 0) return;
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int g = lane >> 2, t = lane & 3;
+  BmStage* my = ring[warp];
+
+  // ---- stage the first records while the plane fragments are fetched
+  const int nchunks = (n + BM_STAGE - 1) / BM_STAGE;
+  auto issue = [&](int c, int id) {      // chunk c, this lane's Gaussian id (already loaded)
+    if (c < nchunks && c * BM_STAGE + lane < n) {
+      const float4* src = rec + 3 * (size_t)id;
+      BmStage& st = my[c % BM_STAGES];
+      cp_async16_b(&st.a[lane], src);
+      cp_async16_b(&st.b[lane], src + 1);
+      cp_async16_b(&st.c[lane], src + 2);
+      st.id[lane] = id;
+    }
+    cp_async_commit_b();
+  };
+  auto load_id = [&](int c) -> int {
+    const int i = c * BM_STAGE + lane;
+    return (c < nchunks && i < n) ? __ldg(vals + start + i) : 0;
+  };
+  {
+    int ids[BM_STAGES - 1];
+#pragma unroll
+    for (int c = 0; c < BM_STAGES - 1; ++c) ids[c] = load_id(c);
+#pragma unroll
+    for (int c = 0; c < BM_STAGES - 1; ++c) issue(c, ids[c]);
+  }
+  int id_pf = load_id(BM_STAGES - 1);
+
+  // ---- the tile's planes as B fragments (fp16 hi/lo), kept for the whole unit; see gbuf_frag_kernel
+  uint32_t B[NREG];
+  {
+    const uint4* ft = frag + (size_t)tile * (NREG / 4) * 32 + lane;
+#pragma unroll
+    for (int r4 = 0; r4 < NREG / 4; ++r4) {
+      const uint4 v = __ldg(ft + r4 * 32);
+      B[4 * r4] = v.x; B[4 * r4 + 1] = v.y; B[4 * r4 + 2] = v.z; B[4 * r4 + 3] = v.w;
+    }
+  }
+  const float k_us = __ldg(tile_scale + tile);       // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
+  // this lane's four pixel-centre coordinates on each axis
+  float cx[4], cy[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = 8 * (q >> 1) + 2 * t + (q & 1);
+    cx[q] = (float)(tx * TILE + idx) + 0.5f;
+    cy[q] = (float)(ty * TILE + idx) + 0.5f;
+  }
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int c = 0; c < nchunks; ++c) {
+    issue(c + BM_STAGES - 1, id_pf);
+    id_pf = load_id(c + BM_STAGES);
+    cp_async_wait_b<BM_STAGES - 1>();
+    __syncwarp();
+    const BmStage& st = my[c % BM_STAGES];
+#pragma unroll 1
+    for (int bt = 0; bt < 2; ++bt) {
+      const int base = c * BM_STAGE + bt * 16;
+      if (base >= n) break;                        // warp-uniform
+      const int j[2] = {bt * 16 + g, bt * 16 + g + 8};
+      bool act[2], zero_op[2];
+      float4 ra[2], rb[2], rc[2];
+      float fx[2][4], fy[2][4];                    // the factors scaled by 2^8 (fp16 range), WITHOUT opacity
+      float opk[2];                                // opacity * k_us: applied in the FP32 epilogue
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        act[e] = (c * BM_STAGE + j[e]) < n;
+        ra[e] = st.a[j[e]];
+        rb[e] = st.b[j[e]];
+        rc[e] = st.c[j[e]];
+        // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: sweep with op = 1
+        zero_op[e] = (ra[e].z == -INFINITY);
+        opk[e] = zero_op[e] ? k_us : ex2_approx(ra[e].z) * k_us;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float dx = cx[q] - ra[e].x, dy = cy[q] - rb[e].x;
+          const float vx = ex2_approx(fmaf(ra[e].y * dx, dx, 8.0f));
+          const float vy = ex2_approx(fmaf(rb[e].y * dy, dy, 8.0f));
+          fx[e][q] = act[e] ? vx : 0.0f;           // padding rows of the last step contribute nothing
+          fy[e][q] = act[e] ? vy : 0.0f;
+        }
+      }
+      // A fragments (m16n8k16): a0 = (Gaussian g; K = 2t, 2t+1), a1 = (g+8; same K), a2 = (g; K = 2t+8, 2t+9),
+      // a3 = (g+8; same) -- K slots 2t, 2t+1, 2t+8, 2t+9 are this lane's coordinates q = 0..3.
+      uint32_t Ax[4], Ay[4];
+      Ax[0] = pack_h2(fx[0][0], fx[0][1]); Ax[1] = pack_h2(fx[1][0], fx[1][1]);
+      Ax[2] = pack_h2(fx[0][2], fx[0][3]); Ax[3] = pack_h2(fx[1][2], fx[1][3]);
+      Ay[0] = pack_h2(fy[0][0], fy[0][1]); Ay[1] = pack_h2(fy[1][0], fy[1][1]);
+      Ay[2] = pack_h2(fy[0][2], fy[0][3]); Ay[3] = pack_h2(fy[1][2], fy[1][3]);
+      // per-Gaussian accumulators: e = 0 -> Gaussian g, e = 1 -> Gaussian g+8
+      float dC[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // dR dG dB dZ
+      float S[2] = {0.f, 0.f}, Sx[2] = {0.f, 0.f}, Sxx[2] = {0.f, 0.f}, Sy[2] = {0.f, 0.f}, Syy[2] = {0.f, 0.f};
+
+      // ---- U = fx . G  (rows come back: accumulator (e, q = 2h+{0,1}) = d[2e + {0,1}] of half h)
+      {
+        float D[CH][2][4];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r0 = (ch * 2 + h) * 4;         // hi: r0, r0+1 ; lo: r0+2, r0+3
+            mma_f16(D[ch][h], Ax, B[r0 + 2], B[r0 + 3], zero4);
+            mma_f16(D[ch][h], Ax, B[r0], B[r0 + 1], D[ch][h]);
+          }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int h = q >> 1, k = 2 * e + (q & 1);
+            const float uR = D[0][h][k], uG = D[1][h][k], uB = D[2][h][k], uW = D[3][h][k];
+            float T = fmaf(rc[e].x, uR, fmaf(rc[e].y, uG, fmaf(rc[e].z, uB, uW)));
+            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][h][k], T);
+            const float f = fy[e][q] * opk[e], dy = cy[q] - rb[e].x;
+            const float a = f * T;
+            S[e] += a;
+            Sy[e] = fmaf(a, dy, Sy[e]);
+            Syy[e] = fmaf(a * dy, dy, Syy[e]);
+            dC[e][0] = fmaf(f, uR, dC[e][0]);
+            dC[e][1] = fmaf(f, uG, dC[e][1]);
+            dC[e][2] = fmaf(f, uB, dC[e][2]);
+            if (DEPTH) dC[e][3] = fmaf(f, D[CH - 1][h][k], dC[e][3]);
+          }
+      }
+      // ---- V = fy . G  (columns come back)
+      {
+        float D[CH][2][4];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r0 = CH * 8 + (ch * 2 + h) * 4;
+            mma_f16(D[ch][h], Ay, B[r0 + 2], B[r0 + 3], zero4);
+            mma_f16(D[ch][h], Ay, B[r0], B[r0 + 1], D[ch][h]);
+          }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int h = q >> 1, k = 2 * e + (q & 1);
+            float T = fmaf(rc[e].x, D[0][h][k], fmaf(rc[e].y, D[1][h][k], fmaf(rc[e].z, D[2][h][k], D[3][h][k])));
+            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][h][k], T);
+            const float dx = cx[q] - ra[e].x;
+            const float b = fx[e][q] * opk[e] * T * dx;
+            Sx[e] += b;
+            Sxx[e] = fmaf(b, dx, Sxx[e]);
+          }
+      }
+      // ---- sum over the quad (the 4 lanes that share Gaussians g, g+8), then two vector REDs per Gaussian
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+          for (int q = 0; q < (DEPTH ? 4 : 3); ++q) dC[e][q] += __shfl_xor_sync(0xffffffffu, dC[e][q], o);
+          S[e] += __shfl_xor_sync(0xffffffffu, S[e], o);
+          Sx[e] += __shfl_xor_sync(0xffffffffu, Sx[e], o);
+          Sxx[e] += __shfl_xor_sync(0xffffffffu, Sxx[e], o);
+          Sy[e] += __shfl_xor_sync(0xffffffffu, Sy[e], o);
+          Syy[e] += __shfl_xor_sync(0xffffffffu, Syy[e], o);
+        }
+        if (zero_op[e]) { dC[e][0] = dC[e][1] = dC[e][2] = dC[e][3] = Sx[e] = Sxx[e] = Sy[e] = Syy[e] = 0.0f; }
+      }
+      {
+        const int e = t >> 1;                      // lanes t=0,1 write Gaussian g, lanes t=2,3 Gaussian g+8
+        const bool on = e ? act[1] : act[0];
+        const int id = st.id[e ? j[1] : j[0]];
+        float v0, v1, v2, v3;
+        if (t & 1) { v0 = e ? S[1] : S[0]; v1 = e ? Sx[1] : Sx[0]; v2 = e ? Sxx[1] : Sxx[0]; v3 = e ? Sy[1] : Sy[0]; }
+        else       { v0 = e ? dC[1][0] : dC[0][0]; v1 = e ? dC[1][1] : dC[0][1]; v2 = e ? dC[1][2] : dC[0][2]; v3 = e ? dC[1][3] : dC[0][3]; }
+        if (on) {
+          float* dst = gacc + (size_t)id * GACC_F;
+          red_add_v4(dst + 4 * (t & 1), v0, v1, v2, v3);
+          if ((t & 1) == 0) atomicAdd(dst + 8, e ? Syy[1] : Syy[0]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cp_async_wait_b<0>();
+}
+
+static bool use_simt_bwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2S_BWD_SIMT"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
                           const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,
                           float* gacc, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
-  if (g_depth != nullptr) {
-    gbuf_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
+  const bool depth = g_depth != nullptr;
+  if (use_simt_bwd()) {   // development cross-check: the FP32-pipe kernel (v3)
+    if (depth) gbuf_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
+    else       gbuf_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
     B2S_LAUNCH_CHECK();
-    blend_wsum_bwd_kernel<true><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
+    if (depth) blend_wsum_bwd_kernel<true><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
+    else       blend_wsum_bwd_kernel<false><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
   } else {
-    gbuf_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
+    // gbuf region: [tile][20 uint4][32 lanes] fragments (10 KB per tile), then one scale per tile
+    uint32_t* frag = reinterpret_cast<uint32_t*>(gbuf);
+    float* tile_scale = gbuf + (size_t)vp.n_tiles * GBUF_FRAG_WORDS;
+    if (depth) gbuf_frag_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, frag, tile_scale);
+    else       gbuf_frag_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, frag, tile_scale);
     B2S_LAUNCH_CHECK();
-    blend_wsum_bwd_kernel<false><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
+    const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
+    const uint4* f4 = reinterpret_cast<const uint4*>(frag);
+    if (depth) blend_wsum_bwd_mma_kernel<true><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+    else       blend_wsum_bwd_mma_kernel<false><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;

@@ -13,6 +13,8 @@
 // packed f32x2 instructions.  Because the weighted sum is order independent, a tile whose list
 // spans several units is summed from per-unit partial accumulators by finalize_kernel (fixed
 // order: deterministic).  Bound: FP32 pipe, ~5.5 lane-cycles per evaluated pixel-pair.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -201,6 +203,162 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
   }
 }
 
+// ---- v4 (torch-style weighted sum): the rank-1 updates as GEMMs on the tensor cores ----------------
+// With w_i(r,c) = fy_i[r] fx_i[c] every accumulator plane of a tile is a matrix product over the
+// tile's Gaussian list (the K dimension):
+//   ACC_ch[r][c] = sum_i fy_i[r] * (v_i,ch * fx_i[c]),   v_i = (red, green, blue, 1 [, zabs])
+// M = 16 rows, N = 16 columns x CH planes, K = Gaussians: mma.sync m16n8k8, FP32 accumulate.
+// The image must match the reference to 1e-4 ABSOLUTE (north_star), which plain TF32 inputs
+// (2^-11 relative) do not guarantee, so both operands are split hi + lo (3xTF32):
+//   fy fx = fy_hi fx_hi + fy_lo fx_hi + fy_hi fx_lo   (dropped term ~2^-22)
+// One warp owns a work unit and consumes 8 Gaussians per step: lane (g = lane/4, t = lane%4)
+// evaluates Gaussians t and t+4 of the step at rows g, g+8 and columns g, g+8 (8 MUFU.EX2), which is
+// exactly its share of the A (rows x Gaussians) and B (Gaussians x columns) fragments, and ends up
+// holding pixels (rows g, g+8) x (columns 2t, 2t+1, 8+2t, 9+2t) of every plane.
+// The native "exact" mode (per-pixel w < 1e-5 cut, bbox mask: not separable) stays on the FP32 kernel above.
+constexpr int FM_WARPS = 4;
+constexpr int FM_STAGE = 32;
+constexpr int FM_STAGES = 3;
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u; }
+__device__ __forceinline__ void mma_tf32_acc(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(FM_WARPS * 32)
+blend_wsum_fwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                          const int2* __restrict__ units, float* __restrict__ partial, float* __restrict__ out_rgb,
+                          float* __restrict__ out_alpha, float* __restrict__ out_depth, float* __restrict__ acc,
+                          uint8_t* __restrict__ out_rgba) {
+  constexpr int CH = DEPTH ? 5 : 4;      // planes R G B W [D]
+  __shared__ __align__(16) FwStage ring[FM_WARPS][FM_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * FM_WARPS + warp;
+  if (u >= unit_start[vp.n_tiles]) return;             // warps are independent: no block barrier below
+  const int2 ud = units[u];
+  const int tile = ud.x;
+  const int2 rg = ranges[tile];
+  const int start = rg.x + ud.y * SEG;
+  const int n = max(0, min(SEG, rg.y - start));
+  const int nseg = unit_start[tile + 1] - unit_start[tile];
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int g = lane >> 2, t = lane & 3;
+  FwStage* my = ring[warp];
+
+  const int nchunks = (n + FM_STAGE - 1) / FM_STAGE;
+  auto issue = [&](int c, int id) {
+    if (c < nchunks && c * FM_STAGE + lane < n) {
+      const float4* src = rec + 3 * (size_t)id;
+      FwStage& st = my[c % FM_STAGES];
+      cp_async16(&st.a[lane], src);
+      cp_async16(&st.b[lane], src + 1);
+      cp_async16(&st.c[lane], src + 2);
+    }
+    cp_async_commit();
+  };
+  auto load_id = [&](int c) -> int {
+    const int i = c * FM_STAGE + lane;
+    return (c < nchunks && i < n) ? __ldg(vals + start + i) : 0;
+  };
+  {
+    int ids[FM_STAGES - 1];
+#pragma unroll
+    for (int c = 0; c < FM_STAGES - 1; ++c) ids[c] = load_id(c);
+#pragma unroll
+    for (int c = 0; c < FM_STAGES - 1; ++c) issue(c, ids[c]);
+  }
+  int id_pf = load_id(FM_STAGES - 1);    // ids run one stage ahead of the record gathers
+
+  float D[CH][2][4];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) D[ch][h][k] = 0.0f;
+  const float cy0 = (float)(ty * TILE + g) + 0.5f, cy1 = cy0 + 8.0f;     // rows g, g+8
+  const float cx0 = (float)(tx * TILE + g) + 0.5f, cx1 = cx0 + 8.0f;     // columns g, g+8
+
+  for (int c = 0; c < nchunks; ++c) {
+    issue(c + FM_STAGES - 1, id_pf);
+    id_pf = load_id(c + FM_STAGES);
+    cp_async_wait<FM_STAGES - 1>();
+    __syncwarp();
+    const FwStage& st = my[c % FM_STAGES];
+    const int left = n - c * FM_STAGE;               // Gaussians in this chunk (may exceed 32)
+#pragma unroll 2
+    for (int sp = 0; sp < FM_STAGE / 8; ++sp) {
+      if (sp * 8 >= left) break;                     // warp-uniform
+      float fy[2][2], fx[2][2], v[2][4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = sp * 8 + t + 4 * e;
+        const bool on = j < left;                    // padding of the last step: zero weight, clean values
+        const float4 ra = st.a[j], rb = st.b[j], rc = st.c[j];
+        const float dy0 = cy0 - rb.x, dy1 = cy1 - rb.x, dx0 = cx0 - ra.x, dx1 = cx1 - ra.x;
+        const float y0v = ex2_approx(rb.y * dy0 * dy0), y1v = ex2_approx(rb.y * dy1 * dy1);
+        const float x0v = ex2_approx(fmaf(ra.y * dx0, dx0, ra.z)), x1v = ex2_approx(fmaf(ra.y * dx1, dx1, ra.z));
+        fy[e][0] = on ? y0v : 0.0f; fy[e][1] = on ? y1v : 0.0f;
+        fx[e][0] = on ? x0v : 0.0f; fx[e][1] = on ? x1v : 0.0f;
+        v[e][0] = on ? rc.x : 0.0f; v[e][1] = on ? rc.y : 0.0f; v[e][2] = on ? rc.z : 0.0f; v[e][3] = on ? rc.w : 0.0f;
+      }
+      // A = fy: a0 = (row g, Gaussian t), a1 = (row g+8, t), a2 = (row g, t+4), a3 = (row g+8, t+4)
+      uint32_t Ah[4], Al[4];
+      {
+        const float av[4] = {fy[0][0], fy[0][1], fy[1][0], fy[1][1]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { Ah[k] = tf32_hi(av[k]); Al[k] = tf32_lo(av[k], Ah[k]); }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // B = v * fx at column 8h+g: b0 = Gaussian t, b1 = Gaussian t+4
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          float b0, b1;
+          if (ch == 3) { b0 = fx[0][h]; b1 = fx[1][h]; }                       // weight plane
+          else if (ch == 4) { b0 = v[0][3] * fx[0][h]; b1 = v[1][3] * fx[1][h]; }   // depth plane
+          else { b0 = v[0][ch] * fx[0][h]; b1 = v[1][ch] * fx[1][h]; }
+          uint32_t Bh[2], Bl[2];
+          Bh[0] = tf32_hi(b0); Bh[1] = tf32_hi(b1);
+          Bl[0] = tf32_lo(b0, Bh[0]); Bl[1] = tf32_lo(b1, Bh[1]);
+          mma_tf32_acc(D[ch][h], Al, Bh);
+          mma_tf32_acc(D[ch][h], Ah, Bl);
+          mma_tf32_acc(D[ch][h], Ah, Bh);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+
+  // accumulator fragment -> pixels: D[ch][h] = {(row g, col 8h+2t), (g, 8h+2t+1), (g+8, 8h+2t), (g+8, 8h+2t+1)}
+  const size_t hw = (size_t)vp.width * vp.height;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = g + 8 * (k >> 1), cc = 8 * h + 2 * t + (k & 1);
+      const float R = D[0][h][k], G = D[1][h][k], B = D[2][h][k], W = D[3][h][k], Dz = DEPTH ? D[CH - 1][h][k] : 0.0f;
+      if (nseg <= 1) {
+        const int xi = tx * TILE + cc, yi = ty * TILE + r;
+        if (xi < vp.width && yi < vp.height)
+          write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, B, W, Dz, out_rgb, out_alpha, out_depth, acc, out_rgba);
+      } else {
+        float* dst = partial + (size_t)u * 5 * TILE_PIX + r * TILE + cc;
+        dst[0] = R;
+        dst[TILE_PIX] = G;
+        dst[2 * TILE_PIX] = B;
+        dst[3 * TILE_PIX] = W;
+        if (DEPTH) dst[4 * TILE_PIX] = Dz;
+      }
+    }
+}
+
 // Sums the per-unit partial accumulators of tiles that span several units, in unit order.
 template <bool DEPTH>
 __global__ void __launch_bounds__(TILE_PIX)
@@ -236,8 +394,14 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
 #define B2S_FW(DD, EE)                                                                                              \
   blend_wsum_fwd_kernel<DD, EE><<<blocks, FW_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, partial, \
                                                                    out_rgb, out_alpha, out_depth, acc, out_rgba)
+#define B2S_FWM(DD)                                                                                                   \
+  blend_wsum_fwd_mma_kernel<DD><<<(int)((unit_cap + FM_WARPS - 1) / FM_WARPS), FM_WARPS * 32, 0, st>>>(               \
+      vp, rec, vals, ranges, unit_start, units, partial, out_rgb, out_alpha, out_depth, acc, out_rgba)
+  static const bool simt = [] { const char* e = getenv("B2S_FWD_SIMT"); return e != nullptr && e[0] == '1'; }();
   if (vp.exact_bbox) { if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
-  else               { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }
+  else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
+  else               { if (depth) B2S_FWM(true); else B2S_FWM(false); }
+#undef B2S_FWM
 #undef B2S_FW
   B2S_LAUNCH_CHECK();
   if (depth)

@@ -11,6 +11,7 @@ constexpr int TILE = B2S_TILE;        // 16x16 pixel tiles
 constexpr int TILE_PIX = TILE * TILE;
 constexpr int REC_F4 = 3;             // per-Gaussian blend record: 3 x float4 = 48 B
 constexpr int GACC_F = 12;            // per-Gaussian backward accumulator: 12 floats = 48 B
+constexpr int GBUF_FRAG_WORDS = 80 * 32;   // per-tile g-buffer as fp16 hi/lo MMA fragments: 80 registers x 32 lanes
 
 // Per-view constants handed to every kernel by value.
 struct ViewParams {
@@ -179,7 +180,7 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   L.gacc = o;  o += align_up(nn * GACC_F * 4);
   const size_t tiles = (size_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
   L.partial = o; o += align_up((size_t)max_units(width, height, max_pairs) * 5 * TILE_PIX * 4);
-  L.gbuf = o;  o += align_up(tiles * TILE_PIX * 20);   // float4 g + float gD per pixel, tile-major
+  L.gbuf = o;  o += align_up(tiles * GBUF_FRAG_WORDS * 4) + align_up(tiles * 4);   // plane fragments + per-tile scale
   L.cs_table = o; o += align_up((size_t)CS_NB * tiles * 4);
   L.cs_total = o; o += align_up(tiles * 4);
   L.total = o;
