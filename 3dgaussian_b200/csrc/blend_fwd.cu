@@ -13,6 +13,7 @@
 // packed f32x2 instructions.  Because the weighted sum is order independent, a tile whose list
 // spans several units is summed from per-unit partial accumulators by finalize_kernel (fixed
 // order: deterministic).  Bound: FP32 pipe, ~5.5 lane-cycles per evaluated pixel-pair.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -359,6 +360,169 @@ blend_wsum_fwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     }
 }
 
+// ---- v5: the same GEMM with fp16 operands, K = 16 Gaussians per MMA (3xFP16) ----------------------
+// mma.sync m16n8k16 issues at the same rate as the TF32 m16n8k8 (profiles/microbench/mma_rate_b200.txt)
+// and consumes twice the Gaussians, so the hi/lo-split product costs 1.5 HMMA per (Gaussian,tile)
+// instead of 3.  fp16 has TF32's 11-bit significand; its narrow exponent is handled by scaling both
+// factors by 2^8 inside the ex2 argument (free) and un-scaling the accumulators once at the end:
+//   fy*2^8 in (0, 256],  v*fx*2^8 <= 256*op*v (clamped to 65000 = op*v up to 253),
+//   values below 2^-14 (true factor < 2.4e-7) lose relative precision but stay within 2^-25 absolute.
+// Lane (g, t) evaluates Gaussians 2t, 2t+1, 2t+8, 2t+9 of the step at rows g, g+8 and columns g, g+8
+// (16 MUFU.EX2): exactly its A (rows x Gaussians) and B (Gaussians x columns) fragment slots.
+// Padding slots of the last step hold a record with px = py = 1e18 (factor underflows to 0): no selects.
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  hi = h2_bits(h);
+  lo = h2_bits(__floats2half2_rn(x0 - f.x, x1 - f.y));
+}
+__device__ __forceinline__ void mma_f16_acc(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(FM_WARPS * 32)
+blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                          const int2* __restrict__ units, float* __restrict__ partial, float* __restrict__ out_rgb,
+                          float* __restrict__ out_alpha, float* __restrict__ out_depth, float* __restrict__ acc,
+                          uint8_t* __restrict__ out_rgba) {
+  constexpr int CH = DEPTH ? 5 : 4;      // planes R G B W [D]
+  __shared__ __align__(16) FwStage ring[FM_WARPS][FM_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * FM_WARPS + warp;
+  if (u >= unit_start[vp.n_tiles]) return;             // warps are independent: no block barrier below
+  const int2 ud = units[u];
+  const int tile = ud.x;
+  const int2 rg = ranges[tile];
+  const int start = rg.x + ud.y * SEG;
+  const int n = max(0, min(SEG, rg.y - start));
+  const int nseg = unit_start[tile + 1] - unit_start[tile];
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int g = lane >> 2, t = lane & 3;
+  FwStage* my = ring[warp];
+
+  const int nchunks = (n + FM_STAGE - 1) / FM_STAGE;
+  auto issue = [&](int c, int id) {
+    if (c < nchunks) {
+      FwStage& st = my[c % FM_STAGES];
+      if (c * FM_STAGE + lane < n) {
+        const float4* src = rec + 3 * (size_t)id;
+        cp_async16(&st.a[lane], src);
+        cp_async16(&st.b[lane], src + 1);
+        cp_async16(&st.c[lane], src + 2);
+      } else {   // padding: a record whose factors underflow to exactly 0
+        st.a[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.b[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.c[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+    }
+    cp_async_commit();
+  };
+  auto load_id = [&](int c) -> int {
+    const int i = c * FM_STAGE + lane;
+    return (c < nchunks && i < n) ? __ldg(vals + start + i) : 0;
+  };
+  {
+    int ids[FM_STAGES - 1];
+#pragma unroll
+    for (int c = 0; c < FM_STAGES - 1; ++c) ids[c] = load_id(c);
+#pragma unroll
+    for (int c = 0; c < FM_STAGES - 1; ++c) issue(c, ids[c]);
+  }
+  int id_pf = load_id(FM_STAGES - 1);    // ids run one stage ahead of the record gathers
+
+  float D[CH][2][4];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) D[ch][h][k] = 0.0f;
+  const float cy0 = (float)(ty * TILE + g) + 0.5f, cy1 = cy0 + 8.0f;     // rows g, g+8
+  const float cx0 = (float)(tx * TILE + g) + 0.5f, cx1 = cx0 + 8.0f;     // columns g, g+8
+
+  for (int c = 0; c < nchunks; ++c) {
+    issue(c + FM_STAGES - 1, id_pf);
+    id_pf = load_id(c + FM_STAGES);
+    cp_async_wait<FM_STAGES - 1>();
+    __syncwarp();
+    const FwStage& st = my[c % FM_STAGES];
+    const int left = n - c * FM_STAGE;               // Gaussians in this chunk (may exceed 32)
+#pragma unroll 1
+    for (int sp = 0; sp < FM_STAGE / 16; ++sp) {
+      if (sp * 16 >= left) break;                    // warp-uniform
+      // e = 0..3 -> Gaussians 2t, 2t+1, 2t+8, 2t+9 of the step (the K slots of a0/a1 | a2/a3 and b0 | b1)
+      float fy[4][2], fx[4][2], v[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = sp * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
+        const float4 ra = st.a[j], rb = st.b[j], rc = st.c[j];
+        const float dy0 = cy0 - rb.x, dy1 = cy1 - rb.x, dx0 = cx0 - ra.x, dx1 = cx1 - ra.x;
+        fy[e][0] = ex2_approx(fmaf(rb.y * dy0, dy0, 8.0f));
+        fy[e][1] = ex2_approx(fmaf(rb.y * dy1, dy1, 8.0f));
+        fx[e][0] = ex2_approx(fmaf(ra.y * dx0, dx0, ra.z + 8.0f));
+        fx[e][1] = ex2_approx(fmaf(ra.y * dx1, dx1, ra.z + 8.0f));
+        v[e][0] = rc.x; v[e][1] = rc.y; v[e][2] = rc.z; v[e][3] = rc.w;
+      }
+      // A = fy: a0 = (row g; K 2t, 2t+1), a1 = (row g+8; same), a2 = (row g; K 2t+8, 2t+9), a3 = (row g+8; same)
+      uint32_t Ah[4], Al[4];
+      split_h2(fy[0][0], fy[1][0], Ah[0], Al[0]);
+      split_h2(fy[0][1], fy[1][1], Ah[1], Al[1]);
+      split_h2(fy[2][0], fy[3][0], Ah[2], Al[2]);
+      split_h2(fy[2][1], fy[3][1], Ah[3], Al[3]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // B = v * fx at column 8h+g: b0 = (K 2t, 2t+1), b1 = (K 2t+8, 2t+9)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          float b[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (ch == 3) b[e] = fx[e][h];                                        // weight plane
+            else b[e] = fminf(v[e][ch == 4 ? 3 : ch] * fx[e][h], 65000.0f);     // colour planes, depth plane
+          }
+          uint32_t Bh0, Bl0, Bh1, Bl1;
+          split_h2(b[0], b[1], Bh0, Bl0);
+          split_h2(b[2], b[3], Bh1, Bl1);
+          mma_f16_acc(D[ch][h], Al, Bh0, Bh1);
+          mma_f16_acc(D[ch][h], Ah, Bl0, Bl1);
+          mma_f16_acc(D[ch][h], Ah, Bh0, Bh1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+
+  // accumulator fragment -> pixels: D[ch][h] = {(row g, col 8h+2t), (g, 8h+2t+1), (g+8, 8h+2t), (g+8, 8h+2t+1)}
+  const size_t hw = (size_t)vp.width * vp.height;
+  const float us = 1.0f / 65536.0f;      // the two 2^8 factor scales
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = g + 8 * (k >> 1), cc = 8 * h + 2 * t + (k & 1);
+      const float R = D[0][h][k] * us, G = D[1][h][k] * us, B = D[2][h][k] * us, W = D[3][h][k] * us,
+                  Dz = DEPTH ? D[CH - 1][h][k] * us : 0.0f;
+      if (nseg <= 1) {
+        const int xi = tx * TILE + cc, yi = ty * TILE + r;
+        if (xi < vp.width && yi < vp.height)
+          write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, B, W, Dz, out_rgb, out_alpha, out_depth, acc, out_rgba);
+      } else {
+        float* dst = partial + (size_t)u * 5 * TILE_PIX + r * TILE + cc;
+        dst[0] = R;
+        dst[TILE_PIX] = G;
+        dst[2 * TILE_PIX] = B;
+        dst[3 * TILE_PIX] = W;
+        if (DEPTH) dst[4 * TILE_PIX] = Dz;
+      }
+    }
+}
+
 // Sums the per-unit partial accumulators of tiles that span several units, in unit order.
 template <bool DEPTH>
 __global__ void __launch_bounds__(TILE_PIX)
@@ -394,13 +558,15 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
 #define B2S_FW(DD, EE)                                                                                              \
   blend_wsum_fwd_kernel<DD, EE><<<blocks, FW_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, partial, \
                                                                    out_rgb, out_alpha, out_depth, acc, out_rgba)
-#define B2S_FWM(DD)                                                                                                   \
-  blend_wsum_fwd_mma_kernel<DD><<<(int)((unit_cap + FM_WARPS - 1) / FM_WARPS), FM_WARPS * 32, 0, st>>>(               \
+#define B2S_FWM(KERN, DD)                                                                                             \
+  KERN<DD><<<(int)((unit_cap + FM_WARPS - 1) / FM_WARPS), FM_WARPS * 32, 0, st>>>(                                    \
       vp, rec, vals, ranges, unit_start, units, partial, out_rgb, out_alpha, out_depth, acc, out_rgba)
   static const bool simt = [] { const char* e = getenv("B2S_FWD_SIMT"); return e != nullptr && e[0] == '1'; }();
+  static const bool tf32 = [] { const char* e = getenv("B2S_FWD_TF32"); return e != nullptr && e[0] == '1'; }();
   if (vp.exact_bbox) { if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
   else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
-  else               { if (depth) B2S_FWM(true); else B2S_FWM(false); }
+  else if (tf32)     { if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
+  else               { if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }
 #undef B2S_FWM
 #undef B2S_FW
   B2S_LAUNCH_CHECK();
