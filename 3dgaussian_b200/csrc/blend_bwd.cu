@@ -367,8 +367,8 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(BM_WARPS * 32)
+template <bool DEPTH, int MINB>
+__global__ void __launch_bounds__(BM_WARPS * 32, MINB)
 blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
                           const int2* __restrict__ units, const uint4* __restrict__ frag,
@@ -392,13 +392,20 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   // ---- stage the first records while the plane fragments are fetched
   const int nchunks = (n + BM_STAGE - 1) / BM_STAGE;
   auto issue = [&](int c, int id) {      // chunk c, this lane's Gaussian id (already loaded)
-    if (c < nchunks && c * BM_STAGE + lane < n) {
-      const float4* src = rec + 3 * (size_t)id;
+    if (c < nchunks) {
       BmStage& st = my[c % BM_STAGES];
-      cp_async16_b(&st.a[lane], src);
-      cp_async16_b(&st.b[lane], src + 1);
-      cp_async16_b(&st.c[lane], src + 2);
-      st.id[lane] = id;
+      if (c * BM_STAGE + lane < n) {
+        const float4* src = rec + 3 * (size_t)id;
+        cp_async16_b(&st.a[lane], src);
+        cp_async16_b(&st.b[lane], src + 1);
+        cp_async16_b(&st.c[lane], src + 2);
+        st.id[lane] = id;
+      } else {   // padding of the last step: a record whose factors underflow to exactly 0 (no selects below)
+        st.a[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.b[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.c[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        st.id[lane] = -1;
+      }
     }
     cp_async_commit_b();
   };
@@ -447,26 +454,18 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       const int base = c * BM_STAGE + bt * 16;
       if (base >= n) break;                        // warp-uniform
       const int j[2] = {bt * 16 + g, bt * 16 + g + 8};
-      bool act[2], zero_op[2];
       float4 ra[2], rb[2], rc[2];
       float fx[2][4], fy[2][4];                    // the factors scaled by 2^8 (fp16 range), WITHOUT opacity
-      float opk[2];                                // opacity * k_us: applied in the FP32 epilogue
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        act[e] = (c * BM_STAGE + j[e]) < n;
         ra[e] = st.a[j[e]];
         rb[e] = st.b[j[e]];
         rc[e] = st.c[j[e]];
-        // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: sweep with op = 1
-        zero_op[e] = (ra[e].z == -INFINITY);
-        opk[e] = zero_op[e] ? k_us : ex2_approx(ra[e].z) * k_us;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float dx = cx[q] - ra[e].x, dy = cy[q] - rb[e].x;
-          const float vx = ex2_approx(fmaf(ra[e].y * dx, dx, 8.0f));
-          const float vy = ex2_approx(fmaf(rb[e].y * dy, dy, 8.0f));
-          fx[e][q] = act[e] ? vx : 0.0f;           // padding rows of the last step contribute nothing
-          fy[e][q] = act[e] ? vy : 0.0f;
+          fx[e][q] = ex2_approx(fmaf(ra[e].y * dx, dx, 8.0f));
+          fy[e][q] = ex2_approx(fmaf(rb[e].y * dy, dy, 8.0f));
         }
       }
       // A fragments (m16n8k16): a0 = (Gaussian g; K = 2t, 2t+1), a1 = (g+8; same K), a2 = (g; K = 2t+8, 2t+9),
@@ -476,90 +475,100 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       Ax[2] = pack_h2(fx[0][2], fx[0][3]); Ax[3] = pack_h2(fx[1][2], fx[1][3]);
       Ay[0] = pack_h2(fy[0][0], fy[0][1]); Ay[1] = pack_h2(fy[1][0], fy[1][1]);
       Ay[2] = pack_h2(fy[0][2], fy[0][3]); Ay[3] = pack_h2(fy[1][2], fy[1][3]);
-      // per-Gaussian accumulators: e = 0 -> Gaussian g, e = 1 -> Gaussian g+8
-      float dC[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // dR dG dB dZ
-      float S[2] = {0.f, 0.f}, Sx[2] = {0.f, 0.f}, Sxx[2] = {0.f, 0.f}, Sy[2] = {0.f, 0.f}, Syy[2] = {0.f, 0.f};
+      // per-Gaussian partial sums of this lane: e = 0 -> Gaussian g, e = 1 -> Gaussian g+8;
+      //   P[e][0..3] = dR dG dB dZ     P[e][4..7] = S Sx Sxx Sy     Syy[e]
+      float P[2][8], Syy[2] = {0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) P[e][k] = 0.0f;
 
-      // ---- U = fx . G  (rows come back: accumulator (e, q = 2h+{0,1}) = d[2e + {0,1}] of half h)
-      {
-        float D[CH][2][4];
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
+      for (int h = 0; h < 2; ++h) {
+        // ---- U = fx . G for rows 8h..8h+7 (accumulator (e, q = 2h+{0,1}) = d[2e + {0,1}])
+        float D[CH][4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r0 = (ch * 2 + h) * 4;         // hi: r0, r0+1 ; lo: r0+2, r0+3
-            mma_f16(D[ch][h], Ax, B[r0 + 2], B[r0 + 3], zero4);
-            mma_f16(D[ch][h], Ax, B[r0], B[r0 + 1], D[ch][h]);
-          }
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int h = q >> 1, k = 2 * e + (q & 1);
-            const float uR = D[0][h][k], uG = D[1][h][k], uB = D[2][h][k], uW = D[3][h][k];
-            float T = fmaf(rc[e].x, uR, fmaf(rc[e].y, uG, fmaf(rc[e].z, uB, uW)));
-            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][h][k], T);
-            const float f = fy[e][q] * opk[e], dy = cy[q] - rb[e].x;
-            const float a = f * T;
-            S[e] += a;
-            Sy[e] = fmaf(a, dy, Sy[e]);
-            Syy[e] = fmaf(a * dy, dy, Syy[e]);
-            dC[e][0] = fmaf(f, uR, dC[e][0]);
-            dC[e][1] = fmaf(f, uG, dC[e][1]);
-            dC[e][2] = fmaf(f, uB, dC[e][2]);
-            if (DEPTH) dC[e][3] = fmaf(f, D[CH - 1][h][k], dC[e][3]);
-          }
-      }
-      // ---- V = fy . G  (columns come back)
-      {
-        float D[CH][2][4];
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r0 = CH * 8 + (ch * 2 + h) * 4;
-            mma_f16(D[ch][h], Ay, B[r0 + 2], B[r0 + 3], zero4);
-            mma_f16(D[ch][h], Ay, B[r0], B[r0 + 1], D[ch][h]);
-          }
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int h = q >> 1, k = 2 * e + (q & 1);
-            float T = fmaf(rc[e].x, D[0][h][k], fmaf(rc[e].y, D[1][h][k], fmaf(rc[e].z, D[2][h][k], D[3][h][k])));
-            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][h][k], T);
-            const float dx = cx[q] - ra[e].x;
-            const float b = fx[e][q] * opk[e] * T * dx;
-            Sx[e] += b;
-            Sxx[e] = fmaf(b, dx, Sxx[e]);
-          }
-      }
-      // ---- sum over the quad (the 4 lanes that share Gaussians g, g+8), then two vector REDs per Gaussian
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-#pragma unroll
-          for (int q = 0; q < (DEPTH ? 4 : 3); ++q) dC[e][q] += __shfl_xor_sync(0xffffffffu, dC[e][q], o);
-          S[e] += __shfl_xor_sync(0xffffffffu, S[e], o);
-          Sx[e] += __shfl_xor_sync(0xffffffffu, Sx[e], o);
-          Sxx[e] += __shfl_xor_sync(0xffffffffu, Sxx[e], o);
-          Sy[e] += __shfl_xor_sync(0xffffffffu, Sy[e], o);
-          Syy[e] += __shfl_xor_sync(0xffffffffu, Syy[e], o);
+        for (int ch = 0; ch < CH; ++ch) {
+          const int r0 = (ch * 2 + h) * 4;           // hi: r0, r0+1 ; lo: r0+2, r0+3
+          mma_f16(D[ch], Ax, B[r0 + 2], B[r0 + 3], zero4);
+          mma_f16(D[ch], Ax, B[r0], B[r0 + 1], D[ch]);
         }
-        if (zero_op[e]) { dC[e][0] = dC[e][1] = dC[e][2] = dC[e][3] = Sx[e] = Sxx[e] = Sy[e] = Syy[e] = 0.0f; }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int q = 2 * h + qq, k = 2 * e + qq;
+            const float uR = D[0][k], uG = D[1][k], uB = D[2][k], uW = D[3][k];
+            float T = fmaf(rc[e].x, uR, fmaf(rc[e].y, uG, fmaf(rc[e].z, uB, uW)));
+            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][k], T);
+            const float f = fy[e][q], dy = cy[q] - rb[e].x;
+            const float a = f * T;
+            P[e][4] += a;
+            P[e][7] = fmaf(a, dy, P[e][7]);
+            Syy[e] = fmaf(a * dy, dy, Syy[e]);
+            P[e][0] = fmaf(f, uR, P[e][0]);
+            P[e][1] = fmaf(f, uG, P[e][1]);
+            P[e][2] = fmaf(f, uB, P[e][2]);
+            if (DEPTH) P[e][3] = fmaf(f, D[CH - 1][k], P[e][3]);
+          }
       }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // ---- V = fy . G for columns 8h..8h+7
+        float D[CH][4];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          const int r0 = CH * 8 + (ch * 2 + h) * 4;
+          mma_f16(D[ch], Ay, B[r0 + 2], B[r0 + 3], zero4);
+          mma_f16(D[ch], Ay, B[r0], B[r0 + 1], D[ch]);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int q = 2 * h + qq, k = 2 * e + qq;
+            float T = fmaf(rc[e].x, D[0][k], fmaf(rc[e].y, D[1][k], fmaf(rc[e].z, D[2][k], D[3][k])));
+            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][k], T);
+            const float dx = cx[q] - ra[e].x;
+            const float b = fx[e][q] * T * dx;
+            P[e][5] += b;
+            P[e][6] = fmaf(b, dx, P[e][6]);
+          }
+      }
+      // ---- sum over the quad (the 4 lanes t = 0..3 share Gaussians g, g+8) by transposition: lane t ends
+      // with group t of {e0: dR dG dB dZ | e0: S Sx Sxx Sy | e1: dR.. | e1: S..} summed over the quad.
+      const bool up = (t & 2) != 0;                // lanes 2,3 keep Gaussian g+8, lanes 0,1 keep Gaussian g
+      const bool odd = (t & 1) != 0;               // odd lanes keep {S Sx Sxx Sy}, even lanes {dR dG dB dZ}
+      float v4[4];
       {
-        const int e = t >> 1;                      // lanes t=0,1 write Gaussian g, lanes t=2,3 Gaussian g+8
-        const bool on = e ? act[1] : act[0];
-        const int id = st.id[e ? j[1] : j[0]];
-        float v0, v1, v2, v3;
-        if (t & 1) { v0 = e ? S[1] : S[0]; v1 = e ? Sx[1] : Sx[0]; v2 = e ? Sxx[1] : Sxx[0]; v3 = e ? Sy[1] : Sy[0]; }
-        else       { v0 = e ? dC[1][0] : dC[0][0]; v1 = e ? dC[1][1] : dC[0][1]; v2 = e ? dC[1][2] : dC[0][2]; v3 = e ? dC[1][3] : dC[0][3]; }
-        if (on) {
+        float keep[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float send = up ? P[0][k] : P[1][k];
+          keep[k] = (up ? P[1][k] : P[0][k]) + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float send = odd ? keep[k] : keep[4 + k];
+          v4[k] = (odd ? keep[4 + k] : keep[k]) + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+      }
+      float syy = (up ? Syy[1] : Syy[0]) + __shfl_xor_sync(0xffffffffu, up ? Syy[0] : Syy[1], 2);
+      syy += __shfl_xor_sync(0xffffffffu, syy, 1);
+      {
+        const int id = st.id[up ? j[1] : j[0]];
+        const float lop = up ? ra[1].z : ra[0].z;
+        // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
+        const bool zop = (lop == -INFINITY);
+        const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
+        if (id >= 0) {
           float* dst = gacc + (size_t)id * GACC_F;
-          red_add_v4(dst + 4 * (t & 1), v0, v1, v2, v3);
-          if ((t & 1) == 0) atomicAdd(dst + 8, e ? Syy[1] : Syy[0]);
+          if (odd) {
+            red_add_v4(dst + 4, v4[0] * opk, zop ? 0.f : v4[1] * opk, zop ? 0.f : v4[2] * opk, zop ? 0.f : v4[3] * opk);
+          } else if (!zop) {
+            red_add_v4(dst, v4[0] * opk, v4[1] * opk, v4[2] * opk, v4[3] * opk);
+            atomicAdd(dst + 8, syy * opk);
+          }
         }
       }
     }
@@ -595,8 +604,10 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     B2S_LAUNCH_CHECK();
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);
-    if (depth) blend_wsum_bwd_mma_kernel<true><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
-    else       blend_wsum_bwd_mma_kernel<false><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+    static const bool minb4 = [] { const char* e = getenv("B2S_BWD_MINB"); return e != nullptr && e[0] == '4'; }();
+    if (depth) blend_wsum_bwd_mma_kernel<true, 1><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+    else if (minb4) blend_wsum_bwd_mma_kernel<false, 4><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+    else       blend_wsum_bwd_mma_kernel<false, 3><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
