@@ -22,7 +22,7 @@ EXPORTS = [
     "b2s_count_pairs", "b2s_forward", "b2s_backward", "b2s_state_info", "b2s_render_rgba8",
     "b2s_render_rgba8_host", "b2s_dump_bins", "b2s_sort_tmp_bytes", "b2s_sort_pairs", "b2s_fit_loss",
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_backward_params",
-    "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
+    "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
 ]
 
 
@@ -93,6 +93,11 @@ def lib() -> C.CDLL:
         L.b2s_adam_step.restype = i32
         L.b2s_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
                                     i64, i64, C.c_float, i64, i64, C.c_float, vp]
+        L.b2s_densify_workspace_bytes.restype = sz
+        L.b2s_densify_workspace_bytes.argtypes = [i32]
+        L.b2s_densify_prune.restype = i32
+        L.b2s_densify_prune.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, C.c_float, C.c_uint64, C.c_uint64,
+                                        vp, vp, vp, vp, C.POINTER(C.c_int), vp, sz, vp]
         L.b2s_launch_count.restype = i64
         L.b2s_launch_count.argtypes = []
         L.b2s_num_stages.restype = i32

@@ -635,6 +635,29 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
                      opac_begin, opac_end, reg_opacity, (cudaStream_t)stream);
 }
 
+size_t b2s_densify_workspace_bytes(int n) { return densify_workspace_bytes(n) + 256; }
+
+int b2s_densify_prune(b2s_ctx* ctx, const float* means, const float* scales_raw, const float* opacities_raw,
+                      const float* colors, int n, int color_floats, int max_gaussians, double densify_ratio,
+                      float prune_opacity, uint64_t seed, uint64_t iteration, float* out_means, float* out_scales_raw,
+                      float* out_opacities_raw, float* out_colors, int* n_new_host, void* workspace, size_t ws_bytes,
+                      void* stream) {
+  if (ctx == nullptr || means == nullptr || scales_raw == nullptr || opacities_raw == nullptr || colors == nullptr ||
+      out_means == nullptr || out_scales_raw == nullptr || out_opacities_raw == nullptr || out_colors == nullptr ||
+      n_new_host == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (n < 0 || color_floats <= 0 || max_gaussians < 0) { set_error("bad n / color_floats / max_gaussians"); return B2S_ERR_INVALID; }
+  if (ws_bytes < b2s_densify_workspace_bytes(n)) { set_error("densify workspace too small"); return B2S_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int* n_new_dev = (int*)((char*)workspace + densify_workspace_bytes(n));
+  int rc = launch_densify_prune(means, scales_raw, opacities_raw, colors, n, color_floats, max_gaussians, densify_ratio,
+                                prune_opacity, seed, iteration, out_means, out_scales_raw, out_opacities_raw, out_colors,
+                                n_new_dev, workspace, st);
+  if (rc != B2S_OK) return rc;
+  B2S_CUDA_TRY(cudaMemcpyAsync(n_new_host, n_new_dev, 4, cudaMemcpyDeviceToHost, st));
+  B2S_CUDA_TRY(cudaStreamSynchronize(st));
+  return B2S_OK;
+}
+
 int64_t b2s_launch_count(void) { return (int64_t)g_launches.load(); }
 int b2s_num_stages(void) { return ST_COUNT; }
 const char* b2s_stage_name(int stage) {

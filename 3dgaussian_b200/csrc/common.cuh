@@ -251,6 +251,12 @@ int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev,
                           const float* means, const float* scales, const float* colors, const float* opac, int n,
                           const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
                           int accumulate, cudaStream_t st);
+int launch_scan_i32(int* data, int len, int* bs, cudaStream_t st);
+size_t densify_workspace_bytes(int n);
+int launch_densify_prune(const float* means, const float* scales_raw, const float* op_raw, const float* colors, int n,
+                         int color_floats, int max_gaussians, double ratio, float prune_opacity, unsigned long long seed,
+                         unsigned long long iter, float* o_means, float* o_scales, float* o_op, float* o_colors,
+                         int* n_new_dev, void* ws, cudaStream_t st);
 int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
                     int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum,
                     cudaStream_t st);

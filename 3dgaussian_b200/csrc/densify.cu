@@ -196,6 +196,10 @@ dp_scatter_kernel(int n, int cf, const float* __restrict__ means, const float* _
   }
 }
 
+__global__ void dp_sum_kernel(const DpState* S, int* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *out = S->n1 + S->add_n;
+}
+
 struct DpLayout { size_t state, keys, keep, sel, gt, eq, scanA, scanB, bs, total; };
 static DpLayout dp_layout(int n) {
   const size_t nn = (size_t)(n > 0 ? n : 1);
@@ -277,18 +281,7 @@ int launch_densify_prune(const float* means, const float* scales_raw, const floa
                                             (unsigned)seed, (unsigned)(seed >> 32), (unsigned)iter, (unsigned)(iter >> 32),
                                             o_means, o_scales, o_op, o_colors);
   B2S_LAUNCH_CHECK();
-  // n_new = n1 + add_n
-  dp_total_kernel<<<1, 32, 0, st>>>(scanB, sel, n, (int*)&S->pad);
-  B2S_LAUNCH_CHECK();
-  B2S_CUDA_TRY(cudaMemcpyAsync(&S->count0, n_new_dev, 4, cudaMemcpyDeviceToDevice, st));   // reuse count0 = n1
-  return B2S_OK;
-}
-
-__global__ void dp_sum_kernel(const DpState* S, int* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *out = S->n1 + S->add_n;
-}
-int launch_densify_total(const void* ws, int* n_new_dev, cudaStream_t st) {
-  dp_sum_kernel<<<1, 32, 0, st>>>((const DpState*)ws, n_new_dev);
+  dp_sum_kernel<<<1, 32, 0, st>>>(S, n_new_dev);     // n_new = survivors + clones
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

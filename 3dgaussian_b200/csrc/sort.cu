@@ -186,6 +186,9 @@ radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const int* 
   }
 }
 
+// exclusive scan of `len` ints in place; bs: (len/4096 + 2) ints of scratch
+int launch_scan_i32(int* data, int len, int* bs, cudaStream_t st) { return len > 0 ? scan_i32_inplace(data, len, bs, st) : B2S_OK; }
+
 int launch_sort(unsigned long long* keysA, int* valsA, unsigned long long* keysB, int* valsB, int64_t cap,
                 const int* count_dev, int begin_bit, int end_bit, int* hist, int* hsum, int* result_in_B,
                 cudaStream_t st) {

@@ -48,16 +48,7 @@ class FitDriver:
                                              mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
                                              cutoff_sigma=cutoff_sigma, sh_coeffs=self.sh, sort_depth=0,
                                              act_flags=act) for i in self.views}
-        c = 3 * self.sh
-        # segment starts are padded to 64 floats (256 B): the kernels read colours with 16-byte loads
-        al = lambda x: (x + 63) // 64 * 64
-        self.o_means = 0
-        self.o_scales = al(3 * n)
-        self.o_opac = self.o_scales + al(3 * n)
-        self.o_colors = self.o_opac + al(n)
-        self.count = self.o_colors + al(c * n)
-        z = lambda: torch.zeros(self.count, dtype=torch.float32, device=device)
-        self.p, self.g, self.m, self.v = z(), z(), z(), z()
+        self._layout(self.n)
         self.step_no = 0
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=device)
         self.rgb = torch.empty((height, width, 3), dtype=torch.float32, device=device)
@@ -82,6 +73,20 @@ class FitDriver:
         self.gacc = torch.empty((max(nv, 1), max(self.n, 1), 12), dtype=torch.float32, device=device)
         self._copy_stream = None
         self._stage = None
+
+    def _layout(self, n: int):
+        """Flat fp32 layout [means 3n | scales_raw 3n | opacities_raw n | colours 3K n]; segment starts are
+        padded to 64 floats (256 B): the kernels read colours with 16-byte loads."""
+        self.n = int(n)
+        c = 3 * self.sh
+        al = lambda x: (x + 63) // 64 * 64
+        self.o_means = 0
+        self.o_scales = al(3 * n)
+        self.o_opac = self.o_scales + al(3 * n)
+        self.o_colors = self.o_opac + al(n)
+        self.count = self.o_colors + al(c * n)
+        z = lambda: torch.zeros(self.count, dtype=torch.float32, device=self.dev)
+        self.p, self.g, self.m, self.v = z(), z(), z(), z()
 
     # ---- parameter views -------------------------------------------------------------------
     def _seg(self, buf, off, numel): return buf[off:off + numel]
@@ -236,6 +241,41 @@ class FitDriver:
                 self._ev_free[slot].record(main)
             self._finish_step()
             return float(self.loss_dev.item())
+
+    # ---- densify / prune ----------------------------------------------------------------------
+    def densify_prune(self, iteration: int, max_gaussians: int, densify_ratio: float = 0.15,
+                      prune_opacity: float = 0.05, seed: int = 0) -> int:
+        """Device-side _densify_and_prune (reference python/fit_multiview_stub.py:140-197, called every
+        densify_prune_interval iterations, :318-325): compacts the survivors, appends the clones, rebuilds
+        the flat buffers for the new count and resets the Adam state like the reference's fresh optimizer.
+        Philox(seed, iteration, source index) jitter => identical on every rank, no broadcast."""
+        L = capi.lib()
+        n, cf = self.n, 3 * self.sh
+        cap = max(int(max_gaussians), n, 1)
+        with torch.cuda.device(self.dev):
+            om = torch.empty((cap, 3), dtype=torch.float32, device=self.dev)
+            os_ = torch.empty((cap, 3), dtype=torch.float32, device=self.dev)
+            oo = torch.empty((cap,), dtype=torch.float32, device=self.dev)
+            oc = torch.empty((cap, cf), dtype=torch.float32, device=self.dev)
+            wsb = L.b2s_densify_workspace_bytes(n)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+            n_new = C.c_int(0)
+            capi.check(L.b2s_densify_prune(capi.ctx(self.dev.index), self._pp(self.o_means), self._pp(self.o_scales),
+                                           self._pp(self.o_opac), self._pp(self.o_colors), n, cf, int(max_gaussians),
+                                           float(densify_ratio), float(prune_opacity), int(seed), int(iteration),
+                                           _ptr(om), _ptr(os_), _ptr(oo), _ptr(oc), C.byref(n_new), _ptr(ws), wsb,
+                                           _stream()))
+            k = int(n_new.value)
+            self._layout(k)                                    # new p/g and zeroed m/v: the Adam reset
+            self.step_no = 0
+            colors = oc[:k].view(k, 3) if self.sh == 1 else oc[:k].view(k, self.sh, 3)
+            with torch.no_grad():
+                self.means().copy_(om[:k]); self.scales_raw().copy_(os_[:k])
+                self.opacities_raw().copy_(oo[:k]); self.colors_raw().copy_(colors)
+            self.gacc = torch.empty((max(len(self.views), 1), max(k, 1), 12), dtype=torch.float32, device=self.dev)
+            self.state = self.ws = None
+            self.plan()
+        return k
 
     def check_overflow(self) -> bool:
         """True if any view since the last call needed more pairs than the buffers hold."""

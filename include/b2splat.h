@@ -180,6 +180,20 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
                   int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
                   float reg_opacity, void* stream);
 
+/* Densify / prune (python/fit_multiview_stub.py:140-197): keep sigmoid(op_raw) > prune_opacity (or the
+ * 64 most opaque if fewer survive), order preserved; then append min(max_gaussians - n1, int(n1 *
+ * densify_ratio)) clones of the most opaque survivors with mean + 0.25*scale*N(0,1), op_raw - 0.1.
+ * The N(0,1) draws are Philox4x32-10(seed, iteration, source index): identical on every rank.
+ * Outputs must hold max(max_gaussians, n) Gaussians; colours have color_floats floats per Gaussian.
+ * The caller resets its Adam state, as the reference does (:319-325).  SYNCHRONISES (returns the new
+ * count in *n_new_host). */
+size_t b2s_densify_workspace_bytes(int n);
+int b2s_densify_prune(b2s_ctx* ctx, const float* means, const float* scales_raw, const float* opacities_raw,
+                      const float* colors, int n, int color_floats, int max_gaussians, double densify_ratio,
+                      float prune_opacity, uint64_t seed, uint64_t iteration, float* out_means,
+                      float* out_scales_raw, float* out_opacities_raw, float* out_colors, int* n_new_host,
+                      void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* number of kernels this library has launched in this process (all contexts) */
 int64_t b2s_launch_count(void);

@@ -94,9 +94,49 @@ def run_r2(name, seed, n, W, H, bg, s_lo, s_hi, edge):
     print("wrote", name, "mean", sorted_img[..., :3].mean(), wsum_img[..., :3].mean())
 
 
+DENSIFY_CASES = [
+    # name, seed, n, sh, max_gaussians, ratio, prune_opacity, op_shift
+    ("densify_basic", 31, 500, 1, 3000, 0.15, 0.05, -2.0),
+    ("densify_room_limited", 32, 400, 4, 420, 0.15, 0.05, -1.0),
+    ("densify_top64", 33, 300, 1, 3000, 0.15, 0.05, -6.0),      # almost everything below the threshold
+]
+
+
+def run_densify(name, seed, n, sh, max_g, ratio, thr, op_shift):
+    """The unmodified reference _densify_and_prune (fit_multiview_stub.py:140-197) on seeded raw parameters."""
+    spec2 = importlib.util.spec_from_file_location("ref_fit", "/root/reference/python/fit_multiview_stub.py")
+    sys.path.insert(0, "/root/reference/python")
+    fitmod = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(fitmod)
+    sys.path.pop(0)
+    r = np.random.RandomState(seed)
+    means = ((r.rand(n, 3) - 0.5) * 1.2).astype(np.float32)
+    scales_raw = (-2.2 + 0.5 * r.randn(n, 3)).astype(np.float32)
+    op_raw = (op_shift + 1.5 * r.randn(n)).astype(np.float32)
+    colors = (0.1 * r.rand(n, 3)).astype(np.float32) if sh == 1 else (0.1 * r.randn(n, sh, 3)).astype(np.float32)
+    params = {"means": torch.nn.Parameter(torch.from_numpy(means.copy())),
+              "scales_raw": torch.nn.Parameter(torch.from_numpy(scales_raw.copy())),
+              "opacities_raw": torch.nn.Parameter(torch.from_numpy(op_raw.copy()))}
+    params["colors_raw" if sh == 1 else "sh_raw"] = torch.nn.Parameter(torch.from_numpy(colors.copy()))
+    torch.manual_seed(seed)
+    out = fitmod._densify_and_prune(params, max_g, ratio, thr)
+    oc = out["colors_raw" if sh == 1 else "sh_raw"]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), means=means, scales_raw=scales_raw, op_raw=op_raw,
+                        colors=colors, max_gaussians=max_g, ratio=ratio, prune_opacity=thr, seed=seed,
+                        out_means=out["means"].detach().numpy(), out_scales_raw=out["scales_raw"].detach().numpy(),
+                        out_op_raw=out["opacities_raw"].detach().numpy(), out_colors=oc.detach().numpy())
+    print("wrote", name, "n", n, "->", out["means"].shape[0])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "densify":
+        for c in DENSIFY_CASES:
+            run_densify(*c)
+        sys.exit(0)
     ocpu.build()
     for c in R1_CASES:
         run_r1(*c)
     for c in R2_CASES:
         run_r2(*c)
+    for c in DENSIFY_CASES:
+        run_densify(*c)

@@ -160,3 +160,22 @@ def test_adam_restatement_matches_torch():
         opt.step()
         q, m, v = r1.adam_step(q, g, m, v, step, 0.02)
         assert torch.allclose(q, p.detach(), rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------- densify / prune ----------
+@pytest.mark.parametrize("name", golden_names("densify_"))
+def test_densify_oracle_matches_reference_function(name):
+    """oracle/fit_oracle.py vs the unmodified _densify_and_prune (fit_multiview_stub.py:140-197),
+    including the N(0,1) jitter (same CPU generator seed and call order)."""
+    from oracle import fit_oracle
+    g = load_golden(name)
+    t = lambda k: torch.from_numpy(g[k])
+    torch.manual_seed(int(g["seed"]))
+    m, s, o, c, keep, src = fit_oracle.densify_and_prune(t("means"), t("scales_raw"), t("op_raw"), t("colors"),
+                                                         int(g["max_gaussians"]), float(g["ratio"]),
+                                                         float(g["prune_opacity"]))
+    assert np.array_equal(m.numpy(), g["out_means"])
+    assert np.array_equal(s.numpy(), g["out_scales_raw"])
+    assert np.array_equal(o.numpy(), g["out_op_raw"])
+    assert np.array_equal(c.numpy(), g["out_colors"])
+    assert m.shape[0] == int(keep.sum()) + src.shape[0]
