@@ -5,6 +5,25 @@
 
 namespace b2s {
 
+// Visits the tiles of Gaussian i row-major: the set bits of its mask for rects of at most 8 x 8 tiles
+// (tile_cull_mask), the whole rect otherwise.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(uint2 rc, unsigned long long mask, int tiles_x, F f) {
+  const int tx0 = rc.x & 0xffff, ty0 = rc.x >> 16, tx1 = rc.y & 0xffff, ty1 = rc.y >> 16;
+  const int w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
+  if (w <= 0 || h <= 0) return;
+  if (w <= 8 && h <= 8) {
+    while (mask) {
+      const int b = __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
+      f((ty0 + b / w) * tiles_x + tx0 + b % w);
+    }
+  } else {
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) f(ty * tiles_x + tx);
+  }
+}
+
 // Level 2 of the scan: one block turns the per-preprocess-block sums into exclusive
 // offsets in place, and publishes the total / overflow counters.
 __global__ void __launch_bounds__(1024)
@@ -56,7 +75,7 @@ scan_bsum_kernel(long long* __restrict__ bsum, int nb, long long max_pairs, Coun
 // A Gaussian whose slots would cross max_pairs is dropped whole (overflow was flagged).
 __global__ void __launch_bounds__(PRE_BLOCK)
 emit_kernel(int n, int tiles_x, long long max_pairs, const uint2* __restrict__ rect,
-            const uint32_t* __restrict__ dbits, const int* __restrict__ cnt,
+            const unsigned long long* __restrict__ tmask, const uint32_t* __restrict__ dbits, const int* __restrict__ cnt,
             const long long* __restrict__ bsum, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   __shared__ int wtot[PRE_BLOCK / 32];
   const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
@@ -76,25 +95,23 @@ emit_kernel(int n, int tiles_x, long long max_pairs, const uint2* __restrict__ r
   if (c == 0) return;
   long long o = bsum[blockIdx.x] + wbase + (x - c);
   if (o + c > max_pairs) return;
-  const uint2 rc = rect[i];
-  const int tx0 = rc.x & 0xffff, ty0 = rc.x >> 16, tx1 = rc.y & 0xffff, ty1 = rc.y >> 16;
   const unsigned long long d = dbits[i];
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      keys[o] = ((unsigned long long)(uint32_t)(ty * tiles_x + tx) << 32) | d;
-      vals[o] = i;
-      ++o;
-    }
+  for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) {
+    keys[o] = ((unsigned long long)(uint32_t)tile << 32) | d;
+    vals[o] = i;
+    ++o;
+  });
 }
 
-int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const uint32_t* dbits,
+int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
+               const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
                cudaStream_t st) {
   const int nb = (n + PRE_BLOCK - 1) / PRE_BLOCK;
   scan_bsum_kernel<<<1, 1024, 0, st>>>(bsum, nb, (long long)max_pairs, counters);
   B2S_LAUNCH_CHECK();
   if (n > 0 && keys != nullptr) {
-    emit_kernel<<<nb, PRE_BLOCK, 0, st>>>(n, vp.tiles_x, (long long)max_pairs, rect, dbits, cnt, bsum, keys, vals);
+    emit_kernel<<<nb, PRE_BLOCK, 0, st>>>(n, vp.tiles_x, (long long)max_pairs, rect, tmask, dbits, cnt, bsum, keys, vals);
     B2S_LAUNCH_CHECK();
   }
   return B2S_OK;
@@ -173,16 +190,13 @@ constexpr int CS_THREADS = 256;
 
 __global__ void __launch_bounds__(CS_THREADS)
 cs_hist_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
-               int* __restrict__ table) {
+               const unsigned long long* __restrict__ tmask, int* __restrict__ table) {
   extern __shared__ int hist[];
   for (int t = threadIdx.x; t < n_tiles; t += CS_THREADS) hist[t] = 0;
   __syncthreads();
   const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
   for (int i = i0 + threadIdx.x; i < i1; i += CS_THREADS) {
-    const uint2 rc = rect[i];
-    const int tx0 = rc.x & 0xffff, ty0 = rc.x >> 16, tx1 = rc.y & 0xffff, ty1 = rc.y >> 16;
-    for (int ty = ty0; ty <= ty1; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&hist[ty * tiles_x + tx], 1);
+    for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) { atomicAdd(&hist[tile], 1); });
   }
   __syncthreads();
   int* dst = table + (size_t)blockIdx.x * n_tiles;
@@ -300,7 +314,7 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
 
 __global__ void __launch_bounds__(CS_THREADS)
 cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
-                  const int* __restrict__ table, const int2* __restrict__ ranges,
+                  const unsigned long long* __restrict__ tmask, const int* __restrict__ table, const int2* __restrict__ ranges,
                   const Counters* __restrict__ counters, int* __restrict__ vals) {
   extern __shared__ int off[];
   if (counters->overflow) return;
@@ -309,13 +323,10 @@ cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* _
   __syncthreads();
   const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
   for (int i = i0 + threadIdx.x; i < i1; i += CS_THREADS) {
-    const uint2 rc = rect[i];
-    const int tx0 = rc.x & 0xffff, ty0 = rc.x >> 16, tx1 = rc.y & 0xffff, ty1 = rc.y >> 16;
-    for (int ty = ty0; ty <= ty1; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) {
-        const int pos = atomicAdd(&off[ty * tiles_x + tx], 1);
-        vals[pos] = i;
-      }
+    for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) {
+      const int pos = atomicAdd(&off[tile], 1);
+      vals[pos] = i;
+    });
   }
 }
 
@@ -325,7 +336,8 @@ int counting_sort_blocks(int n) {
   return nb < 1 ? 1 : (nb > CS_NB ? CS_NB : nb);
 }
 
-int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, int* table, int* total,
+int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
+                         const unsigned long long* tmask, int* table, int* total,
                          int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int* vals,
                          int stage, cudaStream_t st) {
   static bool attr_set = false;
@@ -338,7 +350,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
   const int nb = counting_sort_blocks(n);
   const int per_block = (n + nb - 1) / nb;
   if (stage == 0) {
-    cs_hist_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, table);
+    cs_hist_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table);
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
@@ -346,7 +358,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
                                            unit_start, units);
     B2S_LAUNCH_CHECK();
   } else {
-    cs_scatter_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, table, ranges, counters,
+    cs_scatter_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,
                                                     vals);
     B2S_LAUNCH_CHECK();
   }

@@ -128,6 +128,7 @@ struct Bufs {  // resolved pointers into state / workspace
   int* vals;
   float* acc;
   uint2* rect;
+  unsigned long long* tmask;
   uint32_t* dbits;
   int* cnt;
   long long* bsum;
@@ -163,6 +164,7 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     const WorkLayout L = work_layout(n, w, h, mp);
     char* q = (char*)ws;
     b.rect = (uint2*)(q + L.rect);
+    b.tmask = (unsigned long long*)(q + L.tmask);
     b.dbits = (uint32_t*)(q + L.dbits);
     b.cnt = (int*)(q + L.cnt);
     b.bsum = (long long*)(q + L.bsum);
@@ -189,7 +191,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   int rc;
   {
     StageTimer t(ctx, ST_PREPROCESS, st);
-    rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+    rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
   }
   if (rc != B2S_OK) return rc;
   const int begin_bit = p->sort_depth ? 0 : 32;
@@ -199,13 +201,13 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     // order inside a tile is irrelevant: group with one counting pass + one scatter pass
     {
       StageTimer t(ctx, ST_BIN, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
                                 B.unit_start, B.units, B.vals, 0, st);
     }
     if (rc != B2S_OK) return rc;
     if (keys_unsorted_copy != nullptr || vals_unsorted_copy != nullptr) {   // dump hook only: the emit order
       Counters* scratch = (Counters*)B.hist;
-      rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, st);
+      rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, st);
       if (rc != B2S_OK) return rc;
       if (keys_unsorted_copy != nullptr)
         B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, B.keysA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
@@ -214,7 +216,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     }
     {
       StageTimer t(ctx, ST_SORT, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
                                 B.unit_start, B.units, B.vals, 1, st);
     }
     if (rc != B2S_OK) return rc;
@@ -227,7 +229,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   int* vB = (passes % 2 == 0) ? B.valsB : B.vals;
   {
     StageTimer t(ctx, ST_BIN, st);
-    rc = launch_bin(vp, n, max_pairs, B.rect, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
+    rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
   }
   if (rc != B2S_OK) return rc;
   if (keys_unsorted_copy != nullptr)
@@ -314,9 +316,9 @@ int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const
   Bufs B = resolve(nullptr, workspace, n, p->width, p->height, 0);
   // the counters live in the (otherwise unused) head of the histogram scratch
   Counters* counters = (Counters*)B.hist;
-  rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, B.rect, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
+  rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
-  rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, st);
+  rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, st);
   if (rc != B2S_OK) return rc;
   Counters h;
   B2S_CUDA_TRY(cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -118,6 +118,33 @@ __device__ __forceinline__ uint32_t depth_bits(float zcam) {
   return ~u;
 }
 
+// Tile culling for the torch-style weighted sum.  A tile of the k-sigma bbox rect is kept iff the pixel centre of
+// the tile nearest to the Gaussian lies inside the k-sigma ELLIPSE (every pixel of a dropped tile has weight
+// < op * exp(-k^2/2), the same bound the bbox itself enforces along the axes).  Bit (ty-ty0)*w + (tx-tx0) of the
+// result, for rects of at most 8 x 8 tiles; explicitly rounded ops in the order of oracle/bins_oracle.c
+// (b2o_tile_mask) so that GPU and CPU agree bit for bit.
+__device__ __forceinline__ unsigned long long tile_cull_mask(float px, float py, float sx, float sy, float k, int tx0,
+                                                             int ty0, int w, int h, bool cull) {
+  const float isx = __fdiv_rn(1.0f, sx), isy = __fdiv_rn(1.0f, sy), kk = __fmul_rn(k, k);
+  float uxx[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float lo = (float)((tx0 + c) * TILE) + 0.5f, hi = lo + (float)(TILE - 1);
+    const float u = __fmul_rn(__fsub_rn(fminf(fmaxf(px, lo), hi), px), isx);
+    uxx[c] = __fmul_rn(u, u);
+  }
+  unsigned long long m = 0ull;
+  for (int r = 0; r < h; ++r) {
+    const float lo = (float)((ty0 + r) * TILE) + 0.5f, hi = lo + (float)(TILE - 1);
+    const float u = __fmul_rn(__fsub_rn(fminf(fmaxf(py, lo), hi), py), isy);
+    const float uyy = __fmul_rn(u, u);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < w && (!cull || __fadd_rn(uxx[c], uyy) <= kk)) m |= 1ull << (r * w + c);
+  }
+  return m;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -129,7 +156,7 @@ struct StateLayout {
   size_t rec, ranges, vals, acc, counters, unit_start, units, total;
 };
 struct WorkLayout {
-  size_t rect, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
+  size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
 };
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
@@ -169,6 +196,7 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   const size_t nb_sort = (mp + SORT_KPB - 1) / SORT_KPB;
   size_t o = 0;
   L.rect = o;  o += align_up(nn * 8);
+  L.tmask = o; o += align_up(nn * 8);   // kept tiles of rects <= 8x8 (tile_cull_mask)
   L.dbits = o; o += align_up(nn * 4);
   L.cnt = o;   o += align_up(nn * 4);
   L.bsum = o;  o += align_up((nb_pre + 1) * 8);
@@ -216,10 +244,11 @@ enum Stage { ST_PREPROCESS = 0, ST_BIN, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_LOS
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------
 int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                      const float* opac, int n, float4* rec, uint2* rect, uint32_t* dbits, int* cnt,
-                      long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/, int* dbg_bbox,
+                      const float* opac, int n, float4* rec, uint2* rect, unsigned long long* tmask, uint32_t* dbits,
+                      int* cnt, long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/, int* dbg_bbox,
                       cudaStream_t st);
-int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const uint32_t* dbits,
+int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
+               const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
                cudaStream_t st);
 // sorts (keysA, valsA) on key bits [begin_bit,end_bit); returns via *result_in_B where the result lives
@@ -231,7 +260,8 @@ int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t 
                   cudaStream_t st);
 // tile-major counting sort (bin.cu): stage 0 = histogram + scans (ranges, units, counters), stage 1 = scatter
 bool counting_sort_fits(int n_tiles);
-int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, int* table, int* total,
+int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
+                         const unsigned long long* tmask, int* table, int* total,
                          int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int* vals,
                          int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);

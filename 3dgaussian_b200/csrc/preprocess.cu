@@ -136,9 +136,9 @@ template <int K>
 __global__ void __launch_bounds__(PRE_BLOCK)
 preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const float* __restrict__ scales,
                   const float* __restrict__ colors, const float* __restrict__ opac, int n,
-                  float4* __restrict__ rec, uint2* __restrict__ rect, uint32_t* __restrict__ dbits,
-                  int* __restrict__ cnt, long long* __restrict__ bsum, float* __restrict__ dbg,
-                  int* __restrict__ dbg_bbox) {
+                  float4* __restrict__ rec, uint2* __restrict__ rect, unsigned long long* __restrict__ tmask,
+                  uint32_t* __restrict__ dbits, int* __restrict__ cnt, long long* __restrict__ bsum,
+                  float* __restrict__ dbg, int* __restrict__ dbg_bbox) {
   const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
   int my_cnt = 0;
   if (i < n) {
@@ -148,12 +148,20 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
     const float op = act_opac(vp, __ldg(opac + i));
     const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
     uint2 rc = make_uint2(1u, 0u);   // empty tile rect (tx1 < tx0) for culled Gaussians
+    unsigned long long tm = 0ull;
     if (pr.ok) {
       const int tx0 = pr.xmin / TILE, tx1 = pr.xmax / TILE, ty0 = pr.ymin / TILE, ty1 = pr.ymax / TILE;
-      my_cnt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+      const int w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
+      my_cnt = w * h;
+      if (w <= 8 && h <= 8) {   // small rects carry an explicit tile mask (culled for the torch-style weighted sum)
+        tm = tile_cull_mask(pr.px, pr.py, pr.sx, pr.sy, vp.k, tx0, ty0, w, h,
+                            vp.style == B2S_STYLE_TORCH && vp.exact_bbox == 0);
+        my_cnt = __popcll(tm);
+      }
       rc = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
     }
     rect[i] = rc;
+    tmask[i] = tm;
     dbits[i] = depth_bits(pr.zcam);
     cnt[i] = my_cnt;
     if (rec != nullptr) {
@@ -216,11 +224,11 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
 }
 
 int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                      const float* opac, int n, float4* rec, uint2* rect, uint32_t* dbits, int* cnt,
-                      long long* bsum, float* dbg, int* dbg_bbox, cudaStream_t st) {
+                      const float* opac, int n, float4* rec, uint2* rect, unsigned long long* tmask, uint32_t* dbits,
+                      int* cnt, long long* bsum, float* dbg, int* dbg_bbox, cudaStream_t st) {
   if (n <= 0) return B2S_OK;
   const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
-#define B2S_PRE(KK) preprocess_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, rec, rect, dbits, cnt, bsum, dbg, dbg_bbox)
+#define B2S_PRE(KK) preprocess_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, rec, rect, tmask, dbits, cnt, bsum, dbg, dbg_bbox)
   switch (vp.sh) {
     case 1: B2S_PRE(1); break;
     case 4: B2S_PRE(4); break;

@@ -212,7 +212,7 @@ def cpu_fit_sample(args, n_slice=1024, w=480, h=270, steps=1, warmup=0):
             "cores": torch.get_num_threads()}
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -227,7 +227,7 @@ def run_reference(args):
                          "sec_per_sample": r["sec_per_sample"], "dense_pairs_per_s": r["pairs_per_s"]},
         "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
 
 
 def workload_config(args):
@@ -279,10 +279,26 @@ def render_bench(device, frames=20):
 
 
 # ------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at
+    communicator creation), so stdout is pointed at stderr for the duration of the run and the JSON line is
+    written to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line: dict):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    out_fd = _claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out_fd)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -468,7 +484,7 @@ def main():
                                           "P2_all_ranks": float(p2_all.item())},
         "overflow": bool(overflowed),
     }
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -43,6 +43,29 @@ uint32_t b2o_depth_bits(float zcam) {
   return ~u;
 }
 
+/* Kept tiles of a rect of at most 8 x 8 tiles: bit (ty-ty0)*w + (tx-tx0).  With cull != 0 a tile is kept iff its
+ * pixel centre nearest to the Gaussian lies inside the k-sigma ellipse (the torch-style weighted sum only; every
+ * pixel of a dropped tile has weight < op*exp(-k^2/2)).  Mirrors tile_cull_mask() of csrc/common.cuh op for op. */
+uint64_t b2o_tile_mask(float px, float py, float sx, float sy, float k, int tx0, int ty0, int w, int h, int tile,
+                       int cull) {
+  const float isx = 1.0f / sx, isy = 1.0f / sy, kk = k * k;
+  float uxx[8];
+  for (int c = 0; c < 8; ++c) {
+    const float lo = (float)((tx0 + c) * tile) + 0.5f, hi = lo + (float)(tile - 1);
+    const float u = (fminf(fmaxf(px, lo), hi) - px) * isx;
+    uxx[c] = u * u;
+  }
+  uint64_t m = 0;
+  for (int r = 0; r < h; ++r) {
+    const float lo = (float)((ty0 + r) * tile) + 0.5f, hi = lo + (float)(tile - 1);
+    const float u = (fminf(fmaxf(py, lo), hi) - py) * isy;
+    const float uyy = u * u;
+    for (int c = 0; c < w; ++c)
+      if (!cull || uxx[c] + uyy <= kk) m |= (uint64_t)1 << (r * w + c);
+  }
+  return m;
+}
+
 /* Per-Gaussian projection + bbox + tile rect.  Arrays are caller-allocated, length n
  * (bbox/rect: 4n, xmin ymin xmax ymax / tx0 ty0 tx1 ty1, inclusive).  cnt[i] = number
  * of tiles touched (0 when culled).  Returns the total number of (Gaussian,tile) pairs. */
@@ -50,7 +73,7 @@ int64_t b2o_project(const float* means, const float* scales, const float* opac,
                     const float* view, const float* proj, int n, int width, int height,
                     float k, int tile, int style,
                     float* px_o, float* py_o, float* sx_o, float* sy_o, float* zabs_o,
-                    float* zcam_o, int32_t* bbox, int32_t* rect, int32_t* cnt) {
+                    float* zcam_o, int32_t* bbox, int32_t* rect, int32_t* cnt, uint64_t* tmask, int cull) {
   const float fx = fabsf(proj[0]), fy = fabsf(proj[5]);
   const float wm1 = (float)(width - 1), hm1 = (float)(height - 1);
   int64_t total = 0;
@@ -91,6 +114,7 @@ int64_t b2o_project(const float* means, const float* scales, const float* opac,
       bbox[4 * i] = bbox[4 * i + 1] = 0; bbox[4 * i + 2] = bbox[4 * i + 3] = -1;
       rect[4 * i] = rect[4 * i + 1] = 0; rect[4 * i + 2] = rect[4 * i + 3] = -1;
       cnt[i] = 0;
+      tmask[i] = 0;
       continue;
     }
     const int xmin = (int)fmaxf(lox, 0.0f), xmax = (int)fminf(hix, wm1);
@@ -98,7 +122,13 @@ int64_t b2o_project(const float* means, const float* scales, const float* opac,
     bbox[4 * i] = xmin; bbox[4 * i + 1] = ymin; bbox[4 * i + 2] = xmax; bbox[4 * i + 3] = ymax;
     const int tx0 = xmin / tile, tx1 = xmax / tile, ty0 = ymin / tile, ty1 = ymax / tile;
     rect[4 * i] = tx0; rect[4 * i + 1] = ty0; rect[4 * i + 2] = tx1; rect[4 * i + 3] = ty1;
-    cnt[i] = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
+    cnt[i] = tw * th;
+    tmask[i] = 0;
+    if (tw <= 8 && th <= 8) {      /* small rects carry an explicit tile mask */
+      tmask[i] = b2o_tile_mask(px, py, sx, sy, k, tx0, ty0, tw, th, tile, cull);
+      cnt[i] = __builtin_popcountll(tmask[i]);
+    }
     total += cnt[i];
   }
   return total;
@@ -106,14 +136,17 @@ int64_t b2o_project(const float* means, const float* scales, const float* opac,
 
 /* Emit (key,value) pairs: Gaussian i writes its tiles row-major at off[i]+j, where off
  * is the exclusive prefix sum of cnt.  key = tile_id << 32 | depth_bits(zcam). */
-void b2o_emit(const int32_t* rect, const int32_t* cnt, const float* zcam, int n, int tiles_x,
+void b2o_emit(const int32_t* rect, const int32_t* cnt, const uint64_t* tmask, const float* zcam, int n, int tiles_x,
               uint64_t* keys, int32_t* vals) {
   int64_t o = 0;
   for (int i = 0; i < n; ++i) {
     if (cnt[i] == 0) continue;
     const uint64_t d = b2o_depth_bits(zcam[i]);
+    const int tw = rect[4 * i + 2] - rect[4 * i] + 1, th = rect[4 * i + 3] - rect[4 * i + 1] + 1;
+    const int masked = tw <= 8 && th <= 8;
     for (int ty = rect[4 * i + 1]; ty <= rect[4 * i + 3]; ++ty)
       for (int tx = rect[4 * i]; tx <= rect[4 * i + 2]; ++tx) {
+        if (masked && !((tmask[i] >> ((ty - rect[4 * i + 1]) * tw + (tx - rect[4 * i]))) & 1)) continue;
         keys[o] = ((uint64_t)(uint32_t)(ty * tiles_x + tx) << 32) | d;
         vals[o] = i;
         ++o;

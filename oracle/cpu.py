@@ -67,7 +67,7 @@ def have_r2ref() -> bool:
 
 
 def bin_gaussians(means, scales, opac, view, proj, width, height, k=5.0, tile=16, style=0,
-                  begin_bit=0):
+                  begin_bit=0, cull=None):
     """Full integer pipeline on the CPU.  Returns a dict of numpy arrays."""
     lib = b2o()
     means, scales, opac = _f32(means), _f32(scales), _f32(opac)
@@ -78,17 +78,21 @@ def bin_gaussians(means, scales, opac, view, proj, width, height, k=5.0, tile=16
     bbox = np.zeros((max(n, 1), 4), np.int32)
     rect = np.zeros((max(n, 1), 4), np.int32)
     cnt = np.zeros(max(n, 1), np.int32)
+    tmask = np.zeros(max(n, 1), np.uint64)
+    if cull is None:
+        cull = style == 0          # elliptical tile culling belongs to the torch-style weighted sum only
     FP, IP = C.c_float, C.c_int32
     total = lib.b2o_project(_p(means, FP), _p(scales, FP), _p(opac, FP), _p(view, FP), _p(proj, FP),
                             C.c_int(n), C.c_int(width), C.c_int(height), C.c_float(k), C.c_int(tile),
                             C.c_int(style), _p(px, FP), _p(py, FP), _p(sx, FP), _p(sy, FP),
-                            _p(zabs, FP), _p(zcam, FP), _p(bbox, IP), _p(rect, IP), _p(cnt, IP))
+                            _p(zabs, FP), _p(zcam, FP), _p(bbox, IP), _p(rect, IP), _p(cnt, IP),
+                            _p(tmask, C.c_uint64), C.c_int(1 if cull else 0))
     tiles_x = (width + tile - 1) // tile
     tiles_y = (height + tile - 1) // tile
     n_tiles = tiles_x * tiles_y
     keys = np.zeros(max(total, 1), np.uint64)
     vals = np.zeros(max(total, 1), np.int32)
-    lib.b2o_emit(_p(rect, IP), _p(cnt, IP), _p(zcam, FP), C.c_int(n), C.c_int(tiles_x),
+    lib.b2o_emit(_p(rect, IP), _p(cnt, IP), _p(tmask, C.c_uint64), _p(zcam, FP), C.c_int(n), C.c_int(tiles_x),
                  _p(keys, C.c_uint64), _p(vals, IP))
     keys_unsorted, vals_unsorted = keys[:total].copy(), vals[:total].copy()
     tile_bits = max(1, int(np.ceil(np.log2(max(n_tiles, 2)))))

@@ -87,11 +87,23 @@ def test_c_binning_invariants(name, begin_bit):
     for t in range(ranges.shape[0]):
         s, e = ranges[t]
         assert np.all(tiles[s:e] == t) and (e - s) == int((tiles == t).sum())
-    # every pixel of every bbox lies in a tile the Gaussian was binned to
+    # elliptical tile culling (torch style): every bbox pixel INSIDE the 5-sigma ellipse lies in a binned tile ...
     for i in np.nonzero(b["cnt"])[0][:50]:
         x0, y0, x1, y1 = b["bbox"][i]
         tl = set(tiles[vals == i].tolist())
-        assert {(y // 16) * b["tiles_x"] + (x // 16) for y in (y0, y1) for x in (x0, x1)} <= tl
+        ys, xs = np.mgrid[y0:y1 + 1, x0:x1 + 1]
+        q = ((xs + 0.5 - b["px"][i]) / b["sx"][i]) ** 2 + ((ys + 0.5 - b["py"][i]) / b["sy"][i]) ** 2
+        inside = q <= 24.99
+        assert set(((ys[inside] // 16) * b["tiles_x"] + xs[inside] // 16).tolist()) <= tl
+    # ... and without culling every pixel of the bbox does
+    u = ocpu.bin_gaussians(g["means"], g["scales"], g["opac"], g["view"], g["proj"], W, H, k=5.0,
+                           begin_bit=begin_bit, cull=False)
+    ut = (u["keys"] >> np.uint64(32)).astype(np.int64)
+    assert u["total"] >= b["total"]
+    for i in np.nonzero(u["cnt"])[0][:50]:
+        x0, y0, x1, y1 = u["bbox"][i]
+        tl = set(ut[u["vals"] == i].tolist())
+        assert {(y // 16) * u["tiles_x"] + (x // 16) for y in (y0, y1) for x in (x0, x1)} <= tl
     # bbox formula of the reference renderers: max(0,floor(p-k*s)) .. min(W-1,ceil(p+k*s))
     on = b["cnt"] > 0
     assert np.array_equal(b["bbox"][on, 0], np.maximum(0, np.floor(b["px"] - 5 * b["sx"]))[on].astype(np.int32))
