@@ -1,6 +1,8 @@
 // Tile binning: exclusive scan of per-Gaussian tile counts, (tile|depth) key emission and
 // tile-range extraction.  No counterpart in the reference (its CUDA path scatters with
 // atomics, src/renderer.cu:89-103); the contract is oracle/bins_oracle.c, bit for bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -13,10 +15,15 @@ __device__ __forceinline__ void for_each_tile(uint2 rc, unsigned long long mask,
   const int w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
   if (w <= 0 || h <= 0) return;
   if (w <= 8 && h <= 8) {
-    while (mask) {
-      const int b = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
-      f((ty0 + b / w) * tiles_x + tx0 + b % w);
+    const unsigned row_bits = (1u << w) - 1u;
+    for (int r = 0; r < h; ++r) {
+      unsigned rb = (unsigned)(mask >> (r * w)) & row_bits;
+      const int base = (ty0 + r) * tiles_x + tx0;
+      while (rb) {
+        const int c = __ffs((int)rb) - 1;
+        rb &= rb - 1;
+        f(base + c);
+      }
     }
   } else {
     for (int ty = ty0; ty <= ty1; ++ty)
@@ -186,21 +193,21 @@ int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_st
 // HBM traffic: 8 B/Gaussian (rect) twice + 4 B per pair written once; the 4 B x nb x tiles table
 // stays in L2.  The order of ids inside (block, tile) follows the atomics, i.e. it is not
 // reproducible run to run; the set is (tests compare per-tile sorted lists with the oracle).
-constexpr int CS_THREADS = 256;
+constexpr int CS_THREADS = 1024;
 
-__global__ void __launch_bounds__(CS_THREADS)
+__global__ void __launch_bounds__(1024)
 cs_hist_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
                const unsigned long long* __restrict__ tmask, int* __restrict__ table) {
   extern __shared__ int hist[];
-  for (int t = threadIdx.x; t < n_tiles; t += CS_THREADS) hist[t] = 0;
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) hist[t] = 0;
   __syncthreads();
   const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
-  for (int i = i0 + threadIdx.x; i < i1; i += CS_THREADS) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) { atomicAdd(&hist[tile], 1); });
   }
   __syncthreads();
   int* dst = table + (size_t)blockIdx.x * n_tiles;
-  for (int t = threadIdx.x; t < n_tiles; t += CS_THREADS) dst[t] = hist[t];
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) dst[t] = hist[t];
 }
 
 // table[b][t] <- exclusive prefix over b, total[t] = column sum.  A block owns 32 tiles; warp w
@@ -237,92 +244,88 @@ cs_colscan_kernel(int* __restrict__ table, int nb, int n_tiles, int* __restrict_
 }
 
 // One block: exclusive scan of the per-tile totals -> ranges, counters and the work-unit table
-// (same unit definition as units_kernel).
+// (same unit definition as units_kernel).  Thread t owns the contiguous chunk of tiles
+// [t*per, (t+1)*per): one pass to sum its chunk, ONE block-wide scan of the 1024 chunk sums, one pass to
+// write -- two barriers instead of four per 1024 tiles.
 __global__ void __launch_bounds__(1024)
 cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pairs, int2* __restrict__ ranges,
                    Counters* __restrict__ counters, int unit_cap, int* __restrict__ unit_start,
                    int2* __restrict__ units) {
-  __shared__ long long wtot[32];
-  __shared__ int utot[32];
-  __shared__ long long carry_s;
-  __shared__ int ucarry_s;
-  __shared__ int overflow_s;
+  __shared__ long long wsum[32];
+  __shared__ int wunits[32];
+  __shared__ long long grand_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // pass 0: grand total -> overflow decision (on overflow nothing is rendered: kept = 0)
-  {
-    long long s = 0;
-    for (int t = threadIdx.x; t < n_tiles; t += 1024) s += total[t];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) wtot[wid] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      long long g = 0;
-      for (int q = 0; q < 32; ++q) g += wtot[q];
-      const int ov = g > max_pairs ? 1 : 0;
-      counters->needed = g;
-      counters->kept = ov ? 0 : (int)g;
-      counters->overflow = ov;
-      overflow_s = ov;
-      carry_s = 0;
-      ucarry_s = 0;
-    }
-    __syncthreads();
+  const int per = (n_tiles + 1023) / 1024;
+  const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
+  long long c_sum = 0;
+  int u_sum = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int c = total[t];
+    c_sum += c;
+    u_sum += c > 0 ? (c + SEG - 1) / SEG : 1;
   }
-  const int ov = overflow_s;
-  for (int base = 0; base < n_tiles; base += 1024) {
-    const int t = base + threadIdx.x;
-    const int c = (t < n_tiles && !ov) ? total[t] : 0;
-    const int v = (t < n_tiles) ? (c > 0 ? (c + SEG - 1) / SEG : 1) : 0;
-    long long x = c;
-    int y = v;
+  // inclusive warp scans of (pairs, units)
+  long long x = c_sum;
+  int y = u_sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long xx = __shfl_up_sync(0xffffffffu, x, o);
+    const int yy = __shfl_up_sync(0xffffffffu, y, o);
+    if (lane >= o) { x += xx; y += yy; }
+  }
+  if (lane == 31) { wsum[wid] = x; wunits[wid] = y; }
+  __syncthreads();
+  if (wid == 0) {
+    long long a = wsum[lane];
+    int b = wunits[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const long long xx = __shfl_up_sync(0xffffffffu, x, o);
-      const int yy = __shfl_up_sync(0xffffffffu, y, o);
-      if (lane >= o) { x += xx; y += yy; }
+      const long long aa = __shfl_up_sync(0xffffffffu, a, o);
+      const int bb = __shfl_up_sync(0xffffffffu, b, o);
+      if (lane >= o) { a += aa; b += bb; }
     }
-    if (lane == 31) { wtot[wid] = x; utot[wid] = y; }
-    __syncthreads();
-    if (wid == 0) {
-      long long a = wtot[lane];
-      int b = utot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long aa = __shfl_up_sync(0xffffffffu, a, o);
-        const int bb = __shfl_up_sync(0xffffffffu, b, o);
-        if (lane >= o) { a += aa; b += bb; }
-      }
-      wtot[lane] = a;
-      utot[lane] = b;
-    }
-    __syncthreads();
-    const long long start = carry_s + (wid > 0 ? wtot[wid - 1] : 0) + (x - c);
-    const int ustart = ucarry_s + (wid > 0 ? utot[wid - 1] : 0) + (y - v);
-    if (t < n_tiles) {
-      ranges[t] = c > 0 ? make_int2((int)start, (int)start + c) : make_int2(0, 0);   // empty tiles read (0,0) like the radix path
-      unit_start[t] = ustart;
-      for (int s = 0; s < v; ++s)
-        if (ustart + s < unit_cap) units[ustart + s] = make_int2(t, s);
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_s += wtot[31]; ucarry_s += utot[31]; }
-    __syncthreads();
+    wsum[lane] = a;
+    wunits[lane] = b;
+    if (lane == 31) grand_s = a;
   }
-  if (threadIdx.x == 0) unit_start[n_tiles] = ucarry_s < unit_cap ? ucarry_s : unit_cap;
+  __syncthreads();
+  const long long grand = grand_s;
+  const bool ov = grand > max_pairs;              // on overflow nothing is rendered: kept = 0, every range empty
+  long long start = (wid > 0 ? wsum[wid - 1] : 0) + (x - c_sum);
+  int ustart = (wid > 0 ? wunits[wid - 1] : 0) + (y - u_sum);
+  if (ov) {   // every tile keeps exactly one (empty) unit
+    ustart = t0;
+  }
+  for (int t = t0; t < t1; ++t) {
+    const int c = ov ? 0 : total[t];
+    const int v = c > 0 ? (c + SEG - 1) / SEG : 1;
+    ranges[t] = c > 0 ? make_int2((int)start, (int)start + c) : make_int2(0, 0);   // empty tiles read (0,0) like the radix path
+    unit_start[t] = ustart;
+    for (int s = 0; s < v; ++s)
+      if (ustart + s < unit_cap) units[ustart + s] = make_int2(t, s);
+    start += c;
+    ustart += v;
+  }
+  if (threadIdx.x == 0) {
+    counters->needed = grand;
+    counters->kept = ov ? 0 : (int)grand;
+    counters->overflow = ov ? 1 : 0;
+    const int nu = ov ? n_tiles : wunits[31];
+    unit_start[n_tiles] = nu < unit_cap ? nu : unit_cap;
+  }
 }
 
-__global__ void __launch_bounds__(CS_THREADS)
+__global__ void __launch_bounds__(1024)
 cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
                   const unsigned long long* __restrict__ tmask, const int* __restrict__ table, const int2* __restrict__ ranges,
                   const Counters* __restrict__ counters, int* __restrict__ vals) {
   extern __shared__ int off[];
   if (counters->overflow) return;
   const int* src = table + (size_t)blockIdx.x * n_tiles;
-  for (int t = threadIdx.x; t < n_tiles; t += CS_THREADS) off[t] = ranges[t].x + src[t];
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) off[t] = ranges[t].x + src[t];
   __syncthreads();
   const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
-  for (int i = i0 + threadIdx.x; i < i1; i += CS_THREADS) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) {
       const int pos = atomicAdd(&off[tile], 1);
       vals[pos] = i;
@@ -349,8 +352,10 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
   }
   const int nb = counting_sort_blocks(n);
   const int per_block = (n + nb - 1) / nb;
+  static const int threads = [] { const char* e = getenv("B2S_CS_THREADS"); const int v = e ? atoi(e) : 0;
+                                  return (v == 256 || v == 512 || v == 1024) ? v : CS_THREADS; }();
   if (stage == 0) {
-    cs_hist_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table);
+    cs_hist_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table);
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
@@ -358,7 +363,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
                                            unit_start, units);
     B2S_LAUNCH_CHECK();
   } else {
-    cs_scatter_kernel<<<nb, CS_THREADS, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,
+    cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,
                                                     vals);
     B2S_LAUNCH_CHECK();
   }
