@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb2splat.so")
+LIB_PATH = os.environ.get("B2S_LIB_PATH") or os.path.join(_HERE, "csrc", "libb2splat.so")   # override: A/B experiments
 
 MODE_WSUM, MODE_SORTED = 0, 1
 STYLE_TORCH, STYLE_NATIVE = 0, 1

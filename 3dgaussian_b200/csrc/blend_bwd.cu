@@ -577,6 +577,26 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   cp_async_wait_b<0>();
 }
 
+// Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (bits 0..2 of the blend
+// record's b.z, written by preprocess_kernel) into the spare slot 9 of its row, where the chain-rule kernel
+// finds it next to the sums -- the blend kernel itself never touches it.
+__global__ void __launch_bounds__(256)
+gacc_init_kernel(const float4* __restrict__ rec, float4* __restrict__ gacc, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float m = rec[3 * (size_t)i + 1].z;
+  gacc[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  gacc[3 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  gacc[3 * (size_t)i + 2] = make_float4(0.f, m, 0.f, 0.f);
+}
+
+int launch_gacc_init(const float4* rec, float* gacc, int n, cudaStream_t st) {
+  if (n <= 0) return B2S_OK;
+  gacc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(rec, reinterpret_cast<float4*>(gacc), n);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 static bool use_simt_bwd() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("B2S_BWD_SIMT"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }

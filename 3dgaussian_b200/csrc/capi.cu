@@ -367,7 +367,8 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   {
     StageTimer t(ctx, ST_BLEND_BWD, st);
-    B2S_CUDA_TRY(cudaMemsetAsync(B.gacc, 0, (size_t)n * GACC_F * sizeof(float), st));
+    rc = launch_gacc_init(B.rec, B.gacc, n, st);
+    if (rc != B2S_OK) return rc;
     rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, B.gbuf, B.gacc, st);
   }
@@ -406,7 +407,8 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   StageTimer t(ctx, ST_BLEND_BWD, st);
-  B2S_CUDA_TRY(cudaMemsetAsync(gacc_out, 0, (size_t)n * GACC_F * sizeof(float), st));
+  rc = launch_gacc_init(B.rec, gacc_out, n, st);
+  if (rc != B2S_OK) return rc;
   return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, B.gbuf, gacc_out, st);
 }

@@ -271,6 +271,7 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           cudaStream_t st);
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                             float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
+int launch_gacc_init(const float4* rec, float* gacc, int n, cudaStream_t st);
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
                           const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,

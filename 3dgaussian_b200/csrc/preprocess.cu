@@ -184,7 +184,11 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
         a.w = __int_as_float(pr.xmin | (pr.xmax << 16));
         b.x = pr.py;
         b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
-        b.z = lg ? 0.0f : 1.0f;
+        // torch style: bits 0..2 = the colour channel is inside [0,1], i.e. clamp(0,1) passes its gradient
+        // (torch_renderer.py:144); consumed by the blend backward.  As a float this is a denormal (== 0 to ex2.ftz).
+        const int cmask = (craw[0] >= 0.0f && craw[0] <= 1.0f ? 1 : 0) | (craw[1] >= 0.0f && craw[1] <= 1.0f ? 2 : 0) |
+                          (craw[2] >= 0.0f && craw[2] <= 1.0f ? 4 : 0);
+        b.z = lg ? __int_as_float(cmask) : 1.0f;
         b.w = __int_as_float(pr.ymin | (pr.ymax << 16));
         c.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
         c.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
@@ -397,22 +401,10 @@ preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ vi
               if (sub == s2) { lb[j] = b[s2 * KL + j]; lbx[j] = bx[s2 * KL + j]; lby[j] = by[s2 * KL + j]; lbz[j] = bz[s2 * KL + j]; }
             }
           }
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < KL; ++j) {
-            c0 = fmaf(lb[j], coef[3 * j], c0);
-            c1 = fmaf(lb[j], coef[3 * j + 1], c1);
-            c2 = fmaf(lb[j], coef[3 * j + 2], c2);
-          }
-#pragma unroll
-          for (int o = 1; o < LPG; o <<= 1) {
-            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-          }
-          const float dc0 = (ok && c0 >= 0.0f && c0 <= 1.0f) ? dC[0] : 0.0f;
-          const float dc1 = (ok && c1 >= 0.0f && c1 <= 1.0f) ? dC[1] : 0.0f;
-          const float dc2 = (ok && c2 >= 0.0f && c2 <= 1.0f) ? dC[2] : 0.0f;
+          // colour clamp mask (torch_renderer.py:144) planted next to the sums by gacc_init_kernel
+          const int cmask = __float_as_int(g2.y);
+          const float dc0 = (ok && (cmask & 1)) ? dC[0] : 0.0f, dc1 = (ok && (cmask & 2)) ? dC[1] : 0.0f,
+                      dc2 = (ok && (cmask & 4)) ? dC[2] : 0.0f;
           float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
 #pragma unroll
           for (int j = 0; j < KL; ++j) {
@@ -473,6 +465,187 @@ preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ vi
   }
 }
 
+// ---- K = 16 (SH degree 3): warp-uniform coefficient groups ----------------------------------------
+// The generic kernel above lets 4 lanes share a Gaussian, which makes every lane repeat the projection chain and
+// evaluate all 16 basis functions + 48 derivatives to use 4 of them.  Here the split is per WARP: a block of 8
+// warps covers 64 Gaussians x 4 coefficient groups, warp w handles group (w & 3) of Gaussians (w >> 2)*32 + lane.
+// `sub` is warp uniform, so each warp evaluates only its own 4 basis functions (compile-time indices, dead code
+// eliminated) and only the group-0 warps run the projection / sigma / opacity chain.  The direction gradient is
+// linear in the per-group partial sums, so every warp folds its share into a private d/dmean and the four are added
+// through shared memory once, after the view loop.
+template <int SUB>
+__device__ __forceinline__ void sh16_group_accumulate(const ViewParams& vp, float mx, float my, float mz,
+                                                      const float (&coef)[12], float dc0, float dc1, float dc2,
+                                                      float (&gcoef)[12], float (&gm)[3]) {
+  const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
+  const float r = sqrtf(vx * vx + vy * vy + vz * vz);
+  const float rinv = 1.0f / (r + 1e-8f);
+  const float dx = vx * rinv, dy = vy * rinv, dz = vz * rinv;
+  float b[16], bx[16], by[16], bz[16];
+  sh_basis(dx, dy, dz, 16, b);
+  sh_basis_grad(dx, dy, dz, 16, bx, by, bz);
+  float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    constexpr int K0 = 4 * SUB;
+    const float s = coef[3 * j] * dc0 + coef[3 * j + 1] * dc1 + coef[3 * j + 2] * dc2;
+    gcoef[3 * j] = fmaf(b[K0 + j], dc0, gcoef[3 * j]);
+    gcoef[3 * j + 1] = fmaf(b[K0 + j], dc1, gcoef[3 * j + 1]);
+    gcoef[3 * j + 2] = fmaf(b[K0 + j], dc2, gcoef[3 * j + 2]);
+    dd0 = fmaf(bx[K0 + j], s, dd0);
+    dd1 = fmaf(by[K0 + j], s, dd1);
+    dd2 = fmaf(bz[K0 + j], s, dd2);
+  }
+  // d = v/(r+eps), v = cam - m :  dv = dd/(r+eps) - v (v.dd) / (r (r+eps)^2) ; dm = -dv
+  const float vdd = vx * dd0 + vy * dd1 + vz * dd2;
+  const float k2 = (r > 0.0f) ? vdd * rinv * rinv / r : 0.0f;
+  gm[0] -= dd0 * rinv - vx * k2;
+  gm[1] -= dd1 * rinv - vy * k2;
+  gm[2] -= dd2 * rinv - vz * k2;
+}
+
+__global__ void __launch_bounds__(PRE_BLOCK)
+preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict__ views, int num_views,
+                           const float* __restrict__ means, const float* __restrict__ scales,
+                           const float* __restrict__ colors, const float* __restrict__ opac, int n,
+                           const float4* __restrict__ gacc, float* __restrict__ g_means, float* __restrict__ g_scales,
+                           float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
+  static_assert(PRE_BLOCK == 256, "8 warps: 2 x 32 Gaussians x 4 coefficient groups");
+  __shared__ ViewParams sv[BWD_VIEWS_SMEM];
+  __shared__ float gm_part[3][3][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp & 3, slot = (warp >> 2) * 32 + lane;
+  const int i = blockIdx.x * 64 + slot;
+  const bool live = i < n;
+  const int ii = live ? i : 0;
+
+  const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
+              mz = __ldg(means + 3 * (size_t)ii + 2);
+  float raw_s0 = 0.f, raw_s1 = 0.f, raw_op = 0.f;
+  if (sub == 0) {
+    raw_s0 = __ldg(scales + 3 * (size_t)ii);
+    raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
+    raw_op = __ldg(opac + ii);
+  }
+  float coef[12], gcoef[12];
+  {
+    const float4* cp = reinterpret_cast<const float4*>(colors + (size_t)ii * 48 + sub * 12);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = __ldg(cp + q);
+      coef[4 * q] = v.x; coef[4 * q + 1] = v.y; coef[4 * q + 2] = v.z; coef[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) gcoef[q] = 0.0f;
+  }
+  float gm[3] = {0.f, 0.f, 0.f}, gs0 = 0.f, gs1 = 0.f, gop = 0.f;
+
+  for (int vbase = 0; vbase < num_views; vbase += BWD_VIEWS_SMEM) {
+    const int vcount = min(BWD_VIEWS_SMEM, num_views - vbase);
+    if (views != nullptr) {
+      __syncthreads();
+      const int words = vcount * (int)(sizeof(ViewParams) / 4);
+      const int* src = reinterpret_cast<const int*>(views + vbase);
+      int* dst = reinterpret_cast<int*>(sv);
+      for (int q = threadIdx.x; q < words; q += PRE_BLOCK) dst[q] = src[q];
+      __syncthreads();
+    }
+    for (int vl = 0; vl < vcount; ++vl) {
+      const ViewParams& vp = (views != nullptr) ? sv[vl] : single;
+      const float4* ga = gacc + ((size_t)(vbase + vl) * n + ii) * 3;
+      const float4 g0 = __ldg(ga);     // {dR, dG, dB, dZ}: zero row when the Gaussian is culled in this view
+      const float4 g2 = __ldg(ga + 2); // {Syy, colour clamp mask, -, -}
+      const int cmask = __float_as_int(g2.y);
+      const float dc0 = (cmask & 1) ? g0.x : 0.0f, dc1 = (cmask & 2) ? g0.y : 0.0f, dc2 = (cmask & 4) ? g0.z : 0.0f;
+      if (sub == 0) {                  // warp uniform: projection -> sigma / opacity / position chain
+        const float4 g1 = __ldg(ga + 1);
+        const float s0 = act_scale(vp, raw_s0), s1 = act_scale(vp, raw_s1), op = act_opac(vp, raw_op);
+        const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+        if (pr.ok) {
+          float dZ = g0.w;
+          const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
+          float go = (op > 0.0f) ? S / op : S;
+          if (vp.act & B2S_ACT_OPACITY_SIGMOID) go *= op * (1.0f - op);
+          gop += go;
+          const float isx2 = 1.0f / (pr.sx * pr.sx), isy2 = 1.0f / (pr.sy * pr.sy);
+          const float dpx = Sx * isx2, dpy = Sy * isy2;
+          const float dsx = Sxx * isx2 / pr.sx, dsy = Syy * isy2 / pr.sy;
+          if (pr.ax >= 1.0f) {
+            const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s0 > 0.f) - (s0 < 0.f)) : 1.0f;
+            float t = dsx * sgn * (0.5f * vp.wf * vp.fx / pr.zabs);
+            if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s0);
+            gs0 += t;
+            dZ -= dsx * pr.ax / pr.zabs;
+          }
+          if (pr.ay >= 1.0f) {
+            const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s1 > 0.f) - (s1 < 0.f)) : 1.0f;
+            float t = dsy * sgn * (0.5f * vp.hf * vp.fy / pr.zabs);
+            if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s1);
+            gs1 += t;
+            dZ -= dsy * pr.ay / pr.zabs;
+          }
+          float dcam[4] = {0.f, 0.f, 0.f, 0.f};
+          if (fabsf(pr.zcam) >= 1e-6f) dcam[2] = dZ * ((pr.zcam > 0.f) ? 1.0f : -1.0f);
+          const float dnx = dpx * 0.5f * vp.wm1, dny = -dpy * 0.5f * vp.hm1;
+          float dclip[4];
+          dclip[0] = dnx / pr.wsafe;
+          dclip[1] = dny / pr.wsafe;
+          dclip[2] = 0.0f;
+          dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) / pr.wsafe;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dcam[c] = fmaf(vp.proj[4 * r + c], dclip[r], dcam[c]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) gm[c] = fmaf(vp.view[4 * r + c], dcam[r], gm[c]);
+        }
+      }
+      // colour: dC is zero for culled Gaussians and masked by the clamp above
+      switch (sub) {
+        case 0: sh16_group_accumulate<0>(vp, mx, my, mz, coef, dc0, dc1, dc2, gcoef, gm); break;
+        case 1: sh16_group_accumulate<1>(vp, mx, my, mz, coef, dc0, dc1, dc2, gcoef, gm); break;
+        case 2: sh16_group_accumulate<2>(vp, mx, my, mz, coef, dc0, dc1, dc2, gcoef, gm); break;
+        default: sh16_group_accumulate<3>(vp, mx, my, mz, coef, dc0, dc1, dc2, gcoef, gm); break;
+      }
+    }
+  }
+  // fold the four groups' d/dmean
+  if (sub != 0) {
+    gm_part[sub - 1][0][slot] = gm[0];
+    gm_part[sub - 1][1][slot] = gm[1];
+    gm_part[sub - 1][2][slot] = gm[2];
+  }
+  __syncthreads();
+  if (!live) return;
+  if (sub == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gm[c] += gm_part[0][c][slot] + gm_part[1][c][slot] + gm_part[2][c][slot];
+    if (accumulate) {
+      g_means[3 * (size_t)i] += gm[0]; g_means[3 * (size_t)i + 1] += gm[1]; g_means[3 * (size_t)i + 2] += gm[2];
+      g_scales[3 * (size_t)i] += gs0; g_scales[3 * (size_t)i + 1] += gs1;
+      g_opac[i] += gop;
+    } else {
+      g_means[3 * (size_t)i] = gm[0]; g_means[3 * (size_t)i + 1] = gm[1]; g_means[3 * (size_t)i + 2] = gm[2];
+      g_scales[3 * (size_t)i] = gs0; g_scales[3 * (size_t)i + 1] = gs1; g_scales[3 * (size_t)i + 2] = 0.0f;
+      g_opac[i] = gop;
+    }
+  }
+  if (g_colors != nullptr) {
+    float4* gp = reinterpret_cast<float4*>(g_colors + (size_t)i * 48 + sub * 12);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float4 v = make_float4(gcoef[4 * q], gcoef[4 * q + 1], gcoef[4 * q + 2], gcoef[4 * q + 3]);
+      if (accumulate) {
+        const float4 o = gp[q];
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      gp[q] = v;
+    }
+  }
+}
+
 int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,
                           const float* means, const float* scales, const float* colors, const float* opac, int n,
                           const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
@@ -488,7 +661,15 @@ int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev,
     case 1: B2S_PREB(1, 1); break;
     case 4: B2S_PREB(4, 1); break;
     case 9: B2S_PREB(9, 1); break;
-    case 16: B2S_PREB(16, 4); break;
+    case 16:
+      if (colors != nullptr && g_colors != nullptr) {
+        preprocess_bwd_sh16_kernel<<<(n + 63) / 64, PRE_BLOCK, 0, st>>>(one, views_dev, num_views, means, scales, colors, opac, n,
+                                                                       reinterpret_cast<const float4*>(gacc), g_means, g_scales,
+                                                                       g_colors, g_opac, accumulate);
+      } else {
+        B2S_PREB(16, 4);
+      }
+      break;
     default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", sh); return B2S_ERR_INVALID;
   }
 #undef B2S_PREB
