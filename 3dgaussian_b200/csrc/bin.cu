@@ -251,16 +251,22 @@ __global__ void __launch_bounds__(1024)
 cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pairs, int2* __restrict__ ranges,
                    Counters* __restrict__ counters, int unit_cap, int* __restrict__ unit_start,
                    int2* __restrict__ units) {
+  extern __shared__ int ts_smem[];                 // cnt[n_tiles] then ustart[n_tiles]
+  int* cnt = ts_smem;
+  int* ust = ts_smem + n_tiles;
   __shared__ long long wsum[32];
   __shared__ int wunits[32];
   __shared__ long long grand_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // coalesced fetch of the per-tile totals: every load of the block is in flight at once
+  for (int t = threadIdx.x; t < n_tiles; t += 1024) cnt[t] = total[t];
+  __syncthreads();
   const int per = (n_tiles + 1023) / 1024;
   const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
   long long c_sum = 0;
   int u_sum = 0;
   for (int t = t0; t < t1; ++t) {
-    const int c = total[t];
+    const int c = cnt[t];
     c_sum += c;
     u_sum += c > 0 ? (c + SEG - 1) / SEG : 1;
   }
@@ -293,25 +299,35 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
   const bool ov = grand > max_pairs;              // on overflow nothing is rendered: kept = 0, every range empty
   long long start = (wid > 0 ? wsum[wid - 1] : 0) + (x - c_sum);
   int ustart = (wid > 0 ? wunits[wid - 1] : 0) + (y - u_sum);
-  if (ov) {   // every tile keeps exactly one (empty) unit
-    ustart = t0;
-  }
+  if (ov) ustart = t0;                            // every tile keeps exactly one (empty) unit
+  // chunk pass in shared memory: cnt[t] <- start of the tile's range (its count is recovered from the next
+  // start), ust[t] <- first unit
+  int nunits = ov ? n_tiles : wunits[31];
   for (int t = t0; t < t1; ++t) {
-    const int c = ov ? 0 : total[t];
-    const int v = c > 0 ? (c + SEG - 1) / SEG : 1;
-    ranges[t] = c > 0 ? make_int2((int)start, (int)start + c) : make_int2(0, 0);   // empty tiles read (0,0) like the radix path
-    unit_start[t] = ustart;
-    for (int s = 0; s < v; ++s)
-      if (ustart + s < unit_cap) units[ustart + s] = make_int2(t, s);
+    const int c = ov ? 0 : cnt[t];
+    ust[t] = ustart;
+    ustart += c > 0 ? (c + SEG - 1) / SEG : 1;
+    cnt[t] = (int)start;
     start += c;
-    ustart += v;
+  }
+  __syncthreads();
+  // coalesced write-out
+  const int kept = ov ? 0 : (int)grand;
+  for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+    const int s0 = cnt[t], s1 = (t + 1 < n_tiles) ? cnt[t + 1] : kept;
+    const int c = ov ? 0 : s1 - s0;
+    ranges[t] = c > 0 ? make_int2(s0, s1) : make_int2(0, 0);   // empty tiles read (0,0) like the radix path
+    const int u0 = ust[t];
+    unit_start[t] = u0;
+    const int v = c > 0 ? (c + SEG - 1) / SEG : 1;
+    for (int q = 0; q < v; ++q)
+      if (u0 + q < unit_cap) units[u0 + q] = make_int2(t, q);
   }
   if (threadIdx.x == 0) {
     counters->needed = grand;
-    counters->kept = ov ? 0 : (int)grand;
+    counters->kept = kept;
     counters->overflow = ov ? 1 : 0;
-    const int nu = ov ? n_tiles : wunits[31];
-    unit_start[n_tiles] = nu < unit_cap ? nu : unit_cap;
+    unit_start[n_tiles] = nunits < unit_cap ? nunits : unit_cap;
   }
 }
 
@@ -333,7 +349,7 @@ cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* _
   }
 }
 
-bool counting_sort_fits(int n_tiles) { return (size_t)n_tiles * 4 <= CS_MAX_SMEM; }
+bool counting_sort_fits(int n_tiles) { return (size_t)n_tiles * 8 <= CS_MAX_SMEM; }   // tile scan stages 2 ints per tile
 int counting_sort_blocks(int n) {
   int nb = (n + CS_THREADS - 1) / CS_THREADS;
   return nb < 1 ? 1 : (nb > CS_NB ? CS_NB : nb);
@@ -348,6 +364,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
   if (!attr_set) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(cs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
     B2S_CUDA_TRY(cudaFuncSetAttribute(cs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
+    B2S_CUDA_TRY(cudaFuncSetAttribute(cs_tilescan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
     attr_set = true;
   }
   const int nb = counting_sort_blocks(n);
@@ -359,7 +376,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
-    cs_tilescan_kernel<<<1, 1024, 0, st>>>(total, vp.n_tiles, (long long)max_pairs, ranges, counters, (int)unit_cap,
+    cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, (long long)max_pairs, ranges, counters, (int)unit_cap,
                                            unit_start, units);
     B2S_LAUNCH_CHECK();
   } else {

@@ -81,29 +81,58 @@ gbuf_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __r
 // Register index = ((ch*2 + h)*2 + part)*2 + slot, h = N/8, part = hi|lo, slot = K/8; B2 follows B1.
 // Layout in memory: [tile][register/4][lane] uint4  -> the consumer's loads are coalesced LDG.128.
 // tile_scale[tile] = 2^-(sG + 16): undoes 2^sG and the 2^8 applied to each of fx, fy ... see the consumer.
-template <bool DEPTH>
+// LOSS = true is the fit-loop fusion (python/fit_multiview_stub.py:292-297): the per-view loss
+//   mean|rgb - tgt| + w_sil * mean|alpha - mask|
+// is evaluated here straight from the accumulators (rgb and alpha are recomputed, not read back from images) and
+// its image gradients feed the g-buffer in registers; the block's loss share goes to *loss_accum.
+// The fragment image of the tile (NREG x 32 words) is assembled in shared memory and written with coalesced
+// 16-byte stores.
+template <bool DEPTH, bool LOSS>
 __global__ void __launch_bounds__(TILE_PIX)
 gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __restrict__ g_rgb,
-                 const float* __restrict__ g_alpha, const float* __restrict__ g_depth, uint32_t* __restrict__ frag,
-                 float* __restrict__ tile_scale) {
+                 const float* __restrict__ g_alpha, const float* __restrict__ g_depth, const float* __restrict__ tgt,
+                 const float* __restrict__ mask, float w_sil, float scale, float* __restrict__ loss_accum,
+                 uint32_t* __restrict__ frag, float* __restrict__ tile_scale) {
   constexpr int CH = DEPTH ? 5 : 4;
   constexpr int NREG = CH * 16;
   __shared__ float wmax[TILE_PIX / 32];
+  __shared__ float wloss[TILE_PIX / 32];
+  __shared__ __align__(16) __half sfrag[NREG * 32 * 2];
   const int tile = blockIdx.x, q = threadIdx.x;
   const int r = q >> 4, c = q & 15;
   const int xi = (tile % vp.tiles_x) * TILE + c, yi = (tile / vp.tiles_x) * TILE + r;
   const size_t hw = (size_t)vp.width * vp.height;
   float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float loss = 0.f;
   if (xi < vp.width && yi < vp.height) {
     const size_t p = (size_t)yi * vp.width + xi;
     const float A0 = acc[p], A1 = acc[hw + p], A2 = acc[2 * hw + p], W = acc[3 * hw + p];
     const float inv = 1.0f / (1.0f + W);
     const float o0 = (vp.bg[0] + A0) * inv, o1 = (vp.bg[1] + A1) * inv, o2 = (vp.bg[2] + A2) * inv;
-    v[0] = (o0 >= 0.f && o0 <= 1.f) ? g_rgb[3 * p] * inv : 0.f;
-    v[1] = (o1 >= 0.f && o1 <= 1.f) ? g_rgb[3 * p + 1] * inv : 0.f;
-    v[2] = (o2 >= 0.f && o2 <= 1.f) ? g_rgb[3 * p + 2] * inv : 0.f;
+    float gr0, gr1, gr2, ga = 0.f;
+    if constexpr (LOSS) {
+      const float inv3 = 1.0f / (3.0f * (float)hw), inv1 = 1.0f / (float)hw;
+      const float d0 = fminf(fmaxf(o0, 0.f), 1.f) - tgt[3 * p], d1 = fminf(fmaxf(o1, 0.f), 1.f) - tgt[3 * p + 1],
+                  d2 = fminf(fmaxf(o2, 0.f), 1.f) - tgt[3 * p + 2];
+      loss = (fabsf(d0) + fabsf(d1) + fabsf(d2)) * inv3;
+      const float k = scale * inv3;
+      gr0 = k * (float)((d0 > 0.f) - (d0 < 0.f));
+      gr1 = k * (float)((d1 > 0.f) - (d1 < 0.f));
+      gr2 = k * (float)((d2 > 0.f) - (d2 < 0.f));
+      if (mask != nullptr) {
+        const float da = fminf(fmaxf(W * inv, 0.f), 1.f) - mask[p];
+        loss = fmaf(w_sil * inv1, fabsf(da), loss);
+        ga = scale * w_sil * inv1 * (float)((da > 0.f) - (da < 0.f));
+      }
+    } else {
+      gr0 = g_rgb[3 * p]; gr1 = g_rgb[3 * p + 1]; gr2 = g_rgb[3 * p + 2];
+      if (g_alpha != nullptr) ga = g_alpha[p];
+    }
+    v[0] = (o0 >= 0.f && o0 <= 1.f) ? gr0 * inv : 0.f;
+    v[1] = (o1 >= 0.f && o1 <= 1.f) ? gr1 * inv : 0.f;
+    v[2] = (o2 >= 0.f && o2 <= 1.f) ? gr2 * inv : 0.f;
     v[3] = -(v[0] * o0 + v[1] * o1 + v[2] * o2);
-    if (g_alpha != nullptr) v[3] = fmaf(g_alpha[p], inv * inv, v[3]);
+    v[3] = fmaf(ga, inv * inv, v[3]);
     if (DEPTH) {
       const float D = acc[4 * hw + p];
       const float iw = 1.0f / (W + 1e-6f);
@@ -116,8 +145,11 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) m = fmaxf(m, fabsf(v[ch]));
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((q & 31) == 0) wmax[q >> 5] = m;
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (LOSS) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  }
+  if ((q & 31) == 0) { wmax[q >> 5] = m; wloss[q >> 5] = loss; }
   __syncthreads();
   m = 0.f;
 #pragma unroll
@@ -128,12 +160,19 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     frexpf(m, &e);                 // 2^(e-1) <= m < 2^e
     sG = min(max(12 - e, -60), 60);
   }
-  const float scale = ldexpf(1.0f, sG);
-  if (q == 0) tile_scale[tile] = ldexpf(1.0f, -(sG + 16));
-  __half* out = reinterpret_cast<__half*>(frag) + (size_t)tile * NREG * 32 * 2;
+  const float sc = ldexpf(1.0f, sG);
+  if (q == 0) {
+    tile_scale[tile] = ldexpf(1.0f, -(sG + 16));
+    if (LOSS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < TILE_PIX / 32; ++w) t += wloss[w];
+      atomicAdd(loss_accum, scale * t);
+    }
+  }
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
-    const float x = v[ch] * scale;
+    const float x = v[ch] * sc;
     const __half hi = __float2half_rn(x);
     const __half lo = __float2half_rn(x - __half2float(hi));
 #pragma unroll
@@ -142,15 +181,20 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
       {   // B1: N = row r, K = column c
         const int h = r >> 3, g = r & 7, slot = c >> 3, t = (c & 7) >> 1, half = c & 1;
         const int reg = ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
-        out[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+        sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
       }
       {   // B2: N = column c, K = row r
         const int h = c >> 3, g = c & 7, slot = r >> 3, t = (r & 7) >> 1, half = r & 1;
         const int reg = CH * 8 + ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
-        out[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+        sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
       }
     }
   }
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(frag + (size_t)tile * NREG * 32);
+  const uint4* src = reinterpret_cast<const uint4*>(sfrag);
+#pragma unroll
+  for (int k = q; k < NREG * 32 / 4; k += TILE_PIX) out[k] = src[k];
 }
 
 // ---- TMA bulk copy helpers (global -> shared, completion on an mbarrier) ------------------------
@@ -577,22 +621,22 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   cp_async_wait_b<0>();
 }
 
-// Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (bits 0..2 of the blend
-// record's b.z, written by preprocess_kernel) into the spare slot 9 of its row, where the chain-rule kernel
-// finds it next to the sums -- the blend kernel itself never touches it.
+// Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (written by
+// preprocess_kernel into the view state) into the spare slot 9 of its row, where the chain-rule kernel finds it
+// next to the sums -- the blend kernel itself never touches it.
 __global__ void __launch_bounds__(256)
-gacc_init_kernel(const float4* __restrict__ rec, float4* __restrict__ gacc, int n) {
+gacc_init_kernel(const uint8_t* __restrict__ cmask, float4* __restrict__ gacc, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  const float m = rec[3 * (size_t)i + 1].z;
+  const float m = __int_as_float((int)cmask[i]);
   gacc[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
   gacc[3 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
   gacc[3 * (size_t)i + 2] = make_float4(0.f, m, 0.f, 0.f);
 }
 
-int launch_gacc_init(const float4* rec, float* gacc, int n, cudaStream_t st) {
+int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st) {
   if (n <= 0) return B2S_OK;
-  gacc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(rec, reinterpret_cast<float4*>(gacc), n);
+  gacc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(cmask, reinterpret_cast<float4*>(gacc), n);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -605,11 +649,11 @@ static bool use_simt_bwd() {
 
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
-                          const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,
-                          float* gacc, cudaStream_t st) {
+                          const float* g_rgb, const float* g_alpha, const float* g_depth, const FitLossArgs* fl,
+                          float* gbuf, float* gacc, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
   const bool depth = g_depth != nullptr;
-  if (use_simt_bwd()) {   // development cross-check: the FP32-pipe kernel (v3)
+  if (use_simt_bwd() && fl == nullptr) {   // development cross-check: the FP32-pipe kernel (v3)
     if (depth) gbuf_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
     else       gbuf_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
     B2S_LAUNCH_CHECK();
@@ -619,8 +663,15 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     // gbuf region: [tile][20 uint4][32 lanes] fragments (10 KB per tile), then one scale per tile
     uint32_t* frag = reinterpret_cast<uint32_t*>(gbuf);
     float* tile_scale = gbuf + (size_t)vp.n_tiles * GBUF_FRAG_WORDS;
-    if (depth) gbuf_frag_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, frag, tile_scale);
-    else       gbuf_frag_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, frag, tile_scale);
+    if (fl != nullptr)
+      gbuf_frag_kernel<false, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
+                                                                    fl->scale, fl->loss_accum, frag, tile_scale);
+    else if (depth)
+      gbuf_frag_kernel<true, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
+                                                                    nullptr, frag, tile_scale);
+    else
+      gbuf_frag_kernel<false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
+                                                                     nullptr, frag, tile_scale);
     B2S_LAUNCH_CHECK();
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);

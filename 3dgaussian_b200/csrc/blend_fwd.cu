@@ -136,7 +136,7 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
       const float d = coord - h.x;
       float f;
       if constexpr (!EXACT) {
-        f = ex2_approx(fmaf(h.y * d, d, h.z));
+        f = ex2_approx(fmaf(h.y * d, d, half ? 0.0f : h.z));   // the y record's third slot holds packed colour halves
       } else {
         f = h.z * ex2_approx(h.y * d * d);
         const int bb = __float_as_int(h.w);
@@ -371,6 +371,7 @@ blend_wsum_fwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 // (16 MUFU.EX2): exactly its A (rows x Gaussians) and B (Gaussians x columns) fragment slots.
 // Padding slots of the last step hold a record with px = py = 1e18 (factor underflows to 0): no selects.
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_h2(uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
   const float2 f = __half22float2(h);
@@ -414,7 +415,7 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
         cp_async16(&st.a[lane], src);
         cp_async16(&st.b[lane], src + 1);
         cp_async16(&st.c[lane], src + 2);
-      } else {   // padding: a record whose factors underflow to exactly 0
+      } else {   // padding: a record whose factors underflow to exactly 0 (and whose colour halves are 0)
         st.a[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
         st.b[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
         st.c[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -456,17 +457,20 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     for (int sp = 0; sp < FM_STAGE / 16; ++sp) {
       if (sp * 16 >= left) break;                    // warp-uniform
       // e = 0..3 -> Gaussians 2t, 2t+1, 2t+8, 2t+9 of the step (the K slots of a0/a1 | a2/a3 and b0 | b1)
-      float fy[4][2], fx[4][2], v[4][4];
+      float fy[4][2], fx[4][2], zv[4];
+      uint32_t cw[4][3];                             // the clamped colour pre-split as f16 {hi | lo << 16}: r, g, b
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = sp * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
-        const float4 ra = st.a[j], rb = st.b[j], rc = st.c[j];
+        const float4 ra = st.a[j], rb = st.b[j];
         const float dy0 = cy0 - rb.x, dy1 = cy1 - rb.x, dx0 = cx0 - ra.x, dx1 = cx1 - ra.x;
+        const float lop8 = fminf(ra.z, 7.99f) + 8.0f;           // fx * 2^8 stays inside fp16 (op <= 253)
         fy[e][0] = ex2_approx(fmaf(rb.y * dy0, dy0, 8.0f));
         fy[e][1] = ex2_approx(fmaf(rb.y * dy1, dy1, 8.0f));
-        fx[e][0] = ex2_approx(fmaf(ra.y * dx0, dx0, ra.z + 8.0f));
-        fx[e][1] = ex2_approx(fmaf(ra.y * dx1, dx1, ra.z + 8.0f));
-        v[e][0] = rc.x; v[e][1] = rc.y; v[e][2] = rc.z; v[e][3] = rc.w;
+        fx[e][0] = ex2_approx(fmaf(ra.y * dx0, dx0, lop8));
+        fx[e][1] = ex2_approx(fmaf(ra.y * dx1, dx1, lop8));
+        cw[e][0] = __float_as_uint(ra.w); cw[e][1] = __float_as_uint(rb.w); cw[e][2] = __float_as_uint(rb.z);
+        if (DEPTH) zv[e] = st.c[j].w;
       }
       // A = fy: a0 = (row g; K 2t, 2t+1), a1 = (row g+8; same), a2 = (row g; K 2t+8, 2t+9), a3 = (row g+8; same)
       uint32_t Ah[4], Al[4];
@@ -474,23 +478,44 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       split_h2(fy[0][1], fy[1][1], Ah[1], Al[1]);
       split_h2(fy[2][0], fy[3][0], Ah[2], Al[2]);
       split_h2(fy[2][1], fy[3][1], Ah[3], Al[3]);
+      // colour halves paired along K like the B fragment: p = 0 -> Gaussians (2t, 2t+1), p = 1 -> (2t+8, 2t+9)
+      __half2 VH[2][3], VL[2][3];
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          VH[p][ch] = u32_h2(__byte_perm(cw[2 * p][ch], cw[2 * p + 1][ch], 0x5410));
+          VL[p][ch] = u32_h2(__byte_perm(cw[2 * p][ch], cw[2 * p + 1][ch], 0x7632));
+        }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        // B = v * fx at column 8h+g: b0 = (K 2t, 2t+1), b1 = (K 2t+8, 2t+9)
+        // B = v * fx at column 8h+g: b0 = (K 2t, 2t+1), b1 = (K 2t+8, 2t+9).  The weight plane is fx itself,
+        // split hi + lo once; a colour plane is formed from the two splits with packed half arithmetic:
+        //   hi = rn(vh fxh),  lo = (vh fxh - hi) [exact: one HFMA2] + vh fxl + vl fxh      (vl fxl ~ 2^-22 dropped)
+        uint32_t Fh[2], Fl[2];
+        split_h2(fx[0][h], fx[1][h], Fh[0], Fl[0]);
+        split_h2(fx[2][h], fx[3][h], Fh[1], Fl[1]);
+        const __half2 fh0 = u32_h2(Fh[0]), fh1 = u32_h2(Fh[1]), fl0 = u32_h2(Fl[0]), fl1 = u32_h2(Fl[1]);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          float b[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (ch == 3) b[e] = fx[e][h];                                        // weight plane
-            else b[e] = fminf(v[e][ch == 4 ? 3 : ch] * fx[e][h], 65000.0f);     // colour planes, depth plane
-          }
+        for (int ch = 0; ch < 3; ++ch) {
+          const __half2 p0 = __hmul2(VH[0][ch], fh0), p1 = __hmul2(VH[1][ch], fh1);
+          __half2 l0 = __hfma2(VH[0][ch], fh0, __hneg2(p0)), l1 = __hfma2(VH[1][ch], fh1, __hneg2(p1));
+          l0 = __hfma2(VH[0][ch], fl0, l0); l1 = __hfma2(VH[1][ch], fl1, l1);
+          l0 = __hfma2(VL[0][ch], fh0, l0); l1 = __hfma2(VL[1][ch], fh1, l1);
+          mma_f16_acc(D[ch][h], Al, h2_bits(p0), h2_bits(p1));
+          mma_f16_acc(D[ch][h], Ah, h2_bits(l0), h2_bits(l1));
+          mma_f16_acc(D[ch][h], Ah, h2_bits(p0), h2_bits(p1));
+        }
+        mma_f16_acc(D[3][h], Al, Fh[0], Fh[1]);
+        mma_f16_acc(D[3][h], Ah, Fl[0], Fl[1]);
+        mma_f16_acc(D[3][h], Ah, Fh[0], Fh[1]);
+        if (DEPTH) {     // depth plane: zabs is an arbitrary fp32, formed and split in FP32
           uint32_t Bh0, Bl0, Bh1, Bl1;
-          split_h2(b[0], b[1], Bh0, Bl0);
-          split_h2(b[2], b[3], Bh1, Bl1);
-          mma_f16_acc(D[ch][h], Al, Bh0, Bh1);
-          mma_f16_acc(D[ch][h], Ah, Bl0, Bl1);
-          mma_f16_acc(D[ch][h], Ah, Bh0, Bh1);
+          split_h2(fminf(zv[0] * fx[0][h], 65000.0f), fminf(zv[1] * fx[1][h], 65000.0f), Bh0, Bl0);
+          split_h2(fminf(zv[2] * fx[2][h], 65000.0f), fminf(zv[3] * fx[3][h], 65000.0f), Bh1, Bl1);
+          mma_f16_acc(D[CH - 1][h], Al, Bh0, Bh1);
+          mma_f16_acc(D[CH - 1][h], Ah, Bl0, Bl1);
+          mma_f16_acc(D[CH - 1][h], Ah, Bh0, Bh1);
         }
       }
     }

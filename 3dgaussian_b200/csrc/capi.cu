@@ -127,6 +127,7 @@ struct Bufs {  // resolved pointers into state / workspace
   int2* ranges;
   int* vals;
   float* acc;
+  uint8_t* cmask;
   uint2* rect;
   unsigned long long* tmask;
   uint32_t* dbits;
@@ -159,6 +160,7 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.acc = (float*)(s + S.acc);
     b.unit_start = (int*)(s + S.unit_start);
     b.units = (int2*)(s + S.units);
+    b.cmask = (uint8_t*)(s + S.cmask);
   }
   if (ws != nullptr) {
     const WorkLayout L = work_layout(n, w, h, mp);
@@ -191,7 +193,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   int rc;
   {
     StageTimer t(ctx, ST_PREPROCESS, st);
-    rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+    rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
   }
   if (rc != B2S_OK) return rc;
   const int begin_bit = p->sort_depth ? 0 : 32;
@@ -316,7 +318,7 @@ int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const
   Bufs B = resolve(nullptr, workspace, n, p->width, p->height, 0);
   // the counters live in the (otherwise unused) head of the histogram scratch
   Counters* counters = (Counters*)B.hist;
-  rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
+  rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, nullptr, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
   rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, st);
   if (rc != B2S_OK) return rc;
@@ -330,10 +332,11 @@ int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const
 int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* colors,
                 const float* opacities, int n, int64_t max_pairs, float* out_rgb, float* out_alpha,
                 float* out_depth, void* state, size_t state_bytes, void* workspace, size_t ws_bytes, void* stream) {
-  if (ctx == nullptr || out_rgb == nullptr || state == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (ctx == nullptr || state == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   ViewParams vp;
   int rc = make_view(p, &vp);
   if (rc != B2S_OK) return rc;
+  if (out_rgb == nullptr && vp.mode == B2S_MODE_SORTED) { set_error("out_rgb is NULL (only the weighted-sum mode keeps its result in the state)"); return B2S_ERR_INVALID; }
   rc = check_sizes(n, p->width, p->height, max_pairs, state_bytes, true, ws_bytes);
   if (rc != B2S_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -367,10 +370,10 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   {
     StageTimer t(ctx, ST_BLEND_BWD, st);
-    rc = launch_gacc_init(B.rec, B.gacc, n, st);
+    rc = launch_gacc_init(B.cmask, B.gacc, n, st);
     if (rc != B2S_OK) return rc;
     rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
-                               g_depth, B.gbuf, B.gacc, st);
+                               g_depth, nullptr, B.gbuf, B.gacc, st);
   }
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_PREPROCESS_BWD, st);
@@ -407,10 +410,36 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   StageTimer t(ctx, ST_BLEND_BWD, st);
-  rc = launch_gacc_init(B.rec, gacc_out, n, st);
+  rc = launch_gacc_init(B.cmask, gacc_out, n, st);
   if (rc != B2S_OK) return rc;
   return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
-                               g_depth, B.gbuf, gacc_out, st);
+                               g_depth, nullptr, B.gbuf, gacc_out, st);
+}
+
+int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
+                           const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
+                           void* workspace, size_t ws_bytes, float* gacc_out, void* stream) {
+  if (ctx == nullptr || tgt == nullptr || loss_accum == nullptr || state == nullptr || workspace == nullptr ||
+      gacc_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode != B2S_MODE_WSUM || vp.exact_bbox || vp.style != B2S_STYLE_TORCH) {
+    set_error("backward is implemented for the weighted-sum torch-style mode only");
+    return B2S_ERR_UNSUPPORTED;
+  }
+  rc = check_sizes(n, p->width, p->height, max_pairs, 0, false, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
+  const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum};
+  StageTimer t(ctx, ST_BLEND_BWD, st);
+  if (n > 0) {
+    rc = launch_gacc_init(B.cmask, gacc_out, n, st);
+    if (rc != B2S_OK) return rc;
+  }
+  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, nullptr, nullptr,
+                               nullptr, &fl, B.gbuf, gacc_out, st);
 }
 
 int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,

@@ -153,7 +153,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // ---- state / workspace layout (all offsets 256-B aligned) -------------------------------
 struct StateLayout {
-  size_t rec, ranges, vals, acc, counters, unit_start, units, total;
+  size_t rec, ranges, vals, acc, counters, unit_start, units, cmask, total;
 };
 struct WorkLayout {
   size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
@@ -184,6 +184,7 @@ inline StateLayout state_layout(int n, int width, int height, int64_t max_pairs)
   L.acc = o;      o += align_up((size_t)width * height * 5 * 4);
   L.unit_start = o; o += align_up((size_t)(tiles + 1) * 4);
   L.units = o;    o += align_up((size_t)max_units(width, height, max_pairs) * 8);
+  L.cmask = o;    o += align_up((size_t)(n > 0 ? n : 1));   // colour clamp mask, 1 B per Gaussian (torch_renderer.py:144)
   L.total = o;
   return L;
 }
@@ -244,9 +245,9 @@ enum Stage { ST_PREPROCESS = 0, ST_BIN, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_LOS
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------
 int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                      const float* opac, int n, float4* rec, uint2* rect, unsigned long long* tmask, uint32_t* dbits,
-                      int* cnt, long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/, int* dbg_bbox,
-                      cudaStream_t st);
+                      const float* opac, int n, float4* rec, uint8_t* cmask, uint2* rect, unsigned long long* tmask,
+                      uint32_t* dbits, int* cnt, long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/,
+                      int* dbg_bbox, cudaStream_t st);
 int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
                const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
@@ -271,11 +272,19 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           cudaStream_t st);
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                             float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
-int launch_gacc_init(const float4* rec, float* gacc, int n, cudaStream_t st);
+int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st);
+// fl != null: the image gradients are those of the fit loss, evaluated from the saved accumulators inside the
+// g-buffer kernel (g_rgb / g_alpha / g_depth are ignored)
+struct FitLossArgs {
+  const float* tgt;
+  const float* mask;     // may be null
+  float w_sil, scale;
+  float* loss_accum;
+};
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
-                          const float* g_rgb, const float* g_alpha, const float* g_depth, float* gbuf,
-                          float* gacc, cudaStream_t st);
+                          const float* g_rgb, const float* g_alpha, const float* g_depth, const FitLossArgs* fl,
+                          float* gbuf, float* gacc, cudaStream_t st);
 // single != null: one view passed by value (views_dev must be null, num_views 1, gacc = n x 12 floats);
 // else views_dev[num_views] in device memory and gacc = num_views x n x 12 floats.
 int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,

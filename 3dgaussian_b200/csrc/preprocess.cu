@@ -5,6 +5,7 @@
 //   python/torch_renderer.py:57-106,143-150   and the per-thread prologue of
 //   src/renderer.cu:41-84 (AoS stride-3 loads, no culling of work).
 // HBM-bound: algorithmic bytes per Gaussian*view = 28 + 12*sh (read) + 48+16 (write).
+#include <cuda_fp16.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -125,18 +126,31 @@ __device__ __forceinline__ void eval_color(const ViewParams& vp, const float* c,
 
 constexpr float NEG_HALF_LOG2E = -0.72134752044448170368f;  // -0.5 * log2(e)
 
+// x in [0,1] as two fp16 numbers hi + lo (22 significant bits), packed {low half = hi, high half = lo}
+__device__ __forceinline__ float split_f16_pair(float x) {
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  return __uint_as_float((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16));
+}
+
 // Forward: one thread per Gaussian.  Writes the 48-byte blend record
-//   rec[3i+0] = {px, qx, lop, bbox x (min|max<<16)}   qx = -0.5*log2(e)/sx^2, lop = log2(op)
-//   rec[3i+1] = {py, qy, 0,   bbox y (min|max<<16)}   so  w = 2^(qx dx^2 + lop) * 2^(qy dy^2)
+//   rec[3i+0] = {px, qx, lop, red  as f16 hi|lo}   qx = -0.5*log2(e)/sx^2, lop = log2(op)
+//   rec[3i+1] = {py, qy, blue as f16 hi|lo, green as f16 hi|lo}   so  w = 2^(qx dx^2 + lop) * 2^(qy dy^2)
 //   rec[3i+2] = {r, g, b, zabs}
-//   (exact_bbox mode keeps op and 1 in the third slots: w = op*2^(qx dx^2) * 1*2^(qy dy^2))
+//   The f16 pairs (low half = fp16(c), high half = fp16(c - hi)) are the clamped colour pre-split for the
+//   tensor-core forward, which forms its fp16 hi/lo B operands from them with packed half arithmetic.
+//   exact_bbox mode (native styles) keeps  {px, qx, op, bbox x (min|max<<16)}, {py, qy, 1, bbox y}:
+//   w = op*2^(qx dx^2) * 1*2^(qy dy^2), cut to the pixel bbox.
+// cmask[i] (torch style): bit q = colour channel q is inside [0,1], i.e. clamp(0,1) passes its gradient
+// (torch_renderer.py:144); consumed by the blend backward through gacc_init_kernel.
 // plus the tile rect / depth bits / tile count consumed by the binning kernels, and the
 // per-block sum of tile counts (first level of the exclusive scan).
 template <int K>
 __global__ void __launch_bounds__(PRE_BLOCK)
 preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const float* __restrict__ scales,
                   const float* __restrict__ colors, const float* __restrict__ opac, int n,
-                  float4* __restrict__ rec, uint2* __restrict__ rect, unsigned long long* __restrict__ tmask,
+                  float4* __restrict__ rec, uint8_t* __restrict__ cmask_out, uint2* __restrict__ rect,
+                  unsigned long long* __restrict__ tmask,
                   uint32_t* __restrict__ dbits, int* __restrict__ cnt, long long* __restrict__ bsum,
                   float* __restrict__ dbg, int* __restrict__ dbg_bbox) {
   const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
@@ -166,6 +180,7 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
     cnt[i] = my_cnt;
     if (rec != nullptr) {
       float4 a, b, c;
+      int cm = 0;
       if (pr.ok) {
         float craw[3], dir[3], rinv;
         if (colors != nullptr) {
@@ -178,22 +193,20 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
         // The reference's Gaussians are axis aligned, so the weight is separable:
         //   w(x,y) = [op * exp(-dx^2/2sx^2)] * [exp(-dy^2/2sy^2)]  -- one x record, one y record.
         const bool lg = (vp.exact_bbox == 0);        // log-domain opacity unless the native exact mode
-        a.x = pr.px;
-        a.y = NEG_HALF_LOG2E / (pr.sx * pr.sx);
-        a.z = lg ? log2f(op) : op;
-        a.w = __int_as_float(pr.xmin | (pr.xmax << 16));
-        b.x = pr.py;
-        b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
-        // torch style: bits 0..2 = the colour channel is inside [0,1], i.e. clamp(0,1) passes its gradient
-        // (torch_renderer.py:144); consumed by the blend backward.  As a float this is a denormal (== 0 to ex2.ftz).
-        const int cmask = (craw[0] >= 0.0f && craw[0] <= 1.0f ? 1 : 0) | (craw[1] >= 0.0f && craw[1] <= 1.0f ? 2 : 0) |
-                          (craw[2] >= 0.0f && craw[2] <= 1.0f ? 4 : 0);
-        b.z = lg ? __int_as_float(cmask) : 1.0f;
-        b.w = __int_as_float(pr.ymin | (pr.ymax << 16));
         c.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
         c.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
         c.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
         c.w = pr.zabs;
+        a.x = pr.px;
+        a.y = NEG_HALF_LOG2E / (pr.sx * pr.sx);
+        a.z = lg ? log2f(op) : op;
+        a.w = lg ? split_f16_pair(c.x) : __int_as_float(pr.xmin | (pr.xmax << 16));
+        b.x = pr.py;
+        b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
+        b.z = lg ? split_f16_pair(c.z) : 1.0f;
+        b.w = lg ? split_f16_pair(c.y) : __int_as_float(pr.ymin | (pr.ymax << 16));
+        cm = (craw[0] >= 0.0f && craw[0] <= 1.0f ? 1 : 0) | (craw[1] >= 0.0f && craw[1] <= 1.0f ? 2 : 0) |
+             (craw[2] >= 0.0f && craw[2] <= 1.0f ? 4 : 0);
       } else {
         a = make_float4(0.f, 0.f, (vp.exact_bbox == 0) ? -INFINITY : 0.0f, __int_as_float(0));
         b = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
@@ -202,6 +215,7 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
       rec[3 * (size_t)i] = a;
       rec[3 * (size_t)i + 1] = b;
       rec[3 * (size_t)i + 2] = c;
+      if (cmask_out != nullptr) cmask_out[i] = (uint8_t)cm;
     }
     if (dbg != nullptr) {
       dbg[i] = pr.px; dbg[(size_t)n + i] = pr.py; dbg[2 * (size_t)n + i] = pr.sx;
@@ -228,11 +242,11 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
 }
 
 int launch_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* colors,
-                      const float* opac, int n, float4* rec, uint2* rect, unsigned long long* tmask, uint32_t* dbits,
-                      int* cnt, long long* bsum, float* dbg, int* dbg_bbox, cudaStream_t st) {
+                      const float* opac, int n, float4* rec, uint8_t* cmask, uint2* rect, unsigned long long* tmask,
+                      uint32_t* dbits, int* cnt, long long* bsum, float* dbg, int* dbg_bbox, cudaStream_t st) {
   if (n <= 0) return B2S_OK;
   const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
-#define B2S_PRE(KK) preprocess_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, rec, rect, tmask, dbits, cnt, bsum, dbg, dbg_bbox)
+#define B2S_PRE(KK) preprocess_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(vp, means, scales, colors, opac, n, rec, cmask, rect, tmask, dbits, cnt, bsum, dbg, dbg_bbox)
   switch (vp.sh) {
     case 1: B2S_PRE(1); break;
     case 4: B2S_PRE(4); break;
@@ -479,7 +493,7 @@ __device__ __forceinline__ void sh16_group_accumulate(const ViewParams& vp, floa
                                                       float (&gcoef)[12], float (&gm)[3]) {
   const float vx = vp.cam[0] - mx, vy = vp.cam[1] - my, vz = vp.cam[2] - mz;
   const float r = sqrtf(vx * vx + vy * vy + vz * vz);
-  const float rinv = 1.0f / (r + 1e-8f);
+  const float rinv = __frcp_rn(r + 1e-8f);
   const float dx = vx * rinv, dy = vy * rinv, dz = vz * rinv;
   float b[16], bx[16], by[16], bz[16];
   sh_basis(dx, dy, dz, 16, b);
@@ -498,7 +512,7 @@ __device__ __forceinline__ void sh16_group_accumulate(const ViewParams& vp, floa
   }
   // d = v/(r+eps), v = cam - m :  dv = dd/(r+eps) - v (v.dd) / (r (r+eps)^2) ; dm = -dv
   const float vdd = vx * dd0 + vy * dd1 + vz * dd2;
-  const float k2 = (r > 0.0f) ? vdd * rinv * rinv / r : 0.0f;
+  const float k2 = (r > 0.0f) ? vdd * rinv * rinv * __frcp_rn(r) : 0.0f;
   gm[0] -= dd0 * rinv - vx * k2;
   gm[1] -= dd1 * rinv - vy * k2;
   gm[2] -= dd2 * rinv - vz * k2;
@@ -521,12 +535,21 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
 
   const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
               mz = __ldg(means + 3 * (size_t)ii + 2);
-  float raw_s0 = 0.f, raw_s1 = 0.f, raw_op = 0.f;
+  // activations are view independent (every view of a fit shares act_flags): once per Gaussian, not per view
+  const ViewParams& v0 = (views != nullptr) ? views[0] : single;
+  const int act = v0.act;
+  float s0 = 0.f, s1 = 0.f, op = 0.f, ds0 = 1.f, ds1 = 1.f, dop = 1.f;   // activated values, d activation / d raw
   if (sub == 0) {
-    raw_s0 = __ldg(scales + 3 * (size_t)ii);
-    raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
-    raw_op = __ldg(opac + ii);
+    const float raw_s0 = __ldg(scales + 3 * (size_t)ii), raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
+    const float raw_op = __ldg(opac + ii);
+    s0 = raw_s0; s1 = raw_s1; op = raw_op;
+    if (act & B2S_ACT_SCALES_SOFTPLUS) {
+      s0 = softplusf_acc(raw_s0) + 1e-3f; s1 = softplusf_acc(raw_s1) + 1e-3f;
+      ds0 = sigmoidf_acc(raw_s0); ds1 = sigmoidf_acc(raw_s1);
+    }
+    if (act & B2S_ACT_OPACITY_SIGMOID) { op = sigmoidf_acc(raw_op); dop = op * (1.0f - op); }
   }
+  const float inv_op = (op > 0.0f) ? dop / op : dop;   // at op == 0 the blend backward accumulated sum E*t directly
   float coef[12], gcoef[12];
   {
     const float4* cp = reinterpret_cast<const float4*>(colors + (size_t)ii * 48 + sub * 12);
@@ -550,48 +573,51 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
       for (int q = threadIdx.x; q < words; q += PRE_BLOCK) dst[q] = src[q];
       __syncthreads();
     }
+    // the next view's sums are fetched while this view's chain runs (the loop is otherwise one long
+    // dependent chain behind three 16-byte loads)
+    const float4* ga = gacc + ((size_t)vbase * n + ii) * 3;
+    float4 g0 = __ldg(ga), g1 = make_float4(0.f, 0.f, 0.f, 0.f), g2 = __ldg(ga + 2);
+    if (sub == 0) g1 = __ldg(ga + 1);
     for (int vl = 0; vl < vcount; ++vl) {
       const ViewParams& vp = (views != nullptr) ? sv[vl] : single;
-      const float4* ga = gacc + ((size_t)(vbase + vl) * n + ii) * 3;
-      const float4 g0 = __ldg(ga);     // {dR, dG, dB, dZ}: zero row when the Gaussian is culled in this view
-      const float4 g2 = __ldg(ga + 2); // {Syy, colour clamp mask, -, -}
-      const int cmask = __float_as_int(g2.y);
-      const float dc0 = (cmask & 1) ? g0.x : 0.0f, dc1 = (cmask & 2) ? g0.y : 0.0f, dc2 = (cmask & 4) ? g0.z : 0.0f;
+      const float4 c0 = g0, c1 = g1, c2 = g2;
+      if (vl + 1 < vcount) {
+        const float4* gn = gacc + ((size_t)(vbase + vl + 1) * n + ii) * 3;
+        g0 = __ldg(gn); g2 = __ldg(gn + 2);
+        if (sub == 0) g1 = __ldg(gn + 1);
+      }
+      // c0 = {dR, dG, dB, dZ} (zero row when the Gaussian is culled in this view), c2 = {Syy, colour clamp mask, -, -}
+      const int cmask = __float_as_int(c2.y);
+      const float dc0 = (cmask & 1) ? c0.x : 0.0f, dc1 = (cmask & 2) ? c0.y : 0.0f, dc2 = (cmask & 4) ? c0.z : 0.0f;
       if (sub == 0) {                  // warp uniform: projection -> sigma / opacity / position chain
-        const float4 g1 = __ldg(ga + 1);
-        const float s0 = act_scale(vp, raw_s0), s1 = act_scale(vp, raw_s1), op = act_opac(vp, raw_op);
         const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
         if (pr.ok) {
-          float dZ = g0.w;
-          const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
-          float go = (op > 0.0f) ? S / op : S;
-          if (vp.act & B2S_ACT_OPACITY_SIGMOID) go *= op * (1.0f - op);
-          gop += go;
-          const float isx2 = 1.0f / (pr.sx * pr.sx), isy2 = 1.0f / (pr.sy * pr.sy);
+          float dZ = c0.w;
+          const float S = c1.x, Sx = c1.y, Sxx = c1.z, Sy = c1.w, Syy = c2.x;
+          gop = fmaf(S, inv_op, gop);
+          const float rsx = __frcp_rn(pr.sx), rsy = __frcp_rn(pr.sy), rz = __frcp_rn(pr.zabs);
+          const float isx2 = rsx * rsx, isy2 = rsy * rsy;
           const float dpx = Sx * isx2, dpy = Sy * isy2;
-          const float dsx = Sxx * isx2 / pr.sx, dsy = Syy * isy2 / pr.sy;
-          if (pr.ax >= 1.0f) {
+          const float dsx = Sxx * isx2 * rsx, dsy = Syy * isy2 * rsy;
+          if (pr.ax >= 1.0f) {         // clamp_min(1) passes the gradient on [1, inf)
             const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s0 > 0.f) - (s0 < 0.f)) : 1.0f;
-            float t = dsx * sgn * (0.5f * vp.wf * vp.fx / pr.zabs);
-            if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s0);
-            gs0 += t;
-            dZ -= dsx * pr.ax / pr.zabs;
+            gs0 = fmaf(dsx * sgn, 0.5f * vp.wf * vp.fx * rz, gs0);
+            dZ -= dsx * pr.ax * rz;
           }
           if (pr.ay >= 1.0f) {
             const float sgn = (vp.style == B2S_STYLE_TORCH) ? ((s1 > 0.f) - (s1 < 0.f)) : 1.0f;
-            float t = dsy * sgn * (0.5f * vp.hf * vp.fy / pr.zabs);
-            if (vp.act & B2S_ACT_SCALES_SOFTPLUS) t *= sigmoidf_acc(raw_s1);
-            gs1 += t;
-            dZ -= dsy * pr.ay / pr.zabs;
+            gs1 = fmaf(dsy * sgn, 0.5f * vp.hf * vp.fy * rz, gs1);
+            dZ -= dsy * pr.ay * rz;
           }
           float dcam[4] = {0.f, 0.f, 0.f, 0.f};
           if (fabsf(pr.zcam) >= 1e-6f) dcam[2] = dZ * ((pr.zcam > 0.f) ? 1.0f : -1.0f);
+          const float rw = __frcp_rn(pr.wsafe);
           const float dnx = dpx * 0.5f * vp.wm1, dny = -dpy * 0.5f * vp.hm1;
           float dclip[4];
-          dclip[0] = dnx / pr.wsafe;
-          dclip[1] = dny / pr.wsafe;
+          dclip[0] = dnx * rw;
+          dclip[1] = dny * rw;
           dclip[2] = 0.0f;
-          dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) / pr.wsafe;
+          dclip[3] = (fabsf(pr.w) < 1e-8f) ? 0.0f : -(dnx * pr.ndcx + dny * pr.ndcy) * rw;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -611,6 +637,8 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
       }
     }
   }
+  gs0 *= ds0;    // d softplus / d raw, applied once to the view sums
+  gs1 *= ds1;
   // fold the four groups' d/dmean
   if (sub != 0) {
     gm_part[sub - 1][0][slot] = gm[0];

@@ -33,7 +33,8 @@ class FitDriver:
                  cameras: Sequence[Tuple[Sequence[float], Sequence[float]]], device: torch.device,
                  lr: float = 0.02, silhouette_weight: float = 0.2, reg_opacity: float = 1e-3,
                  reg_scale: float = 1e-3, cutoff_sigma: float = 5.0, background=(0.0, 0.0, 0.0),
-                 rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25):
+                 rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
+                 fused_loss: bool = True):
         if device.type != "cuda":
             raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
         self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
@@ -51,14 +52,24 @@ class FitDriver:
         self._layout(self.n)
         self.step_no = 0
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=device)
-        self.rgb = torch.empty((height, width, 3), dtype=torch.float32, device=device)
-        self.alpha = torch.empty((height, width), dtype=torch.float32, device=device)
-        self.g_rgb = torch.empty_like(self.rgb)
-        self.g_alpha = torch.empty_like(self.alpha)
+        # View lanes: lane l owns its own per-view buffers (images, image gradients, state, workspace, loss and
+        # overflow accumulators) and a CUDA stream; view k of this rank runs on lane k % lanes, so the small
+        # latency-bound kernels of one view (scans, finalize, loss, g-buffer) overlap the blend kernels of another.
+        self.lanes = max(1, int(lanes))
+        self.active_lanes = self.lanes            # <= lanes; 1 serialises the views on the caller's stream
+        self.fused_loss = bool(fused_loss)
+        self.rgb_l = [torch.empty((height, width, 3), dtype=torch.float32, device=device) for _ in range(self.lanes)]
+        self.alpha_l = [torch.empty((height, width), dtype=torch.float32, device=device) for _ in range(self.lanes)]
+        self.g_rgb_l = [torch.empty_like(t) for t in self.rgb_l]
+        self.g_alpha_l = [torch.empty_like(t) for t in self.alpha_l]
+        self.loss_l = [torch.zeros(1, dtype=torch.float32, device=device) for _ in range(self.lanes)]
+        self.overflow_l = [torch.zeros(1, dtype=torch.int32, device=device) for _ in range(self.lanes)]
+        self.rgb, self.alpha = self.rgb_l[0], self.alpha_l[0]
         self.pair_slack = pair_slack
         self.max_pairs = 0
         self.state = self.ws = None
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.state_l = self.ws_l = None
+        self._lane_streams = None
         self.targets: dict = {}
         self.masks: dict = {}
         # per-view constant blocks for the multi-view chain rule, uploaded once (cameras are fixed)
@@ -134,9 +145,10 @@ class FitDriver:
             L = capi.lib()
             self.state_bytes = L.b2s_state_bytes(self.n, self.W, self.H, self.max_pairs)
             self.ws_bytes = L.b2s_workspace_bytes(self.n, self.W, self.H, self.max_pairs)
-            self.state = torch.empty(self.state_bytes, dtype=torch.uint8, device=self.dev)
-            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
-            self._counters = self.state[:16].view(torch.int32)   # needed(lo,hi), kept, overflow
+            self.state_l = [torch.empty(self.state_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
+            self.ws_l = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
+            self._counters_l = [st[:16].view(torch.int32) for st in self.state_l]   # needed(lo,hi), kept, overflow
+            self.state, self.ws = self.state_l[0], self.ws_l[0]
         return worst
 
     # ---- targets -------------------------------------------------------------------------------
@@ -158,19 +170,54 @@ class FitDriver:
         return out_rgb, out_alpha
 
     # ---- one fit iteration -------------------------------------------------------------------
-    def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor]):
+    def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor], lane: int = 0):
+        """forward + loss + blend backward of view i on the CURRENT stream with lane `lane`'s buffers."""
         L, ctx, st = capi.lib(), capi.ctx(self.dev.index), _stream()
         pc = C.byref(self.params_c[i])
+        rgb, alpha, g_rgb, g_alpha = self.rgb_l[lane], self.alpha_l[lane], self.g_rgb_l[lane], self.g_alpha_l[lane]
+        state, ws = self.state_l[lane], self.ws_l[lane]
+        if self.fused_loss:
+            # accumulators only: the loss and its image gradients are evaluated inside the g-buffer kernel
+            capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
+                                     self._pp(self.o_opac), self.n, self.max_pairs, None, None, None,
+                                     _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
+            self.overflow_l[lane] += self._counters_l[lane][3]
+            capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask), self.w_sil,
+                                                1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), _ptr(ws),
+                                                self.ws_bytes, _ptr(self.gacc[slot]), st))
+            return
         capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
-                                 self._pp(self.o_opac), self.n, self.max_pairs, _ptr(self.rgb), _ptr(self.alpha), None,
-                                 _ptr(self.state), self.state_bytes, _ptr(self.ws), self.ws_bytes, st))
-        self.overflow += self._counters[3]
-        capi.check(L.b2s_fit_loss(ctx, _ptr(self.rgb), _ptr(self.alpha), _ptr(tgt), _ptr(mask), self.W, self.H,
-                                  self.w_sil, 1.0 / self.num_views, _ptr(self.g_rgb),
-                                  _ptr(self.g_alpha) if mask is not None else None, _ptr(self.loss_dev), st))
-        capi.check(L.b2s_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(self.g_rgb),
-                                        _ptr(self.g_alpha) if mask is not None else None, None, _ptr(self.state),
-                                        _ptr(self.ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
+                                 self._pp(self.o_opac), self.n, self.max_pairs, _ptr(rgb), _ptr(alpha), None,
+                                 _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
+        self.overflow_l[lane] += self._counters_l[lane][3]
+        capi.check(L.b2s_fit_loss(ctx, _ptr(rgb), _ptr(alpha), _ptr(tgt), _ptr(mask), self.W, self.H,
+                                  self.w_sil, 1.0 / self.num_views, _ptr(g_rgb),
+                                  _ptr(g_alpha) if mask is not None else None, _ptr(self.loss_l[lane]), st))
+        capi.check(L.b2s_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(g_rgb),
+                                        _ptr(g_alpha) if mask is not None else None, None, _ptr(state),
+                                        _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
+
+    def _streams(self):
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.lanes)]
+            self._lane_done = [torch.cuda.Event() for _ in range(self.lanes)]
+            self._step_begin = torch.cuda.Event()
+        return self._lane_streams
+
+    def _fork(self, main):
+        """Lane streams start after everything already queued on the caller's stream (the last Adam step)."""
+        streams = self._streams()
+        self._step_begin.record(main)
+        for s in streams:
+            s.wait_event(self._step_begin)
+
+    def _join(self, main):
+        for l, s in enumerate(self._streams()):
+            self._lane_done[l].record(s)
+            main.wait_event(self._lane_done[l])
+        self.loss_dev.copy_(self.loss_l[0])                            # fixed order: deterministic
+        for t in self.loss_l[1:]:
+            self.loss_dev += t
 
     def _finish_step(self):
         # chain rule over ALL local views in one pass: gradients written once (no per-view read-modify-write)
@@ -197,48 +244,72 @@ class FitDriver:
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            self.loss_dev.zero_()
-            for k, i in enumerate(self.views):
-                self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i))
+            main = torch.cuda.current_stream()
+            for t in self.loss_l:
+                t.zero_()
+            nl = max(1, min(self.active_lanes, self.lanes))
+            if nl == 1:
+                for k, i in enumerate(self.views):
+                    self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i))
+                self.loss_dev.copy_(self.loss_l[0])
+            else:
+                self._fork(main)
+                for k, i in enumerate(self.views):
+                    lane = k % nl
+                    with torch.cuda.stream(self._lane_streams[lane]):
+                        self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i), lane)
+                self._join(main)
             self._finish_step()
         return self.loss_dev
 
     def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None) -> float:
         """Same iteration fed from PINNED HOST buffers: every view's target (and mask) is copied
-        host->device inside the step (double-buffered on a side stream so the copy of view k+1
-        overlaps the kernels of view k) and the loss is read back to the host at the end."""
+        host->device inside the step (two staging slots per lane on a side stream, so the copy of a later
+        view overlaps the kernels of the current ones) and the loss is read back to the host at the end."""
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
+            nl = max(1, min(self.active_lanes, self.lanes))
+            nslots = 2 * self.lanes
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.dev)
-                self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(2)]
-                self._ev_ready = [torch.cuda.Event() for _ in range(2)]
-                self._ev_free = [torch.cuda.Event() for _ in range(2)]
+                self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(nslots)]
+                self._ev_ready = [torch.cuda.Event() for _ in range(nslots)]
+                self._ev_free = [torch.cuda.Event() for _ in range(nslots)]
             main = torch.cuda.current_stream()
-            self.loss_dev.zero_()
+            for t in self.loss_l:
+                t.zero_()
             use_mask = host_masks is not None
+            if nl > 1:
+                self._fork(main)
 
             def issue(k):
-                slot = k % 2
+                slot = k % nslots
                 i = self.views[k]
                 with torch.cuda.stream(self._copy_stream):
-                    if k >= 2:
+                    if k >= nslots:
                         self._copy_stream.wait_event(self._ev_free[slot])
                     self._stage[slot][0].copy_(host_targets[i], non_blocking=True)
                     if use_mask:
                         self._stage[slot][1].copy_(host_masks[i], non_blocking=True)
                     self._ev_ready[slot].record(self._copy_stream)
 
-            if self.views:
-                issue(0)
+            nv = len(self.views)
+            for k in range(min(nl, nv)):
+                issue(k)
             for k, i in enumerate(self.views):
-                if k + 1 < len(self.views):
-                    issue(k + 1)
-                slot = k % 2
-                main.wait_event(self._ev_ready[slot])
-                self._view_fwd_bwd(k, i, self._stage[slot][0], self._stage[slot][1] if use_mask else None)
-                self._ev_free[slot].record(main)
+                if k + nl < nv:
+                    issue(k + nl)
+                slot, lane = k % nslots, k % nl
+                st = self._lane_streams[lane] if nl > 1 else main
+                with torch.cuda.stream(st):
+                    st.wait_event(self._ev_ready[slot])
+                    self._view_fwd_bwd(k, i, self._stage[slot][0], self._stage[slot][1] if use_mask else None, lane)
+                    self._ev_free[slot].record(st)
+            if nl > 1:
+                self._join(main)
+            else:
+                self.loss_dev.copy_(self.loss_l[0])
             self._finish_step()
             return float(self.loss_dev.item())
 
@@ -273,12 +344,13 @@ class FitDriver:
                 self.means().copy_(om[:k]); self.scales_raw().copy_(os_[:k])
                 self.opacities_raw().copy_(oo[:k]); self.colors_raw().copy_(colors)
             self.gacc = torch.empty((max(len(self.views), 1), max(k, 1), 12), dtype=torch.float32, device=self.dev)
-            self.state = self.ws = None
+            self.state = self.ws = self.state_l = self.ws_l = None
             self.plan()
         return k
 
     def check_overflow(self) -> bool:
         """True if any view since the last call needed more pairs than the buffers hold."""
-        v = int(self.overflow.item())
-        self.overflow.zero_()
+        v = sum(int(t.item()) for t in self.overflow_l)
+        for t in self.overflow_l:
+            t.zero_()
         return v != 0

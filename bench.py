@@ -34,9 +34,6 @@ import torch  # noqa: E402
 import scenes  # noqa: E402
 
 METRIC = "fit iters/s (fwd+bwd+Adam, all views)"
-# issue slots (warp instructions per lane) per evaluated pixel-pair, from the SASS inner loops
-# (DESIGN.md section 4): forward 8 FP32 + 1 MUFU.EX2, backward 11 FP32 + 1 MUFU.EX2 (+1 LDS)
-INSTR_PER_PAIR = {"blend_fwd": 9.5, "blend_bwd": 12.0}
 NUM_SMS, LANES_PER_SM = 148, 128
 
 
@@ -52,6 +49,7 @@ def parse_args():
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--lanes", type=int, default=4, help="concurrent view lanes (CUDA streams) per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-render", action="store_true")
@@ -234,7 +232,7 @@ def workload_config(args):
     return {"workload": f"synthetic fit: {args.n} Gaussians SH{args.sh} (N,{args.sh},3), {args.views} orbit views at "
                         f"{args.width}x{args.height}, fwd+bwd+Adam, views sharded over ranks (BASELINE configs[3])",
             "gaussians": args.n, "sh_coeffs": args.sh, "views": args.views, "width": args.width, "height": args.height,
-            "cutoff_sigma": 5.0, "loss": "L1 recon + 0.2*L1 silhouette + 1e-3 reg", "parallelism": "views round-robin",
+            "cutoff_sigma": 5.0, "loss": "L1 recon + 0.2*L1 silhouette + 1e-3 reg", "parallelism": "views round-robin over ranks",
             "l2_note": "per-step inputs (params 220 MB + targets/masks 2.1 GB at N=1) exceed the 126 MB L2"}
 
 
@@ -334,7 +332,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- the model being fitted (seed 1234) ----
-    drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world)
+    drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes)
     means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
@@ -352,9 +350,6 @@ def main():
     barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if not args.no_timing:
-        capi.timing_enable(local_rank, True)
-        capi.timing_read(local_rank)
     launches0 = capi.lib().b2s_launch_count()
     if sampler:
         sampler.start()
@@ -368,8 +363,26 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     launches = capi.lib().b2s_launch_count() - launches0
-    stages = capi.timing_read(local_rank) if not args.no_timing else {}
-    capi.timing_enable(local_rank, False)
+    # ---- per-stage CUDA-event spans.  With one lane the stages of the timed steps themselves are bracketed; with
+    # several lanes kernels of different views overlap and a span no longer times one kernel, so the SAME K steps are
+    # repeated once more on a single lane with the brackets on (its total is reported as ms_per_step_one_lane).
+    stages, ms_one_lane = {}, None
+    if not args.no_timing:
+        drv.active_lanes = 1
+        drv.step()
+        capi.timing_enable(local_rank, True)
+        capi.timing_read(local_rank)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0e.record()
+        for _ in range(args.steps):
+            drv.step()
+        t1e.record()
+        barrier()
+        ms_one_lane = t0e.elapsed_time(t1e) / args.steps
+        stages = capi.timing_read(local_rank)
+        capi.timing_enable(local_rank, False)
+        drv.active_lanes = drv.lanes
     overflowed = drv.check_overflow()
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     p2_all = torch.tensor([p2], device=device, dtype=torch.float64)
@@ -424,11 +437,18 @@ def main():
     n, sh, hw = args.n, args.sh, args.width * args.height
     n_tiles = ((args.width + 15) // 16) * ((args.height + 15) // 16)
     passes = (max(1, math.ceil(math.log2(max(n_tiles, 2)))) + 7) // 8     # tile bits only (sort_depth=0)
-    alg_bytes = {   # per view (per step for adam), DESIGN.md section 4
+    alg_bytes = {   # per span (= per view; preprocess_bwd and adam: per step), DESIGN.md section 4
         "preprocess": n * (28 + 12 * sh + 64), "bin": n * 16 + p1 * 12, "sort": passes * p1 * 32, "ranges": p1 * 8,
-        "loss": hw * 48, "preprocess_bwd": n * (48 + 28 + 12 * sh + 2 * (28 + 12 * sh)),
-        "adam": (7 + 3 * sh) * n * 28 / max(nv, 1),
+        "loss": hw * 48, "preprocess_bwd": n * (48 * nv + 2 * (28 + 12 * sh)),
+        "adam": (7 + 3 * sh) * n * 28,
     }
+    # SURVEY 8(d) per-unit figures of the blend: FP32 lane-instructions (+1 MUFU.EX2) per algorithmic pixel-pair,
+    # each FP32 instruction counted as one FMA = 2 flop
+    flop_per_pair = {"blend_fwd": 2 * 11 + 1, "blend_bwd": 2 * 24 + 1}
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+    tensor_src = ("measured dense bf16, sustained (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks
+                  else "nominal 2250 TFLOP/s dense bf16 (B200_PROFILING.md fallback)")
+    fp32_pipe_tflops = issue_peak * 2 / 1e12
     table = {}
     for name, (sms, spans) in stages.items():
         if spans == 0:
@@ -436,26 +456,35 @@ def main():
         per_launch_ms = sms / spans
         row = {"ms_per_step": sms / args.steps, "spans": spans, "ms_per_span": per_launch_ms}
         if name in alg_bytes:
-            per_span_bytes = alg_bytes[name] if name != "adam" else (7 + 3 * sh) * n * 28
-            gbs = per_span_bytes / (per_launch_ms * 1e-3) / 1e9
+            gbs = alg_bytes[name] / (per_launch_ms * 1e-3) / 1e9
             row.update({"bound": "hbm", "achieved_gbs": gbs, "frac": gbs / hbm_peak})
         else:
             pairs_per_span = p2_rank0 / max(nv, 1)
-            ginstr = pairs_per_span * INSTR_PER_PAIR[name] / (per_launch_ms * 1e-3)
-            row.update({"bound": "fp32_issue", "achieved_ginstr_s": ginstr / 1e9, "frac": ginstr / issue_peak,
+            tflops = pairs_per_span * flop_per_pair[name] / (per_launch_ms * 1e-3) / 1e12
+            row.update({"bound": "tensor", "achieved_tflops": tflops, "frac": tflops / tensor_peak,
+                        "x_fp32_pipe_peak": tflops / fp32_pipe_tflops,
                         "gpairs_s": pairs_per_span / (per_launch_ms * 1e-3) / 1e9})
         table[name] = row
     roofline = None
     if "blend_bwd" in table:
         b = table["blend_bwd"]
-        roofline = {"kernel": "blend_wsum_bwd_kernel", "bound": "fp32_issue",
-                    "achieved": b["achieved_ginstr_s"], "peak": issue_peak / 1e9, "unit": "Ginstr/s (FP32 lane-instructions)",
-                    "frac": b["frac"], "traffic": None,
-                    "note": f"algorithmic pixel-pairs P2={p2_rank0 / max(nv, 1):.3e}/view x {INSTR_PER_PAIR['blend_bwd']} issue "
-                            f"slots/pair; peak = 148 SMs x 128 lanes x {sm_mhz:.0f} MHz (SM clock measured under load); "
-                            f"tile-pairs P1<={p1:.3e}/view => the kernel evaluates 256*P1 = {256 * p1 / max(p2_rank0 / max(nv, 1), 1):.2f}x P2; "
-                            f"the path has no tensor-core stage (north_star); HBM-bound stages are in roofline_stages vs {hbm_src}",
-                    "share_of_step": b["ms_per_step"] / ms_per_step}
+        traffic = None
+        try:   # dram bytes of the kernel from the committed ncu --set full capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["blend_wsum_bwd_mma_kernel"]
+        except Exception:
+            pass
+        roofline = {"kernel": "blend_wsum_bwd_mma_kernel", "bound": "tensor",
+                    "achieved": b["achieved_tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": b["frac"], "traffic": traffic,
+                    "note": f"algorithmic work = P2 pixel-pairs/view ({p2_rank0 / max(nv, 1):.3e}) x {flop_per_pair['blend_bwd']} flop "
+                            f"(SURVEY 8d: 24 FP32 + 1 MUFU per pair) / mean launch span; peak = {tensor_src}. The kernel runs the "
+                            f"separable sums as fp16 hi/lo mma.sync GEMMs, so the same work is {b['x_fp32_pipe_peak']:.2f}x the FP32-pipe "
+                            f"peak ({fp32_pipe_tflops:.1f} TFLOP/s at {sm_mhz:.0f} MHz); it is bound by operand generation "
+                            f"(MUFU.EX2 + fp16 splits + FP32 epilogue issue slots), not by MMA rate (DESIGN.md section 5). "
+                            f"tile-pairs P1<={p1:.3e}/view; HBM-bound stages are in roofline_stages vs {hbm_src}",
+                    "share_of_step": b["ms_per_step"] / (ms_one_lane or ms_per_step),
+                    "timing": "mean CUDA-event span of the kernel over the K steps repeated on one lane right after the "
+                              "timed region (the timed region itself overlaps views on --lanes streams)"}
 
     cpu = None
     if not args.no_cpu and world == 1:
@@ -479,7 +508,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_stages": table, "cpu_baseline": cpu, "render": render,
+        "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "cpu_baseline": cpu, "render": render,
         "loss_last": loss_last, "pairs": {"P1_tile_pairs_worst_view": worst_p1, "P2_pixel_pairs_rank0_views": p2_rank0,
                                           "P2_all_ranks": float(p2_all.item())},
         "overflow": bool(overflowed),

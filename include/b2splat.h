@@ -94,8 +94,9 @@ int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const
                     size_t ws_bytes, void* stream);
 
 /* ---- differentiable render (stands in for render_gaussians_torch) --------------------- */
-/* out_rgb (H,W,3), out_alpha (H,W), out_depth (H,W) float32; alpha/depth may be NULL.
- * colors: (N,3) or (N,sh_coeffs,3).  If the view needs more than max_pairs pairs the extra
+/* out_rgb (H,W,3), out_alpha (H,W), out_depth (H,W) float32; alpha/depth may be NULL, and in the
+ * weighted-sum mode out_rgb may be NULL too (the fit loop: the accumulators kept in `state` are all
+ * b2s_fit_backward_blend needs).  colors: (N,3) or (N,sh_coeffs,3).  If the view needs more than max_pairs pairs the extra
  * ones are dropped and state's overflow counter is set (query with b2s_state_info). */
 int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales,
                 const float* colors, const float* opacities, int n, int64_t max_pairs,
@@ -124,6 +125,13 @@ int b2s_pack_views(const b2s_params* params, int num_views, void* out_host);
 int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* g_rgb,
                        const float* g_alpha, const float* g_depth, const void* state, void* workspace,
                        size_t ws_bytes, float* gacc_out, void* stream);
+/* b2s_fit_loss + b2s_backward_blend in one call (python/fit_multiview_stub.py:292-297 and its backward): the
+ * per-view loss  mean|rgb-tgt| + w_sil*mean|alpha-mask|  is evaluated from the accumulators b2s_forward left
+ * in `state` and its image gradients, scaled by `scale` (1/V), go straight into the blend backward; no
+ * rgb / alpha / gradient images are read or written.  mask may be NULL.  Adds scale*loss to *loss_accum. */
+int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
+                           const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
+                           void* workspace, size_t ws_bytes, float* gacc_out, void* stream);
 /* Chain rule over all views: views_dev = device copy of the b2s_pack_views block. */
 int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
                         const float* scales, const float* colors, const float* opacities, int n,

@@ -132,6 +132,42 @@ def test_step_from_host_equals_device_step():
     assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_view_lanes_equal_single_stream(lanes):
+    """Views spread over concurrent CUDA-stream lanes: same loss (fixed summation order) and the same
+    parameters as the one-stream schedule, through both the device-target and the host-target entry."""
+    S = _setup(4, V=5)
+    d1, d2, d3 = _driver(S), _driver(S, lanes=lanes), _driver(S, lanes=lanes)
+    host_t = {i: torch.from_numpy(S["tgts"][i]).pin_memory() for i in range(S["V"])}
+    host_m = {i: torch.from_numpy(S["masks"][i]).pin_memory() for i in range(S["V"])}
+    for _ in range(3):
+        l1 = float(d1.step().item())
+        l2 = float(d2.step().item())
+        l3 = d3.step_from_host(host_t, host_m)
+        assert abs(l1 - l2) <= 1e-6 and abs(l1 - l3) <= 1e-6
+    assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
+    assert rel_l2(d1.p.cpu().numpy(), d3.p.cpu().numpy()) <= 1e-4
+    assert not d2.check_overflow()
+
+
+def test_fused_loss_backward_equals_separate_kernels():
+    """b2s_fit_backward_blend (loss evaluated from the accumulators inside the g-buffer kernel) against
+    b2s_forward -> b2s_fit_loss -> b2s_backward_blend: same loss, same gradients up to the atomics' order."""
+    S = _setup(16, V=4)
+    d1, d2 = _driver(S, fused_loss=False), _driver(S, fused_loss=True)
+    for _ in range(2):
+        l1, l2 = float(d1.step().item()), float(d2.step().item())
+        assert abs(l1 - l2) <= 1e-6
+        assert rel_l2(d1.g.cpu().numpy(), d2.g.cpu().numpy()) <= 1e-5
+    S = _setup(1, V=2)
+    for m in (True, False):      # with and without silhouette masks
+        d1, d2 = _driver(S, fused_loss=False), _driver(S, fused_loss=True)
+        if not m:
+            d1.masks, d2.masks = {}, {}
+        assert abs(float(d1.step().item()) - float(d2.step().item())) <= 1e-6
+        assert rel_l2(d1.g.cpu().numpy(), d2.g.cpu().numpy()) <= 1e-5
+
+
 def test_dropin_training_loop_matches_oracle_loop():
     """The reference script's flow (nn.Parameters -> activations -> per-view render -> loss ->
     backward -> torch Adam) through the drop-in render_gaussians_torch."""
