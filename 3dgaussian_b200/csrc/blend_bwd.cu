@@ -411,6 +411,148 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
 
+// One MMA step of the backward: 16 Gaussians (slots bt*16 .. bt*16+15 of the staged chunk) against the tile's
+// planes.  getB(r4) returns fragment registers 4*r4 .. 4*r4+3 of this lane (see gbuf_frag_kernel).
+template <bool DEPTH, class GetB>
+__device__ __forceinline__ void bwd_mma_step(const BmStage& st, int bt, int g, int t, const float (&cx)[4],
+                                             const float (&cy)[4], float k_us, GetB getB, float* __restrict__ gacc) {
+  constexpr int CH = DEPTH ? 5 : 4;
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  const int j[2] = {bt * 16 + g, bt * 16 + g + 8};
+  float4 ra[2], rb[2], rc[2];
+  // factors scaled by 2^8 (fp16 range), WITHOUT opacity, and the pixel offsets, as (q = 2h, 2h+1) pairs:
+  // the FP32 epilogue below runs on packed f32x2 instructions (half the issue slots)
+  float2 fx2[2][2], fy2[2][2], dx2[2][2], dy2[2][2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    ra[e] = st.a[j[e]];
+    rb[e] = st.b[j[e]];
+    rc[e] = st.c[j[e]];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float dxa = cx[2 * h] - ra[e].x, dxb = cx[2 * h + 1] - ra[e].x;
+      const float dya = cy[2 * h] - rb[e].x, dyb = cy[2 * h + 1] - rb[e].x;
+      dx2[e][h] = make_float2(dxa, dxb);
+      dy2[e][h] = make_float2(dya, dyb);
+      fx2[e][h] = make_float2(ex2_approx(fmaf(ra[e].y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra[e].y * dxb, dxb, 8.0f)));
+      fy2[e][h] = make_float2(ex2_approx(fmaf(rb[e].y * dya, dya, 8.0f)), ex2_approx(fmaf(rb[e].y * dyb, dyb, 8.0f)));
+    }
+  }
+  // A fragments (m16n8k16): a0 = (Gaussian g; K = 2t, 2t+1), a1 = (g+8; same K), a2 = (g; K = 2t+8, 2t+9),
+  // a3 = (g+8; same) -- K slots 2t, 2t+1, 2t+8, 2t+9 are this lane's coordinates q = 0..3.
+  uint32_t Ax[4], Ay[4];
+  Ax[0] = pack_h2(fx2[0][0].x, fx2[0][0].y); Ax[1] = pack_h2(fx2[1][0].x, fx2[1][0].y);
+  Ax[2] = pack_h2(fx2[0][1].x, fx2[0][1].y); Ax[3] = pack_h2(fx2[1][1].x, fx2[1][1].y);
+  Ay[0] = pack_h2(fy2[0][0].x, fy2[0][0].y); Ay[1] = pack_h2(fy2[1][0].x, fy2[1][0].y);
+  Ay[2] = pack_h2(fy2[0][1].x, fy2[0][1].y); Ay[3] = pack_h2(fy2[1][1].x, fy2[1][1].y);
+  // per-Gaussian partial sums of this lane as (q even, q odd) pairs, added horizontally after the sweeps:
+  //   Q[e][0..3] = dR dG dB dZ     Q[e][4..7] = S Sx Sxx Sy     Q[e][8] = Syy        (e = 0 -> Gaussian g, 1 -> g+8)
+  float2 Q[2][9];
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Q[e][k] = make_float2(0.f, 0.f);
+  float2 col2[2][4];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    col2[e][0] = bc2(rc[e].x); col2[e][1] = bc2(rc[e].y); col2[e][2] = bc2(rc[e].z); col2[e][3] = bc2(rc[e].w);
+  }
+
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // ---- U = fx . G for rows 8h..8h+7: accumulator pair (d[2e], d[2e+1]) = Gaussian e at rows q = 2h, 2h+1
+    float D[CH][4];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const uint4 b = getB(ch * 2 + h);              // {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
+      mma_f16(D[ch], Ax, b.z, b.w, zero4);
+      mma_f16(D[ch], Ax, b.x, b.y, D[ch]);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float2 uR = make_float2(D[0][2 * e], D[0][2 * e + 1]), uG = make_float2(D[1][2 * e], D[1][2 * e + 1]),
+                   uB = make_float2(D[2][2 * e], D[2][2 * e + 1]), uW = make_float2(D[3][2 * e], D[3][2 * e + 1]);
+      float2 T = __ffma2_rn(col2[e][0], uR, __ffma2_rn(col2[e][1], uG, __ffma2_rn(col2[e][2], uB, uW)));
+      if (DEPTH) {
+        const float2 uD = make_float2(D[CH - 1][2 * e], D[CH - 1][2 * e + 1]);
+        T = __ffma2_rn(col2[e][3], uD, T);
+        Q[e][3] = __ffma2_rn(fy2[e][h], uD, Q[e][3]);
+      }
+      const float2 a = __fmul2_rn(fy2[e][h], T);
+      Q[e][4] = __fadd2_rn(Q[e][4], a);
+      Q[e][7] = __ffma2_rn(a, dy2[e][h], Q[e][7]);
+      Q[e][8] = __ffma2_rn(__fmul2_rn(a, dy2[e][h]), dy2[e][h], Q[e][8]);
+      Q[e][0] = __ffma2_rn(fy2[e][h], uR, Q[e][0]);
+      Q[e][1] = __ffma2_rn(fy2[e][h], uG, Q[e][1]);
+      Q[e][2] = __ffma2_rn(fy2[e][h], uB, Q[e][2]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // ---- V = fy . G for columns 8h..8h+7
+    float D[CH][4];
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const uint4 b = getB(CH * 2 + ch * 2 + h);
+      mma_f16(D[ch], Ay, b.z, b.w, zero4);
+      mma_f16(D[ch], Ay, b.x, b.y, D[ch]);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float2 vR = make_float2(D[0][2 * e], D[0][2 * e + 1]), vG = make_float2(D[1][2 * e], D[1][2 * e + 1]),
+                   vB = make_float2(D[2][2 * e], D[2][2 * e + 1]), vW = make_float2(D[3][2 * e], D[3][2 * e + 1]);
+      float2 T = __ffma2_rn(col2[e][0], vR, __ffma2_rn(col2[e][1], vG, __ffma2_rn(col2[e][2], vB, vW)));
+      if (DEPTH) T = __ffma2_rn(col2[e][3], make_float2(D[CH - 1][2 * e], D[CH - 1][2 * e + 1]), T);
+      const float2 b = __fmul2_rn(__fmul2_rn(fx2[e][h], T), dx2[e][h]);
+      Q[e][5] = __fadd2_rn(Q[e][5], b);
+      Q[e][6] = __ffma2_rn(b, dx2[e][h], Q[e][6]);
+    }
+  }
+  float P[2][8], Syy[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) P[e][k] = Q[e][k].x + Q[e][k].y;
+    Syy[e] = Q[e][8].x + Q[e][8].y;
+  }
+  // ---- sum over the quad (the 4 lanes t = 0..3 share Gaussians g, g+8) by transposition: lane t ends
+  // with group t of {e0: dR dG dB dZ | e0: S Sx Sxx Sy | e1: dR.. | e1: S..} summed over the quad.
+  const bool up = (t & 2) != 0;                // lanes 2,3 keep Gaussian g+8, lanes 0,1 keep Gaussian g
+  const bool odd = (t & 1) != 0;               // odd lanes keep {S Sx Sxx Sy}, even lanes {dR dG dB dZ}
+  float v4[4];
+  {
+    float keep[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float send = up ? P[0][k] : P[1][k];
+      keep[k] = (up ? P[1][k] : P[0][k]) + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = odd ? keep[k] : keep[4 + k];
+      v4[k] = (odd ? keep[4 + k] : keep[k]) + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  }
+  float syy = (up ? Syy[1] : Syy[0]) + __shfl_xor_sync(0xffffffffu, up ? Syy[0] : Syy[1], 2);
+  syy += __shfl_xor_sync(0xffffffffu, syy, 1);
+  {
+    const int id = st.id[up ? j[1] : j[0]];
+    const float lop = up ? ra[1].z : ra[0].z;
+    // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
+    const bool zop = (lop == -INFINITY);
+    const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
+    if (id >= 0) {
+      float* dst = gacc + (size_t)id * GACC_F;
+      if (odd) {
+        red_add_v4(dst + 4, v4[0] * opk, zop ? 0.f : v4[1] * opk, zop ? 0.f : v4[2] * opk, zop ? 0.f : v4[3] * opk);
+      } else if (!zop) {
+        red_add_v4(dst, v4[0] * opk, v4[1] * opk, v4[2] * opk, v4[3] * opk);
+        atomicAdd(dst + 8, syy * opk);
+      }
+    }
+  }
+}
+
 template <bool DEPTH, int MINB>
 __global__ void __launch_bounds__(BM_WARPS * 32, MINB)
 blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
@@ -485,7 +627,6 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     cx[q] = (float)(tx * TILE + idx) + 0.5f;
     cy[q] = (float)(ty * TILE + idx) + 0.5f;
   }
-  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int c = 0; c < nchunks; ++c) {
     issue(c + BM_STAGES - 1, id_pf);
@@ -497,124 +638,106 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     for (int bt = 0; bt < 2; ++bt) {
       const int base = c * BM_STAGE + bt * 16;
       if (base >= n) break;                        // warp-uniform
-      const int j[2] = {bt * 16 + g, bt * 16 + g + 8};
-      float4 ra[2], rb[2], rc[2];
-      float fx[2][4], fy[2][4];                    // the factors scaled by 2^8 (fp16 range), WITHOUT opacity
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        ra[e] = st.a[j[e]];
-        rb[e] = st.b[j[e]];
-        rc[e] = st.c[j[e]];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float dx = cx[q] - ra[e].x, dy = cy[q] - rb[e].x;
-          fx[e][q] = ex2_approx(fmaf(ra[e].y * dx, dx, 8.0f));
-          fy[e][q] = ex2_approx(fmaf(rb[e].y * dy, dy, 8.0f));
-        }
-      }
-      // A fragments (m16n8k16): a0 = (Gaussian g; K = 2t, 2t+1), a1 = (g+8; same K), a2 = (g; K = 2t+8, 2t+9),
-      // a3 = (g+8; same) -- K slots 2t, 2t+1, 2t+8, 2t+9 are this lane's coordinates q = 0..3.
-      uint32_t Ax[4], Ay[4];
-      Ax[0] = pack_h2(fx[0][0], fx[0][1]); Ax[1] = pack_h2(fx[1][0], fx[1][1]);
-      Ax[2] = pack_h2(fx[0][2], fx[0][3]); Ax[3] = pack_h2(fx[1][2], fx[1][3]);
-      Ay[0] = pack_h2(fy[0][0], fy[0][1]); Ay[1] = pack_h2(fy[1][0], fy[1][1]);
-      Ay[2] = pack_h2(fy[0][2], fy[0][3]); Ay[3] = pack_h2(fy[1][2], fy[1][3]);
-      // per-Gaussian partial sums of this lane: e = 0 -> Gaussian g, e = 1 -> Gaussian g+8;
-      //   P[e][0..3] = dR dG dB dZ     P[e][4..7] = S Sx Sxx Sy     Syy[e]
-      float P[2][8], Syy[2] = {0.f, 0.f};
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) P[e][k] = 0.0f;
+      bwd_mma_step<DEPTH>(st, bt, g, t, cx, cy, k_us,
+                          [&](int r4) { return make_uint4(B[4 * r4], B[4 * r4 + 1], B[4 * r4 + 2], B[4 * r4 + 3]); }, gacc);
+    }
+    __syncwarp();
+  }
+  cp_async_wait_b<0>();
+}
 
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        // ---- U = fx . G for rows 8h..8h+7 (accumulator (e, q = 2h+{0,1}) = d[2e + {0,1}])
-        float D[CH][4];
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          const int r0 = (ch * 2 + h) * 4;           // hi: r0, r0+1 ; lo: r0+2, r0+3
-          mma_f16(D[ch], Ax, B[r0 + 2], B[r0 + 3], zero4);
-          mma_f16(D[ch], Ax, B[r0], B[r0 + 1], D[ch]);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const int q = 2 * h + qq, k = 2 * e + qq;
-            const float uR = D[0][k], uG = D[1][k], uB = D[2][k], uW = D[3][k];
-            float T = fmaf(rc[e].x, uR, fmaf(rc[e].y, uG, fmaf(rc[e].z, uB, uW)));
-            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][k], T);
-            const float f = fy[e][q], dy = cy[q] - rb[e].x;
-            const float a = f * T;
-            P[e][4] += a;
-            P[e][7] = fmaf(a, dy, P[e][7]);
-            Syy[e] = fmaf(a * dy, dy, Syy[e]);
-            P[e][0] = fmaf(f, uR, P[e][0]);
-            P[e][1] = fmaf(f, uG, P[e][1]);
-            P[e][2] = fmaf(f, uB, P[e][2]);
-            if (DEPTH) P[e][3] = fmaf(f, D[CH - 1][k], P[e][3]);
-          }
+// ---- v6: one CTA per work unit, the plane fragments in shared memory ------------------------------------
+// The register-resident fragments of the kernel above (64-80 registers) cap it at 12 warps per SM, and every
+// warp is one long dependent chain (LDS -> exponent -> EX2 -> pack -> 2 chained HMMA -> FP32 epilogue -> quad
+// shuffles -> RED), so the SM idles on latency.  Here the 4 warps of a CTA share ONE tile: its fragment image
+// (8-10 KB) is fetched once into shared memory and each MMA pair reads its 4 registers with one LDS.128
+// (conflict free: lane-major uint4); warp w takes the 32-Gaussian chunks w, w+4, ... of the unit.  Every Gaussian
+// still belongs to exactly one warp step, so there is no cross-warp reduction.
+template <bool DEPTH>
+__global__ void __launch_bounds__(BM_WARPS * 32, 4)
+blend_wsum_bwd_cta_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                          const int2* __restrict__ units, const uint4* __restrict__ frag,
+                          const float* __restrict__ tile_scale, float* __restrict__ gacc) {
+  constexpr int CH = DEPTH ? 5 : 4;
+  constexpr int NREG = CH * 16;
+  __shared__ __align__(16) BmStage ring[BM_WARPS][BM_STAGES];
+  __shared__ __align__(16) uint4 sB[NREG / 4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x;
+  if (u >= unit_start[vp.n_tiles]) return;             // block-uniform
+  const int2 ud = units[u];
+  const int tile = ud.x;
+  const int2 rg = ranges[tile];
+  const int start = rg.x + ud.y * SEG;
+  const int n = min(SEG, rg.y - start);
+  if (n <= 0) return;                                   // block-uniform
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int g = lane >> 2, t = lane & 3;
+  BmStage* my = ring[warp];
+
+  // the tile's plane fragments: first cp.async group of every thread (groups retire in order)
+  {
+    const uint4* ft = frag + (size_t)tile * (NREG / 4) * 32;
+    uint4* dst = &sB[0][0];
+    for (int k = threadIdx.x; k < (NREG / 4) * 32; k += BM_WARPS * 32) cp_async16_b(dst + k, ft + k);
+    cp_async_commit_b();
+  }
+  // chunks of this warp: global chunk index = warp + BM_WARPS * k
+  const int nchunks_all = (n + BM_STAGE - 1) / BM_STAGE;
+  const int nchunks = (nchunks_all - warp + BM_WARPS - 1) / BM_WARPS;      // may be 0
+  auto issue = [&](int k, int id) {      // local chunk k, this lane's Gaussian id (already loaded)
+    if (k < nchunks) {
+      BmStage& st = my[k % BM_STAGES];
+      if ((warp + BM_WARPS * k) * BM_STAGE + lane < n) {
+        const float4* src = rec + 3 * (size_t)id;
+        cp_async16_b(&st.a[lane], src);
+        cp_async16_b(&st.b[lane], src + 1);
+        cp_async16_b(&st.c[lane], src + 2);
+        st.id[lane] = id;
+      } else {   // padding of the last step: a record whose factors underflow to exactly 0 (no selects below)
+        st.a[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.b[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
+        st.c[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        st.id[lane] = -1;
       }
+    }
+    cp_async_commit_b();
+  };
+  auto load_id = [&](int k) -> int {
+    const int i = (warp + BM_WARPS * k) * BM_STAGE + lane;
+    return (k < nchunks && i < n) ? __ldg(vals + start + i) : 0;
+  };
+  {
+    int ids[BM_STAGES - 1];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        // ---- V = fy . G for columns 8h..8h+7
-        float D[CH][4];
+    for (int k = 0; k < BM_STAGES - 1; ++k) ids[k] = load_id(k);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          const int r0 = CH * 8 + (ch * 2 + h) * 4;
-          mma_f16(D[ch], Ay, B[r0 + 2], B[r0 + 3], zero4);
-          mma_f16(D[ch], Ay, B[r0], B[r0 + 1], D[ch]);
-        }
+    for (int k = 0; k < BM_STAGES - 1; ++k) issue(k, ids[k]);
+  }
+  int id_pf = load_id(BM_STAGES - 1);
+  const float k_us = __ldg(tile_scale + tile);       // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
+  float cx[4], cy[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const int q = 2 * h + qq, k = 2 * e + qq;
-            float T = fmaf(rc[e].x, D[0][k], fmaf(rc[e].y, D[1][k], fmaf(rc[e].z, D[2][k], D[3][k])));
-            if (DEPTH) T = fmaf(rc[e].w, D[CH - 1][k], T);
-            const float dx = cx[q] - ra[e].x;
-            const float b = fx[e][q] * T * dx;
-            P[e][5] += b;
-            P[e][6] = fmaf(b, dx, P[e][6]);
-          }
-      }
-      // ---- sum over the quad (the 4 lanes t = 0..3 share Gaussians g, g+8) by transposition: lane t ends
-      // with group t of {e0: dR dG dB dZ | e0: S Sx Sxx Sy | e1: dR.. | e1: S..} summed over the quad.
-      const bool up = (t & 2) != 0;                // lanes 2,3 keep Gaussian g+8, lanes 0,1 keep Gaussian g
-      const bool odd = (t & 1) != 0;               // odd lanes keep {S Sx Sxx Sy}, even lanes {dR dG dB dZ}
-      float v4[4];
-      {
-        float keep[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float send = up ? P[0][k] : P[1][k];
-          keep[k] = (up ? P[1][k] : P[0][k]) + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float send = odd ? keep[k] : keep[4 + k];
-          v4[k] = (odd ? keep[4 + k] : keep[k]) + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-      }
-      float syy = (up ? Syy[1] : Syy[0]) + __shfl_xor_sync(0xffffffffu, up ? Syy[0] : Syy[1], 2);
-      syy += __shfl_xor_sync(0xffffffffu, syy, 1);
-      {
-        const int id = st.id[up ? j[1] : j[0]];
-        const float lop = up ? ra[1].z : ra[0].z;
-        // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
-        const bool zop = (lop == -INFINITY);
-        const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
-        if (id >= 0) {
-          float* dst = gacc + (size_t)id * GACC_F;
-          if (odd) {
-            red_add_v4(dst + 4, v4[0] * opk, zop ? 0.f : v4[1] * opk, zop ? 0.f : v4[2] * opk, zop ? 0.f : v4[3] * opk);
-          } else if (!zop) {
-            red_add_v4(dst, v4[0] * opk, v4[1] * opk, v4[2] * opk, v4[3] * opk);
-            atomicAdd(dst + 8, syy * opk);
-          }
-        }
-      }
+  for (int q = 0; q < 4; ++q) {
+    const int idx = 8 * (q >> 1) + 2 * t + (q & 1);
+    cx[q] = (float)(tx * TILE + idx) + 0.5f;
+    cy[q] = (float)(ty * TILE + idx) + 0.5f;
+  }
+  cp_async_wait_b<BM_STAGES - 1>();                    // the fragment group (oldest) has landed for this thread
+  __syncthreads();                                     // ... and for every thread of the CTA
+
+  for (int k = 0; k < nchunks; ++k) {
+    issue(k + BM_STAGES - 1, id_pf);
+    id_pf = load_id(k + BM_STAGES);
+    cp_async_wait_b<BM_STAGES - 1>();
+    __syncwarp();
+    const BmStage& st = my[k % BM_STAGES];
+    const int c = warp + BM_WARPS * k;
+#pragma unroll 1
+    for (int bt = 0; bt < 2; ++bt) {
+      if (c * BM_STAGE + bt * 16 >= n) break;          // warp-uniform
+      bwd_mma_step<DEPTH>(st, bt, g, t, cx, cy, k_us, [&](int r4) { return sB[r4][lane]; }, gacc);
     }
     __syncwarp();
   }
@@ -676,6 +799,11 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);
     static const bool minb4 = [] { const char* e = getenv("B2S_BWD_MINB"); return e != nullptr && e[0] == '4'; }();
+    static const bool regb = [] { const char* e = getenv("B2S_BWD_REGB"); return e != nullptr && e[0] == '1'; }();
+    if (!regb) {
+      if (depth) blend_wsum_bwd_cta_kernel<true><<<(int)unit_cap, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+      else       blend_wsum_bwd_cta_kernel<false><<<(int)unit_cap, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
+    } else
     if (depth) blend_wsum_bwd_mma_kernel<true, 1><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
     else if (minb4) blend_wsum_bwd_mma_kernel<false, 4><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
     else       blend_wsum_bwd_mma_kernel<false, 3><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);

@@ -445,6 +445,7 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       for (int k = 0; k < 4; ++k) D[ch][h][k] = 0.0f;
   const float cy0 = (float)(ty * TILE + g) + 0.5f, cy1 = cy0 + 8.0f;     // rows g, g+8
   const float cx0 = (float)(tx * TILE + g) + 0.5f, cx1 = cx0 + 8.0f;     // columns g, g+8
+  const float2 ncy = make_float2(-cy0, -cy1), ncx = make_float2(-cx0, -cx1);
 
   for (int c = 0; c < nchunks; ++c) {
     issue(c + FM_STAGES - 1, id_pf);
@@ -453,9 +454,11 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     __syncwarp();
     const FwStage& st = my[c % FM_STAGES];
     const int left = n - c * FM_STAGE;               // Gaussians in this chunk (may exceed 32)
-#pragma unroll 1
+    // both 16-Gaussian steps of the stage run unconditionally (slots past the list hold padding records), so the
+    // two steps are one straight-line block the scheduler can interleave: each is a long dependent chain
+    // LDS -> exponent -> EX2 -> fp16 split -> HFMA2 -> 3 chained HMMA
+#pragma unroll
     for (int sp = 0; sp < FM_STAGE / 16; ++sp) {
-      if (sp * 16 >= left) break;                    // warp-uniform
       // e = 0..3 -> Gaussians 2t, 2t+1, 2t+8, 2t+9 of the step (the K slots of a0/a1 | a2/a3 and b0 | b1)
       float fy[4][2], fx[4][2], zv[4];
       uint32_t cw[4][3];                             // the clamped colour pre-split as f16 {hi | lo << 16}: r, g, b
@@ -463,12 +466,15 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       for (int e = 0; e < 4; ++e) {
         const int j = sp * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
         const float4 ra = st.a[j], rb = st.b[j];
-        const float dy0 = cy0 - rb.x, dy1 = cy1 - rb.x, dx0 = cx0 - ra.x, dx1 = cx1 - ra.x;
+        // exponents of the two rows / two columns as packed f32x2 (the sign of d is irrelevant: it is squared)
+        const float2 dy = __fadd2_rn(bcast2(rb.x), ncy), dx = __fadd2_rn(bcast2(ra.x), ncx);
         const float lop8 = fminf(ra.z, 7.99f) + 8.0f;           // fx * 2^8 stays inside fp16 (op <= 253)
-        fy[e][0] = ex2_approx(fmaf(rb.y * dy0, dy0, 8.0f));
-        fy[e][1] = ex2_approx(fmaf(rb.y * dy1, dy1, 8.0f));
-        fx[e][0] = ex2_approx(fmaf(ra.y * dx0, dx0, lop8));
-        fx[e][1] = ex2_approx(fmaf(ra.y * dx1, dx1, lop8));
+        const float2 ay = __ffma2_rn(__fmul2_rn(bcast2(rb.y), dy), dy, bcast2(8.0f));
+        const float2 ax = __ffma2_rn(__fmul2_rn(bcast2(ra.y), dx), dx, bcast2(lop8));
+        fy[e][0] = ex2_approx(ay.x);
+        fy[e][1] = ex2_approx(ay.y);
+        fx[e][0] = ex2_approx(ax.x);
+        fx[e][1] = ex2_approx(ax.y);
         cw[e][0] = __float_as_uint(ra.w); cw[e][1] = __float_as_uint(rb.w); cw[e][2] = __float_as_uint(rb.z);
         if (DEPTH) zv[e] = st.c[j].w;
       }
