@@ -646,104 +646,6 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   cp_async_wait_b<0>();
 }
 
-// ---- v6: one CTA per work unit, the plane fragments in shared memory ------------------------------------
-// The register-resident fragments of the kernel above (64-80 registers) cap it at 12 warps per SM, and every
-// warp is one long dependent chain (LDS -> exponent -> EX2 -> pack -> 2 chained HMMA -> FP32 epilogue -> quad
-// shuffles -> RED), so the SM idles on latency.  Here the 4 warps of a CTA share ONE tile: its fragment image
-// (8-10 KB) is fetched once into shared memory and each MMA pair reads its 4 registers with one LDS.128
-// (conflict free: lane-major uint4); warp w takes the 32-Gaussian chunks w, w+4, ... of the unit.  Every Gaussian
-// still belongs to exactly one warp step, so there is no cross-warp reduction.
-template <bool DEPTH>
-__global__ void __launch_bounds__(BM_WARPS * 32, 4)
-blend_wsum_bwd_cta_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
-                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
-                          const int2* __restrict__ units, const uint4* __restrict__ frag,
-                          const float* __restrict__ tile_scale, float* __restrict__ gacc) {
-  constexpr int CH = DEPTH ? 5 : 4;
-  constexpr int NREG = CH * 16;
-  __shared__ __align__(16) BmStage ring[BM_WARPS][BM_STAGES];
-  __shared__ __align__(16) uint4 sB[NREG / 4][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x;
-  if (u >= unit_start[vp.n_tiles]) return;             // block-uniform
-  const int2 ud = units[u];
-  const int tile = ud.x;
-  const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = min(SEG, rg.y - start);
-  if (n <= 0) return;                                   // block-uniform
-  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
-  const int g = lane >> 2, t = lane & 3;
-  BmStage* my = ring[warp];
-
-  // the tile's plane fragments: first cp.async group of every thread (groups retire in order)
-  {
-    const uint4* ft = frag + (size_t)tile * (NREG / 4) * 32;
-    uint4* dst = &sB[0][0];
-    for (int k = threadIdx.x; k < (NREG / 4) * 32; k += BM_WARPS * 32) cp_async16_b(dst + k, ft + k);
-    cp_async_commit_b();
-  }
-  // chunks of this warp: global chunk index = warp + BM_WARPS * k
-  const int nchunks_all = (n + BM_STAGE - 1) / BM_STAGE;
-  const int nchunks = (nchunks_all - warp + BM_WARPS - 1) / BM_WARPS;      // may be 0
-  auto issue = [&](int k, int id) {      // local chunk k, this lane's Gaussian id (already loaded)
-    if (k < nchunks) {
-      BmStage& st = my[k % BM_STAGES];
-      if ((warp + BM_WARPS * k) * BM_STAGE + lane < n) {
-        const float4* src = rec + 3 * (size_t)id;
-        cp_async16_b(&st.a[lane], src);
-        cp_async16_b(&st.b[lane], src + 1);
-        cp_async16_b(&st.c[lane], src + 2);
-        st.id[lane] = id;
-      } else {   // padding of the last step: a record whose factors underflow to exactly 0 (no selects below)
-        st.a[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
-        st.b[lane] = make_float4(1e18f, -1.0f, 0.0f, 0.0f);
-        st.c[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        st.id[lane] = -1;
-      }
-    }
-    cp_async_commit_b();
-  };
-  auto load_id = [&](int k) -> int {
-    const int i = (warp + BM_WARPS * k) * BM_STAGE + lane;
-    return (k < nchunks && i < n) ? __ldg(vals + start + i) : 0;
-  };
-  {
-    int ids[BM_STAGES - 1];
-#pragma unroll
-    for (int k = 0; k < BM_STAGES - 1; ++k) ids[k] = load_id(k);
-#pragma unroll
-    for (int k = 0; k < BM_STAGES - 1; ++k) issue(k, ids[k]);
-  }
-  int id_pf = load_id(BM_STAGES - 1);
-  const float k_us = __ldg(tile_scale + tile);       // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
-  float cx[4], cy[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int idx = 8 * (q >> 1) + 2 * t + (q & 1);
-    cx[q] = (float)(tx * TILE + idx) + 0.5f;
-    cy[q] = (float)(ty * TILE + idx) + 0.5f;
-  }
-  cp_async_wait_b<BM_STAGES - 1>();                    // the fragment group (oldest) has landed for this thread
-  __syncthreads();                                     // ... and for every thread of the CTA
-
-  for (int k = 0; k < nchunks; ++k) {
-    issue(k + BM_STAGES - 1, id_pf);
-    id_pf = load_id(k + BM_STAGES);
-    cp_async_wait_b<BM_STAGES - 1>();
-    __syncwarp();
-    const BmStage& st = my[k % BM_STAGES];
-    const int c = warp + BM_WARPS * k;
-#pragma unroll 1
-    for (int bt = 0; bt < 2; ++bt) {
-      if (c * BM_STAGE + bt * 16 >= n) break;          // warp-uniform
-      bwd_mma_step<DEPTH>(st, bt, g, t, cx, cy, k_us, [&](int r4) { return sB[r4][lane]; }, gacc);
-    }
-    __syncwarp();
-  }
-  cp_async_wait_b<0>();
-}
-
 // Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (written by
 // preprocess_kernel into the view state) into the spare slot 9 of its row, where the chain-rule kernel finds it
 // next to the sums -- the blend kernel itself never touches it.
@@ -799,11 +701,6 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);
     static const bool minb4 = [] { const char* e = getenv("B2S_BWD_MINB"); return e != nullptr && e[0] == '4'; }();
-    static const bool regb = [] { const char* e = getenv("B2S_BWD_REGB"); return e != nullptr && e[0] == '1'; }();
-    if (!regb) {
-      if (depth) blend_wsum_bwd_cta_kernel<true><<<(int)unit_cap, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
-      else       blend_wsum_bwd_cta_kernel<false><<<(int)unit_cap, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
-    } else
     if (depth) blend_wsum_bwd_mma_kernel<true, 1><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
     else if (minb4) blend_wsum_bwd_mma_kernel<false, 4><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);
     else       blend_wsum_bwd_mma_kernel<false, 3><<<blocks, BM_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, f4, tile_scale, gacc);

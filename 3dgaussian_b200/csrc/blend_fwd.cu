@@ -453,7 +453,6 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     cp_async_wait<FM_STAGES - 1>();
     __syncwarp();
     const FwStage& st = my[c % FM_STAGES];
-    const int left = n - c * FM_STAGE;               // Gaussians in this chunk (may exceed 32)
     // both 16-Gaussian steps of the stage run unconditionally (slots past the list hold padding records), so the
     // two steps are one straight-line block the scheduler can interleave: each is a long dependent chain
     // LDS -> exponent -> EX2 -> fp16 split -> HFMA2 -> 3 chained HMMA

@@ -161,7 +161,10 @@ struct WorkLayout {
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
 // to ~5000 Gaussians; one CTA per tile left the SMs idle a third of the time).
-constexpr int SEG = 512;
+#ifndef B2S_SEG
+#define B2S_SEG 512
+#endif
+constexpr int SEG = B2S_SEG;
 inline int64_t max_units(int width, int height, int64_t max_pairs) {
   const int64_t tiles = (int64_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
   return (max_pairs > 0 ? max_pairs : 0) / SEG + tiles;   // sum_t max(1, ceil(c_t/SEG)) <= P1/SEG + tiles
