@@ -22,6 +22,7 @@ EXPORTS = [
     "b2s_count_pairs", "b2s_forward", "b2s_backward", "b2s_state_info", "b2s_render_rgba8",
     "b2s_render_rgba8_host", "b2s_dump_bins", "b2s_sort_tmp_bytes", "b2s_sort_pairs", "b2s_fit_loss",
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_fit_backward_blend", "b2s_backward_params",
+    "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
 ]
 
@@ -75,7 +76,13 @@ def lib() -> C.CDLL:
         L.b2s_backward_blend.restype = i32
         L.b2s_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp]
         L.b2s_fit_backward_blend.restype = i32
-        L.b2s_fit_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, C.c_float, C.c_float, vp, vp, vp, sz, vp, vp]
+        L.b2s_fit_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp, vp]
+        L.b2s_prepared_view_bytes.restype = sz
+        L.b2s_prepared_view_bytes.argtypes = [i32]
+        L.b2s_preprocess_views.restype = i32
+        L.b2s_preprocess_views.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+        L.b2s_forward_prepared.restype = i32
+        L.b2s_forward_prepared.argtypes = [vp, PP, vp, i32, i64, vp, vp, vp, vp, sz, vp, sz, vp]
         L.b2s_backward_params.restype = i32
         L.b2s_backward_params.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp]
         L.b2s_state_info.restype = i32

@@ -184,16 +184,29 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
   return b;
 }
 
+// Points the per-view inputs of the binning / blend stages at one view block of b2s_preprocess_views.
+static void use_prepared(Bufs& b, const void* prepared_view, int n) {
+  const PreparedLayout L = prepared_layout(n);
+  char* q = (char*)const_cast<void*>(prepared_view);
+  b.rec = (float4*)(q + L.rec);
+  b.cmask = (uint8_t*)(q + L.cmask);
+  b.rect = (uint2*)(q + L.rect);
+  b.tmask = (unsigned long long*)(q + L.tmask);
+}
+
 // projection -> count -> scan -> emit -> sort -> ranges.  On return the sorted Gaussian ids are
 // in B.vals (state) and the sorted keys in *keys_sorted.
 static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
                        const float* colors, const float* opac, int n, int64_t max_pairs, const Bufs& B,
                        float* dbg, int* dbg_bbox, unsigned long long** keys_sorted,
                        unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
-  int rc;
-  {
+  int rc = B2S_OK;
+  if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
     StageTimer t(ctx, ST_PREPROCESS, st);
     rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
+  } else if (p->sort_depth || !counting_sort_fits(vp.n_tiles)) {
+    set_error("prepared views feed the counting-sort path only (sort_depth = 0, at most %d tiles)", (int)(CS_MAX_SMEM / 8));
+    return B2S_ERR_UNSUPPORTED;
   }
   if (rc != B2S_OK) return rc;
   const int begin_bit = p->sort_depth ? 0 : 32;
@@ -350,6 +363,39 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
                                out_alpha, out_depth, B.acc, nullptr, st);
 }
 
+size_t b2s_prepared_view_bytes(int n) { return prepared_layout(n).total; }
+
+int b2s_preprocess_views(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                         const float* scales, const float* colors, const float* opacities, int n, void* prepared,
+                         void* stream) {
+  if (ctx == nullptr || views_dev == nullptr || means == nullptr || scales == nullptr || colors == nullptr ||
+      opacities == nullptr || prepared == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (n < 0 || num_views < 0) { set_error("bad n or num_views"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_PREPROCESS, (cudaStream_t)stream);
+  return launch_preprocess_views((const ViewParams*)views_dev, num_views, sh_coeffs > 0 ? sh_coeffs : 1, means, scales,
+                                 colors, opacities, n, (char*)prepared, (cudaStream_t)stream);
+}
+
+int b2s_forward_prepared(b2s_ctx* ctx, const b2s_params* p, const void* prepared_view, int n, int64_t max_pairs,
+                         float* out_rgb, float* out_alpha, float* out_depth, void* state, size_t state_bytes,
+                         void* workspace, size_t ws_bytes, void* stream) {
+  if (ctx == nullptr || prepared_view == nullptr || state == nullptr || workspace == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  ViewParams vp;
+  int rc = make_view(p, &vp);
+  if (rc != B2S_OK) return rc;
+  if (vp.mode != B2S_MODE_WSUM) { set_error("prepared views are a weighted-sum (fit loop) path"); return B2S_ERR_UNSUPPORTED; }
+  rc = check_sizes(n, p->width, p->height, max_pairs, state_bytes, true, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(state, workspace, n, p->width, p->height, max_pairs);
+  use_prepared(B, prepared_view, n);
+  rc = run_binning(ctx, vp, p, nullptr, nullptr, nullptr, nullptr, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_BLEND_FWD, st);
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, out_rgb,
+                               out_alpha, out_depth, B.acc, nullptr, st);
+}
+
 int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* colors,
                  const float* opacities, int n, int64_t max_pairs, const float* g_rgb, const float* g_alpha,
                  const float* g_depth, const void* state, void* workspace, size_t ws_bytes, float* grad_means,
@@ -418,7 +464,8 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
 
 int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
                            const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
-                           void* workspace, size_t ws_bytes, float* gacc_out, void* stream) {
+                           const void* prepared_view, void* workspace, size_t ws_bytes, float* gacc_out,
+                           void* stream) {
   if (ctx == nullptr || tgt == nullptr || loss_accum == nullptr || state == nullptr || workspace == nullptr ||
       gacc_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   ViewParams vp;
@@ -432,6 +479,7 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
   if (rc != B2S_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
+  if (prepared_view != nullptr) use_prepared(B, prepared_view, n);
   const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum};
   StageTimer t(ctx, ST_BLEND_BWD, st);
   if (n > 0) {

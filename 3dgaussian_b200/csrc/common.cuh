@@ -219,6 +219,23 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   return L;
 }
 
+// Per-view block written by the batched preprocess (b2s_preprocess_views): what launch_preprocess leaves in
+// state (rec, cmask) and workspace (rect, tmask) for the counting-sort path, for one view.
+struct PreparedLayout {
+  size_t rec, cmask, rect, tmask, total;
+};
+inline PreparedLayout prepared_layout(int n) {
+  PreparedLayout L;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  size_t o = 0;
+  L.rec = o;   o += align_up(nn * REC_F4 * 16);
+  L.cmask = o; o += align_up(nn);
+  L.rect = o;  o += align_up(nn * 8);
+  L.tmask = o; o += align_up(nn * 8);
+  L.total = o;
+  return L;
+}
+
 // counters block at the head of the state buffer
 struct Counters {
   long long needed;   // pairs the view produces
@@ -251,6 +268,8 @@ int launch_preprocess(const ViewParams& vp, const float* means, const float* sca
                       const float* opac, int n, float4* rec, uint8_t* cmask, uint2* rect, unsigned long long* tmask,
                       uint32_t* dbits, int* cnt, long long* bsum, float* dbg /*px,py,sx,sy,zabs planes or null*/,
                       int* dbg_bbox, cudaStream_t st);
+int launch_preprocess_views(const ViewParams* views_dev, int num_views, int sh, const float* means, const float* scales,
+                            const float* colors, const float* opac, int n, char* prepared, cudaStream_t st);
 int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
                const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,

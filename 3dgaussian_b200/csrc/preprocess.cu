@@ -133,6 +133,28 @@ __device__ __forceinline__ float split_f16_pair(float x) {
   return __uint_as_float((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16));
 }
 
+// Blend record + clamp mask of one projected Gaussian (layout: see preprocess_kernel).
+__device__ __forceinline__ void make_record(const ViewParams& vp, const Proj& pr, float op, const float* craw, float4& a,
+                                            float4& b, float4& c, int& cm) {
+  // The reference's Gaussians are axis aligned, so the weight is separable:
+  //   w(x,y) = [op * exp(-dx^2/2sx^2)] * [exp(-dy^2/2sy^2)]  -- one x record, one y record.
+  const bool lg = (vp.exact_bbox == 0);        // log-domain opacity unless the native exact mode
+  c.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
+  c.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
+  c.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
+  c.w = pr.zabs;
+  a.x = pr.px;
+  a.y = NEG_HALF_LOG2E / (pr.sx * pr.sx);
+  a.z = lg ? log2f(op) : op;
+  a.w = lg ? split_f16_pair(c.x) : __int_as_float(pr.xmin | (pr.xmax << 16));
+  b.x = pr.py;
+  b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
+  b.z = lg ? split_f16_pair(c.z) : 1.0f;
+  b.w = lg ? split_f16_pair(c.y) : __int_as_float(pr.ymin | (pr.ymax << 16));
+  cm = (craw[0] >= 0.0f && craw[0] <= 1.0f ? 1 : 0) | (craw[1] >= 0.0f && craw[1] <= 1.0f ? 2 : 0) |
+       (craw[2] >= 0.0f && craw[2] <= 1.0f ? 4 : 0);
+}
+
 // Forward: one thread per Gaussian.  Writes the 48-byte blend record
 //   rec[3i+0] = {px, qx, lop, red  as f16 hi|lo}   qx = -0.5*log2(e)/sx^2, lop = log2(op)
 //   rec[3i+1] = {py, qy, blue as f16 hi|lo, green as f16 hi|lo}   so  w = 2^(qx dx^2 + lop) * 2^(qy dy^2)
@@ -190,23 +212,7 @@ preprocess_kernel(const ViewParams vp, const float* __restrict__ means, const fl
         } else {
           craw[0] = craw[1] = craw[2] = 0.0f;
         }
-        // The reference's Gaussians are axis aligned, so the weight is separable:
-        //   w(x,y) = [op * exp(-dx^2/2sx^2)] * [exp(-dy^2/2sy^2)]  -- one x record, one y record.
-        const bool lg = (vp.exact_bbox == 0);        // log-domain opacity unless the native exact mode
-        c.x = fminf(fmaxf(craw[0], 0.0f), 1.0f);
-        c.y = fminf(fmaxf(craw[1], 0.0f), 1.0f);
-        c.z = fminf(fmaxf(craw[2], 0.0f), 1.0f);
-        c.w = pr.zabs;
-        a.x = pr.px;
-        a.y = NEG_HALF_LOG2E / (pr.sx * pr.sx);
-        a.z = lg ? log2f(op) : op;
-        a.w = lg ? split_f16_pair(c.x) : __int_as_float(pr.xmin | (pr.xmax << 16));
-        b.x = pr.py;
-        b.y = NEG_HALF_LOG2E / (pr.sy * pr.sy);
-        b.z = lg ? split_f16_pair(c.z) : 1.0f;
-        b.w = lg ? split_f16_pair(c.y) : __int_as_float(pr.ymin | (pr.ymax << 16));
-        cm = (craw[0] >= 0.0f && craw[0] <= 1.0f ? 1 : 0) | (craw[1] >= 0.0f && craw[1] <= 1.0f ? 2 : 0) |
-             (craw[2] >= 0.0f && craw[2] <= 1.0f ? 4 : 0);
+        make_record(vp, pr, op, craw, a, b, c, cm);
       } else {
         a = make_float4(0.f, 0.f, (vp.exact_bbox == 0) ? -INFINITY : 0.0f, __int_as_float(0));
         b = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
@@ -259,6 +265,91 @@ int launch_preprocess(const ViewParams& vp, const float* means, const float* sca
   return B2S_OK;
 }
 
+// Forward for ALL local views of a fit iteration in one launch: the parameters -- above all the (N,K,3)
+// coefficients, 192 B per Gaussian at K = 16, the dominant HBM read of the per-view kernel -- are read once
+// and kept in registers while the view loop writes each view's blend record, clamp mask, tile rect and tile
+// mask (the inputs of the counting-sort path; cnt / dbits / bsum belong to the radix path and are not produced).
+// HBM: (28 + 12K) B read per Gaussian + 65 B written per Gaussian*view.
+constexpr int PRE_VIEWS_SMEM = 32;
+
+template <int K>
+__global__ void __launch_bounds__(PRE_BLOCK)
+preprocess_views_kernel(const ViewParams* __restrict__ views, int num_views, const float* __restrict__ means,
+                        const float* __restrict__ scales, const float* __restrict__ colors,
+                        const float* __restrict__ opac, int n, char* __restrict__ prepared, PreparedLayout L) {
+  __shared__ ViewParams sv[PRE_VIEWS_SMEM];
+  const int i = blockIdx.x * PRE_BLOCK + threadIdx.x;
+  const bool live = i < n;
+  const int ii = live ? i : 0;
+  const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
+              mz = __ldg(means + 3 * (size_t)ii + 2);
+  const float raw_s0 = __ldg(scales + 3 * (size_t)ii), raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
+  const float raw_op = __ldg(opac + ii);
+  float coef[K * 3];
+  load_coeffs<K>(colors, ii, coef);
+  // activations are view independent (every view of a fit shares act_flags)
+  const ViewParams& v0 = views[0];
+  const float s0 = act_scale(v0, raw_s0), s1 = act_scale(v0, raw_s1), op = act_opac(v0, raw_op);
+  for (int vbase = 0; vbase < num_views; vbase += PRE_VIEWS_SMEM) {
+    const int vcount = min(PRE_VIEWS_SMEM, num_views - vbase);
+    __syncthreads();
+    {
+      const int words = vcount * (int)(sizeof(ViewParams) / 4);
+      const int* src = reinterpret_cast<const int*>(views + vbase);
+      int* dst = reinterpret_cast<int*>(sv);
+      for (int q = threadIdx.x; q < words; q += PRE_BLOCK) dst[q] = src[q];
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int vl = 0; vl < vcount; ++vl) {
+      const ViewParams& vp = sv[vl];
+      char* base = prepared + (size_t)(vbase + vl) * L.total;
+      float4* rec = reinterpret_cast<float4*>(base + L.rec);
+      const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
+      uint2 rc = make_uint2(1u, 0u);   // empty tile rect (tx1 < tx0) for culled Gaussians
+      unsigned long long tm = 0ull;
+      float4 a = make_float4(0.f, 0.f, (vp.exact_bbox == 0) ? -INFINITY : 0.0f, __int_as_float(0)),
+             b = make_float4(0.f, 0.f, 0.f, __int_as_float(0)), c = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cm = 0;
+      if (pr.ok) {
+        const int tx0 = pr.xmin / TILE, tx1 = pr.xmax / TILE, ty0 = pr.ymin / TILE, ty1 = pr.ymax / TILE;
+        const int w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
+        if (w <= 8 && h <= 8)
+          tm = tile_cull_mask(pr.px, pr.py, pr.sx, pr.sy, vp.k, tx0, ty0, w, h,
+                              vp.style == B2S_STYLE_TORCH && vp.exact_bbox == 0);
+        rc = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+        float craw[3], dir[3], rinv;
+        eval_color<K>(vp, coef, mx, my, mz, craw, dir, &rinv);
+        make_record(vp, pr, op, craw, a, b, c, cm);
+      }
+      rec[3 * (size_t)i] = a;
+      rec[3 * (size_t)i + 1] = b;
+      rec[3 * (size_t)i + 2] = c;
+      reinterpret_cast<uint8_t*>(base + L.cmask)[i] = (uint8_t)cm;
+      reinterpret_cast<uint2*>(base + L.rect)[i] = rc;
+      reinterpret_cast<unsigned long long*>(base + L.tmask)[i] = tm;
+    }
+  }
+}
+
+int launch_preprocess_views(const ViewParams* views_dev, int num_views, int sh, const float* means, const float* scales,
+                            const float* colors, const float* opac, int n, char* prepared, cudaStream_t st) {
+  if (n <= 0 || num_views <= 0) return B2S_OK;
+  const int blocks = (n + PRE_BLOCK - 1) / PRE_BLOCK;
+  const PreparedLayout L = prepared_layout(n);
+#define B2S_PREV(KK) preprocess_views_kernel<KK><<<blocks, PRE_BLOCK, 0, st>>>(views_dev, num_views, means, scales, colors, opac, n, prepared, L)
+  switch (sh) {
+    case 1: B2S_PREV(1); break;
+    case 4: B2S_PREV(4); break;
+    case 9: B2S_PREV(9); break;
+    case 16: B2S_PREV(16); break;
+    default: set_error("sh_coeffs must be 1, 4, 9 or 16 (got %d)", sh); return B2S_ERR_INVALID;
+  }
+#undef B2S_PREV
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 // Backward chain rule, for ONE OR MANY views in a single pass over the parameters.
 //   gacc[v][12i..] = {dR,dG,dB,dZ, S,Sx,Sxx,Sy, Syy,-,-,-} from the blend backward of view v, where
 //   S = sum w*t, Sx = sum w*t*dx, Sxx = sum w*t*dx^2 (same for y).
@@ -271,7 +362,7 @@ int launch_preprocess(const ViewParams& vp, const float* means, const float* sca
 // LPG lanes share a Gaussian: lane `sub` owns SH coefficients [sub*KL, sub*KL+KL), so a warp reads
 // and writes the (N,K,3) arrays as contiguous 16-byte pieces (coalesced), and the few cross-lane
 // sums (raw colour, d colour / d direction) are quad shuffles.
-constexpr int BWD_VIEWS_SMEM = 32;   // views staged in shared memory per chunk
+constexpr int BWD_VIEWS_SMEM = 32;   // views staged in shared memory per chunk (a multiple of 4)
 
 template <int K, int LPG>
 __global__ void __launch_bounds__(PRE_BLOCK)
@@ -484,9 +575,10 @@ preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ vi
 // evaluate all 16 basis functions + 48 derivatives to use 4 of them.  Here the split is per WARP: a block of 8
 // warps covers 64 Gaussians x 4 coefficient groups, warp w handles group (w & 3) of Gaussians (w >> 2)*32 + lane.
 // `sub` is warp uniform, so each warp evaluates only its own 4 basis functions (compile-time indices, dead code
-// eliminated) and only the group-0 warps run the projection / sigma / opacity chain.  The direction gradient is
-// linear in the per-group partial sums, so every warp folds its share into a private d/dmean and the four are added
-// through shared memory once, after the view loop.
+// eliminated).  The projection / sigma / opacity / position chain of view v runs on the warp with (v & 3) == sub,
+// so the four warps of a Gaussian carry the same load.  Every gradient is linear in the per-warp partial sums:
+// each warp keeps private d/dmean, d/dscale, d/dopacity sums and the four are added through shared memory once,
+// after the view loop.
 template <int SUB>
 __device__ __forceinline__ void sh16_group_accumulate(const ViewParams& vp, float mx, float my, float mz,
                                                       const float (&coef)[12], float dc0, float dc1, float dc2,
@@ -526,7 +618,7 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
                            float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
   static_assert(PRE_BLOCK == 256, "8 warps: 2 x 32 Gaussians x 4 coefficient groups");
   __shared__ ViewParams sv[BWD_VIEWS_SMEM];
-  __shared__ float gm_part[3][3][64];
+  __shared__ float part[3][6][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp & 3, slot = (warp >> 2) * 32 + lane;
   const int i = blockIdx.x * 64 + slot;
@@ -538,8 +630,8 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
   // activations are view independent (every view of a fit shares act_flags): once per Gaussian, not per view
   const ViewParams& v0 = (views != nullptr) ? views[0] : single;
   const int act = v0.act;
-  float s0 = 0.f, s1 = 0.f, op = 0.f, ds0 = 1.f, ds1 = 1.f, dop = 1.f;   // activated values, d activation / d raw
-  if (sub == 0) {
+  float s0, s1, op, ds0 = 1.f, ds1 = 1.f, dop = 1.f;   // activated values, d activation / d raw
+  {
     const float raw_s0 = __ldg(scales + 3 * (size_t)ii), raw_s1 = __ldg(scales + 3 * (size_t)ii + 1);
     const float raw_op = __ldg(opac + ii);
     s0 = raw_s0; s1 = raw_s1; op = raw_op;
@@ -577,19 +669,20 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
     // dependent chain behind three 16-byte loads)
     const float4* ga = gacc + ((size_t)vbase * n + ii) * 3;
     float4 g0 = __ldg(ga), g1 = make_float4(0.f, 0.f, 0.f, 0.f), g2 = __ldg(ga + 2);
-    if (sub == 0) g1 = __ldg(ga + 1);
+    if (sub == 0) g1 = __ldg(ga + 1);                  // BWD_VIEWS_SMEM % 4 == 0: view vbase belongs to group 0
     for (int vl = 0; vl < vcount; ++vl) {
       const ViewParams& vp = (views != nullptr) ? sv[vl] : single;
       const float4 c0 = g0, c1 = g1, c2 = g2;
+      const bool mine = (vl & 3) == sub;               // warp uniform: this warp runs the projection chain of the view
       if (vl + 1 < vcount) {
         const float4* gn = gacc + ((size_t)(vbase + vl + 1) * n + ii) * 3;
         g0 = __ldg(gn); g2 = __ldg(gn + 2);
-        if (sub == 0) g1 = __ldg(gn + 1);
+        if (((vl + 1) & 3) == sub) g1 = __ldg(gn + 1);
       }
       // c0 = {dR, dG, dB, dZ} (zero row when the Gaussian is culled in this view), c2 = {Syy, colour clamp mask, -, -}
       const int cmask = __float_as_int(c2.y);
       const float dc0 = (cmask & 1) ? c0.x : 0.0f, dc1 = (cmask & 2) ? c0.y : 0.0f, dc2 = (cmask & 4) ? c0.z : 0.0f;
-      if (sub == 0) {                  // warp uniform: projection -> sigma / opacity / position chain
+      if (mine) {                      // projection -> sigma / opacity / position chain
         const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
         if (pr.ok) {
           float dZ = c0.w;
@@ -639,17 +732,19 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
   }
   gs0 *= ds0;    // d softplus / d raw, applied once to the view sums
   gs1 *= ds1;
-  // fold the four groups' d/dmean
+  // fold the four warps' partial sums
   if (sub != 0) {
-    gm_part[sub - 1][0][slot] = gm[0];
-    gm_part[sub - 1][1][slot] = gm[1];
-    gm_part[sub - 1][2][slot] = gm[2];
+    float* dst = &part[sub - 1][0][slot];
+    dst[0] = gm[0]; dst[64] = gm[1]; dst[128] = gm[2]; dst[192] = gs0; dst[256] = gs1; dst[320] = gop;
   }
   __syncthreads();
   if (!live) return;
   if (sub == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gm[c] += gm_part[0][c][slot] + gm_part[1][c][slot] + gm_part[2][c][slot];
+    for (int c = 0; c < 3; ++c) gm[c] += part[0][c][slot] + part[1][c][slot] + part[2][c][slot];
+    gs0 += part[0][3][slot] + part[1][3][slot] + part[2][3][slot];
+    gs1 += part[0][4][slot] + part[1][4][slot] + part[2][4][slot];
+    gop += part[0][5][slot] + part[1][5][slot] + part[2][5][slot];
     if (accumulate) {
       g_means[3 * (size_t)i] += gm[0]; g_means[3 * (size_t)i + 1] += gm[1]; g_means[3 * (size_t)i + 2] += gm[2];
       g_scales[3 * (size_t)i] += gs0; g_scales[3 * (size_t)i + 1] += gs1;

@@ -34,7 +34,7 @@ class FitDriver:
                  lr: float = 0.02, silhouette_weight: float = 0.2, reg_opacity: float = 1e-3,
                  reg_scale: float = 1e-3, cutoff_sigma: float = 5.0, background=(0.0, 0.0, 0.0),
                  rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
-                 fused_loss: bool = True):
+                 fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30):
         if device.type != "cuda":
             raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
         self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
@@ -58,6 +58,9 @@ class FitDriver:
         self.lanes = max(1, int(lanes))
         self.active_lanes = self.lanes            # <= lanes; 1 serialises the views on the caller's stream
         self.fused_loss = bool(fused_loss)
+        self.batched_preprocess = bool(batched_preprocess) and self.fused_loss
+        self.prepared_budget = int(prepared_budget_bytes)
+        self.prepared = None
         self.rgb_l = [torch.empty((height, width, 3), dtype=torch.float32, device=device) for _ in range(self.lanes)]
         self.alpha_l = [torch.empty((height, width), dtype=torch.float32, device=device) for _ in range(self.lanes)]
         self.g_rgb_l = [torch.empty_like(t) for t in self.rgb_l]
@@ -149,6 +152,11 @@ class FitDriver:
             self.ws_l = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
             self._counters_l = [st[:16].view(torch.int32) for st in self.state_l]   # needed(lo,hi), kept, overflow
             self.state, self.ws = self.state_l[0], self.ws_l[0]
+            # batched preprocess: one block per local view (b2s_preprocess_views), if it fits the budget
+            self.prepared = None
+            self.pv_bytes = int(L.b2s_prepared_view_bytes(self.n))
+            if self.batched_preprocess and self.views and self.pv_bytes * len(self.views) <= self.prepared_budget:
+                self.prepared = torch.empty(self.pv_bytes * len(self.views), dtype=torch.uint8, device=self.dev)
         return worst
 
     # ---- targets -------------------------------------------------------------------------------
@@ -178,13 +186,19 @@ class FitDriver:
         state, ws = self.state_l[lane], self.ws_l[lane]
         if self.fused_loss:
             # accumulators only: the loss and its image gradients are evaluated inside the g-buffer kernel
-            capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
-                                     self._pp(self.o_opac), self.n, self.max_pairs, None, None, None,
-                                     _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
+            pv = None
+            if self.prepared is not None:
+                pv = C.c_void_p(self.prepared.data_ptr() + slot * self.pv_bytes)
+                capi.check(L.b2s_forward_prepared(ctx, pc, pv, self.n, self.max_pairs, None, None, None,
+                                                  _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
+            else:
+                capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales),
+                                         self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, None,
+                                         None, None, _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
             self.overflow_l[lane] += self._counters_l[lane][3]
             capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask), self.w_sil,
-                                                1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), _ptr(ws),
-                                                self.ws_bytes, _ptr(self.gacc[slot]), st))
+                                                1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), pv,
+                                                _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
             return
         capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
                                  self._pp(self.o_opac), self.n, self.max_pairs, _ptr(rgb), _ptr(alpha), None,
@@ -196,6 +210,14 @@ class FitDriver:
         capi.check(L.b2s_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(g_rgb),
                                         _ptr(g_alpha) if mask is not None else None, None, _ptr(state),
                                         _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
+
+    def _preprocess_all(self):
+        """Per-Gaussian stage of every local view in one launch (parameters read once per iteration)."""
+        if self.prepared is not None:
+            capi.check(capi.lib().b2s_preprocess_views(
+                capi.ctx(self.dev.index), _ptr(self.views_dev), len(self.views), self.sh, self._pp(self.o_means),
+                self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n, _ptr(self.prepared),
+                _stream()))
 
     def _streams(self):
         if self._lane_streams is None:
@@ -247,6 +269,7 @@ class FitDriver:
             main = torch.cuda.current_stream()
             for t in self.loss_l:
                 t.zero_()
+            self._preprocess_all()
             nl = max(1, min(self.active_lanes, self.lanes))
             if nl == 1:
                 for k, i in enumerate(self.views):
@@ -279,6 +302,7 @@ class FitDriver:
             main = torch.cuda.current_stream()
             for t in self.loss_l:
                 t.zero_()
+            self._preprocess_all()
             use_mask = host_masks is not None
             if nl > 1:
                 self._fork(main)
@@ -344,7 +368,7 @@ class FitDriver:
                 self.means().copy_(om[:k]); self.scales_raw().copy_(os_[:k])
                 self.opacities_raw().copy_(oo[:k]); self.colors_raw().copy_(colors)
             self.gacc = torch.empty((max(len(self.views), 1), max(k, 1), 12), dtype=torch.float32, device=self.dev)
-            self.state = self.ws = self.state_l = self.ws_l = None
+            self.state = self.ws = self.state_l = self.ws_l = self.prepared = None
             self.plan()
         return k
 

@@ -131,7 +131,21 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
  * rgb / alpha / gradient images are read or written.  mask may be NULL.  Adds scale*loss to *loss_accum. */
 int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
                            const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
+                           const void* prepared_view /* NULL unless the forward was b2s_forward_prepared */,
                            void* workspace, size_t ws_bytes, float* gacc_out, void* stream);
+
+/* Batched per-Gaussian stage of the fit loop: projection, sigma, SH colour, tile rect and tile mask of EVERY
+ * local view in one launch -- the parameters (192 B of SH coefficients per Gaussian at degree 3) are read once
+ * per iteration instead of once per view.  views_dev = device copy of the b2s_pack_views block; `prepared`
+ * receives num_views blocks of b2s_prepared_view_bytes(n) bytes.  b2s_forward_prepared then renders view v
+ * from block v (weighted-sum mode, sort_depth = 0 only) exactly as b2s_forward would from the parameters. */
+size_t b2s_prepared_view_bytes(int n);
+int b2s_preprocess_views(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                         const float* scales, const float* colors, const float* opacities, int n, void* prepared,
+                         void* stream);
+int b2s_forward_prepared(b2s_ctx* ctx, const b2s_params* p, const void* prepared_view, int n, int64_t max_pairs,
+                         float* out_rgb, float* out_alpha, float* out_depth, void* state, size_t state_bytes,
+                         void* workspace, size_t ws_bytes, void* stream);
 /* Chain rule over all views: views_dev = device copy of the b2s_pack_views block. */
 int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
                         const float* scales, const float* colors, const float* opacities, int n,

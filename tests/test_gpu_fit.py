@@ -168,6 +168,19 @@ def test_fused_loss_backward_equals_separate_kernels():
         assert rel_l2(d1.g.cpu().numpy(), d2.g.cpu().numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("sh", [1, 4, 16])
+def test_batched_preprocess_equals_per_view(sh):
+    """b2s_preprocess_views + b2s_forward_prepared (parameters read once per iteration) against the per-view
+    b2s_forward: identical records, so the same loss and gradients up to the order of the float atomics."""
+    S = _setup(sh, V=5)
+    d1, d2 = _driver(S, batched_preprocess=False), _driver(S, batched_preprocess=True)
+    assert d1.prepared is None and d2.prepared is not None
+    for _ in range(2):
+        l1, l2 = float(d1.step().item()), float(d2.step().item())
+        assert abs(l1 - l2) <= 1e-7
+        assert rel_l2(d1.g.cpu().numpy(), d2.g.cpu().numpy()) <= 1e-5
+
+
 def test_dropin_training_loop_matches_oracle_loop():
     """The reference script's flow (nn.Parameters -> activations -> per-view render -> loss ->
     backward -> torch Adam) through the drop-in render_gaussians_torch."""
