@@ -34,7 +34,8 @@ class FitDriver:
                  lr: float = 0.02, silhouette_weight: float = 0.2, reg_opacity: float = 1e-3,
                  reg_scale: float = 1e-3, cutoff_sigma: float = 5.0, background=(0.0, 0.0, 0.0),
                  rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
-                 fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30):
+                 fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30,
+                 view_groups: int = 1):
         if device.type != "cuda":
             raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
         self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
@@ -60,6 +61,7 @@ class FitDriver:
         self.fused_loss = bool(fused_loss)
         self.batched_preprocess = bool(batched_preprocess) and self.fused_loss
         self.prepared_budget = int(prepared_budget_bytes)
+        self.view_groups = max(1, int(view_groups))
         self.prepared = None
         self.rgb_l = [torch.empty((height, width, 3), dtype=torch.float32, device=device) for _ in range(self.lanes)]
         self.alpha_l = [torch.empty((height, width), dtype=torch.float32, device=device) for _ in range(self.lanes)]
@@ -211,46 +213,98 @@ class FitDriver:
                                         _ptr(g_alpha) if mask is not None else None, None, _ptr(state),
                                         _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
 
-    def _preprocess_all(self):
-        """Per-Gaussian stage of every local view in one launch (parameters read once per iteration)."""
-        if self.prepared is not None:
+    def _preprocess_views(self, a: int, b: int):
+        """Per-Gaussian stage of local views [a, b) in one launch (parameters read once per group)."""
+        if self.prepared is not None and b > a:
+            vb = capi.lib().b2s_view_block_bytes()
             capi.check(capi.lib().b2s_preprocess_views(
-                capi.ctx(self.dev.index), _ptr(self.views_dev), len(self.views), self.sh, self._pp(self.o_means),
-                self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n, _ptr(self.prepared),
-                _stream()))
+                capi.ctx(self.dev.index), C.c_void_p(self.views_dev.data_ptr() + a * vb), b - a, self.sh,
+                self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n,
+                C.c_void_p(self.prepared.data_ptr() + a * self.pv_bytes), _stream()))
+
+    def _chain_rule(self, a: int, b: int, accumulate: bool):
+        """Chain rule over local views [a, b): every Gaussian's gradients summed over the views in registers."""
+        vb = capi.lib().b2s_view_block_bytes()
+        capi.check(capi.lib().b2s_backward_params(
+            capi.ctx(self.dev.index), C.c_void_p(self.views_dev.data_ptr() + a * vb), b - a, self.sh,
+            self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n,
+            _ptr(self.gacc[a]), self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_colors),
+            self._gp(self.o_opac), 1 if accumulate else 0, _stream()))
 
     def _streams(self):
         if self._lane_streams is None:
             self._lane_streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.lanes)]
-            self._lane_done = [torch.cuda.Event() for _ in range(self.lanes)]
+            self._tail_stream = torch.cuda.Stream(device=self.dev)
             self._step_begin = torch.cuda.Event()
+            self._tail_done = torch.cuda.Event()
         return self._lane_streams
 
-    def _fork(self, main):
-        """Lane streams start after everything already queued on the caller's stream (the last Adam step)."""
-        streams = self._streams()
-        self._step_begin.record(main)
-        for s in streams:
-            s.wait_event(self._step_begin)
+    def _iterate(self, inputs):
+        """One pass over this rank's views: forward + loss + blend backward per view, chain rule, on `lanes`
+        concurrent streams.  inputs(k, stream) -> (target, mask, done_callback) for local view k.
 
-    def _join(self, main):
-        for l, s in enumerate(self._streams()):
-            self._lane_done[l].record(s)
-            main.wait_event(self._lane_done[l])
-        self.loss_dev.copy_(self.loss_l[0])                            # fixed order: deterministic
-        for t in self.loss_l[1:]:
+        With several lanes the views are cut into `view_groups` groups and pipelined: the caller's stream runs the
+        batched preprocess of every group (group g+1's while the lanes blend group g), the lanes wait for their
+        group's records, and a tail stream folds each finished group into the gradients (accumulating after the
+        first) while later groups are still blending -- only the first group's preprocess and the last group's
+        chain rule are exposed."""
+        main = torch.cuda.current_stream()
+        nv = len(self.views)
+        nl = max(1, min(self.active_lanes, self.lanes))
+        for t in self.loss_l:
+            t.zero_()
+        if nv == 0:
+            self.g.zero_()
+            self.loss_dev.zero_()
+            return
+        if nl == 1:
+            self._preprocess_views(0, nv)
+            for k in range(nv):
+                tgt, mask, done = inputs(k, main)
+                self._view_fwd_bwd(k, self.views[k], tgt, mask, 0)
+                if done is not None:
+                    done(main)
+            self.loss_dev.copy_(self.loss_l[0])
+            self._chain_rule(0, nv, False)
+            return
+        streams = self._streams()
+        tail = self._tail_stream
+        self._step_begin.record(main)
+        for st in streams + [tail]:
+            st.wait_event(self._step_begin)       # after everything queued on the caller's stream (the last Adam)
+        G = max(1, min(self.view_groups, nv // nl))
+        bounds = [(g * nv) // G for g in range(G + 1)]
+        pre_ev = []
+        for g in range(G):                         # every group's preprocess is queued up front on the caller's stream
+            self._preprocess_views(bounds[g], bounds[g + 1])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            pre_ev.append(ev)
+        for g in range(G):
+            a, b = bounds[g], bounds[g + 1]
+            used = sorted({k % nl for k in range(a, b)})
+            for l in used:
+                streams[l].wait_event(pre_ev[g])
+            for k in range(a, b):
+                lane = k % nl
+                with torch.cuda.stream(streams[lane]):
+                    tgt, mask, done = inputs(k, streams[lane])
+                    self._view_fwd_bwd(k, self.views[k], tgt, mask, lane)
+                    if done is not None:
+                        done(streams[lane])
+            for l in used:
+                ev = torch.cuda.Event()
+                ev.record(streams[l])
+                tail.wait_event(ev)
+            with torch.cuda.stream(tail):
+                self._chain_rule(a, b, g > 0)
+        self._tail_done.record(tail)
+        main.wait_event(self._tail_done)           # the tail has waited for every lane
+        self.loss_dev.copy_(self.loss_l[0])        # fixed order: deterministic
+        for t in self.loss_l[1:nl]:
             self.loss_dev += t
 
     def _finish_step(self):
-        # chain rule over ALL local views in one pass: gradients written once (no per-view read-modify-write)
-        if self.views:
-            capi.check(capi.lib().b2s_backward_params(
-                capi.ctx(self.dev.index), _ptr(self.views_dev), len(self.views), self.sh, self._pp(self.o_means),
-                self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n, _ptr(self.gacc),
-                self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_colors), self._gp(self.o_opac), 0,
-                _stream()))
-        else:
-            self.g.zero_()
         if self.world > 1:
             torch.distributed.all_reduce(self.g, group=self.pg)
             torch.distributed.all_reduce(self.loss_dev, group=self.pg)
@@ -266,22 +320,7 @@ class FitDriver:
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            main = torch.cuda.current_stream()
-            for t in self.loss_l:
-                t.zero_()
-            self._preprocess_all()
-            nl = max(1, min(self.active_lanes, self.lanes))
-            if nl == 1:
-                for k, i in enumerate(self.views):
-                    self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i))
-                self.loss_dev.copy_(self.loss_l[0])
-            else:
-                self._fork(main)
-                for k, i in enumerate(self.views):
-                    lane = k % nl
-                    with torch.cuda.stream(self._lane_streams[lane]):
-                        self._view_fwd_bwd(k, i, self.targets[i], self.masks.get(i), lane)
-                self._join(main)
+            self._iterate(lambda k, st: (self.targets[self.views[k]], self.masks.get(self.views[k]), None))
             self._finish_step()
         return self.loss_dev
 
@@ -292,48 +331,39 @@ class FitDriver:
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            nl = max(1, min(self.active_lanes, self.lanes))
             nslots = 2 * self.lanes
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.dev)
                 self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(nslots)]
                 self._ev_ready = [torch.cuda.Event() for _ in range(nslots)]
                 self._ev_free = [torch.cuda.Event() for _ in range(nslots)]
-            main = torch.cuda.current_stream()
-            for t in self.loss_l:
-                t.zero_()
-            self._preprocess_all()
             use_mask = host_masks is not None
-            if nl > 1:
-                self._fork(main)
-
-            def issue(k):
-                slot = k % nslots
-                i = self.views[k]
-                with torch.cuda.stream(self._copy_stream):
-                    if k >= nslots:
-                        self._copy_stream.wait_event(self._ev_free[slot])
-                    self._stage[slot][0].copy_(host_targets[i], non_blocking=True)
-                    if use_mask:
-                        self._stage[slot][1].copy_(host_masks[i], non_blocking=True)
-                    self._ev_ready[slot].record(self._copy_stream)
-
             nv = len(self.views)
-            for k in range(min(nl, nv)):
-                issue(k)
-            for k, i in enumerate(self.views):
-                if k + nl < nv:
-                    issue(k + nl)
-                slot, lane = k % nslots, k % nl
-                st = self._lane_streams[lane] if nl > 1 else main
-                with torch.cuda.stream(st):
-                    st.wait_event(self._ev_ready[slot])
-                    self._view_fwd_bwd(k, i, self._stage[slot][0], self._stage[slot][1] if use_mask else None, lane)
-                    self._ev_free[slot].record(st)
-            if nl > 1:
-                self._join(main)
-            else:
-                self.loss_dev.copy_(self.loss_l[0])
+            issued = [0]
+
+            def issue_upto(k_hi):
+                # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
+                while issued[0] < min(k_hi, nv):
+                    k = issued[0]
+                    slot = k % nslots
+                    i = self.views[k]
+                    with torch.cuda.stream(self._copy_stream):
+                        if k >= nslots:
+                            self._copy_stream.wait_event(self._ev_free[slot])
+                        self._stage[slot][0].copy_(host_targets[i], non_blocking=True)
+                        if use_mask:
+                            self._stage[slot][1].copy_(host_masks[i], non_blocking=True)
+                        self._ev_ready[slot].record(self._copy_stream)
+                    issued[0] += 1
+
+            def inputs(k, st):
+                issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
+                slot = k % nslots
+                st.wait_event(self._ev_ready[slot])
+                return (self._stage[slot][0], self._stage[slot][1] if use_mask else None,
+                        lambda s, slot=slot: self._ev_free[slot].record(s))
+
+            self._iterate(inputs)
             self._finish_step()
             return float(self.loss_dev.item())
 
