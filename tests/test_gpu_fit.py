@@ -177,7 +177,7 @@ def test_batched_preprocess_equals_per_view(sh):
     assert d1.prepared is None and d2.prepared is not None
     for _ in range(2):
         l1, l2 = float(d1.step().item()), float(d2.step().item())
-        assert abs(l1 - l2) <= 1e-7
+        assert abs(l1 - l2) <= 1e-6        # the loss is summed with float atomics
         assert rel_l2(d1.g.cpu().numpy(), d2.g.cpu().numpy()) <= 1e-5
 
 
