@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # workload overrides (the defaults ARE the benchmark; overrides are for smoke tests)
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--gaussians", "--n", dest="n", type=int, default=1_000_000)
     ap.add_argument("--sh", type=int, default=16)
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--width", type=int, default=1920)
@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-timing", action="store_true", help="do not bracket stages with CUDA events")
+    ap.add_argument("--s-lo", type=float, default=0.004, help="synthetic scale range (SURVEY 8d: 0.004..0.02 at 1 M)")
+    ap.add_argument("--s-hi", type=float, default=0.02)
+    ap.add_argument("--densify-every", type=int, default=0,
+                    help="call FitDriver.densify_prune every K timed steps (BASELINE configs[4]); 0 = never")
     ap.add_argument("--render-only", action="store_true", help="only the render config (BASELINE configs[2]); for profiling")
     return ap.parse_args()
 
@@ -335,7 +339,7 @@ def main():
 
     # ---- targets: renders of a second seeded Gaussian set (seed 4321) through our renderer ----
     gt = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world)
-    gm, gs, gc, go = synth_gaussians(args.n, args.sh, 4321, device)
+    gm, gs, gc, go = synth_gaussians(args.n, args.sh, 4321, device, args.s_lo, args.s_hi)
     gsr, gor, gcr = to_raw(gs, go, gc, args.sh)
     gt.set_params(gm, gsr, gor, gcr)
     gt.plan()
@@ -350,7 +354,7 @@ def main():
 
     # ---- the model being fitted (seed 1234) ----
     drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes)
-    means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device)
+    means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device, args.s_lo, args.s_hi)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
     worst_p1 = drv.plan()
@@ -373,8 +377,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    n_after = []
+    for it in range(args.steps):
         drv.step()
+        if args.densify_every > 0 and (it + 1) % args.densify_every == 0 and it + 1 < args.steps:
+            # fit_multiview_stub.py:318-325: prune / clone on the device, Adam state reset, buffers re-planned
+            n_after.append(drv.densify_prune(it + 1, max_gaussians=int(args.n * 1.2), seed=1234))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -384,7 +392,7 @@ def main():
     # several lanes kernels of different views overlap and a span no longer times one kernel, so the SAME K steps are
     # repeated once more on a single lane with the brackets on (its total is reported as ms_per_step_one_lane).
     stages, ms_one_lane = {}, None
-    if not args.no_timing:
+    if not args.no_timing and args.densify_every == 0:
         drv.active_lanes = 1
         drv.step()
         capi.timing_enable(local_rank, True)
@@ -528,7 +536,7 @@ def main():
         "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "cpu_baseline": cpu, "render": render,
         "loss_last": loss_last, "pairs": {"P1_tile_pairs_worst_view": worst_p1, "P2_pixel_pairs_rank0_views": p2_rank0,
                                           "P2_all_ranks": float(p2_all.item())},
-        "overflow": bool(overflowed),
+        "overflow": bool(overflowed), "densify": {"every": args.densify_every, "gaussians_after": n_after},
     }
     _emit(out_fd, line)
     if world > 1:
