@@ -22,7 +22,7 @@ EXPORTS = [
     "b2s_count_pairs", "b2s_forward", "b2s_backward", "b2s_state_info", "b2s_render_rgba8",
     "b2s_render_rgba8_host", "b2s_dump_bins", "b2s_sort_tmp_bytes", "b2s_sort_pairs", "b2s_fit_loss",
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_fit_backward_blend", "b2s_backward_params",
-    "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared",
+    "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
 ]
 
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
         L.b2s_sort_pairs.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, sz, vp]
         L.b2s_fit_loss.restype = i32
         L.b2s_fit_loss.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp, vp]
+        L.b2s_u8_to_f32.restype = i32
+        L.b2s_u8_to_f32.argtypes = [vp, vp, vp, i64, vp]
         L.b2s_adam_step.restype = i32
         L.b2s_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
                                     i64, i64, C.c_float, i64, i64, C.c_float, vp]

@@ -706,6 +706,12 @@ int b2s_fit_loss(b2s_ctx* ctx, const float* rgb, const float* alpha, const float
   return launch_fit_loss(rgb, alpha, tgt, mask, width, height, w_sil, scale, g_rgb, g_alpha, loss_accum, (cudaStream_t)stream);
 }
 
+int b2s_u8_to_f32(b2s_ctx* ctx, const uint8_t* src, float* dst, int64_t count, void* stream) {
+  if (ctx == nullptr || src == nullptr || dst == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (count < 0) { set_error("bad count"); return B2S_ERR_INVALID; }
+  return launch_u8_to_f32(src, dst, count, (cudaStream_t)stream);
+}
+
 int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t count, int step,
                   float lr, float beta1, float beta2, float eps, int64_t scales_begin, int64_t scales_end,
                   float reg_scale, int64_t opac_begin, int64_t opac_end, float reg_opacity, void* stream) {

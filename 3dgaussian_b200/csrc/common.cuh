@@ -322,6 +322,7 @@ int launch_densify_prune(const float* means, const float* scales_raw, const floa
 int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, const float* mask, int width,
                     int height, float w_sil, float scale, float* g_rgb, float* g_alpha, float* loss_accum,
                     cudaStream_t st);
+int launch_u8_to_f32(const uint8_t* src, float* dst, int64_t count, cudaStream_t st);
 int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,
                 float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
                 float reg_op, cudaStream_t st);

@@ -52,6 +52,38 @@ int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, cons
   return B2S_OK;
 }
 
+// Target ingestion: 8-bit image planes -> float32 in [0,1] (np.asarray(img, float32) / 255.0,
+// python/fit_multiview_stub.py:16-23) on the device, so a fit fed from host memory moves 1 B instead of
+// 4 B per value over PCIe.  16 bytes in, 64 bytes out per thread.
+__global__ void __launch_bounds__(256)
+u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long count) {
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 16;
+  if (i >= count) return;
+  if (i + 16 <= count && (reinterpret_cast<uintptr_t>(src + i) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst + i) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = (float)(w[q] & 0xff) / 255.0f;
+      o.y = (float)((w[q] >> 8) & 0xff) / 255.0f;
+      o.z = (float)((w[q] >> 16) & 0xff) / 255.0f;
+      o.w = (float)(w[q] >> 24) / 255.0f;
+      reinterpret_cast<float4*>(dst + i)[q] = o;
+    }
+  } else {
+    for (long long k = i; k < count && k < i + 16; ++k) dst[k] = (float)src[k] / 255.0f;
+  }
+}
+
+int launch_u8_to_f32(const uint8_t* src, float* dst, int64_t count, cudaStream_t st) {
+  if (count <= 0) return B2S_OK;
+  const long long blocks = (count + 16 * 256 - 1) / (16 * 256);
+  u8_to_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, (long long)count);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 // p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)    (torch.optim.Adam, single-tensor form)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,

@@ -327,7 +327,8 @@ class FitDriver:
     def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None) -> float:
         """Same iteration fed from PINNED HOST buffers: every view's target (and mask) is copied
         host->device inside the step (two staging slots per lane on a side stream, so the copy of a later
-        view overlaps the kernels of the current ones) and the loss is read back to the host at the end."""
+        view overlaps the kernels of the current ones) and the loss is read back to the host at the end.
+        Targets / masks may be float32 in [0,1] or uint8 (decoded image bytes, converted on the device)."""
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
@@ -337,9 +338,24 @@ class FitDriver:
                 self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(nslots)]
                 self._ev_ready = [torch.cuda.Event() for _ in range(nslots)]
                 self._ev_free = [torch.cuda.Event() for _ in range(nslots)]
+                self._stage_u8 = {}
             use_mask = host_masks is not None
             nv = len(self.views)
             issued = [0]
+
+            def upload(dst, src, slot, which):
+                """host -> stage; 8-bit images cross PCIe as bytes and are converted on the device
+                (np.asarray(img, float32) / 255, fit_multiview_stub.py:16-23)."""
+                if src.dtype == torch.uint8:
+                    key = (slot, which)
+                    if key not in self._stage_u8:
+                        self._stage_u8[key] = torch.empty(src.shape, dtype=torch.uint8, device=self.dev)
+                    raw = self._stage_u8[key]
+                    raw.copy_(src, non_blocking=True)
+                    capi.check(capi.lib().b2s_u8_to_f32(capi.ctx(self.dev.index), _ptr(raw), _ptr(dst), raw.numel(),
+                                                        _stream()))
+                else:
+                    dst.copy_(src, non_blocking=True)
 
             def issue_upto(k_hi):
                 # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
@@ -350,9 +366,9 @@ class FitDriver:
                     with torch.cuda.stream(self._copy_stream):
                         if k >= nslots:
                             self._copy_stream.wait_event(self._ev_free[slot])
-                        self._stage[slot][0].copy_(host_targets[i], non_blocking=True)
+                        upload(self._stage[slot][0], host_targets[i], slot, 0)
                         if use_mask:
-                            self._stage[slot][1].copy_(host_masks[i], non_blocking=True)
+                            upload(self._stage[slot][1], host_masks[i], slot, 1)
                         self._ev_ready[slot].record(self._copy_stream)
                     issued[0] += 1
 

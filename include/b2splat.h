@@ -192,6 +192,10 @@ int b2s_fit_loss(b2s_ctx* ctx, const float* rgb, const float* alpha, const float
                  const float* mask, int width, int height, float w_sil, float scale,
                  float* g_rgb, float* g_alpha, float* loss_accum, void* stream);
 
+/* Target ingestion: dst[i] = src[i] / 255 for `count` 8-bit values (np.asarray(img, float32) / 255.0,
+ * python/fit_multiview_stub.py:16-23), so host-fed targets cross PCIe as bytes. */
+int b2s_u8_to_f32(b2s_ctx* ctx, const uint8_t* src, float* dst, int64_t count, void* stream);
+
 /* torch.optim.Adam step (defaults beta=(0.9,0.999), eps=1e-8, no weight decay) over a flat
  * parameter buffer; step is 1-based.  Optional fused regulariser gradients of
  *   reg_opacity*mean(sigmoid(op_raw)) + reg_scale*mean(softplus(scales_raw)+1e-3)
