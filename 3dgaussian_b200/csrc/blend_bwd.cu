@@ -87,7 +87,11 @@ gbuf_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __r
 // its image gradients feed the g-buffer in registers; the block's loss share goes to *loss_accum.
 // The fragment image of the tile (NREG x 32 words) is assembled in shared memory and written with coalesced
 // 16-byte stores.
-template <bool DEPTH, bool LOSS>
+// UMMA = true stores the same hi/lo planes as the four K-major shared-memory operand matrices of the tcgen05
+// backward instead (see blend_wsum_bwd_umma_kernel): [U_hi | U_lo | V_hi | V_lo], each N = CH*16 rows x K = 16
+// halves in the canonical no-swizzle layout (8-row x 16-byte core matrices),
+//   U: row n = ch*16 + r, k = c        V: row n = ch*16 + c, k = r.
+template <bool DEPTH, bool LOSS, bool UMMA>
 __global__ void __launch_bounds__(TILE_PIX)
 gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __restrict__ g_rgb,
                  const float* __restrict__ g_alpha, const float* __restrict__ g_depth, const float* __restrict__ tgt,
@@ -178,15 +182,22 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
       const __half val = part ? lo : hi;
-      {   // B1: N = row r, K = column c
-        const int h = r >> 3, g = r & 7, slot = c >> 3, t = (c & 7) >> 1, half = c & 1;
-        const int reg = ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
-        sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
-      }
-      {   // B2: N = column c, K = row r
-        const int h = c >> 3, g = c & 7, slot = r >> 3, t = (r & 7) >> 1, half = r & 1;
-        const int reg = CH * 8 + ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
-        sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+      if constexpr (UMMA) {
+        constexpr int NR = CH * 16;                 // operand rows; one matrix = NR x 16 halves
+        const int nu = ch * 16 + r, nv = ch * 16 + c;
+        sfrag[(0 + part) * NR * 16 + (c >> 3) * NR * 8 + (nu >> 3) * 64 + (nu & 7) * 8 + (c & 7)] = val;   // U: k = c
+        sfrag[(2 + part) * NR * 16 + (r >> 3) * NR * 8 + (nv >> 3) * 64 + (nv & 7) * 8 + (r & 7)] = val;   // V: k = r
+      } else {
+        {   // B1: N = row r, K = column c
+          const int h = r >> 3, g = r & 7, slot = c >> 3, t = (c & 7) >> 1, half = c & 1;
+          const int reg = ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
+          sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+        }
+        {   // B2: N = column c, K = row r
+          const int h = c >> 3, g = c & 7, slot = r >> 3, t = (r & 7) >> 1, half = r & 1;
+          const int reg = CH * 8 + ((ch * 2 + h) * 2 + part) * 2 + slot, lane = g * 4 + t;
+          sfrag[((size_t)((reg >> 2) * 32 + lane) * 4 + (reg & 3)) * 2 + half] = val;
+        }
       }
     }
   }
@@ -646,6 +657,220 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   cp_async_wait_b<0>();
 }
 
+// ---- v7: the separable sums on the 5th-generation tensor cores (tcgen05 / TMEM) ---------------------------
+// The backward's natural M dimension is the GAUSSIAN: for the 128 Gaussians of a batch
+//   U[i][(ch,r)] = sum_c fx_i[c] G_ch[r][c]      V[i][(ch,c)] = sum_r fy_i[r] G_ch[r][c]
+// are two 128 x 64 x 16 products -- one tcgen05.mma each per plane half (hi, lo accumulate in TMEM) -- against
+// the tile's planes, which sit in shared memory as K-major operand matrices for the whole unit.  One thread owns
+// one Gaussian: it evaluates its 16 + 16 factors (32 MUFU.EX2), writes them as one fp16 row of the two A operands,
+// and after the MMA reads ITS accumulator row (TMEM lane = thread) with tcgen05.ld: all 16 rows and 16 columns
+// of its Gaussian arrive in its own registers, so the FP32 epilogue is thread local -- no quad shuffles, no
+// fragment bookkeeping, and no HMMA issue slots (mma.sync tops out at a quarter of the tcgen05 rate).
+//   CTA = 128 threads = 4 warps (warp w reads TMEM lanes 32w..32w+31), 128 TMEM columns (U: 0..63, V: 64..127),
+//   16 KB of shared memory; 4 CTAs per SM cover each other's MMA round trips.
+// Operand layout: K-major, no swizzle (8-row x 16-byte core matrices; row groups 128 B apart, the two K chunks
+// `rows*16` B apart), validated by profiles/microbench/umma_probe.cu.
+constexpr int BT_THREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;       // leading byte offset: between the K chunks
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;       // stride byte offset: between 8-row groups
+  d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+  return d;                                               // base offset 0, SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 4)
+blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                           const int2* __restrict__ units, const uint4* __restrict__ planes,
+                           const float* __restrict__ tile_scale, float* __restrict__ gacc) {
+  constexpr int NR = 64;                                   // operand rows of a plane matrix: 4 planes x 16
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
+  __shared__ __align__(128) uint4 sP[4 * NR * 16 * 2 / 16];      // U_hi | U_lo | V_hi | V_lo, 2 KB each
+  __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
+  __shared__ __align__(8) unsigned long long bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int u = blockIdx.x;
+  if (u >= unit_start[vp.n_tiles]) return;                 // block-uniform
+  const int2 ud = units[u];
+  const int tile = ud.x;
+  const int2 rg = ranges[tile];
+  const int start = rg.x + ud.y * SEG;
+  const int n = min(SEG, rg.y - start);
+  if (n <= 0) return;                                      // block-uniform
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {                                          // the tile's planes: ONE bulk copy (async proxy, lands on bar_load)
+    mbar_expect_tx(&bar_load, 4 * NR * 16 * 2);
+    bulk_g2s(sP, planes + (size_t)tile * (4 * NR * 16 * 2 / 16), 4 * NR * 16 * 2, &bar_load);
+  }
+  const float k_us = __ldg(tile_scale + tile);            // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
+  const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
+  // this thread's A rows (row tid): K chunk 0 at +0, K chunk 1 at +2048 B
+  uint4* rowx = &sA[0][(tid >> 3) * 8 + (tid & 7)];
+  uint4* rowy = &sA[1][(tid >> 3) * 8 + (tid & 7)];
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+
+  const int nbatch = (n + BT_THREADS - 1) / BT_THREADS;
+  int id = (tid < n) ? __ldg(vals + start + tid) : -1;
+  float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, rc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (id >= 0) {
+    ra = __ldg(rec + 3 * (size_t)id);
+    rb = __ldg(rec + 3 * (size_t)id + 1);
+    rc = __ldg(rec + 3 * (size_t)id + 2);
+  }
+  uint32_t phase = 0;
+  for (int bi = 0; bi < nbatch; ++bi) {
+    // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
+    const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
+    float2 fx2[8], fy2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dxa = dx0 + (float)(2 * j), dxb = dx0 + (float)(2 * j + 1);
+      const float dya = dy0 + (float)(2 * j), dyb = dy0 + (float)(2 * j + 1);
+      fx2[j] = make_float2(ex2_approx(fmaf(ra.y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra.y * dxb, dxb, 8.0f)));
+      fy2[j] = make_float2(ex2_approx(fmaf(rb.y * dya, dya, 8.0f)), ex2_approx(fmaf(rb.y * dyb, dyb, 8.0f)));
+    }
+    rowx[0]   = make_uint4(pack_h2(fx2[0].x, fx2[0].y), pack_h2(fx2[1].x, fx2[1].y), pack_h2(fx2[2].x, fx2[2].y), pack_h2(fx2[3].x, fx2[3].y));
+    rowx[128] = make_uint4(pack_h2(fx2[4].x, fx2[4].y), pack_h2(fx2[5].x, fx2[5].y), pack_h2(fx2[6].x, fx2[6].y), pack_h2(fx2[7].x, fx2[7].y));
+    rowy[0]   = make_uint4(pack_h2(fy2[0].x, fy2[0].y), pack_h2(fy2[1].x, fy2[1].y), pack_h2(fy2[2].x, fy2[2].y), pack_h2(fy2[3].x, fy2[3].y));
+    rowy[128] = make_uint4(pack_h2(fy2[4].x, fy2[4].y), pack_h2(fy2[5].x, fy2[5].y), pack_h2(fy2[6].x, fy2[6].y), pack_h2(fy2[7].x, fy2[7].y));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();                                       // every row written; every thread done reading TMEM (previous batch)
+    if (tid == 0) {
+      if (bi == 0) mbar_wait(&bar_load, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint64_t dax = umma_desc_kmajor(smem_u32(&sA[0][0]), 128 * 16, 128), day = umma_desc_kmajor(smem_u32(&sA[1][0]), 128 * 16, 128);
+      const uint32_t pb = smem_u32(&sP[0]);
+      umma_f16(tmem,      dax, umma_desc_kmajor(pb,            NR * 16, 128), IDESC, 0);    // U  = fx . G_hi
+      umma_f16(tmem,      dax, umma_desc_kmajor(pb + 2048,     NR * 16, 128), IDESC, 1);    // U += fx . G_lo
+      umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 2 * 2048, NR * 16, 128), IDESC, 0);    // V  = fy . G_hi
+      umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
+    }
+    // ---- next batch's record: its loads fly during the MMA round trip and the epilogue
+    const int cur_id = id;
+    const float4 col = rc;
+    const float lop = ra.z;
+    int nid = -1;
+    float4 na = make_float4(1e18f, -1.0f, 0.0f, 0.0f), nb4 = na, nc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bi + 1 < nbatch) {
+      const int i = (bi + 1) * BT_THREADS + tid;
+      if (i < n) {
+        nid = __ldg(vals + start + i);
+        na = __ldg(rec + 3 * (size_t)nid);
+        nb4 = __ldg(rec + 3 * (size_t)nid + 1);
+        nc = __ldg(rec + 3 * (size_t)nid + 2);
+      }
+    }
+    mbar_wait(&bar_mma, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+    // ---- thread-local epilogue: this Gaussian's 16 rows (U) and 16 columns (V), packed f32x2
+    const float2 cR = bc2(col.x), cG = bc2(col.y), cB = bc2(col.z);
+    float2 aR = make_float2(0.f, 0.f), aG = aR, aB = aR, aS = aR, aSy = aR, aSyy = aR, aSx = aR, aSxx = aR;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                          // rows 8h .. 8h+7
+      float uR[8], uG[8], uB[8], uW[8];
+      tmem_ld8(taddr + 0 * 16 + 8 * h, uR);
+      tmem_ld8(taddr + 1 * 16 + 8 * h, uG);
+      tmem_ld8(taddr + 2 * 16 + 8 * h, uB);
+      tmem_ld8(taddr + 3 * 16 + 8 * h, uW);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = 8 * h + 2 * j;
+        const float2 vR = make_float2(uR[2 * j], uR[2 * j + 1]), vG = make_float2(uG[2 * j], uG[2 * j + 1]),
+                     vB = make_float2(uB[2 * j], uB[2 * j + 1]), vW = make_float2(uW[2 * j], uW[2 * j + 1]);
+        const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+        const float2 f = fy2[r >> 1];
+        const float2 dy = make_float2(dy0 + (float)r, dy0 + (float)(r + 1));
+        const float2 a = __fmul2_rn(f, T);
+        aS = __fadd2_rn(aS, a);
+        aSy = __ffma2_rn(a, dy, aSy);
+        aSyy = __ffma2_rn(__fmul2_rn(a, dy), dy, aSyy);
+        aR = __ffma2_rn(f, vR, aR);
+        aG = __ffma2_rn(f, vG, aG);
+        aB = __ffma2_rn(f, vB, aB);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                          // columns 8h .. 8h+7
+      float vR8[8], vG8[8], vB8[8], vW8[8];
+      tmem_ld8(taddr + NR + 0 * 16 + 8 * h, vR8);
+      tmem_ld8(taddr + NR + 1 * 16 + 8 * h, vG8);
+      tmem_ld8(taddr + NR + 2 * 16 + 8 * h, vB8);
+      tmem_ld8(taddr + NR + 3 * 16 + 8 * h, vW8);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 8 * h + 2 * j;
+        const float2 vR = make_float2(vR8[2 * j], vR8[2 * j + 1]), vG = make_float2(vG8[2 * j], vG8[2 * j + 1]),
+                     vB = make_float2(vB8[2 * j], vB8[2 * j + 1]), vW = make_float2(vW8[2 * j], vW8[2 * j + 1]);
+        const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+        const float2 dx = make_float2(dx0 + (float)c, dx0 + (float)(c + 1));
+        const float2 b = __fmul2_rn(__fmul2_rn(fx2[c >> 1], T), dx);
+        aSx = __fadd2_rn(aSx, b);
+        aSxx = __ffma2_rn(b, dx, aSxx);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next batch's barrier
+    if (cur_id >= 0) {
+      // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
+      const bool zop = (lop == -INFINITY);
+      const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
+      float* dst = gacc + (size_t)cur_id * GACC_F;
+      const float S = (aS.x + aS.y) * opk;
+      if (!zop) {
+        red_add_v4(dst, (aR.x + aR.y) * opk, (aG.x + aG.y) * opk, (aB.x + aB.y) * opk, 0.0f);
+        red_add_v4(dst + 4, S, (aSx.x + aSx.y) * opk, (aSxx.x + aSxx.y) * opk, (aSy.x + aSy.y) * opk);
+        atomicAdd(dst + 8, (aSyy.x + aSyy.y) * opk);
+      } else {
+        red_add_v4(dst + 4, S, 0.0f, 0.0f, 0.0f);
+      }
+    }
+    id = nid; ra = na; rb = nb4; rc = nc;
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128) : "memory");
+}
+
 // Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (written by
 // preprocess_kernel into the view state) into the spare slot 9 of its row, where the chain-rule kernel finds it
 // next to the sums -- the blend kernel itself never touches it.
@@ -688,16 +913,31 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     // gbuf region: [tile][20 uint4][32 lanes] fragments (10 KB per tile), then one scale per tile
     uint32_t* frag = reinterpret_cast<uint32_t*>(gbuf);
     float* tile_scale = gbuf + (size_t)vp.n_tiles * GBUF_FRAG_WORDS;
-    if (fl != nullptr)
-      gbuf_frag_kernel<false, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
-                                                                    fl->scale, fl->loss_accum, frag, tile_scale);
+    // the tcgen05 kernel covers the 4-plane case (no depth gradient); B2S_BWD_MMASYNC=1 keeps the mma.sync kernel
+    static const bool mmasync = [] { const char* e = getenv("B2S_BWD_MMASYNC"); return e != nullptr && e[0] == '1'; }();
+    const bool umma = !depth && !mmasync;
+    if (fl != nullptr && umma)
+      gbuf_frag_kernel<false, true, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
+                                                                          fl->scale, fl->loss_accum, frag, tile_scale);
+    else if (fl != nullptr)
+      gbuf_frag_kernel<false, true, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
+                                                                           fl->scale, fl->loss_accum, frag, tile_scale);
     else if (depth)
-      gbuf_frag_kernel<true, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
-                                                                    nullptr, frag, tile_scale);
+      gbuf_frag_kernel<true, false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
+                                                                           nullptr, frag, tile_scale);
+    else if (umma)
+      gbuf_frag_kernel<false, false, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
+                                                                           nullptr, frag, tile_scale);
     else
-      gbuf_frag_kernel<false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
-                                                                     nullptr, frag, tile_scale);
+      gbuf_frag_kernel<false, false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
+                                                                            nullptr, frag, tile_scale);
     B2S_LAUNCH_CHECK();
+    if (umma) {
+      blend_wsum_bwd_umma_kernel<<<(int)unit_cap, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+                                                                       reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
+      B2S_LAUNCH_CHECK();
+      return B2S_OK;
+    }
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);
     static const bool minb4 = [] { const char* e = getenv("B2S_BWD_MINB"); return e != nullptr && e[0] == '4'; }();
