@@ -706,24 +706,19 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
                            const int2* __restrict__ units, const uint4* __restrict__ planes,
                            const float* __restrict__ tile_scale, float* __restrict__ gacc) {
   constexpr int NR = 64;                                   // operand rows of a plane matrix: 4 planes x 16
+  constexpr uint32_t PLANE_BYTES = 4 * NR * 16 * 2;        // U_hi | U_lo | V_hi | V_lo, 2 KB each
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
-  __shared__ __align__(128) uint4 sP[4 * NR * 16 * 2 / 16];      // U_hi | U_lo | V_hi | V_lo, 2 KB each
+  __shared__ __align__(128) uint4 sP[2][PLANE_BYTES / 16];       // the planes of the current and of the next unit's tile
   __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
-  __shared__ __align__(8) unsigned long long bar_load, bar_mma;
+  __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
   __shared__ uint32_t tmem_base_s;
-  const int u = blockIdx.x;
-  if (u >= unit_start[vp.n_tiles]) return;                 // block-uniform
-  const int2 ud = units[u];
-  const int tile = ud.x;
-  const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = min(SEG, rg.y - start);
-  if (n <= 0) return;                                      // block-uniform
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int nunits = unit_start[vp.n_tiles];
+  if ((int)blockIdx.x >= nunits) return;                   // block-uniform
 
   if (tid == 0) {
-    mbar_init(&bar_load, 1);
+    mbar_init(&bar_load[0], 1);
+    mbar_init(&bar_load[1], 1);
     mbar_init(&bar_mma, 1);
   }
   if (warp == 0) {
@@ -734,138 +729,172 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {                                          // the tile's planes: ONE bulk copy (async proxy, lands on bar_load)
-    mbar_expect_tx(&bar_load, 4 * NR * 16 * 2);
-    bulk_g2s(sP, planes + (size_t)tile * (4 * NR * 16 * 2 / 16), 4 * NR * 16 * 2, &bar_load);
-  }
-  const float k_us = __ldg(tile_scale + tile);            // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
-  const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
   // this thread's A rows (row tid): K chunk 0 at +0, K chunk 1 at +2048 B
   uint4* rowx = &sA[0][(tid >> 3) * 8 + (tid & 7)];
   uint4* rowy = &sA[1][(tid >> 3) * 8 + (tid & 7)];
   const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint64_t dax = umma_desc_kmajor(smem_u32(&sA[0][0]), 128 * 16, 128), day = umma_desc_kmajor(smem_u32(&sA[1][0]), 128 * 16, 128);
 
-  const int nbatch = (n + BT_THREADS - 1) / BT_THREADS;
-  int id = (tid < n) ? __ldg(vals + start + tid) : -1;
+  // ---- persistent loop over this CTA's units u = blockIdx.x, +gridDim.x, ...; a "step" is one batch of 128
+  // Gaussians of a unit.  The record of the next step (possibly the first batch of the next unit) and the planes
+  // of the next unit are fetched one step / one unit ahead.
+  struct Unit { int tile, start, n; };
+  auto unit_of = [&](int u) -> Unit {
+    Unit q = {0, 0, 0};
+    if (u < nunits) {
+      const int2 ud = units[u];
+      const int2 rg = ranges[ud.x];
+      q.tile = ud.x;
+      q.start = rg.x + ud.y * SEG;
+      q.n = max(0, min(SEG, rg.y - q.start));
+    }
+    return q;
+  };
+  auto fetch_planes = [&](int tile, int buf) {             // ONE bulk copy (async proxy), lands on bar_load[buf]
+    mbar_expect_tx(&bar_load[buf], PLANE_BYTES);
+    bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_BYTES / 16), PLANE_BYTES, &bar_load[buf]);
+  };
+  int u = blockIdx.x;
+  Unit cur = unit_of(u);
+  while (u < nunits && cur.n == 0) { u += gridDim.x; cur = unit_of(u); }     // empty tiles keep one empty unit
+  if (u < nunits && tid == 0) fetch_planes(cur.tile, 0);
+  int id = -1;
   float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, rc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (id >= 0) {
+  if (u < nunits && tid < cur.n) {
+    id = __ldg(vals + cur.start + tid);
     ra = __ldg(rec + 3 * (size_t)id);
     rb = __ldg(rec + 3 * (size_t)id + 1);
     rc = __ldg(rec + 3 * (size_t)id + 2);
   }
   uint32_t phase = 0;
-  for (int bi = 0; bi < nbatch; ++bi) {
-    // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
-    const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
-    float2 fx2[8], fy2[8];
+  int kbuf = 0;                                            // units processed so far: plane buffer = kbuf & 1
+  while (u < nunits) {
+    // the next non-empty unit of this CTA and its planes
+    int un = u + gridDim.x;
+    Unit nxt = unit_of(un);
+    while (un < nunits && nxt.n == 0) { un += gridDim.x; nxt = unit_of(un); }
+    if (un < nunits && tid == 0) fetch_planes(nxt.tile, (kbuf + 1) & 1);   // that buffer's last reader (unit kbuf-1) has retired
+    const float k_us = __ldg(tile_scale + cur.tile);      // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
+    const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
+    const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
+    const uint32_t pb = smem_u32(&sP[kbuf & 1][0]);
+    const int nbatch = (cur.n + BT_THREADS - 1) / BT_THREADS;
+    for (int bi = 0; bi < nbatch; ++bi) {
+      // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
+      const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
+      float2 fx2[8], fy2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dxa = dx0 + (float)(2 * j), dxb = dx0 + (float)(2 * j + 1);
-      const float dya = dy0 + (float)(2 * j), dyb = dy0 + (float)(2 * j + 1);
-      fx2[j] = make_float2(ex2_approx(fmaf(ra.y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra.y * dxb, dxb, 8.0f)));
-      fy2[j] = make_float2(ex2_approx(fmaf(rb.y * dya, dya, 8.0f)), ex2_approx(fmaf(rb.y * dyb, dyb, 8.0f)));
-    }
-    rowx[0]   = make_uint4(pack_h2(fx2[0].x, fx2[0].y), pack_h2(fx2[1].x, fx2[1].y), pack_h2(fx2[2].x, fx2[2].y), pack_h2(fx2[3].x, fx2[3].y));
-    rowx[128] = make_uint4(pack_h2(fx2[4].x, fx2[4].y), pack_h2(fx2[5].x, fx2[5].y), pack_h2(fx2[6].x, fx2[6].y), pack_h2(fx2[7].x, fx2[7].y));
-    rowy[0]   = make_uint4(pack_h2(fy2[0].x, fy2[0].y), pack_h2(fy2[1].x, fy2[1].y), pack_h2(fy2[2].x, fy2[2].y), pack_h2(fy2[3].x, fy2[3].y));
-    rowy[128] = make_uint4(pack_h2(fy2[4].x, fy2[4].y), pack_h2(fy2[5].x, fy2[5].y), pack_h2(fy2[6].x, fy2[6].y), pack_h2(fy2[7].x, fy2[7].y));
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();                                       // every row written; every thread done reading TMEM (previous batch)
-    if (tid == 0) {
-      if (bi == 0) mbar_wait(&bar_load, 0);
+      for (int j = 0; j < 8; ++j) {
+        const float dxa = dx0 + (float)(2 * j), dxb = dx0 + (float)(2 * j + 1);
+        const float dya = dy0 + (float)(2 * j), dyb = dy0 + (float)(2 * j + 1);
+        fx2[j] = make_float2(ex2_approx(fmaf(ra.y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra.y * dxb, dxb, 8.0f)));
+        fy2[j] = make_float2(ex2_approx(fmaf(rb.y * dya, dya, 8.0f)), ex2_approx(fmaf(rb.y * dyb, dyb, 8.0f)));
+      }
+      rowx[0]   = make_uint4(pack_h2(fx2[0].x, fx2[0].y), pack_h2(fx2[1].x, fx2[1].y), pack_h2(fx2[2].x, fx2[2].y), pack_h2(fx2[3].x, fx2[3].y));
+      rowx[128] = make_uint4(pack_h2(fx2[4].x, fx2[4].y), pack_h2(fx2[5].x, fx2[5].y), pack_h2(fx2[6].x, fx2[6].y), pack_h2(fx2[7].x, fx2[7].y));
+      rowy[0]   = make_uint4(pack_h2(fy2[0].x, fy2[0].y), pack_h2(fy2[1].x, fy2[1].y), pack_h2(fy2[2].x, fy2[2].y), pack_h2(fy2[3].x, fy2[3].y));
+      rowy[128] = make_uint4(pack_h2(fy2[4].x, fy2[4].y), pack_h2(fy2[5].x, fy2[5].y), pack_h2(fy2[6].x, fy2[6].y), pack_h2(fy2[7].x, fy2[7].y));
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();                                     // every row written; every thread done reading TMEM (previous step)
+      if (tid == 0) {
+        if (bi == 0) mbar_wait(&bar_load[kbuf & 1], (uint32_t)(kbuf >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        umma_f16(tmem,      dax, umma_desc_kmajor(pb,            NR * 16, 128), IDESC, 0);    // U  = fx . G_hi
+        umma_f16(tmem,      dax, umma_desc_kmajor(pb + 2048,     NR * 16, 128), IDESC, 1);    // U += fx . G_lo
+        umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 2 * 2048, NR * 16, 128), IDESC, 0);    // V  = fy . G_hi
+        umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
+      }
+      // ---- the next step's record: its loads fly during the MMA round trip and the epilogue
+      const int cur_id = id;
+      const float4 col = rc;
+      const float lop = ra.z;
+      {
+        const bool last = (bi + 1 == nbatch);
+        const int i = last ? tid : (bi + 1) * BT_THREADS + tid;
+        const int lim = last ? ((un < nunits) ? nxt.n : 0) : cur.n;
+        const int base = last ? nxt.start : cur.start;
+        id = -1;
+        ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f); rb = ra; rc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < lim) {
+          id = __ldg(vals + base + i);
+          ra = __ldg(rec + 3 * (size_t)id);
+          rb = __ldg(rec + 3 * (size_t)id + 1);
+          rc = __ldg(rec + 3 * (size_t)id + 2);
+        }
+      }
+      mbar_wait(&bar_mma, phase);
+      phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint64_t dax = umma_desc_kmajor(smem_u32(&sA[0][0]), 128 * 16, 128), day = umma_desc_kmajor(smem_u32(&sA[1][0]), 128 * 16, 128);
-      const uint32_t pb = smem_u32(&sP[0]);
-      umma_f16(tmem,      dax, umma_desc_kmajor(pb,            NR * 16, 128), IDESC, 0);    // U  = fx . G_hi
-      umma_f16(tmem,      dax, umma_desc_kmajor(pb + 2048,     NR * 16, 128), IDESC, 1);    // U += fx . G_lo
-      umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 2 * 2048, NR * 16, 128), IDESC, 0);    // V  = fy . G_hi
-      umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
-    }
-    // ---- next batch's record: its loads fly during the MMA round trip and the epilogue
-    const int cur_id = id;
-    const float4 col = rc;
-    const float lop = ra.z;
-    int nid = -1;
-    float4 na = make_float4(1e18f, -1.0f, 0.0f, 0.0f), nb4 = na, nc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bi + 1 < nbatch) {
-      const int i = (bi + 1) * BT_THREADS + tid;
-      if (i < n) {
-        nid = __ldg(vals + start + i);
-        na = __ldg(rec + 3 * (size_t)nid);
-        nb4 = __ldg(rec + 3 * (size_t)nid + 1);
-        nc = __ldg(rec + 3 * (size_t)nid + 2);
-      }
-    }
-    mbar_wait(&bar_mma, phase);
-    phase ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
-    // ---- thread-local epilogue: this Gaussian's 16 rows (U) and 16 columns (V), packed f32x2
-    const float2 cR = bc2(col.x), cG = bc2(col.y), cB = bc2(col.z);
-    float2 aR = make_float2(0.f, 0.f), aG = aR, aB = aR, aS = aR, aSy = aR, aSyy = aR, aSx = aR, aSxx = aR;
+      // ---- thread-local epilogue: this Gaussian's 16 rows (U) and 16 columns (V), packed f32x2
+      const float2 cR = bc2(col.x), cG = bc2(col.y), cB = bc2(col.z);
+      float2 aR = make_float2(0.f, 0.f), aG = aR, aB = aR, aS = aR, aSy = aR, aSyy = aR, aSx = aR, aSxx = aR;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                          // rows 8h .. 8h+7
-      float uR[8], uG[8], uB[8], uW[8];
-      tmem_ld8(taddr + 0 * 16 + 8 * h, uR);
-      tmem_ld8(taddr + 1 * 16 + 8 * h, uG);
-      tmem_ld8(taddr + 2 * 16 + 8 * h, uB);
-      tmem_ld8(taddr + 3 * 16 + 8 * h, uW);
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      for (int h = 0; h < 2; ++h) {                        // rows 8h .. 8h+7
+        float uR[8], uG[8], uB[8], uW[8];
+        tmem_ld8(taddr + 0 * 16 + 8 * h, uR);
+        tmem_ld8(taddr + 1 * 16 + 8 * h, uG);
+        tmem_ld8(taddr + 2 * 16 + 8 * h, uB);
+        tmem_ld8(taddr + 3 * 16 + 8 * h, uW);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = 8 * h + 2 * j;
-        const float2 vR = make_float2(uR[2 * j], uR[2 * j + 1]), vG = make_float2(uG[2 * j], uG[2 * j + 1]),
-                     vB = make_float2(uB[2 * j], uB[2 * j + 1]), vW = make_float2(uW[2 * j], uW[2 * j + 1]);
-        const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
-        const float2 f = fy2[r >> 1];
-        const float2 dy = make_float2(dy0 + (float)r, dy0 + (float)(r + 1));
-        const float2 a = __fmul2_rn(f, T);
-        aS = __fadd2_rn(aS, a);
-        aSy = __ffma2_rn(a, dy, aSy);
-        aSyy = __ffma2_rn(__fmul2_rn(a, dy), dy, aSyy);
-        aR = __ffma2_rn(f, vR, aR);
-        aG = __ffma2_rn(f, vG, aG);
-        aB = __ffma2_rn(f, vB, aB);
+        for (int j = 0; j < 4; ++j) {
+          const int r = 8 * h + 2 * j;
+          const float2 vR = make_float2(uR[2 * j], uR[2 * j + 1]), vG = make_float2(uG[2 * j], uG[2 * j + 1]),
+                       vB = make_float2(uB[2 * j], uB[2 * j + 1]), vW = make_float2(uW[2 * j], uW[2 * j + 1]);
+          const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+          const float2 f = fy2[r >> 1];
+          const float2 dy = make_float2(dy0 + (float)r, dy0 + (float)(r + 1));
+          const float2 a = __fmul2_rn(f, T);
+          aS = __fadd2_rn(aS, a);
+          aSy = __ffma2_rn(a, dy, aSy);
+          aSyy = __ffma2_rn(__fmul2_rn(a, dy), dy, aSyy);
+          aR = __ffma2_rn(f, vR, aR);
+          aG = __ffma2_rn(f, vG, aG);
+          aB = __ffma2_rn(f, vB, aB);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                        // columns 8h .. 8h+7
+        float vR8[8], vG8[8], vB8[8], vW8[8];
+        tmem_ld8(taddr + NR + 0 * 16 + 8 * h, vR8);
+        tmem_ld8(taddr + NR + 1 * 16 + 8 * h, vG8);
+        tmem_ld8(taddr + NR + 2 * 16 + 8 * h, vB8);
+        tmem_ld8(taddr + NR + 3 * 16 + 8 * h, vW8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * h + 2 * j;
+          const float2 vR = make_float2(vR8[2 * j], vR8[2 * j + 1]), vG = make_float2(vG8[2 * j], vG8[2 * j + 1]),
+                       vB = make_float2(vB8[2 * j], vB8[2 * j + 1]), vW = make_float2(vW8[2 * j], vW8[2 * j + 1]);
+          const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+          const float2 dx = make_float2(dx0 + (float)c, dx0 + (float)(c + 1));
+          const float2 b = __fmul2_rn(__fmul2_rn(fx2[c >> 1], T), dx);
+          aSx = __fadd2_rn(aSx, b);
+          aSxx = __ffma2_rn(b, dx, aSxx);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next step's barrier
+      if (cur_id >= 0) {
+        // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
+        const bool zop = (lop == -INFINITY);
+        const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
+        float* dst = gacc + (size_t)cur_id * GACC_F;
+        const float S = (aS.x + aS.y) * opk;
+        if (!zop) {
+          red_add_v4(dst, (aR.x + aR.y) * opk, (aG.x + aG.y) * opk, (aB.x + aB.y) * opk, 0.0f);
+          red_add_v4(dst + 4, S, (aSx.x + aSx.y) * opk, (aSxx.x + aSxx.y) * opk, (aSy.x + aSy.y) * opk);
+          atomicAdd(dst + 8, (aSyy.x + aSyy.y) * opk);
+        } else {
+          red_add_v4(dst + 4, S, 0.0f, 0.0f, 0.0f);
+        }
       }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {                          // columns 8h .. 8h+7
-      float vR8[8], vG8[8], vB8[8], vW8[8];
-      tmem_ld8(taddr + NR + 0 * 16 + 8 * h, vR8);
-      tmem_ld8(taddr + NR + 1 * 16 + 8 * h, vG8);
-      tmem_ld8(taddr + NR + 2 * 16 + 8 * h, vB8);
-      tmem_ld8(taddr + NR + 3 * 16 + 8 * h, vW8);
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = 8 * h + 2 * j;
-        const float2 vR = make_float2(vR8[2 * j], vR8[2 * j + 1]), vG = make_float2(vG8[2 * j], vG8[2 * j + 1]),
-                     vB = make_float2(vB8[2 * j], vB8[2 * j + 1]), vW = make_float2(vW8[2 * j], vW8[2 * j + 1]);
-        const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
-        const float2 dx = make_float2(dx0 + (float)c, dx0 + (float)(c + 1));
-        const float2 b = __fmul2_rn(__fmul2_rn(fx2[c >> 1], T), dx);
-        aSx = __fadd2_rn(aSx, b);
-        aSxx = __ffma2_rn(b, dx, aSxx);
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next batch's barrier
-    if (cur_id >= 0) {
-      // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
-      const bool zop = (lop == -INFINITY);
-      const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
-      float* dst = gacc + (size_t)cur_id * GACC_F;
-      const float S = (aS.x + aS.y) * opk;
-      if (!zop) {
-        red_add_v4(dst, (aR.x + aR.y) * opk, (aG.x + aG.y) * opk, (aB.x + aB.y) * opk, 0.0f);
-        red_add_v4(dst + 4, S, (aSx.x + aSx.y) * opk, (aSxx.x + aSxx.y) * opk, (aSy.x + aSy.y) * opk);
-        atomicAdd(dst + 8, (aSyy.x + aSyy.y) * opk);
-      } else {
-        red_add_v4(dst + 4, S, 0.0f, 0.0f, 0.0f);
-      }
-    }
-    id = nid; ra = na; rb = nb4; rc = nc;
+    u = un;
+    cur = nxt;
+    ++kbuf;
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128) : "memory");
@@ -933,7 +962,9 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
                                                                             nullptr, frag, tile_scale);
     B2S_LAUNCH_CHECK();
     if (umma) {
-      blend_wsum_bwd_umma_kernel<<<(int)unit_cap, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
+      const int grid = (int)(unit_cap < 4 * 148 ? unit_cap : 4 * 148);
+      blend_wsum_bwd_umma_kernel<<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
                                                                        reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       B2S_LAUNCH_CHECK();
       return B2S_OK;
