@@ -405,6 +405,10 @@ __device__ __forceinline__ void cp_async16_b(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4_b(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_b() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_b() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -710,6 +714,8 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
   __shared__ __align__(128) uint4 sP[2][PLANE_BYTES / 16];       // the planes of the current and of the next unit's tile
   __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
+  __shared__ __align__(16) float4 sRec[2][3][BT_THREADS];       // records of the current / next step, one per thread
+  __shared__ int sId[2][SEG];                                    // Gaussian ids of the current / next unit
   __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -754,22 +760,37 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     mbar_expect_tx(&bar_load[buf], PLANE_BYTES);
     bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_BYTES / 16), PLANE_BYTES, &bar_load[buf]);
   };
+  // Gaussian ids of a unit and the record of a step are staged with cp.async: every thread copies and later
+  // reads only ITS OWN slots, so cp.async.wait_group orders them without a barrier, and no register waits on a
+  // global load (a warp issues in order: a register prefetch of `rec[id]` stalls on `id` right away).
+  auto fetch_ids = [&](const Unit& q, int buf) {
+    for (int i = tid; i < q.n; i += BT_THREADS) cp_async4_b(&sId[buf][i], vals + q.start + i);
+    cp_async_commit_b();
+  };
+  auto fetch_rec = [&](const Unit& q, int idbuf, int batch, int rbuf) {    // needs sId[idbuf] of this thread landed
+    const int i = batch * BT_THREADS + tid;
+    if (i < q.n) {
+      const float4* src = rec + 3 * (size_t)sId[idbuf][i];
+      cp_async16_b(&sRec[rbuf][0][tid], src);
+      cp_async16_b(&sRec[rbuf][1][tid], src + 1);
+      cp_async16_b(&sRec[rbuf][2][tid], src + 2);
+    }
+    cp_async_commit_b();
+  };
   int u = blockIdx.x;
   Unit cur = unit_of(u);
   while (u < nunits && cur.n == 0) { u += gridDim.x; cur = unit_of(u); }     // empty tiles keep one empty unit
-  if (u < nunits && tid == 0) fetch_planes(cur.tile, 0);
-  int id = -1;
-  float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, rc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (u < nunits && tid < cur.n) {
-    id = __ldg(vals + cur.start + tid);
-    ra = __ldg(rec + 3 * (size_t)id);
-    rb = __ldg(rec + 3 * (size_t)id + 1);
-    rc = __ldg(rec + 3 * (size_t)id + 2);
+  if (u < nunits) {
+    if (tid == 0) fetch_planes(cur.tile, 0);
+    fetch_ids(cur, 0);
+    cp_async_wait_b<0>();
+    fetch_rec(cur, 0, 0, 0);
   }
   uint32_t phase = 0;
-  int kbuf = 0;                                            // units processed so far: plane buffer = kbuf & 1
+  int kbuf = 0;                                            // units processed so far: plane / id buffer = kbuf & 1
+  int step = 0;                                            // steps processed so far: record buffer = step & 1
   while (u < nunits) {
-    // the next non-empty unit of this CTA and its planes
+    // the next non-empty unit of this CTA: its planes and ids are fetched a whole unit ahead
     int un = u + gridDim.x;
     Unit nxt = unit_of(un);
     while (un < nunits && nxt.n == 0) { un += gridDim.x; nxt = unit_of(un); }
@@ -779,7 +800,21 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
     const uint32_t pb = smem_u32(&sP[kbuf & 1][0]);
     const int nbatch = (cur.n + BT_THREADS - 1) / BT_THREADS;
-    for (int bi = 0; bi < nbatch; ++bi) {
+    for (int bi = 0; bi < nbatch; ++bi, ++step) {
+      cp_async_wait_b<0>();                                // this step's record (issued a step ago) and older copies
+      const bool active = bi * BT_THREADS + tid < cur.n;
+      const int cur_id = active ? sId[kbuf & 1][bi * BT_THREADS + tid] : -1;
+      float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, col = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) { ra = sRec[step & 1][0][tid]; rb = sRec[step & 1][1][tid]; col = sRec[step & 1][2][tid]; }
+      const float lop = ra.z;
+      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
+      // the next step's record: its copy flies during this step
+      if (bi + 1 < nbatch) {
+        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
+      } else if (un < nunits) {
+        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
+        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
+      }
       // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
       const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
       float2 fx2[8], fy2[8];
@@ -805,24 +840,6 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 2 * 2048, NR * 16, 128), IDESC, 0);    // V  = fy . G_hi
         umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
-      }
-      // ---- the next step's record: its loads fly during the MMA round trip and the epilogue
-      const int cur_id = id;
-      const float4 col = rc;
-      const float lop = ra.z;
-      {
-        const bool last = (bi + 1 == nbatch);
-        const int i = last ? tid : (bi + 1) * BT_THREADS + tid;
-        const int lim = last ? ((un < nunits) ? nxt.n : 0) : cur.n;
-        const int base = last ? nxt.start : cur.start;
-        id = -1;
-        ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f); rb = ra; rc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < lim) {
-          id = __ldg(vals + base + i);
-          ra = __ldg(rec + 3 * (size_t)id);
-          rb = __ldg(rec + 3 * (size_t)id + 1);
-          rc = __ldg(rec + 3 * (size_t)id + 2);
-        }
       }
       mbar_wait(&bar_mma, phase);
       phase ^= 1u;
