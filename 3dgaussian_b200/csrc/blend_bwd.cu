@@ -704,6 +704,72 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "r"(taddr));
+}
+// tcgen05.wait::ld for the 16 registers of one quad; they are listed as in/out operands so that no use of them can
+// be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_quad(float (&q)[4][4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+f"(q[0][0]), "+f"(q[0][1]), "+f"(q[0][2]), "+f"(q[0][3]), "+f"(q[1][0]), "+f"(q[1][1]), "+f"(q[1][2]),
+                 "+f"(q[1][3]), "+f"(q[2][0]), "+f"(q[2][1]), "+f"(q[2][2]), "+f"(q[2][3]), "+f"(q[3][0]), "+f"(q[3][1]),
+                 "+f"(q[3][2]), "+f"(q[3][3])
+               :
+               : "memory");
+}
+
+// Thread-local epilogue of the tcgen05 backward: this thread's accumulator row -- U at columns [0,64) (plane*16 +
+// row), V at [64,128) (plane*16 + column) of `taddr` -- is streamed through registers in 8 quads of 4 rows /
+// columns x 4 planes.  The loads are software pipelined: quad q+1 is requested right after quad q has landed, so its
+// TMEM round trip hides behind the FP32 work of quad q (tcgen05.wait::ld waits for ALL outstanding loads, so at most
+// one quad may be in flight when it is issued).  fy_pair(p) / fx_pair(p): factors of rows / columns 2p, 2p+1.
+struct BwdSums {
+  float2 aR, aG, aB, aS, aSy, aSyy, aSx, aSxx;
+};
+template <class FyPair, class FxPair>
+__device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float dy0, float2 cR, float2 cG, float2 cB,
+                                              FyPair fy_pair, FxPair fx_pair, BwdSums& A) {
+  float buf[2][4][4];
+  auto request = [&](int q, float (&dst)[4][4]) {
+    const uint32_t base = taddr + (uint32_t)((q >> 2) * 64 + (q & 3) * 4);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) tmem_ld4(base + ch * 16, dst[ch]);
+  };
+  A.aR = A.aG = A.aB = A.aS = A.aSy = A.aSyy = A.aSx = A.aSxx = make_float2(0.f, 0.f);
+  request(0, buf[0]);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    tmem_wait_quad(buf[q & 1]);
+    if (q < 7) request(q + 1, buf[(q + 1) & 1]);
+    float (&b)[4][4] = buf[q & 1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i0 = 4 * (q & 3) + 2 * j;                  // row (U) or column (V) of the pair
+      const float2 vR = make_float2(b[0][2 * j], b[0][2 * j + 1]), vG = make_float2(b[1][2 * j], b[1][2 * j + 1]),
+                   vB = make_float2(b[2][2 * j], b[2][2 * j + 1]), vW = make_float2(b[3][2 * j], b[3][2 * j + 1]);
+      const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+      if (q < 4) {
+        const float2 f = fy_pair(i0 >> 1);
+        const float2 dy = make_float2(dy0 + (float)i0, dy0 + (float)(i0 + 1));
+        const float2 a = __fmul2_rn(f, T);
+        A.aS = __fadd2_rn(A.aS, a);
+        A.aSy = __ffma2_rn(a, dy, A.aSy);
+        A.aSyy = __ffma2_rn(__fmul2_rn(a, dy), dy, A.aSyy);
+        A.aR = __ffma2_rn(f, vR, A.aR);
+        A.aG = __ffma2_rn(f, vG, A.aG);
+        A.aB = __ffma2_rn(f, vB, A.aB);
+      } else {
+        const float2 dx = make_float2(dx0 + (float)i0, dx0 + (float)(i0 + 1));
+        const float2 bb = __fmul2_rn(__fmul2_rn(fx_pair(i0 >> 1), T), dx);
+        A.aSx = __fadd2_rn(A.aSx, bb);
+        A.aSxx = __ffma2_rn(bb, dx, A.aSxx);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(BT_THREADS, 4)
 blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int2* __restrict__ ranges, const int* __restrict__ unit_start,
@@ -846,53 +912,10 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
       // ---- thread-local epilogue: this Gaussian's 16 rows (U) and 16 columns (V), packed f32x2
-      const float2 cR = bc2(col.x), cG = bc2(col.y), cB = bc2(col.z);
-      float2 aR = make_float2(0.f, 0.f), aG = aR, aB = aR, aS = aR, aSy = aR, aSyy = aR, aSx = aR, aSxx = aR;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {                        // rows 8h .. 8h+7
-        float uR[8], uG[8], uB[8], uW[8];
-        tmem_ld8(taddr + 0 * 16 + 8 * h, uR);
-        tmem_ld8(taddr + 1 * 16 + 8 * h, uG);
-        tmem_ld8(taddr + 2 * 16 + 8 * h, uB);
-        tmem_ld8(taddr + 3 * 16 + 8 * h, uW);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = 8 * h + 2 * j;
-          const float2 vR = make_float2(uR[2 * j], uR[2 * j + 1]), vG = make_float2(uG[2 * j], uG[2 * j + 1]),
-                       vB = make_float2(uB[2 * j], uB[2 * j + 1]), vW = make_float2(uW[2 * j], uW[2 * j + 1]);
-          const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
-          const float2 f = fy2[r >> 1];
-          const float2 dy = make_float2(dy0 + (float)r, dy0 + (float)(r + 1));
-          const float2 a = __fmul2_rn(f, T);
-          aS = __fadd2_rn(aS, a);
-          aSy = __ffma2_rn(a, dy, aSy);
-          aSyy = __ffma2_rn(__fmul2_rn(a, dy), dy, aSyy);
-          aR = __ffma2_rn(f, vR, aR);
-          aG = __ffma2_rn(f, vG, aG);
-          aB = __ffma2_rn(f, vB, aB);
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {                        // columns 8h .. 8h+7
-        float vR8[8], vG8[8], vB8[8], vW8[8];
-        tmem_ld8(taddr + NR + 0 * 16 + 8 * h, vR8);
-        tmem_ld8(taddr + NR + 1 * 16 + 8 * h, vG8);
-        tmem_ld8(taddr + NR + 2 * 16 + 8 * h, vB8);
-        tmem_ld8(taddr + NR + 3 * 16 + 8 * h, vW8);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 8 * h + 2 * j;
-          const float2 vR = make_float2(vR8[2 * j], vR8[2 * j + 1]), vG = make_float2(vG8[2 * j], vG8[2 * j + 1]),
-                       vB = make_float2(vB8[2 * j], vB8[2 * j + 1]), vW = make_float2(vW8[2 * j], vW8[2 * j + 1]);
-          const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
-          const float2 dx = make_float2(dx0 + (float)c, dx0 + (float)(c + 1));
-          const float2 b = __fmul2_rn(__fmul2_rn(fx2[c >> 1], T), dx);
-          aSx = __fadd2_rn(aSx, b);
-          aSxx = __ffma2_rn(b, dx, aSxx);
-        }
-      }
+      BwdSums A;
+      umma_epilogue(taddr, dx0, dy0, bc2(col.x), bc2(col.y), bc2(col.z), [&](int p) { return fy2[p]; },
+                    [&](int p) { return fx2[p]; }, A);
+      const float2 aR = A.aR, aG = A.aG, aB = A.aB, aS = A.aS, aSy = A.aSy, aSyy = A.aSyy, aSx = A.aSx, aSxx = A.aSxx;
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next step's barrier
       if (cur_id >= 0) {
         // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
@@ -980,9 +1003,10 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     B2S_LAUNCH_CHECK();
     if (umma) {
       // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
+      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
       const int grid = (int)(unit_cap < 4 * 148 ? unit_cap : 4 * 148);
       blend_wsum_bwd_umma_kernel<<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
-                                                                       reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
+                                                              reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       B2S_LAUNCH_CHECK();
       return B2S_OK;
     }
