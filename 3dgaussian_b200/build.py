@@ -35,7 +35,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "b2splat.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(ROOT, "include", "b2splat.h")]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = []

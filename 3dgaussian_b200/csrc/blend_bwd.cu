@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace b2s {
 
@@ -208,41 +209,6 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
   for (int k = q; k < NREG * 32 / 4; k += TILE_PIX) out[k] = src[k];
 }
 
-// ---- TMA bulk copy helpers (global -> shared, completion on an mbarrier) ------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
-               "l"(gmem_src), "r"(bytes), "r"(b)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  for (int spin = 0; spin < (1 << 20); ++spin) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();   // a bulk copy that never lands is a bug: fail the launch instead of hanging the GPU
-}
-
 __device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
 
 template <bool DEPTH>
@@ -400,18 +366,6 @@ struct BmStage {
   float4 c[BM_STAGE];   // {r, g, b, zabs}
   int id[BM_STAGE];
 };
-
-__device__ __forceinline__ void cp_async16_b(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4_b(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_b() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_b() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {   // {K even, K odd} -> f16x2
   const __half2 h = __floats2half2_rn(lo_k, hi_k);
@@ -675,25 +629,6 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 // Operand layout: K-major, no swizzle (8-row x 16-byte core matrices; row groups 128 B apart, the two K chunks
 // `rows*16` B apart), validated by profiles/microbench/umma_probe.cu.
 constexpr int BT_THREADS = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;       // leading byte offset: between the K chunks
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;       // stride byte offset: between 8-row groups
-  d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
-  return d;                                               // base offset 0, SWIZZLE_NONE
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
-      "r"(accumulate)
-      : "memory");
-}
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];

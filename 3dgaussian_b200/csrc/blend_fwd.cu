@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace b2s {
 
@@ -553,6 +554,257 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     }
 }
 
+// ---- v8: the tile GEMM on the 5th-generation tensor cores (tcgen05 / TMEM) -------------------------------
+// Same product as v5, turned so that a THREAD owns a Gaussian (the K index) and the tile's planes are the M x N
+// accumulator in tensor memory:
+//   D[(plane, column)][row] = sum_i A[(plane, column)][i] * B[row][i],   A = v_plane,i * fx_i[column],  B = fy_i[row]
+// M = 4 planes x 16 columns = 64, N = 16 rows, K = the 128 Gaussians of a batch (8 instructions of K = 16).
+// Both operands are MN-major in shared memory (thread i stores 16-byte groups of 8 consecutive M / N elements of
+// ITS Gaussian: conflict-free STS.128, no transposition), hi/lo split like v5:
+//   D[:, 0:32]  += A_hi . [B_hi | B_lo]     (one N = 32 instruction)
+//   D[:, 0:16]  += A_lo . B_hi              (one N = 16 instruction)         dropped term lo.lo ~ 2^-22
+// The accumulators never pass through registers inside the Gaussian loop: no HMMA issue slots, no fragment
+// shuffles, and the per-Gaussian work (32 MUFU.EX2, fp16 splits, 48 colour products) is plain thread-local code.
+// Per unit the 64 x 32 accumulator is read back once (warp = plane, lane = column), summed hi + lo, exchanged
+// through shared memory and written as pixels (or as the unit's partial planes when the tile has several units).
+//   CTA = 128 threads, 32 TMEM columns, 52 KB of shared memory -> 4 CTAs per SM; persistent over the units.
+// Layout validated by profiles/microbench/umma_probe_mn.cu.  The 5-plane (depth) case stays on v5.
+constexpr int FT_THREADS = 128;
+constexpr uint32_t FT_SBO = FT_THREADS * 16;      // bytes between MN groups of 8: [group][Gaussian] uint4
+struct FtSmem {
+  uint4 Ah[8][FT_THREADS];        // A hi: group = plane * 2 + column / 8
+  uint4 Al[8][FT_THREADS];
+  uint4 B[4][FT_THREADS];         // fy: hi rows 0-7, hi rows 8-15, lo rows 0-7, lo rows 8-15
+  float4 rec[2][2][FT_THREADS];   // x / y records of the current and the next step, one per thread
+  int id[2][SEG];                 // Gaussian ids of the current / next unit
+  unsigned long long bar_mma;
+  uint32_t tmem_base;
+};
+
+// hi + lo split of a packed pair; x - hi is exact in fp32, so the packed FMA (-1 * hi + x) is too
+__device__ __forceinline__ void split_h2v(float2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __float22half2_rn(x);
+  hi = h2_bits(h);
+  lo = h2_bits(__float22half2_rn(__ffma2_rn(__half22float2(h), make_float2(-1.0f, -1.0f), x)));
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 4)
+blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                           const int2* __restrict__ units, float* __restrict__ partial, float* __restrict__ out_rgb,
+                           float* __restrict__ out_alpha, float* __restrict__ acc, uint8_t* __restrict__ out_rgba) {
+  extern __shared__ __align__(128) unsigned char ft_raw[];
+  FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_raw);
+  constexpr uint32_t ID32 = umma_idesc_f16(64, 32, true, true), ID16 = umma_idesc_f16(64, 16, true, true);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nunits = unit_start[vp.n_tiles];
+  if ((int)blockIdx.x >= nunits) return;                   // block-uniform
+  const size_t hw = (size_t)vp.width * vp.height;
+
+  if (tid == 0) mbar_init(&sm.bar_mma, 1);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  // K slice s (Gaussians 16 s .. 16 s + 15) starts 256 B into every MN group: K groups 128 B apart (LBO)
+  const uint64_t dAh = umma_desc(smem_u32(&sm.Ah[0][0]), 128, FT_SBO), dAl = umma_desc(smem_u32(&sm.Al[0][0]), 128, FT_SBO),
+                 dB = umma_desc(smem_u32(&sm.B[0][0]), 128, FT_SBO);
+  float* sOut = reinterpret_cast<float*>(&sm.Ah[0][0]);    // [plane][row * 16 + column], aliases A hi between units
+
+  struct Unit { int tile, start, n, nseg; };
+  auto unit_of = [&](int u) -> Unit {
+    Unit q = {0, 0, 0, 1};
+    if (u < nunits) {
+      const int2 ud = units[u];
+      const int2 rg = ranges[ud.x];
+      q.tile = ud.x;
+      q.start = rg.x + ud.y * SEG;
+      q.n = max(0, min(SEG, rg.y - q.start));
+      q.nseg = unit_start[ud.x + 1] - unit_start[ud.x];
+    }
+    return q;
+  };
+  // pixels q = tid, tid + 128 of a unit: outputs (single-unit tile) or the unit's partial planes
+  auto emit = [&](int u, const Unit& q, int pix, float R, float G, float Bc, float W) {
+    if (q.nseg <= 1) {
+      const int xi = (q.tile % vp.tiles_x) * TILE + (pix & 15), yi = (q.tile / vp.tiles_x) * TILE + (pix >> 4);
+      if (xi < vp.width && yi < vp.height)
+        write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, Bc, W, 0.0f, out_rgb, out_alpha, nullptr, acc, out_rgba);
+    } else {
+      float* dst = partial + (size_t)u * 5 * TILE_PIX + pix;
+      dst[0] = R;
+      dst[TILE_PIX] = G;
+      dst[2 * TILE_PIX] = Bc;
+      dst[3 * TILE_PIX] = W;
+    }
+  };
+  // first / next NON-EMPTY unit of this CTA at or after u; the empty ones on the way (empty tiles keep one unit)
+  // are finished on the spot: their pixels see no Gaussian
+  auto skip_empty = [&](int& u, Unit& q) {
+    q = unit_of(u);
+    while (u < nunits && q.n == 0) {
+      emit(u, q, tid, 0.f, 0.f, 0.f, 0.f);
+      emit(u, q, tid + FT_THREADS, 0.f, 0.f, 0.f, 0.f);
+      u += gridDim.x;
+      q = unit_of(u);
+    }
+  };
+  auto fetch_ids = [&](const Unit& q, int buf) {
+    for (int i = tid; i < q.n; i += FT_THREADS) cp_async4_b(&sm.id[buf][i], vals + q.start + i);
+    cp_async_commit_b();
+  };
+  auto fetch_rec = [&](const Unit& q, int idbuf, int batch, int rbuf) {    // needs id[idbuf] of this thread landed
+    const int i = batch * FT_THREADS + tid;
+    if (i < q.n) {
+      const float4* src = rec + 3 * (size_t)sm.id[idbuf][i];
+      cp_async16_b(&sm.rec[rbuf][0][tid], src);
+      cp_async16_b(&sm.rec[rbuf][1][tid], src + 1);
+    }
+    cp_async_commit_b();
+  };
+
+  int u = blockIdx.x;
+  Unit cur;
+  skip_empty(u, cur);
+  if (u < nunits) {
+    fetch_ids(cur, 0);
+    cp_async_wait_b<0>();
+    fetch_rec(cur, 0, 0, 0);
+  }
+  uint32_t phase = 0;
+  bool pending = false;                                    // an MMA batch has been committed and not yet waited for
+  int kbuf = 0, step = 0;
+  while (u < nunits) {
+    int un = u + gridDim.x;
+    Unit nxt;
+    skip_empty(un, nxt);
+    const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
+    const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
+    const int nbatch = (cur.n + FT_THREADS - 1) / FT_THREADS;
+    for (int bi = 0; bi < nbatch; ++bi, ++step) {
+      cp_async_wait_b<0>();                                // this step's record (issued a step ago) and older copies
+      const bool active = bi * FT_THREADS + tid < cur.n;
+      // padding: a record whose factors underflow to exactly 0 and whose colour halves are 0
+      float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra;
+      if (active) { ra = sm.rec[step & 1][0][tid]; rb = sm.rec[step & 1][1][tid]; }
+      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
+      if (bi + 1 < nbatch) {
+        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
+      } else if (un < nunits) {
+        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
+        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
+      }
+      // ---- factors of this thread's Gaussian at the tile's 16 columns / rows, each scaled by 2^8 (fp16 range),
+      // split into fp16 hi + lo pairs {even, odd}
+      const float dx0 = ra.x - x0, dy0 = rb.x - y0;
+      const float lop8 = fminf(ra.z, 7.99f) + 8.0f;        // fx * 2^8 stays inside fp16 (op <= 253)
+      uint32_t Fh[8], Fl[8], Yh[8], Yl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 off = make_float2(-(float)(2 * j), -(float)(2 * j + 1));
+        const float2 dx = __fadd2_rn(bcast2(dx0), off), dy = __fadd2_rn(bcast2(dy0), off);
+        const float2 ax = __ffma2_rn(__fmul2_rn(bcast2(ra.y), dx), dx, bcast2(lop8));
+        const float2 ay = __ffma2_rn(__fmul2_rn(bcast2(rb.y), dy), dy, bcast2(8.0f));
+        split_h2v(make_float2(ex2_approx(ax.x), ex2_approx(ax.y)), Fh[j], Fl[j]);
+        split_h2v(make_float2(ex2_approx(ay.x), ex2_approx(ay.y)), Yh[j], Yl[j]);
+      }
+      // the previous batch's MMAs read the operand buffers: they must have retired before the stores below
+      // (they were issued a whole factor computation ago)
+      if (pending) { mbar_wait(&sm.bar_mma, phase); phase ^= 1u; pending = false; }
+      sm.B[0][tid] = make_uint4(Yh[0], Yh[1], Yh[2], Yh[3]);
+      sm.B[1][tid] = make_uint4(Yh[4], Yh[5], Yh[6], Yh[7]);
+      sm.B[2][tid] = make_uint4(Yl[0], Yl[1], Yl[2], Yl[3]);
+      sm.B[3][tid] = make_uint4(Yl[4], Yl[5], Yl[6], Yl[7]);
+      sm.Ah[6][tid] = make_uint4(Fh[0], Fh[1], Fh[2], Fh[3]);      // weight plane: fx itself
+      sm.Ah[7][tid] = make_uint4(Fh[4], Fh[5], Fh[6], Fh[7]);
+      sm.Al[6][tid] = make_uint4(Fl[0], Fl[1], Fl[2], Fl[3]);
+      sm.Al[7][tid] = make_uint4(Fl[4], Fl[5], Fl[6], Fl[7]);
+      // colour planes from the pre-split clamped colour (record: f16 {hi | lo << 16}):
+      //   hi = rn(vh fxh),  lo = (vh fxh - hi) [exact: one HFMA2] + vh fxl + vl fxh      (vl fxl ~ 2^-22 dropped)
+      const uint32_t cw[3] = {__float_as_uint(ra.w), __float_as_uint(rb.w), __float_as_uint(rb.z)};
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const __half2 vh = u32_h2(__byte_perm(cw[ch], cw[ch], 0x1010)), vl = u32_h2(__byte_perm(cw[ch], cw[ch], 0x3232));
+        uint32_t P[8], L[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2 fh = u32_h2(Fh[j]), fl = u32_h2(Fl[j]);
+          const __half2 p = __hmul2(vh, fh);
+          __half2 l = __hfma2(vh, fh, __hneg2(p));
+          l = __hfma2(vh, fl, l);
+          l = __hfma2(vl, fh, l);
+          P[j] = h2_bits(p);
+          L[j] = h2_bits(l);
+        }
+        sm.Ah[2 * ch][tid] = make_uint4(P[0], P[1], P[2], P[3]);
+        sm.Ah[2 * ch + 1][tid] = make_uint4(P[4], P[5], P[6], P[7]);
+        sm.Al[2 * ch][tid] = make_uint4(L[0], L[1], L[2], L[3]);
+        sm.Al[2 * ch + 1][tid] = make_uint4(L[4], L[5], L[6], L[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();                                     // every operand column written (and, at bi == 0, the previous unit's accumulator read)
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < FT_THREADS / 16; ++s) {
+          const uint64_t off = (uint64_t)(s * 16);                                  // 256 B in descriptor units
+          umma_f16(tmem, dAh + off, dB + off, ID32, (bi > 0 || s > 0) ? 1u : 0u);   // D[:, 0:32] (+)= A_hi . [B_hi | B_lo]
+          umma_f16(tmem, dAl + off, dB + off, ID16, 1u);                            // D[:, 0:16]  += A_lo . B_hi
+        }
+        umma_commit(&sm.bar_mma);
+      }
+      pending = true;
+    }
+    // ---- unit epilogue: accumulator (warp = plane, lane = column, TMEM column = row | 16 + row) -> pixels
+    mbar_wait(&sm.bar_mma, phase);                         // nbatch >= 1: the unit is not empty
+    phase ^= 1u;
+    pending = false;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+      const float us = 1.0f / 65536.0f;                    // the two 2^8 factor scales
+      if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sOut[warp * TILE_PIX + r * TILE + lane] = (v[r] + v[16 + r]) * us;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next unit's first MMA
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pix = tid + h * FT_THREADS;
+      emit(u, cur, pix, sOut[pix], sOut[TILE_PIX + pix], sOut[2 * TILE_PIX + pix], sOut[3 * TILE_PIX + pix]);
+    }
+    __syncthreads();                                       // sOut aliases the A operand: reads done before the next stores
+    u = un;
+    cur = nxt;
+    ++kbuf;
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(32) : "memory");
+}
+
 // Sums the per-unit partial accumulators of tiles that span several units, in unit order.
 template <bool DEPTH>
 __global__ void __launch_bounds__(TILE_PIX)
@@ -592,9 +844,18 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   KERN<DD><<<(int)((unit_cap + FM_WARPS - 1) / FM_WARPS), FM_WARPS * 32, 0, st>>>(                                    \
       vp, rec, vals, ranges, unit_start, units, partial, out_rgb, out_alpha, out_depth, acc, out_rgba)
   static const bool simt = [] { const char* e = getenv("B2S_FWD_SIMT"); return e != nullptr && e[0] == '1'; }();
+  static const bool mmasync = [] { const char* e = getenv("B2S_FWD_MMASYNC"); return e != nullptr && e[0] == '1'; }();
   static const bool tf32 = [] { const char* e = getenv("B2S_FWD_TF32"); return e != nullptr && e[0] == '1'; }();
   if (vp.exact_bbox) { if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
   else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
+  else if (!depth && !tf32 && !mmasync) {
+    // tcgen05: persistent, 4 CTAs per SM, each strides over the work units (4-plane case; depth stays on v5)
+    // (the attribute is per device: set on every launch, a process may drive several GPUs)
+    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+    const int grid = (int)(unit_cap < 4 * 148 ? unit_cap : 4 * 148);
+    blend_wsum_fwd_umma_kernel<<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
+                                                                          out_rgb, out_alpha, acc, out_rgba);
+  }
   else if (tf32)     { if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
   else               { if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }
 #undef B2S_FWM
