@@ -938,8 +938,8 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     B2S_LAUNCH_CHECK();
     if (umma) {
       // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
-      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
-      const int grid = (int)(unit_cap < 4 * 148 ? unit_cap : 4 * 148);
+      static const int cps = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
+      const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
       blend_wsum_bwd_umma_kernel<<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
                                                               reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       B2S_LAUNCH_CHECK();

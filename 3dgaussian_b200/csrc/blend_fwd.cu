@@ -852,7 +852,8 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
     // tcgen05: persistent, 4 CTAs per SM, each strides over the work units (4-plane case; depth stays on v5)
     // (the attribute is per device: set on every launch, a process may drive several GPUs)
     B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
-    const int grid = (int)(unit_cap < 4 * 148 ? unit_cap : 4 * 148);
+    static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
+    const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
     blend_wsum_fwd_umma_kernel<<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
                                                                           out_rgb, out_alpha, acc, out_rgba);
   }
