@@ -511,17 +511,20 @@ def main():
         b = table["blend_bwd"]
         traffic = None
         try:   # dram bytes of the kernel from the committed ncu --set full capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["blend_wsum_bwd_mma_kernel"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["blend_wsum_bwd_umma_kernel"]
         except Exception:
             pass
-        roofline = {"kernel": "blend_wsum_bwd_mma_kernel", "bound": "tensor",
+        roofline = {"kernel": "blend_wsum_bwd_umma_kernel", "bound": "tensor",
                     "achieved": b["achieved_tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": b["frac"], "traffic": traffic,
                     "note": f"algorithmic work = P2 pixel-pairs/view ({p2_rank0 / max(nv, 1):.3e}) x {flop_per_pair['blend_bwd']} flop "
-                            f"(SURVEY 8d: 24 FP32 + 1 MUFU per pair) / mean launch span; peak = {tensor_src}. The kernel runs the "
-                            f"separable sums as fp16 hi/lo mma.sync GEMMs, so the same work is {b['x_fp32_pipe_peak']:.2f}x the FP32-pipe "
-                            f"peak ({fp32_pipe_tflops:.1f} TFLOP/s at {sm_mhz:.0f} MHz); it is bound by operand generation "
-                            f"(MUFU.EX2 + fp16 splits + FP32 epilogue issue slots), not by MMA rate (DESIGN.md section 5). "
+                            f"(SURVEY 8d: 24 FP32 + 1 MUFU per pair) / mean span of the backward blend stage (gbuf_frag + gacc_init + "
+                            f"blend_wsum_bwd_umma_kernel; the tcgen05 kernel is ~87% of it); peak = {tensor_src}. The kernel runs the "
+                            f"separable sums as fp16 hi/lo tcgen05.mma 128x64x16 products (one thread per Gaussian, accumulators in "
+                            f"TMEM), so the same work is {b['x_fp32_pipe_peak']:.2f}x the FP32-pipe "
+                            f"peak ({fp32_pipe_tflops:.1f} TFLOP/s at {sm_mhz:.0f} MHz); it is bound by the per-step dependent chain "
+                            f"(factor generation -> MMA round trip -> TMEM read-back -> FP32 epilogue) at 4 CTAs/SM, not by MMA rate "
+                            f"(DESIGN.md section 5). "
                             f"tile-pairs P1<={p1:.3e}/view; HBM-bound stages are in roofline_stages vs {hbm_src}",
                     "share_of_step": b["ms_per_step"] / (ms_one_lane or ms_per_step),
                     "timing": "mean CUDA-event span of the kernel over the K steps repeated on one lane right after the "
