@@ -705,6 +705,7 @@ __device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float d
   }
 }
 
+template <bool RECUR>
 __global__ void __launch_bounds__(BT_THREADS, 4)
 blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int2* __restrict__ ranges, const int* __restrict__ unit_start,
@@ -819,12 +820,17 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
       const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
       float2 fx2[8], fy2[8];
+      if (RECUR) {       // by recurrence from the tile centre: 14 MUFU.EX2 + 26 packed multiplies (common.cuh)
+        factors16(ra.y, dx0, 8.0f, fx2);
+        factors16(rb.y, dy0, 8.0f, fy2);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dxa = dx0 + (float)(2 * j), dxb = dx0 + (float)(2 * j + 1);
-        const float dya = dy0 + (float)(2 * j), dyb = dy0 + (float)(2 * j + 1);
-        fx2[j] = make_float2(ex2_approx(fmaf(ra.y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra.y * dxb, dxb, 8.0f)));
-        fy2[j] = make_float2(ex2_approx(fmaf(rb.y * dya, dya, 8.0f)), ex2_approx(fmaf(rb.y * dyb, dyb, 8.0f)));
+        for (int j = 0; j < 8; ++j) {
+          const float dxa = dx0 + (float)(2 * j), dxb = dx0 + (float)(2 * j + 1);
+          const float dya = dy0 + (float)(2 * j), dyb = dy0 + (float)(2 * j + 1);
+          fx2[j] = make_float2(ex2_approx(fmaf(ra.y * dxa, dxa, 8.0f)), ex2_approx(fmaf(ra.y * dxb, dxb, 8.0f)));
+          fy2[j] = make_float2(ex2_approx(fmaf(rb.y * dya, dya, 8.0f)), ex2_approx(fmaf(rb.y * dyb, dyb, 8.0f)));
+        }
       }
       rowx[0]   = make_uint4(pack_h2(fx2[0].x, fx2[0].y), pack_h2(fx2[1].x, fx2[1].y), pack_h2(fx2[2].x, fx2[2].y), pack_h2(fx2[3].x, fx2[3].y));
       rowx[128] = make_uint4(pack_h2(fx2[4].x, fx2[4].y), pack_h2(fx2[5].x, fx2[5].y), pack_h2(fx2[6].x, fx2[6].y), pack_h2(fx2[7].x, fx2[7].y));
@@ -940,8 +946,14 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
       // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
       static const int cps = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
       const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
-      blend_wsum_bwd_umma_kernel<<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
-                                                              reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
+      // B2S_BWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
+      static const bool direct = [] { const char* e = getenv("B2S_BWD_EX2"); return e != nullptr && e[0] == '1'; }();
+      if (direct)
+        blend_wsum_bwd_umma_kernel<false><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+                                                                       reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
+      else
+        blend_wsum_bwd_umma_kernel<true><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+                                                                      reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       B2S_LAUNCH_CHECK();
       return B2S_OK;
     }

@@ -603,6 +603,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
 }
 
+template <bool RECUR>
 __global__ void __launch_bounds__(FT_THREADS, 4)
 blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int2* __restrict__ ranges, const int* __restrict__ unit_start,
@@ -703,8 +704,9 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     for (int bi = 0; bi < nbatch; ++bi, ++step) {
       cp_async_wait_b<0>();                                // this step's record (issued a step ago) and older copies
       const bool active = bi * FT_THREADS + tid < cur.n;
-      // padding: a record whose factors underflow to exactly 0 and whose colour halves are 0
-      float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra;
+      // padding: q = 0 and log2 op = -1000 make every x factor exactly 0 (and every ratio of the recurrence 1: no
+      // 0 * inf), the colour halves are 0; a padded K slot then adds 0 to every accumulator
+      float4 ra = make_float4(0.0f, 0.0f, -1000.0f, 0.0f), rb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (active) { ra = sm.rec[step & 1][0][tid]; rb = sm.rec[step & 1][1][tid]; }
       if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
       if (bi + 1 < nbatch) {
@@ -718,14 +720,25 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       const float dx0 = ra.x - x0, dy0 = rb.x - y0;
       const float lop8 = fminf(ra.z, 7.99f) + 8.0f;        // fx * 2^8 stays inside fp16 (op <= 253)
       uint32_t Fh[8], Fl[8], Yh[8], Yl[8];
+      if (RECUR) {       // by recurrence from the tile centre: 14 MUFU.EX2 + 26 packed multiplies (common.cuh)
+        float2 fx2[8], fy2[8];
+        factors16(ra.y, -dx0, lop8, fx2);
+        factors16(rb.y, -dy0, 8.0f, fy2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 off = make_float2(-(float)(2 * j), -(float)(2 * j + 1));
-        const float2 dx = __fadd2_rn(bcast2(dx0), off), dy = __fadd2_rn(bcast2(dy0), off);
-        const float2 ax = __ffma2_rn(__fmul2_rn(bcast2(ra.y), dx), dx, bcast2(lop8));
-        const float2 ay = __ffma2_rn(__fmul2_rn(bcast2(rb.y), dy), dy, bcast2(8.0f));
-        split_h2v(make_float2(ex2_approx(ax.x), ex2_approx(ax.y)), Fh[j], Fl[j]);
-        split_h2v(make_float2(ex2_approx(ay.x), ex2_approx(ay.y)), Yh[j], Yl[j]);
+        for (int j = 0; j < 8; ++j) {
+          split_h2v(fx2[j], Fh[j], Fl[j]);
+          split_h2v(fy2[j], Yh[j], Yl[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 off = make_float2(-(float)(2 * j), -(float)(2 * j + 1));
+          const float2 dx = __fadd2_rn(bcast2(dx0), off), dy = __fadd2_rn(bcast2(dy0), off);
+          const float2 ax = __ffma2_rn(__fmul2_rn(bcast2(ra.y), dx), dx, bcast2(lop8));
+          const float2 ay = __ffma2_rn(__fmul2_rn(bcast2(rb.y), dy), dy, bcast2(8.0f));
+          split_h2v(make_float2(ex2_approx(ax.x), ex2_approx(ax.y)), Fh[j], Fl[j]);
+          split_h2v(make_float2(ex2_approx(ay.x), ex2_approx(ay.y)), Yh[j], Yl[j]);
+        }
       }
       // the previous batch's MMAs read the operand buffers: they must have retired before the stores below
       // (they were issued a whole factor computation ago)
@@ -851,11 +864,18 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   else if (!depth && !tf32 && !mmasync) {
     // tcgen05: persistent, 4 CTAs per SM, each strides over the work units (4-plane case; depth stays on v5)
     // (the attribute is per device: set on every launch, a process may drive several GPUs)
-    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+    // B2S_FWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
+    static const bool direct = [] { const char* e = getenv("B2S_FWD_EX2"); return e != nullptr && e[0] == '1'; }();
     static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
     const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
-    blend_wsum_fwd_umma_kernel<<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
-                                                                          out_rgb, out_alpha, acc, out_rgba);
+    if (direct)
+      blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
+                                                                                   out_rgb, out_alpha, acc, out_rgba);
+    else
+      blend_wsum_fwd_umma_kernel<true><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
+                                                                                  out_rgb, out_alpha, acc, out_rgba);
   }
   else if (tf32)     { if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
   else               { if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }

@@ -151,6 +151,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// The 16 factors of one axis of one Gaussian over a tile, f[c] = 2^(q (d0 + c)^2 + e0), c = 0..15, returned as pairs
+// out[j] = (f[2j], f[2j+1]).  Evaluated by recurrence from the middle pair (columns 8, 9) outwards in steps of two
+// columns: f[c+2]/f[c] = 2^(q (4 d + 4)), f[c-2]/f[c] = 2^(q (4 - 4 d)), and consecutive ratios differ by the constant
+// 2^(8 q) -- 7 MUFU.EX2 + 13 packed multiplies instead of 16 MUFU.EX2 + 16 FMUL + 16 FFMA.  Every intermediate is a
+// true factor value or a ratio of two of them (|exponent| <= 4 * 0.72 * (cutoff + 8) < 128 because sigma >= 1 px), so
+// nothing overflows; relative error <= (1 + 4 + 6) ulp(ex2.approx) ~ 2.6e-6.  A middle value that underflows (the
+// Gaussian is > 13 sigma from the tile centre) zeroes the whole axis: the largest value lost is exp(-24) at cutoff 7.
+__device__ __forceinline__ void factors16(float q, float d0, float e0, float2 (&out)[8]) {
+  const float d8 = d0 + 8.0f, d9 = d0 + 9.0f;
+  const float2 d = make_float2(d8, d9);
+  const float2 e = __ffma2_rn(__fmul2_rn(make_float2(q, q), d), d, make_float2(e0, e0));
+  const float q4 = 4.0f * q;
+  float2 Ru = make_float2(ex2_approx(q4 * (d8 + 1.0f)), ex2_approx(q4 * (d9 + 1.0f)));
+  float2 Rd = make_float2(ex2_approx(q4 * (1.0f - d8)), ex2_approx(q4 * (1.0f - d9)));
+  const float k = ex2_approx(8.0f * q);
+  const float2 K = make_float2(k, k);
+  float2 U = make_float2(ex2_approx(e.x), ex2_approx(e.y)), D = U;
+  out[4] = U;
+#pragma unroll
+  for (int j = 5; j < 8; ++j) {
+    U = __fmul2_rn(U, Ru);
+    out[j] = U;
+    if (j < 7) Ru = __fmul2_rn(Ru, K);
+  }
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {
+    D = __fmul2_rn(D, Rd);
+    out[j] = D;
+    if (j > 0) Rd = __fmul2_rn(Rd, K);
+  }
+}
+
 // ---- state / workspace layout (all offsets 256-B aligned) -------------------------------
 struct StateLayout {
   size_t rec, ranges, vals, acc, counters, unit_start, units, cmask, total;
