@@ -21,6 +21,7 @@
 //   column sums (for d/dpx, d/dsx): colS[c] = fx[c] * sum_r fy[r] T(r,c)
 // => 8 FFMA per pixel-pair, issued as 4 packed f32x2 instructions + 1 LDS.128 per 4 pairs/channel.
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -185,7 +186,9 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
       const __half val = part ? lo : hi;
       if constexpr (UMMA) {
         constexpr int NR = CH * 16;                 // operand rows; one matrix = NR x 16 halves
-        const int nu = ch * 16 + r, nv = ch * 16 + c;
+        // operand row (= TMEM column of the accumulator) = quad * 16 + plane * 4 + index in quad: the epilogue's
+        // unit of work -- 4 rows / columns x 4 planes -- is 16 consecutive columns, ONE tcgen05.ld
+        const int nu = (r >> 2) * 16 + ch * 4 + (r & 3), nv = (c >> 2) * 16 + ch * 4 + (c & 3);
         sfrag[(0 + part) * NR * 16 + (c >> 3) * NR * 8 + (nu >> 3) * 64 + (nu & 7) * 8 + (c & 7)] = val;   // U: k = c
         sfrag[(2 + part) * NR * 16 + (r >> 3) * NR * 8 + (nv >> 3) * 64 + (nv & 7) * 8 + (r & 7)] = val;   // V: k = r
       } else {
@@ -644,6 +647,14 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
                : "r"(taddr));
 }
+// one quad: 16 consecutive accumulator columns = [plane][index in quad]
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[4][4]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=f"(v[0][0]), "=f"(v[0][1]), "=f"(v[0][2]), "=f"(v[0][3]), "=f"(v[1][0]), "=f"(v[1][1]), "=f"(v[1][2]), "=f"(v[1][3]),
+        "=f"(v[2][0]), "=f"(v[2][1]), "=f"(v[2][2]), "=f"(v[2][3]), "=f"(v[3][0]), "=f"(v[3][1]), "=f"(v[3][2]), "=f"(v[3][3])
+      : "r"(taddr));
+}
 // tcgen05.wait::ld for the 16 registers of one quad; they are listed as in/out operands so that no use of them can
 // be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_quad(float (&q)[4][4]) {
@@ -655,8 +666,8 @@ __device__ __forceinline__ void tmem_wait_quad(float (&q)[4][4]) {
                : "memory");
 }
 
-// Thread-local epilogue of the tcgen05 backward: this thread's accumulator row -- U at columns [0,64) (plane*16 +
-// row), V at [64,128) (plane*16 + column) of `taddr` -- is streamed through registers in 8 quads of 4 rows /
+// Thread-local epilogue of the tcgen05 backward: this thread's accumulator row -- U at columns [0,64) (quad*16 +
+// plane*4 + row%4), V at [64,128) (same with columns) of `taddr` -- is streamed through registers in 8 quads of 4 rows /
 // columns x 4 planes.  The loads are software pipelined: quad q+1 is requested right after quad q has landed, so its
 // TMEM round trip hides behind the FP32 work of quad q (tcgen05.wait::ld waits for ALL outstanding loads, so at most
 // one quad may be in flight when it is issued).  fy_pair(p) / fx_pair(p): factors of rows / columns 2p, 2p+1.
@@ -667,11 +678,7 @@ template <class FyPair, class FxPair>
 __device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float dy0, float2 cR, float2 cG, float2 cB,
                                               FyPair fy_pair, FxPair fx_pair, BwdSums& A) {
   float buf[2][4][4];
-  auto request = [&](int q, float (&dst)[4][4]) {
-    const uint32_t base = taddr + (uint32_t)((q >> 2) * 64 + (q & 3) * 4);
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) tmem_ld4(base + ch * 16, dst[ch]);
-  };
+  auto request = [&](int q, float (&dst)[4][4]) { tmem_ld16(taddr + (uint32_t)(q * 16), dst); };
   A.aR = A.aG = A.aB = A.aS = A.aSy = A.aSyy = A.aSx = A.aSxx = make_float2(0.f, 0.f);
   request(0, buf[0]);
 #pragma unroll
@@ -788,6 +795,22 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     cp_async_wait_b<0>();
     fetch_rec(cur, 0, 0, 0);
   }
+  // sums of the previous step waiting for their REDs: Gaussian id (complemented when op == 0: only S is kept), 8 sums
+  int pend_id = INT_MIN;
+  float pend[8];
+  auto flush_sums = [&]() {
+    if (pend_id == INT_MIN) return;
+    const bool zop = pend_id < 0;
+    float* dst = gacc + (size_t)(zop ? ~pend_id : pend_id) * GACC_F;
+    if (!zop) {
+      red_add_v4(dst, pend[0], pend[1], pend[2], 0.0f);
+      red_add_v4(dst + 4, pend[3], pend[4], pend[5], pend[6]);
+      atomicAdd(dst + 8, pend[7]);
+    } else {
+      red_add_v4(dst + 4, pend[3], 0.0f, 0.0f, 0.0f);
+    }
+    pend_id = INT_MIN;
+  };
   uint32_t phase = 0;
   int kbuf = 0;                                            // units processed so far: plane / id buffer = kbuf & 1
   int step = 0;                                            // steps processed so far: record buffer = step & 1
@@ -803,20 +826,12 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     const uint32_t pb = smem_u32(&sP[kbuf & 1][0]);
     const int nbatch = (cur.n + BT_THREADS - 1) / BT_THREADS;
     for (int bi = 0; bi < nbatch; ++bi, ++step) {
-      cp_async_wait_b<0>();                                // this step's record (issued a step ago) and older copies
+      cp_async_wait_b<0>();                                // this step's record (issued after the previous step's barrier)
       const bool active = bi * BT_THREADS + tid < cur.n;
       const int cur_id = active ? sId[kbuf & 1][bi * BT_THREADS + tid] : -1;
       float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, col = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) { ra = sRec[step & 1][0][tid]; rb = sRec[step & 1][1][tid]; col = sRec[step & 1][2][tid]; }
       const float lop = ra.z;
-      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
-      // the next step's record: its copy flies during this step
-      if (bi + 1 < nbatch) {
-        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
-      } else if (un < nunits) {
-        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
-        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
-      }
       // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
       const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
       float2 fx2[8], fy2[8];
@@ -848,6 +863,19 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
       }
+      // ---- global memory traffic of this thread goes HERE, behind the barrier: fence.proxy.async is a MEMBAR for the
+      // issuing thread, i.e. it waits for every global operation the thread still has in flight.  Issued before the
+      // fence (as in v7) the record gather of the next step and the REDs of the previous one had to complete inside
+      // the step that issued them -- a full L2 round trip on the critical path of every step.  Issued here they have
+      // the MMA round trip, the epilogue and the next step's factor evaluation to land.
+      flush_sums();
+      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
+      if (bi + 1 < nbatch) {
+        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
+      } else if (un < nunits) {
+        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
+        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
+      }
       mbar_wait(&bar_mma, phase);
       phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -858,25 +886,23 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
                     [&](int p) { return fx2[p]; }, A);
       const float2 aR = A.aR, aG = A.aG, aB = A.aB, aS = A.aS, aSy = A.aSy, aSyy = A.aSyy, aSx = A.aSx, aSxx = A.aSxx;
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next step's barrier
+      // the sums of this step are added to gacc after the NEXT barrier (see above)
       if (cur_id >= 0) {
         // op == 0 (log2 op = -inf): forward weight 0, but clamp_min(0) passes dL/dop = sum E*t: keep S with op = 1
         const bool zop = (lop == -INFINITY);
         const float opk = zop ? k_us : ex2_approx(lop) * k_us;   // opacity and the 2^-(sG+16) un-scaling, once
-        float* dst = gacc + (size_t)cur_id * GACC_F;
-        const float S = (aS.x + aS.y) * opk;
-        if (!zop) {
-          red_add_v4(dst, (aR.x + aR.y) * opk, (aG.x + aG.y) * opk, (aB.x + aB.y) * opk, 0.0f);
-          red_add_v4(dst + 4, S, (aSx.x + aSx.y) * opk, (aSxx.x + aSxx.y) * opk, (aSy.x + aSy.y) * opk);
-          atomicAdd(dst + 8, (aSyy.x + aSyy.y) * opk);
-        } else {
-          red_add_v4(dst + 4, S, 0.0f, 0.0f, 0.0f);
-        }
+        const float z = zop ? 0.0f : opk;
+        pend_id = zop ? ~cur_id : cur_id;
+        pend[0] = (aR.x + aR.y) * z; pend[1] = (aG.x + aG.y) * z; pend[2] = (aB.x + aB.y) * z;
+        pend[3] = (aS.x + aS.y) * opk; pend[4] = (aSx.x + aSx.y) * z; pend[5] = (aSxx.x + aSxx.y) * z;
+        pend[6] = (aSy.x + aSy.y) * z; pend[7] = (aSyy.x + aSyy.y) * z;
       }
     }
     u = un;
     cur = nxt;
     ++kbuf;
   }
+  flush_sums();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128) : "memory");
 }
