@@ -128,6 +128,33 @@ class FitDriver:
         self.m.zero_(); self.v.zero_()
         self.step_no = 0
 
+    def reorder_spatial(self, bits: int = 10) -> torch.Tensor:
+        """Stores the Gaussians -- parameters and Adam moments -- in 3-D Morton order of their means and returns the
+        permutation (new index -> old index).  The weighted sum is order independent, so the fit is unchanged; what
+        changes is locality: Gaussians that are neighbours in space are neighbours on screen in EVERY view, so the
+        slice of Gaussians one binning block owns touches a few hundred tiles instead of all of them (its scattered
+        4-byte list writes become runs), and the records / gradient rows a tile gathers share cache lines.  A fit calls
+        it after initialisation and after densify/prune (the reference re-creates every tensor there anyway,
+        python/fit_multiview_stub.py:318-325); it is plain setup work, outside the iteration."""
+        n = self.n
+        if n <= 1:
+            return torch.arange(n, device=self.dev)
+        with torch.no_grad():
+            m = self.means()
+            lo, hi = m.min(0).values, m.max(0).values
+            q = ((m - lo) / (hi - lo).clamp_min(1e-20) * float((1 << bits) - 1)).to(torch.int64).clamp_(0, (1 << bits) - 1)
+            code = torch.zeros(n, dtype=torch.int64, device=self.dev)
+            for b in range(bits):
+                for a in range(3):
+                    code |= ((q[:, a] >> b) & 1) << (3 * b + a)
+            perm = torch.argsort(code, stable=True)
+            segs = ((self.o_means, 3), (self.o_scales, 3), (self.o_opac, 1), (self.o_colors, 3 * self.sh))
+            for buf in (self.p, self.m, self.v):
+                for off, k in segs:
+                    seg = buf[off:off + k * n].view(n, k)
+                    seg.copy_(seg[perm])
+        return perm
+
     def _pp(self, off):  # raw device pointer into a flat buffer
         return C.c_void_p(self.p.data_ptr() + 4 * off)
 

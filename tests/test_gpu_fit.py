@@ -132,6 +132,27 @@ def test_step_from_host_equals_device_step():
     assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
 
 
+def test_spatial_reorder_leaves_the_fit_unchanged():
+    """FitDriver.reorder_spatial permutes parameters and Adam moments into 3-D Morton order: same losses, and the
+    same parameters up to that permutation, as the unpermuted driver."""
+    S = _setup(4, V=4)
+    d1, d2 = _driver(S), _driver(S)
+    for _ in range(2):                      # Adam moments are non-zero when the permutation is applied
+        d1.step(); d2.step()
+    before_p, before_m = d2.means().clone(), d2.m[d2.o_opac:d2.o_opac + d2.n].clone()
+    perm = d2.reorder_spatial()
+    assert sorted(perm.cpu().tolist()) == list(range(d2.n))
+    assert torch.equal(d2.means(), before_p[perm])                      # parameters ...
+    assert torch.equal(d2.m[d2.o_opac:d2.o_opac + d2.n], before_m[perm])   # ... and Adam moments move together
+    for _ in range(3):
+        l1, l2 = float(d1.step().item()), float(d2.step().item())
+        assert abs(l1 - l2) <= 1e-6 * max(1.0, abs(l1))
+    for a, b in ((d1.means(), d2.means()), (d1.scales_raw(), d2.scales_raw()), (d1.opacities_raw(), d2.opacities_raw()),
+                 (d1.colors_raw(), d2.colors_raw())):
+        assert rel_l2(a[perm].cpu().numpy(), b.cpu().numpy()) <= 1e-4
+    assert not d2.check_overflow()
+
+
 @pytest.mark.parametrize("lanes", [2, 3])
 def test_view_lanes_equal_single_stream(lanes):
     """Views spread over concurrent CUDA-stream lanes: same loss (fixed summation order) and the same
