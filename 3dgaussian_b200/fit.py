@@ -445,6 +445,47 @@ class FitDriver:
             self.plan()
         return k
 
+    # ---- checkpoint / resume ---------------------------------------------------------------------
+    def save_checkpoint(self, path) -> None:
+        """Raw parameters + Adam moments + step count as one .npz (the reference only ever writes the ACTIVATED
+        model, python/fit_multiview_stub.py:338-354, and cannot resume; `io.save_gaussians_npz` is that file)."""
+        import numpy as np
+        n = self.n
+        seg = lambda buf, off, k: buf[off:off + k * n].view(n, k).cpu().numpy()
+        arrs = {"format": np.array("b2splat-fit-checkpoint-1"), "n": np.int64(n), "sh_coeffs": np.int64(self.sh),
+                "step": np.int64(self.step_no), "lr": np.float64(self.lr)}
+        for name, buf in (("p", self.p), ("m", self.m), ("v", self.v)):
+            arrs[name + "_means"] = seg(buf, self.o_means, 3)
+            arrs[name + "_scales_raw"] = seg(buf, self.o_scales, 3)
+            arrs[name + "_opacities_raw"] = seg(buf, self.o_opac, 1)[:, 0]
+            arrs[name + "_colors_raw"] = seg(buf, self.o_colors, 3 * self.sh)
+        with open(path, "wb") as f:
+            np.savez(f, **arrs)
+
+    def load_checkpoint(self, path) -> None:
+        """Restores what save_checkpoint wrote; the Gaussian count may differ from the constructor's (a checkpoint
+        taken after densify/prune): the flat buffers and the pair buffers are rebuilt for it."""
+        import numpy as np
+        z = np.load(path, allow_pickle=False)
+        if str(z["format"]) != "b2splat-fit-checkpoint-1":
+            raise ValueError(f"{path}: not a b2splat fit checkpoint")
+        n, sh = int(z["n"]), int(z["sh_coeffs"])
+        if sh != self.sh:
+            raise ValueError(f"{path}: checkpoint has {sh} colour coefficients per Gaussian, the driver {self.sh}")
+        with torch.cuda.device(self.dev):
+            if n != self.n:
+                self._layout(n)
+                self.gacc = torch.empty((max(len(self.views), 1), max(n, 1), 12), dtype=torch.float32, device=self.dev)
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev)
+            with torch.no_grad():
+                for name, buf in (("p", self.p), ("m", self.m), ("v", self.v)):
+                    for key, off, k in (("means", self.o_means, 3), ("scales_raw", self.o_scales, 3),
+                                        ("opacities_raw", self.o_opac, 1), ("colors_raw", self.o_colors, 3 * self.sh)):
+                        buf[off:off + k * n].copy_(t(z[f"{name}_{key}"]).reshape(-1))
+            self.step_no = int(z["step"])
+            self.state = self.ws = self.state_l = self.ws_l = self.prepared = None
+            self.plan()
+
     def check_overflow(self) -> bool:
         """True if any view since the last call needed more pairs than the buffers hold."""
         v = sum(int(t.item()) for t in self.overflow_l)

@@ -153,6 +153,28 @@ def test_spatial_reorder_leaves_the_fit_unchanged():
     assert not d2.check_overflow()
 
 
+def test_checkpoint_resume_continues_the_same_fit(tmp_path):
+    """save_checkpoint / load_checkpoint carry raw parameters, Adam moments and the step count: a resumed driver
+    takes the same steps as the one that kept running (bit-equal state right after the load)."""
+    S = _setup(4, V=3)
+    d1 = _driver(S)
+    for _ in range(3):
+        d1.step()
+    ck = tmp_path / "fit.npz"
+    d1.save_checkpoint(ck)
+    d2 = _driver(S)                       # fresh driver with the initial parameters
+    d2.load_checkpoint(ck)
+    assert d2.step_no == d1.step_no == 3
+    for a, b in ((d1.p, d2.p), (d1.m, d2.m), (d1.v, d2.v)):
+        assert torch.equal(a, b)
+    for _ in range(2):
+        l1, l2 = float(d1.step().item()), float(d2.step().item())
+        assert abs(l1 - l2) <= 1e-6 * max(1.0, abs(l1))
+    assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
+    with pytest.raises(ValueError):
+        _driver(_setup(1, V=3)).load_checkpoint(ck)
+
+
 @pytest.mark.parametrize("lanes", [2, 3])
 def test_view_lanes_equal_single_stream(lanes):
     """Views spread over concurrent CUDA-stream lanes: same loss (fixed summation order) and the same
