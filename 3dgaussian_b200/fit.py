@@ -412,11 +412,13 @@ class FitDriver:
 
     # ---- densify / prune ----------------------------------------------------------------------
     def densify_prune(self, iteration: int, max_gaussians: int, densify_ratio: float = 0.15,
-                      prune_opacity: float = 0.05, seed: int = 0) -> int:
+                      prune_opacity: float = 0.05, seed: int = 0, reorder: bool = False) -> int:
         """Device-side _densify_and_prune (reference python/fit_multiview_stub.py:140-197, called every
         densify_prune_interval iterations, :318-325): compacts the survivors, appends the clones, rebuilds
         the flat buffers for the new count and resets the Adam state like the reference's fresh optimizer.
-        Philox(seed, iteration, source index) jitter => identical on every rank, no broadcast."""
+        Philox(seed, iteration, source index) jitter => identical on every rank, no broadcast.
+        `reorder=True` re-sorts the new set into 3-D Morton order (the reference order -- survivors, then clones --
+        is what `reorder=False` keeps and what the parity tests compare)."""
         L = capi.lib()
         n, cf = self.n, 3 * self.sh
         cap = max(int(max_gaussians), n, 1)
@@ -442,6 +444,8 @@ class FitDriver:
                 self.opacities_raw().copy_(oo[:k]); self.colors_raw().copy_(colors)
             self.gacc = torch.empty((max(len(self.views), 1), max(k, 1), 12), dtype=torch.float32, device=self.dev)
             self.state = self.ws = self.state_l = self.ws_l = self.prepared = None
+            if reorder:          # the clones were appended at the end: restore the spatial order (see reorder_spatial)
+                self.reorder_spatial()
             self.plan()
         return k
 

@@ -390,7 +390,7 @@ def main():
         drv.step()
         if args.densify_every > 0 and (it + 1) % args.densify_every == 0 and it + 1 < args.steps:
             # fit_multiview_stub.py:318-325: prune / clone on the device, Adam state reset, buffers re-planned
-            n_after.append(drv.densify_prune(it + 1, max_gaussians=int(args.n * 1.2), seed=1234))
+            n_after.append(drv.densify_prune(it + 1, max_gaussians=int(args.n * 1.2), seed=1234, reorder=not args.no_reorder))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
