@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--lanes", type=int, default=4, help="concurrent view lanes (CUDA streams) per GPU")
+    ap.add_argument("--view-groups", type=int, default=0,
+                    help="pipeline the local views in this many groups (preprocess ahead, chain rule behind); 0 = auto")
     ap.add_argument("--no-reorder", action="store_true", help="keep the synthetic Gaussians in generation (random) order")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,6 +236,12 @@ def run_reference(args, out_fd):
     _emit(out_fd, line)
 
 
+def VIEW_GROUPS_AUTO(nv_local, lanes):
+    """One group: pipelining the local views in groups (preprocess ahead, chain rule behind) measured slower at 8, 16 and
+    64 views per rank (6.82 -> 7.20 ms at 8 views: the chain rule re-reads the coefficients once per group)."""
+    return 1
+
+
 def workload_config(args):
     return {"workload": f"synthetic fit: {args.n} Gaussians SH{args.sh} (N,{args.sh},3), {args.views} orbit views at "
                         f"{args.width}x{args.height}, fwd+bwd+Adam, views sharded over ranks (BASELINE configs[3])",
@@ -354,7 +362,10 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- the model being fitted (seed 1234) ----
-    drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes)
+    nv_local = len(fit.local_views(args.views, rank, world))
+    view_groups = args.view_groups if args.view_groups > 0 else VIEW_GROUPS_AUTO(nv_local, args.lanes)
+    drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes,
+                        view_groups=view_groups)
     means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device, args.s_lo, args.s_hi)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
@@ -560,7 +571,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "cpu_baseline": cpu, "render": render,
+        "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "view_groups": view_groups, "cpu_baseline": cpu, "render": render,
         "loss_last": loss_last, "pairs": {"P1_tile_pairs_worst_view": worst_p1, "P2_pixel_pairs_rank0_views": p2_rank0,
                                           "P2_all_ranks": float(p2_all.item())},
         "overflow": bool(overflowed), "densify": {"every": args.densify_every, "gaussians_after": n_after},
