@@ -558,14 +558,15 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 // Same product as v5, turned so that a THREAD owns a Gaussian (the K index) and the tile's planes are the M x N
 // accumulator in tensor memory:
 //   D[(plane, column)][row] = sum_i A[(plane, column)][i] * B[row][i],   A = v_plane,i * fx_i[column],  B = fy_i[row]
-// M = 4 planes x 16 columns = 64, N = 16 rows, K = the 128 Gaussians of a batch (8 instructions of K = 16).
+// 4 planes x 16 columns = 64 operand rows (x hi, lo = M 128), 16 tile rows (x hi, lo = N 32), K = the 128 Gaussians of a batch
+// (8 instructions of K = 16).
 // Both operands are MN-major in shared memory (thread i stores 16-byte groups of 8 consecutive M / N elements of
 // ITS Gaussian: conflict-free STS.128, no transposition), hi/lo split like v5:
-//   D[:, 0:32]  += A_hi . [B_hi | B_lo]     (one N = 32 instruction)
-//   D[:, 0:16]  += A_lo . B_hi              (one N = 16 instruction)         dropped term lo.lo ~ 2^-22
+//   D[128][32] += [A_hi ; A_lo] . [B_hi | B_lo]      ONE M = 128, N = 32 instruction per 16 Gaussians: hi and lo rows of A
+//   stacked along M, hi and lo of B side by side along N; the lo.lo quadrant (~2^-22) is computed and ignored
 // The accumulators never pass through registers inside the Gaussian loop: no HMMA issue slots, no fragment
 // shuffles, and the per-Gaussian work (32 MUFU.EX2, fp16 splits, 48 colour products) is plain thread-local code.
-// Per unit the 64 x 32 accumulator is read back once (warp = plane, lane = column), summed hi + lo, exchanged
+// Per unit the 128 x 32 accumulator is read back once (lane = operand row), its three useful quadrants summed, exchanged
 // through shared memory and written as pixels (or as the unit's partial planes when the tile has several units).
 //   CTA = 128 threads, 32 TMEM columns, 52 KB of shared memory -> 4 CTAs per SM; persistent over the units.
 // Layout validated by profiles/microbench/umma_probe_mn.cu.  The 5-plane (depth) case stays on v5.
@@ -611,7 +612,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
                            float* __restrict__ out_alpha, float* __restrict__ acc, uint8_t* __restrict__ out_rgba) {
   extern __shared__ __align__(128) unsigned char ft_raw[];
   FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_raw);
-  constexpr uint32_t ID32 = umma_idesc_f16(64, 32, true, true), ID16 = umma_idesc_f16(64, 16, true, true);
+  constexpr uint32_t IDESC = umma_idesc_f16(128, 32, true, true);   // M = [A_hi ; A_lo] rows, N = [B_hi | B_lo] rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nunits = unit_start[vp.n_tiles];
   if ((int)blockIdx.x >= nunits) return;                   // block-uniform
@@ -627,8 +628,8 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
   // K slice s (Gaussians 16 s .. 16 s + 15) starts 256 B into every MN group: K groups 128 B apart (LBO)
-  const uint64_t dAh = umma_desc(smem_u32(&sm.Ah[0][0]), 128, FT_SBO), dAl = umma_desc(smem_u32(&sm.Al[0][0]), 128, FT_SBO),
-                 dB = umma_desc(smem_u32(&sm.B[0][0]), 128, FT_SBO);
+  // A_hi and A_lo are adjacent: 16 MN groups of 8 rows, FT_SBO apart = ONE 128-row operand
+  const uint64_t dA = umma_desc(smem_u32(&sm.Ah[0][0]), 128, FT_SBO), dB = umma_desc(smem_u32(&sm.B[0][0]), 128, FT_SBO);
   float* sOut = reinterpret_cast<float*>(&sm.Ah[0][0]);    // [plane][row * 16 + column], aliases A hi between units
 
   struct Unit { int tile, start, n, nseg; };
@@ -781,28 +782,36 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 #pragma unroll
         for (int s = 0; s < FT_THREADS / 16; ++s) {
           const uint64_t off = (uint64_t)(s * 16);                                  // 256 B in descriptor units
-          umma_f16(tmem, dAh + off, dB + off, ID32, (bi > 0 || s > 0) ? 1u : 0u);   // D[:, 0:32] (+)= A_hi . [B_hi | B_lo]
-          umma_f16(tmem, dAl + off, dB + off, ID16, 1u);                            // D[:, 0:16]  += A_lo . B_hi
+          umma_f16(tmem, dA + off, dB + off, IDESC, (bi > 0 || s > 0) ? 1u : 0u);   // D (+)= [A_hi ; A_lo] . [B_hi | B_lo]
         }
         umma_commit(&sm.bar_mma);
       }
       pending = true;
     }
-    // ---- unit epilogue: accumulator (warp = plane, lane = column, TMEM column = row | 16 + row) -> pixels
+    // ---- unit epilogue: accumulator -> pixels
     mbar_wait(&sm.bar_mma, phase);                         // nbatch >= 1: the unit is not empty
     phase ^= 1u;
     pending = false;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     {
+      // TMEM lane = operand row: warps 0, 1 hold the hi rows of planes {0,1} / {2,3} (lane = plane % 2 * 16 + column),
+      // warps 2, 3 the lo rows of the same planes; TMEM column = row (x B_hi) | 16 + row (x B_lo).  The lo.lo
+      // quadrant (warps 2, 3, columns 16..31) is the dropped ~2^-22 term.
       float v[32];
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
-      const float us = 1.0f / 65536.0f;                    // the two 2^8 factor scales
-      if (lane < 16) {
+      float* dst = sOut + ((warp & 1) * 2 + (lane >> 4)) * TILE_PIX + (lane & 15);
+      if (warp >= 2) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sOut[warp * TILE_PIX + r * TILE + lane] = (v[r] + v[16 + r]) * us;
+        for (int r = 0; r < 16; ++r) dst[r * TILE] = v[r];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next unit's first MMA
+      __syncthreads();
+      if (warp < 2) {
+        const float us = 1.0f / 65536.0f;                  // the two 2^8 factor scales
+#pragma unroll
+        for (int r = 0; r < 16; ++r) dst[r * TILE] = (dst[r * TILE] + v[r] + v[16 + r]) * us;
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next unit's first MMA
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
