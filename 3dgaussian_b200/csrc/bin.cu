@@ -7,6 +7,10 @@
 
 namespace b2s {
 
+// unit descriptor table (common.cuh: launch_udesc): a unit's class is its number of 128-Gaussian steps
+constexpr int UD_STEP = 128;
+constexpr int UD_NCLS = (SEG + UD_STEP - 1) / UD_STEP;
+
 // Visits the tiles of Gaussian i row-major: the set bits of its mask for rects of at most 8 x 8 tiles
 // (tile_cull_mask), the whole rect otherwise.
 template <typename F>
@@ -181,6 +185,92 @@ int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_st
   return B2S_OK;
 }
 
+// ---- unit descriptor table (see common.cuh: launch_udesc) ---------------------------------------------------
+// One block.  A unit's class is its number of 128-Gaussian steps (1 .. SEG/128); thread t owns the contiguous
+// chunk of tiles [t*per, (t+1)*per), counts its units per class, one block-wide exclusive scan per class gives it
+// a deterministic slot range inside each class, classes are laid out largest first.
+__global__ void __launch_bounds__(1024)
+udesc_kernel(const int2* __restrict__ ranges, const int* __restrict__ unit_start, int n_tiles, int unit_cap,
+             int4* __restrict__ udesc, Counters* __restrict__ counters) {
+  __shared__ int wtot[UD_NCLS][32];
+  __shared__ int cls_total[UD_NCLS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per = (n_tiles + 1023) / 1024;
+  const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
+  int cnt[UD_NCLS];
+#pragma unroll
+  for (int k = 0; k < UD_NCLS; ++k) cnt[k] = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int2 rg = ranges[t];
+    const int c = rg.y - rg.x;
+    if (c <= 0) continue;
+    const int v = (c + SEG - 1) / SEG;
+    if (unit_start[t] + v > unit_cap) continue;            // cannot happen with max_units(); keeps the table in bounds
+    cnt[UD_NCLS - 1] += v - 1;                              // full units
+    const int last = c - (v - 1) * SEG;
+    const int kl = (last + UD_STEP - 1) / UD_STEP - 1;
+#pragma unroll
+    for (int k = 0; k < UD_NCLS; ++k) cnt[k] += (k == kl) ? 1 : 0;
+  }
+  int excl[UD_NCLS];
+#pragma unroll
+  for (int k = 0; k < UD_NCLS; ++k) {
+    int x = cnt[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[k][wid] = x;
+    excl[k] = x - cnt[k];
+  }
+  __syncthreads();
+  if (wid < UD_NCLS) {
+    int sv = wtot[wid][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, sv, o);
+      if (lane >= o) sv += y;
+    }
+    wtot[wid][lane] = sv;                                   // inclusive over warps
+    if (lane == 31) cls_total[wid] = sv;
+  }
+  __syncthreads();
+  int base[UD_NCLS];                                        // first slot of the class: larger classes first
+  int run = 0;
+#pragma unroll
+  for (int k = UD_NCLS - 1; k >= 0; --k) { base[k] = run; run += cls_total[k]; }
+  int slot[UD_NCLS];
+#pragma unroll
+  for (int k = 0; k < UD_NCLS; ++k) slot[k] = base[k] + (wid > 0 ? wtot[k][wid - 1] : 0) + excl[k];
+  for (int t = t0; t < t1; ++t) {
+    const int2 rg = ranges[t];
+    const int c = rg.y - rg.x;
+    if (c <= 0) continue;
+    const int v = (c + SEG - 1) / SEG;
+    const int u0 = unit_start[t];
+    if (u0 + v > unit_cap) continue;
+    const int multi = v > 1 ? (int)0x80000000u : 0;
+    for (int q = 0; q < v; ++q) {
+      const int nq = min(SEG, c - q * SEG);
+      const int k = (nq + UD_STEP - 1) / UD_STEP - 1;
+      int pos = 0;
+#pragma unroll
+      for (int kk = 0; kk < UD_NCLS; ++kk)
+        if (kk == k) pos = slot[kk]++;
+      udesc[pos] = make_int4(t, rg.x + q * SEG, nq, (u0 + q) | multi);
+    }
+  }
+  if (threadIdx.x == 0) counters->n_ne = run;
+}
+
+int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int64_t unit_cap, int4* udesc, Counters* counters,
+                 cudaStream_t st) {
+  udesc_kernel<<<1, 1024, 0, st>>>(ranges, unit_start, n_tiles, (int)unit_cap, udesc, counters);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 // ---- tile-major counting sort (order-independent blend modes) ---------------------------------
 // The weighted-sum blend does not care about the order inside a tile's list, so instead of the
 // multi-pass radix sort the (Gaussian,tile) pairs are grouped with ONE counting pass and ONE
@@ -250,13 +340,14 @@ cs_colscan_kernel(int* __restrict__ table, int nb, int n_tiles, int* __restrict_
 __global__ void __launch_bounds__(1024)
 cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pairs, int2* __restrict__ ranges,
                    Counters* __restrict__ counters, int unit_cap, int* __restrict__ unit_start,
-                   int2* __restrict__ units) {
+                   int2* __restrict__ units, int4* __restrict__ udesc) {
   extern __shared__ int ts_smem[];                 // cnt[n_tiles] then ustart[n_tiles]
   int* cnt = ts_smem;
   int* ust = ts_smem + n_tiles;
   __shared__ long long wsum[32];
   __shared__ int wunits[32];
   __shared__ long long grand_s;
+  __shared__ int wcls[UD_NCLS][32];               // unit descriptor table (launch_udesc): units per step class
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // coalesced fetch of the per-tile totals: every load of the block is in flight at once
   for (int t = threadIdx.x; t < n_tiles; t += 1024) cnt[t] = total[t];
@@ -265,10 +356,32 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
   const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
   long long c_sum = 0;
   int u_sum = 0;
+  int ccnt[UD_NCLS];
+#pragma unroll
+  for (int kk = 0; kk < UD_NCLS; ++kk) ccnt[kk] = 0;
   for (int t = t0; t < t1; ++t) {
     const int c = cnt[t];
     c_sum += c;
     u_sum += c > 0 ? (c + SEG - 1) / SEG : 1;
+    if (c > 0) {
+      const int v = (c + SEG - 1) / SEG;
+      ccnt[UD_NCLS - 1] += v - 1;
+      const int kl = (c - (v - 1) * SEG + UD_STEP - 1) / UD_STEP - 1;
+#pragma unroll
+      for (int kk = 0; kk < UD_NCLS; ++kk) ccnt[kk] += (kk == kl) ? 1 : 0;
+    }
+  }
+  int cexcl[UD_NCLS];
+#pragma unroll
+  for (int kk = 0; kk < UD_NCLS; ++kk) {
+    int z = ccnt[kk];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int zz = __shfl_up_sync(0xffffffffu, z, o);
+      if (lane >= o) z += zz;
+    }
+    if (lane == 31) wcls[kk][wid] = z;
+    cexcl[kk] = z - ccnt[kk];
   }
   // inclusive warp scans of (pairs, units)
   long long x = c_sum;
@@ -293,6 +406,14 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
     wsum[lane] = a;
     wunits[lane] = b;
     if (lane == 31) grand_s = a;
+  } else if (wid <= UD_NCLS) {
+    int z = wcls[wid - 1][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int zz = __shfl_up_sync(0xffffffffu, z, o);
+      if (lane >= o) z += zz;
+    }
+    wcls[wid - 1][lane] = z;                       // inclusive over warps
   }
   __syncthreads();
   const long long grand = grand_s;
@@ -303,10 +424,31 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
   // chunk pass in shared memory: cnt[t] <- start of the tile's range (its count is recovered from the next
   // start), ust[t] <- first unit
   int nunits = ov ? n_tiles : wunits[31];
+  // descriptor slots of this thread's units: classes laid out largest first, tile order inside a class
+  int slot[UD_NCLS];
+  int n_ne = 0;
+#pragma unroll
+  for (int kk = UD_NCLS - 1; kk >= 0; --kk) {
+    slot[kk] = n_ne + (wid > 0 ? wcls[kk][wid - 1] : 0) + cexcl[kk];
+    n_ne += wcls[kk][31];
+  }
   for (int t = t0; t < t1; ++t) {
     const int c = ov ? 0 : cnt[t];
     ust[t] = ustart;
-    ustart += c > 0 ? (c + SEG - 1) / SEG : 1;
+    const int v = c > 0 ? (c + SEG - 1) / SEG : 1;
+    if (c > 0 && ustart + v <= unit_cap) {
+      const int multi = v > 1 ? (int)0x80000000u : 0;
+      for (int q = 0; q < v; ++q) {
+        const int nq = min(SEG, c - q * SEG);
+        const int kq = (nq + UD_STEP - 1) / UD_STEP - 1;
+        int pos = 0;
+#pragma unroll
+        for (int kk = 0; kk < UD_NCLS; ++kk)
+          if (kk == kq) pos = slot[kk]++;
+        udesc[pos] = make_int4(t, (int)start + q * SEG, nq, (ustart + q) | multi);
+      }
+    }
+    ustart += v;
     cnt[t] = (int)start;
     start += c;
   }
@@ -327,6 +469,7 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pai
     counters->needed = grand;
     counters->kept = kept;
     counters->overflow = ov ? 1 : 0;
+    counters->n_ne = ov ? 0 : n_ne;
     unit_start[n_tiles] = nunits < unit_cap ? nunits : unit_cap;
   }
 }
@@ -357,8 +500,8 @@ int counting_sort_blocks(int n) {
 
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, int* table, int* total,
-                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int* vals,
-                         int stage, cudaStream_t st) {
+                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
+                         int* vals, int stage, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = (size_t)vp.n_tiles * 4;
   if (!attr_set) {
@@ -377,7 +520,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
     cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, (long long)max_pairs, ranges, counters, (int)unit_cap,
-                                           unit_start, units);
+                                           unit_start, units, udesc);
     B2S_LAUNCH_CHECK();
   } else {
     cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,

@@ -715,8 +715,8 @@ __device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float d
 template <bool RECUR>
 __global__ void __launch_bounds__(BT_THREADS, 4)
 blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
-                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
-                           const int2* __restrict__ units, const uint4* __restrict__ planes,
+                           const int4* __restrict__ udesc, const Counters* __restrict__ counters,
+                           const uint4* __restrict__ planes,
                            const float* __restrict__ tile_scale, float* __restrict__ gacc) {
   constexpr int NR = 64;                                   // operand rows of a plane matrix: 4 planes x 16
   constexpr uint32_t PLANE_BYTES = 4 * NR * 16 * 2;        // U_hi | U_lo | V_hi | V_lo, 2 KB each
@@ -728,7 +728,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int nunits = unit_start[vp.n_tiles];
+  const int nunits = counters->n_ne;                       // entries of the unit descriptor table (non-empty units, largest first)
   if ((int)blockIdx.x >= nunits) return;                   // block-uniform
 
   if (tid == 0) {
@@ -754,17 +754,8 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   // Gaussians of a unit.  The record of the next step (possibly the first batch of the next unit) and the planes
   // of the next unit are fetched one step / one unit ahead.
   struct Unit { int tile, start, n; };
-  auto unit_of = [&](int u) -> Unit {
-    Unit q = {0, 0, 0};
-    if (u < nunits) {
-      const int2 ud = units[u];
-      const int2 rg = ranges[ud.x];
-      q.tile = ud.x;
-      q.start = rg.x + ud.y * SEG;
-      q.n = max(0, min(SEG, rg.y - q.start));
-    }
-    return q;
-  };
+  auto decode = [&](const int4& d) -> Unit { return Unit{d.x, d.y, d.z}; };
+  const int4 dzero = make_int4(0, 0, 0, 0);
   auto fetch_planes = [&](int tile, int buf) {             // ONE bulk copy (async proxy), lands on bar_load[buf]
     mbar_expect_tx(&bar_load[buf], PLANE_BYTES);
     bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_BYTES / 16), PLANE_BYTES, &bar_load[buf]);
@@ -787,8 +778,10 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     cp_async_commit_b();
   };
   int u = blockIdx.x;
-  Unit cur = unit_of(u);
-  while (u < nunits && cur.n == 0) { u += gridDim.x; cur = unit_of(u); }     // empty tiles keep one empty unit
+  // descriptors run two units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
+  Unit cur = decode(__ldg(udesc + u));
+  int un = u + gridDim.x;
+  int4 d_nxt = un < nunits ? __ldg(udesc + un) : dzero;
   if (u < nunits) {
     if (tid == 0) fetch_planes(cur.tile, 0);
     fetch_ids(cur, 0);
@@ -815,10 +808,10 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   int kbuf = 0;                                            // units processed so far: plane / id buffer = kbuf & 1
   int step = 0;                                            // steps processed so far: record buffer = step & 1
   while (u < nunits) {
-    // the next non-empty unit of this CTA: its planes and ids are fetched a whole unit ahead
-    int un = u + gridDim.x;
-    Unit nxt = unit_of(un);
-    while (un < nunits && nxt.n == 0) { un += gridDim.x; nxt = unit_of(un); }
+    // the next unit of this CTA: its planes and ids are fetched a whole unit ahead
+    const Unit nxt = decode(d_nxt);
+    const int unn = un + gridDim.x;
+    const int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;           // consumed when this unit is done
     if (un < nunits && tid == 0) fetch_planes(nxt.tile, (kbuf + 1) & 1);   // that buffer's last reader (unit kbuf-1) has retired
     const float k_us = __ldg(tile_scale + cur.tile);      // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
     const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
@@ -899,7 +892,9 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       }
     }
     u = un;
+    un = unn;
     cur = nxt;
+    d_nxt = d_nn;
     ++kbuf;
   }
   flush_sums();
@@ -934,7 +929,8 @@ static bool use_simt_bwd() {
 }
 
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                          const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
+                          const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
+                          int64_t unit_cap, const float* acc,
                           const float* g_rgb, const float* g_alpha, const float* g_depth, const FitLossArgs* fl,
                           float* gbuf, float* gacc, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
@@ -975,10 +971,10 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
       // B2S_BWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
       static const bool direct = [] { const char* e = getenv("B2S_BWD_EX2"); return e != nullptr && e[0] == '1'; }();
       if (direct)
-        blend_wsum_bwd_umma_kernel<false><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+        blend_wsum_bwd_umma_kernel<false><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,
                                                                        reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       else
-        blend_wsum_bwd_umma_kernel<true><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units,
+        blend_wsum_bwd_umma_kernel<true><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,
                                                                       reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
       B2S_LAUNCH_CHECK();
       return B2S_OK;

@@ -607,16 +607,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 template <bool RECUR>
 __global__ void __launch_bounds__(FT_THREADS, 4)
 blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
-                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
-                           const int2* __restrict__ units, float* __restrict__ partial, float* __restrict__ out_rgb,
+                           const int2* __restrict__ ranges, const int4* __restrict__ udesc,
+                           const Counters* __restrict__ counters, float* __restrict__ partial, float* __restrict__ out_rgb,
                            float* __restrict__ out_alpha, float* __restrict__ acc, uint8_t* __restrict__ out_rgba) {
   extern __shared__ __align__(128) unsigned char ft_raw[];
   FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_raw);
   constexpr uint32_t IDESC = umma_idesc_f16(128, 32, true, true);   // M = [A_hi ; A_lo] rows, N = [B_hi | B_lo] rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nunits = unit_start[vp.n_tiles];
-  if ((int)blockIdx.x >= nunits) return;                   // block-uniform
+  const int nunits = counters->n_ne;                       // entries of the unit descriptor table (non-empty units, largest first)
   const size_t hw = (size_t)vp.width * vp.height;
+  // ---- tiles without Gaussians are not in the table: their pixels see the background only.  The CTAs share them
+  // (tile = blockIdx.x, + gridDim.x, ...; eight range loads in flight at a time).
+  for (int t0 = blockIdx.x; t0 < vp.n_tiles; t0 += 8 * gridDim.x) {
+    int2 rg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int t = t0 + e * gridDim.x;
+      rg[e] = t < vp.n_tiles ? __ldg(ranges + t) : make_int2(0, 1);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (rg[e].y - rg[e].x > 0) continue;                 // block-uniform
+      const int t = t0 + e * gridDim.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pix = tid + h * FT_THREADS;
+        const int xi = (t % vp.tiles_x) * TILE + (pix & 15), yi = (t / vp.tiles_x) * TILE + (pix >> 4);
+        if (xi < vp.width && yi < vp.height)
+          write_pixel(vp, (size_t)yi * vp.width + xi, hw, 0.f, 0.f, 0.f, 0.f, 0.f, out_rgb, out_alpha, nullptr, acc, out_rgba);
+      }
+    }
+  }
+  if ((int)blockIdx.x >= nunits) return;                   // block-uniform
 
   if (tid == 0) mbar_init(&sm.bar_mma, 1);
   if (warp == 0) {
@@ -632,42 +654,21 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   const uint64_t dA = umma_desc(smem_u32(&sm.Ah[0][0]), 128, FT_SBO), dB = umma_desc(smem_u32(&sm.B[0][0]), 128, FT_SBO);
   float* sOut = reinterpret_cast<float*>(&sm.Ah[0][0]);    // [plane][row * 16 + column], aliases A hi between units
 
-  struct Unit { int tile, start, n, nseg; };
-  auto unit_of = [&](int u) -> Unit {
-    Unit q = {0, 0, 0, 1};
-    if (u < nunits) {
-      const int2 ud = units[u];
-      const int2 rg = ranges[ud.x];
-      q.tile = ud.x;
-      q.start = rg.x + ud.y * SEG;
-      q.n = max(0, min(SEG, rg.y - q.start));
-      q.nseg = unit_start[ud.x + 1] - unit_start[ud.x];
-    }
-    return q;
-  };
+  struct Unit { int tile, start, n, uidx; };               // uidx: unit index (its partial planes) | tile has several units << 31
+  auto decode = [&](const int4& d) -> Unit { return Unit{d.x, d.y, d.z, d.w}; };
+  const int4 dzero = make_int4(0, 0, 0, 0);
   // pixels q = tid, tid + 128 of a unit: outputs (single-unit tile) or the unit's partial planes
-  auto emit = [&](int u, const Unit& q, int pix, float R, float G, float Bc, float W) {
-    if (q.nseg <= 1) {
+  auto emit = [&](const Unit& q, int pix, float R, float G, float Bc, float W) {
+    if (q.uidx >= 0) {
       const int xi = (q.tile % vp.tiles_x) * TILE + (pix & 15), yi = (q.tile / vp.tiles_x) * TILE + (pix >> 4);
       if (xi < vp.width && yi < vp.height)
         write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, Bc, W, 0.0f, out_rgb, out_alpha, nullptr, acc, out_rgba);
     } else {
-      float* dst = partial + (size_t)u * 5 * TILE_PIX + pix;
+      float* dst = partial + (size_t)(q.uidx & 0x7fffffff) * 5 * TILE_PIX + pix;
       dst[0] = R;
       dst[TILE_PIX] = G;
       dst[2 * TILE_PIX] = Bc;
       dst[3 * TILE_PIX] = W;
-    }
-  };
-  // first / next NON-EMPTY unit of this CTA at or after u; the empty ones on the way (empty tiles keep one unit)
-  // are finished on the spot: their pixels see no Gaussian
-  auto skip_empty = [&](int& u, Unit& q) {
-    q = unit_of(u);
-    while (u < nunits && q.n == 0) {
-      emit(u, q, tid, 0.f, 0.f, 0.f, 0.f);
-      emit(u, q, tid + FT_THREADS, 0.f, 0.f, 0.f, 0.f);
-      u += gridDim.x;
-      q = unit_of(u);
     }
   };
   auto fetch_ids = [&](const Unit& q, int buf) {
@@ -684,9 +685,11 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     cp_async_commit_b();
   };
 
+  // descriptors run two units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
   int u = blockIdx.x;
-  Unit cur;
-  skip_empty(u, cur);
+  Unit cur = decode(__ldg(udesc + u));
+  int un = u + gridDim.x;
+  int4 d_nxt = un < nunits ? __ldg(udesc + un) : dzero;
   if (u < nunits) {
     fetch_ids(cur, 0);
     cp_async_wait_b<0>();
@@ -696,9 +699,9 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   bool pending = false;                                    // an MMA batch has been committed and not yet waited for
   int kbuf = 0, step = 0;
   while (u < nunits) {
-    int un = u + gridDim.x;
-    Unit nxt;
-    skip_empty(un, nxt);
+    const Unit nxt = decode(d_nxt);
+    const int unn = un + gridDim.x;
+    const int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;           // consumed when this unit is done
     const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
     const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
     const int nbatch = (cur.n + FT_THREADS - 1) / FT_THREADS;
@@ -816,11 +819,13 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int pix = tid + h * FT_THREADS;
-      emit(u, cur, pix, sOut[pix], sOut[TILE_PIX + pix], sOut[2 * TILE_PIX + pix], sOut[3 * TILE_PIX + pix]);
+      emit(cur, pix, sOut[pix], sOut[TILE_PIX + pix], sOut[2 * TILE_PIX + pix], sOut[3 * TILE_PIX + pix]);
     }
     __syncthreads();                                       // sOut aliases the A operand: reads done before the next stores
     u = un;
+    un = unn;
     cur = nxt;
+    d_nxt = d_nn;
     ++kbuf;
   }
   __syncthreads();
@@ -853,7 +858,8 @@ finalize_kernel(const ViewParams vp, const int* __restrict__ unit_start, const f
 }
 
 int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                          const int* unit_start, const int2* units, int64_t unit_cap, float* partial,
+                          const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
+                          int64_t unit_cap, float* partial,
                           float* out_rgb, float* out_alpha, float* out_depth, float* acc, uint8_t* out_rgba,
                           cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
@@ -880,10 +886,10 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
     static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
     const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
     if (direct)
-      blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
+      blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
                                                                                    out_rgb, out_alpha, acc, out_rgba);
     else
-      blend_wsum_fwd_umma_kernel<true><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, unit_start, units, partial,
+      blend_wsum_fwd_umma_kernel<true><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
                                                                                   out_rgb, out_alpha, acc, out_rgba);
   }
   else if (tf32)     { if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }

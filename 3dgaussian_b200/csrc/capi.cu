@@ -139,6 +139,7 @@ struct Bufs {  // resolved pointers into state / workspace
   float* gacc;
   int* unit_start;
   int2* units;
+  int4* udesc;
   float* partial;
   float* gbuf;
   int* cs_table;
@@ -160,6 +161,7 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.acc = (float*)(s + S.acc);
     b.unit_start = (int*)(s + S.unit_start);
     b.units = (int2*)(s + S.units);
+    b.udesc = (int4*)(s + S.udesc);
     b.cmask = (uint8_t*)(s + S.cmask);
   }
   if (ws != nullptr) {
@@ -217,7 +219,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     {
       StageTimer t(ctx, ST_BIN, st);
       rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
-                                B.unit_start, B.units, B.vals, 0, st);
+                                B.unit_start, B.units, B.udesc, B.vals, 0, st);   // also writes the unit descriptor table
     }
     if (rc != B2S_OK) return rc;
     if (keys_unsorted_copy != nullptr || vals_unsorted_copy != nullptr) {   // dump hook only: the emit order
@@ -232,7 +234,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     {
       StageTimer t(ctx, ST_SORT, st);
       rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
-                                B.unit_start, B.units, B.vals, 1, st);
+                                B.unit_start, B.units, B.udesc, B.vals, 1, st);
     }
     if (rc != B2S_OK) return rc;
     if (keys_sorted != nullptr) *keys_sorted = nullptr;   // this path has no keys
@@ -262,6 +264,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     StageTimer t(ctx, ST_RANGES, st);
     rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
     if (rc == B2S_OK) rc = launch_units(B.ranges, vp.n_tiles, B.unit_cap, B.unit_start, B.units, st);
+    if (rc == B2S_OK) rc = launch_udesc(B.ranges, B.unit_start, vp.n_tiles, B.unit_cap, B.udesc, B.counters, st);
   }
   if (rc != B2S_OK) return rc;
   if (keys_sorted != nullptr) *keys_sorted = ks;
@@ -359,7 +362,7 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, nullptr, st);
-  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, out_rgb,
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, out_rgb,
                                out_alpha, out_depth, B.acc, nullptr, st);
 }
 
@@ -392,7 +395,7 @@ int b2s_forward_prepared(b2s_ctx* ctx, const b2s_params* p, const void* prepared
   rc = run_binning(ctx, vp, p, nullptr, nullptr, nullptr, nullptr, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_BLEND_FWD, st);
-  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, out_rgb,
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, out_rgb,
                                out_alpha, out_depth, B.acc, nullptr, st);
 }
 
@@ -418,7 +421,7 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
     StageTimer t(ctx, ST_BLEND_BWD, st);
     rc = launch_gacc_init(B.cmask, B.gacc, n, st);
     if (rc != B2S_OK) return rc;
-    rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
+    rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, nullptr, B.gbuf, B.gacc, st);
   }
   if (rc != B2S_OK) return rc;
@@ -458,7 +461,7 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
   StageTimer t(ctx, ST_BLEND_BWD, st);
   rc = launch_gacc_init(B.cmask, gacc_out, n, st);
   if (rc != B2S_OK) return rc;
-  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, g_rgb, g_alpha,
+  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, nullptr, B.gbuf, gacc_out, st);
 }
 
@@ -486,7 +489,7 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
     rc = launch_gacc_init(B.cmask, gacc_out, n, st);
     if (rc != B2S_OK) return rc;
   }
-  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.acc, nullptr, nullptr,
+  return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, nullptr, nullptr,
                                nullptr, &fl, B.gbuf, gacc_out, st);
 }
 
@@ -533,7 +536,7 @@ static int render_rgba8_impl(b2s_ctx* ctx, const ViewParams& vp, const b2s_param
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
     return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, out_rgba, st);
-  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.unit_cap, B.partial, nullptr,
+  return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, nullptr,
                                nullptr, nullptr, nullptr, out_rgba, st);
 }
 

@@ -185,7 +185,7 @@ __device__ __forceinline__ void factors16(float q, float d0, float e0, float2 (&
 
 // ---- state / workspace layout (all offsets 256-B aligned) -------------------------------
 struct StateLayout {
-  size_t rec, ranges, vals, acc, counters, unit_start, units, cmask, total;
+  size_t rec, ranges, vals, acc, counters, unit_start, units, udesc, cmask, total;
 };
 struct WorkLayout {
   size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
@@ -219,6 +219,7 @@ inline StateLayout state_layout(int n, int width, int height, int64_t max_pairs)
   L.acc = o;      o += align_up((size_t)width * height * 5 * 4);
   L.unit_start = o; o += align_up((size_t)(tiles + 1) * 4);
   L.units = o;    o += align_up((size_t)max_units(width, height, max_pairs) * 8);
+  L.udesc = o;    o += align_up((size_t)max_units(width, height, max_pairs) * 16);   // non-empty units, largest first
   L.cmask = o;    o += align_up((size_t)(n > 0 ? n : 1));   // colour clamp mask, 1 B per Gaussian (torch_renderer.py:144)
   L.total = o;
   return L;
@@ -273,6 +274,8 @@ struct Counters {
   long long needed;   // pairs the view produces
   int kept;           // pairs actually emitted (<= max_pairs)
   int overflow;       // 1 if needed > max_pairs
+  int n_ne;           // non-empty work units (entries of the unit descriptor table)
+  int pad_[3];
 };
 
 // ---- host-side error plumbing ---------------------------------------------------------------
@@ -317,11 +320,18 @@ int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t 
 bool counting_sort_fits(int n_tiles);
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, int* table, int* total,
-                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int* vals,
-                         int stage, cudaStream_t st);
+                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
+                         int* vals, int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
+// Unit descriptor table of the persistent tcgen05 blend kernels: the NON-EMPTY units as {tile, first pair, pairs,
+// unit index | multi-unit-tile flag << 31}, ordered by their number of 128-Gaussian steps, largest first, so that CTA i
+// taking entries i, i + grid, i + 2 grid, ... gets the same mix of work as every other CTA (static, balanced), and a
+// unit costs ONE 16-byte load instead of the dependent units -> ranges pair.
+int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int64_t unit_cap, int4* udesc, Counters* counters,
+                 cudaStream_t st);
 int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                          const int* unit_start, const int2* units, int64_t unit_cap, float* partial,
+                          const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
+                          int64_t unit_cap, float* partial,
                           float* out_rgb, float* out_alpha, float* out_depth, float* acc, uint8_t* out_rgba,
                           cudaStream_t st);
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
@@ -336,7 +346,8 @@ struct FitLossArgs {
   float* loss_accum;
 };
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                          const int* unit_start, const int2* units, int64_t unit_cap, const float* acc,
+                          const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
+                          int64_t unit_cap, const float* acc,
                           const float* g_rgb, const float* g_alpha, const float* g_depth, const FitLossArgs* fl,
                           float* gbuf, float* gacc, cudaStream_t st);
 // single != null: one view passed by value (views_dev must be null, num_views 1, gacc = n x 12 floats);
