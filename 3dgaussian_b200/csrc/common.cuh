@@ -133,14 +133,20 @@ __device__ __forceinline__ unsigned long long tile_cull_mask(float px, float py,
     const float u = __fmul_rn(__fsub_rn(fminf(fmaxf(px, lo), hi), px), isx);
     uxx[c] = __fmul_rn(u, u);
   }
+  // columns beyond the rect never pass: +inf fails the test below, and without culling the row is just the rect width
+  const uint32_t wmask = (1u << w) - 1u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) uxx[c] = (c < w) ? uxx[c] : INFINITY;
   unsigned long long m = 0ull;
   for (int r = 0; r < h; ++r) {
     const float lo = (float)((ty0 + r) * TILE) + 0.5f, hi = lo + (float)(TILE - 1);
     const float u = __fmul_rn(__fsub_rn(fminf(fmaxf(py, lo), hi), py), isy);
     const float uyy = __fmul_rn(u, u);
+    uint32_t row = 0;                               // the row's columns as 8 bits, placed with ONE 64-bit shift
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c < w && (!cull || __fadd_rn(uxx[c], uyy) <= kk)) m |= 1ull << (r * w + c);
+    for (int c = 0; c < 8; ++c) row |= (__fadd_rn(uxx[c], uyy) <= kk) ? (1u << c) : 0u;
+    row = cull ? row : wmask;
+    m |= (unsigned long long)row << (r * w);
   }
   return m;
 }
