@@ -568,16 +568,16 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 // shuffles, and the per-Gaussian work (32 MUFU.EX2, fp16 splits, 48 colour products) is plain thread-local code.
 // Per unit the 128 x 32 accumulator is read back once (lane = operand row), its three useful quadrants summed, exchanged
 // through shared memory and written as pixels (or as the unit's partial planes when the tile has several units).
-//   CTA = 128 threads, 32 TMEM columns, 52 KB of shared memory -> 4 CTAs per SM; persistent over the units.
+//   CTA = 128 threads, 32 TMEM columns, 44 KB of shared memory -> 5 CTAs per SM; persistent over the units.
 // Layout validated by profiles/microbench/umma_probe_mn.cu.  The 5-plane (depth) case stays on v5.
 constexpr int FT_THREADS = 128;
+constexpr int FT_CTAS = 5;                        // per SM: 44 KB of shared memory, <= 102 registers, 32 TMEM columns each
 constexpr uint32_t FT_SBO = FT_THREADS * 16;      // bytes between MN groups of 8: [group][Gaussian] uint4
 struct FtSmem {
   uint4 Ah[8][FT_THREADS];        // A hi: group = plane * 2 + column / 8
   uint4 Al[8][FT_THREADS];
   uint4 B[4][FT_THREADS];         // fy: hi rows 0-7, hi rows 8-15, lo rows 0-7, lo rows 8-15
-  float4 rec[2][2][FT_THREADS];   // x / y records of the current and the next step, one per thread
-  int id[2][SEG];                 // Gaussian ids of the current / next unit
+  float4 rec[2][FT_THREADS];      // x / y record of the next step, one private slot per thread
   unsigned long long bar_mma;
   uint32_t tmem_base;
 };
@@ -605,7 +605,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 template <bool RECUR>
-__global__ void __launch_bounds__(FT_THREADS, 4)
+__global__ void __launch_bounds__(FT_THREADS, FT_CTAS)
 blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int2* __restrict__ ranges, const int4* __restrict__ udesc,
                            const Counters* __restrict__ counters, float* __restrict__ partial, float* __restrict__ out_rgb,
@@ -671,54 +671,65 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       dst[3 * TILE_PIX] = W;
     }
   };
-  auto fetch_ids = [&](const Unit& q, int buf) {
-    for (int i = tid; i < q.n; i += FT_THREADS) cp_async4_b(&sm.id[buf][i], vals + q.start + i);
-    cp_async_commit_b();
-  };
-  auto fetch_rec = [&](const Unit& q, int idbuf, int batch, int rbuf) {    // needs id[idbuf] of this thread landed
+  // Staging.  The Gaussian id of a step is a coalesced load into a REGISTER, requested two steps ahead (by the time
+  // the next fence -- a MEMBAR for the issuing thread -- comes, it has long landed); the record of a step is
+  // gathered with cp.async into the thread's own shared-memory slot one step ahead (the thread has just moved the
+  // current record from that slot into registers; slots are private, so cp.async.wait_group orders them without a
+  // barrier, and no register waits on a scattered global load).  Nothing else is staged: 44 KB of shared memory
+  // per CTA, five CTAs per SM.  id -1 = slot past the unit's list: the padding record.
+  auto id_of = [&](const Unit& q, int batch) -> int {
     const int i = batch * FT_THREADS + tid;
-    if (i < q.n) {
-      const float4* src = rec + 3 * (size_t)sm.id[idbuf][i];
-      cp_async16_b(&sm.rec[rbuf][0][tid], src);
-      cp_async16_b(&sm.rec[rbuf][1][tid], src + 1);
+    return i < q.n ? __ldg(vals + q.start + i) : -1;
+  };
+  auto fetch_rec = [&](int id) {
+    if (id >= 0) {
+      const float4* src = rec + 3 * (size_t)id;
+      cp_async16_b(&sm.rec[0][tid], src);
+      cp_async16_b(&sm.rec[1][tid], src + 1);
     }
     cp_async_commit_b();
   };
+  auto nbatch_of = [&](const Unit& q) { return (q.n + FT_THREADS - 1) / FT_THREADS; };
 
-  // descriptors run two units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
+  // descriptors run three units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
   int u = blockIdx.x;
   Unit cur = decode(__ldg(udesc + u));
-  int un = u + gridDim.x;
+  int un = u + gridDim.x, unn = un + gridDim.x;
   int4 d_nxt = un < nunits ? __ldg(udesc + un) : dzero;
-  if (u < nunits) {
-    fetch_ids(cur, 0);
-    cp_async_wait_b<0>();
-    fetch_rec(cur, 0, 0, 0);
+  int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;
+  // ids of steps 0 and 1, record of step 0
+  bool act = false;
+  int id1 = -1;
+  {
+    const int id0 = id_of(cur, 0);
+    fetch_rec(id0);
+    act = id0 >= 0;
+    if (1 < nbatch_of(cur)) id1 = id_of(cur, 1);
+    else if (un < nunits) id1 = id_of(decode(d_nxt), 0);
   }
   uint32_t phase = 0;
   bool pending = false;                                    // an MMA batch has been committed and not yet waited for
-  int kbuf = 0, step = 0;
   while (u < nunits) {
-    const Unit nxt = decode(d_nxt);
-    const int unn = un + gridDim.x;
-    const int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;           // consumed when this unit is done
+    const Unit nxt = decode(d_nxt), nn = decode(d_nn);
+    const int un3 = unn + gridDim.x;
+    const int4 d_n3 = un3 < nunits ? __ldg(udesc + un3) : dzero;           // consumed when this unit is done
+    const int nb_nxt = nbatch_of(nxt);
     const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
     const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
     const int nbatch = (cur.n + FT_THREADS - 1) / FT_THREADS;
-    for (int bi = 0; bi < nbatch; ++bi, ++step) {
-      cp_async_wait_b<0>();                                // this step's record (issued a step ago) and older copies
-      const bool active = bi * FT_THREADS + tid < cur.n;
+    for (int bi = 0; bi < nbatch; ++bi) {
+      cp_async_wait_b<0>();                                // this step's record (gathered during the previous step)
       // padding: q = 0 and log2 op = -1000 make every x factor exactly 0 (and every ratio of the recurrence 1: no
       // 0 * inf), the colour halves are 0; a padded K slot then adds 0 to every accumulator
       float4 ra = make_float4(0.0f, 0.0f, -1000.0f, 0.0f), rb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (active) { ra = sm.rec[step & 1][0][tid]; rb = sm.rec[step & 1][1][tid]; }
-      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
-      if (bi + 1 < nbatch) {
-        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
-      } else if (un < nunits) {
-        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
-        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
-      }
+      if (act) { ra = sm.rec[0][tid]; rb = sm.rec[1][tid]; }
+      fetch_rec(id1);                                      // next step's record into the slot just read
+      act = id1 >= 0;
+      // id of the step after next: in this unit, the next one, or (single-step next unit) the one after it
+      if (bi + 2 < nbatch) id1 = id_of(cur, bi + 2);
+      else if (un >= nunits) id1 = -1;
+      else if (bi + 2 - nbatch < nb_nxt) id1 = id_of(nxt, bi + 2 - nbatch);
+      else id1 = unn < nunits ? id_of(nn, 0) : -1;
       // ---- factors of this thread's Gaussian at the tile's 16 columns / rows, each scaled by 2^8 (fp16 range),
       // split into fp16 hi + lo pairs {even, odd}
       const float dx0 = ra.x - x0, dy0 = rb.x - y0;
@@ -824,9 +835,10 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     __syncthreads();                                       // sOut aliases the A operand: reads done before the next stores
     u = un;
     un = unn;
+    unn = un3;
     cur = nxt;
     d_nxt = d_nn;
-    ++kbuf;
+    d_nn = d_n3;
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(32) : "memory");
@@ -883,7 +895,7 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
     B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
     // B2S_FWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
     static const bool direct = [] { const char* e = getenv("B2S_FWD_EX2"); return e != nullptr && e[0] == '1'; }();
-    static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
+    static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= FT_CTAS) ? v : FT_CTAS; }();
     const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
     if (direct)
       blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
