@@ -426,8 +426,9 @@ preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ vi
       const bool ok = pr.ok;      // culled in this view: its gacc row is all zeros (no `continue`: the
                                   // colour block below holds warp shuffles that every lane must reach)
       const float dC[3] = {g0.x, g0.y, g0.z};
-      float dZ = g0.w;
-      const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x;
+      // slot 3 is dZ in rows of a backward pass with a depth gradient (g2.z), else a second home of Syy (gacc_init)
+      float dZ = (g2.z != 0.0f) ? g0.w : 0.0f;
+      const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x + ((g2.z != 0.0f) ? 0.0f : g0.w);
 
       if (ok) {
         // opacity: w = op * E  =>  dL/dop = S / op
@@ -685,8 +686,9 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
       if (mine) {                      // projection -> sigma / opacity / position chain
         const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
         if (pr.ok) {
-          float dZ = c0.w;
-          const float S = c1.x, Sx = c1.y, Sxx = c1.z, Sy = c1.w, Syy = c2.x;
+          // slot 3 is dZ in rows of a backward pass with a depth gradient (c2.z), else a second home of Syy
+          float dZ = (c2.z != 0.0f) ? c0.w : 0.0f;
+          const float S = c1.x, Sx = c1.y, Sxx = c1.z, Sy = c1.w, Syy = c2.x + ((c2.z != 0.0f) ? 0.0f : c0.w);
           gop = fmaf(S, inv_op, gop);
           const float rsx = __frcp_rn(pr.sx), rsy = __frcp_rn(pr.sy), rz = __frcp_rn(pr.zabs);
           const float isx2 = rsx * rsx, isy2 = rsy * rsy;
