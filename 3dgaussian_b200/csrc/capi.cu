@@ -419,7 +419,7 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   {
     StageTimer t(ctx, ST_BLEND_BWD, st);
-    rc = launch_gacc_init(B.cmask, B.gacc, n, g_depth != nullptr, st);
+    rc = launch_gacc_init(B.cmask, B.gacc, n, st);
     if (rc != B2S_OK) return rc;
     rc = launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, nullptr, B.gbuf, B.gacc, st);
@@ -459,7 +459,7 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   StageTimer t(ctx, ST_BLEND_BWD, st);
-  rc = launch_gacc_init(B.cmask, gacc_out, n, g_depth != nullptr, st);
+  rc = launch_gacc_init(B.cmask, gacc_out, n, st);
   if (rc != B2S_OK) return rc;
   return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, g_rgb, g_alpha,
                                g_depth, nullptr, B.gbuf, gacc_out, st);
@@ -486,7 +486,7 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
   const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum};
   StageTimer t(ctx, ST_BLEND_BWD, st);
   if (n > 0) {
-    rc = launch_gacc_init(B.cmask, gacc_out, n, false, st);
+    rc = launch_gacc_init(B.cmask, gacc_out, n, st);
     if (rc != B2S_OK) return rc;
   }
   return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, nullptr, nullptr,

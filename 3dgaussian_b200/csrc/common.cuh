@@ -342,7 +342,7 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           cudaStream_t st);
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                             float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
-int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, bool depth_rows, cudaStream_t st);
+int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st);
 // fl != null: the image gradients are those of the fit loss, evaluated from the saved accumulators inside the
 // g-buffer kernel (g_rgb / g_alpha / g_depth are ignored)
 struct FitLossArgs {

@@ -426,9 +426,8 @@ preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ vi
       const bool ok = pr.ok;      // culled in this view: its gacc row is all zeros (no `continue`: the
                                   // colour block below holds warp shuffles that every lane must reach)
       const float dC[3] = {g0.x, g0.y, g0.z};
-      // slot 3 is dZ in rows of a backward pass with a depth gradient (g2.z), else a second home of Syy (gacc_init)
-      float dZ = (g2.z != 0.0f) ? g0.w : 0.0f;
-      const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g2.x + ((g2.z != 0.0f) ? 0.0f : g0.w);
+      float dZ = g2.x;            // row = {dR, dG, dB, Syy | S, Sx, Sxx, Sy | dZ, colour clamp mask, -, -}
+      const float S = g1.x, Sx = g1.y, Sxx = g1.z, Sy = g1.w, Syy = g0.w;
 
       if (ok) {
         // opacity: w = op * E  =>  dL/dop = S / op
@@ -680,15 +679,14 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
         g0 = __ldg(gn); g2 = __ldg(gn + 2);
         if (((vl + 1) & 3) == sub) g1 = __ldg(gn + 1);
       }
-      // c0 = {dR, dG, dB, dZ} (zero row when the Gaussian is culled in this view), c2 = {Syy, colour clamp mask, -, -}
+      // c0 = {dR, dG, dB, Syy} (zero row when the Gaussian is culled in this view), c2 = {dZ, colour clamp mask, -, -}
       const int cmask = __float_as_int(c2.y);
       const float dc0 = (cmask & 1) ? c0.x : 0.0f, dc1 = (cmask & 2) ? c0.y : 0.0f, dc2 = (cmask & 4) ? c0.z : 0.0f;
       if (mine) {                      // projection -> sigma / opacity / position chain
         const Proj pr = project_gaussian(vp, mx, my, mz, s0, s1, op);
         if (pr.ok) {
-          // slot 3 is dZ in rows of a backward pass with a depth gradient (c2.z), else a second home of Syy
-          float dZ = (c2.z != 0.0f) ? c0.w : 0.0f;
-          const float S = c1.x, Sx = c1.y, Sxx = c1.z, Sy = c1.w, Syy = c2.x + ((c2.z != 0.0f) ? 0.0f : c0.w);
+          float dZ = c2.x;
+          const float S = c1.x, Sx = c1.y, Sxx = c1.z, Sy = c1.w, Syy = c0.w;
           gop = fmaf(S, inv_op, gop);
           const float rsx = __frcp_rn(pr.sx), rsy = __frcp_rn(pr.sy), rz = __frcp_rn(pr.zabs);
           const float isx2 = rsx * rsx, isy2 = rsy * rsy;
