@@ -723,7 +723,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
   __shared__ __align__(128) uint4 sP[2][PLANE_BYTES / 16];       // the planes of the current and of the next unit's tile
   __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
-  __shared__ __align__(16) float4 sRec[2][3][BT_THREADS];       // records of the current / next step, one per thread
+  __shared__ __align__(16) float4 sRec[2][2][BT_THREADS];       // x / y records of the current / next step, one per thread
   __shared__ int sId[2][SEG];                                    // Gaussian ids of the current / next unit
   __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
   __shared__ uint32_t tmem_base_s;
@@ -771,9 +771,8 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     const int i = batch * BT_THREADS + tid;
     if (i < q.n) {
       const float4* src = rec + 3 * (size_t)sId[idbuf][i];
-      cp_async16_b(&sRec[rbuf][0][tid], src);
-      cp_async16_b(&sRec[rbuf][1][tid], src + 1);
-      cp_async16_b(&sRec[rbuf][2][tid], src + 2);
+      cp_async16_b(&sRec[rbuf][0][tid], src);               // two of the record's three float4: the clamped colour
+      cp_async16_b(&sRec[rbuf][1][tid], src + 1);           // is rebuilt from its fp16 hi | lo halves below
     }
     cp_async_commit_b();
   };
@@ -822,7 +821,16 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       const bool active = bi * BT_THREADS + tid < cur.n;
       const int cur_id = active ? sId[kbuf & 1][bi * BT_THREADS + tid] : -1;
       float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, col = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active) { ra = sRec[step & 1][0][tid]; rb = sRec[step & 1][1][tid]; col = sRec[step & 1][2][tid]; }
+      if (active) {
+        ra = sRec[step & 1][0][tid];
+        rb = sRec[step & 1][1][tid];
+        // clamped colour = hi + lo of the forward's pre-split halves (22 significant bits): red in ra.w, green in
+        // rb.w, blue in rb.z, each {hi | lo << 16} -- saves the gather of the record's third float4
+        const uint32_t cr = __float_as_uint(ra.w), cg = __float_as_uint(rb.w), cb = __float_as_uint(rb.z);
+        col.x = __half2float(__ushort_as_half((unsigned short)(cr & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cr >> 16)));
+        col.y = __half2float(__ushort_as_half((unsigned short)(cg & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cg >> 16)));
+        col.z = __half2float(__ushort_as_half((unsigned short)(cb & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cb >> 16)));
+      }
       const float lop = ra.z;
       // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
       const float dx0 = x0 - ra.x, dy0 = y0 - rb.x;
