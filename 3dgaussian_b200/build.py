@@ -19,6 +19,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
+# extra compile-time switches for experiments, e.g. B2S_NVCC_EXTRA="-DB2S_SEG=1024" python 3dgaussian_b200/build.py --force
+NVCC_FLAGS += os.environ.get("B2S_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

@@ -200,7 +200,7 @@ struct WorkLayout {
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
 // to ~5000 Gaussians; one CTA per tile left the SMs idle a third of the time).
 #ifndef B2S_SEG
-#define B2S_SEG 512
+#define B2S_SEG 1024
 #endif
 constexpr int SEG = B2S_SEG;
 inline int64_t max_units(int width, int height, int64_t max_pairs) {
