@@ -723,8 +723,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
   __shared__ __align__(128) uint4 sP[2][PLANE_BYTES / 16];       // the planes of the current and of the next unit's tile
   __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
-  __shared__ __align__(16) float4 sRec[2][2][BT_THREADS];       // x / y records of the current / next step, one per thread
-  __shared__ int sId[2][SEG];                                    // Gaussian ids of the current / next unit
+  __shared__ __align__(16) float4 sRec[2][BT_THREADS];          // x / y record of the next step, one private slot per thread
   __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -760,33 +759,33 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     mbar_expect_tx(&bar_load[buf], PLANE_BYTES);
     bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_BYTES / 16), PLANE_BYTES, &bar_load[buf]);
   };
-  // Gaussian ids of a unit and the record of a step are staged with cp.async: every thread copies and later
-  // reads only ITS OWN slots, so cp.async.wait_group orders them without a barrier, and no register waits on a
-  // global load (a warp issues in order: a register prefetch of `rec[id]` stalls on `id` right away).
-  auto fetch_ids = [&](const Unit& q, int buf) {
-    for (int i = tid; i < q.n; i += BT_THREADS) cp_async4_b(&sId[buf][i], vals + q.start + i);
-    cp_async_commit_b();
-  };
-  auto fetch_rec = [&](const Unit& q, int idbuf, int batch, int rbuf) {    // needs sId[idbuf] of this thread landed
+  // Staging as in the forward: the Gaussian id of a step is a coalesced load into a REGISTER two steps ahead, the
+  // record of a step a cp.async gather into the thread's own slot one step ahead (slots are private: cp.async.wait_group
+  // orders them without a barrier, and no register waits on a scattered global load).  id -1 = slot past the list.
+  auto id_of = [&](const Unit& q, int batch) -> int {
     const int i = batch * BT_THREADS + tid;
-    if (i < q.n) {
-      const float4* src = rec + 3 * (size_t)sId[idbuf][i];
-      cp_async16_b(&sRec[rbuf][0][tid], src);               // two of the record's three float4: the clamped colour
-      cp_async16_b(&sRec[rbuf][1][tid], src + 1);           // is rebuilt from its fp16 hi | lo halves below
+    return i < q.n ? __ldg(vals + q.start + i) : -1;
+  };
+  auto fetch_rec = [&](int id) {
+    if (id >= 0) {
+      const float4* src = rec + 3 * (size_t)id;
+      cp_async16_b(&sRec[0][tid], src);                     // two of the record's three float4: the clamped colour
+      cp_async16_b(&sRec[1][tid], src + 1);                 // is rebuilt from its fp16 hi | lo halves below
     }
     cp_async_commit_b();
   };
+  auto nbatch_of = [&](const Unit& q) { return (q.n + BT_THREADS - 1) / BT_THREADS; };
   int u = blockIdx.x;
-  // descriptors run two units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
+  // descriptors run three units ahead in registers: a unit costs one 16-byte load whose latency nobody waits for
   Unit cur = decode(__ldg(udesc + u));
-  int un = u + gridDim.x;
+  int un = u + gridDim.x, unn = un + gridDim.x;
   int4 d_nxt = un < nunits ? __ldg(udesc + un) : dzero;
-  if (u < nunits) {
-    if (tid == 0) fetch_planes(cur.tile, 0);
-    fetch_ids(cur, 0);
-    cp_async_wait_b<0>();
-    fetch_rec(cur, 0, 0, 0);
-  }
+  int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;
+  if (tid == 0) fetch_planes(cur.tile, 0);
+  int id_cur = id_of(cur, 0), id1 = -1;                    // ids of steps 0 and 1, record of step 0
+  fetch_rec(id_cur);
+  if (1 < nbatch_of(cur)) id1 = id_of(cur, 1);
+  else if (un < nunits) id1 = id_of(decode(d_nxt), 0);
   // sums of the previous step waiting for their REDs: Gaussian id (complemented when op == 0: only S is kept), 8 sums
   int pend_id = INT_MIN;
   float pend[8];
@@ -803,27 +802,27 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     pend_id = INT_MIN;
   };
   uint32_t phase = 0;
-  int kbuf = 0;                                            // units processed so far: plane / id buffer = kbuf & 1
-  int step = 0;                                            // steps processed so far: record buffer = step & 1
+  int kbuf = 0;                                            // units processed so far: plane buffer = kbuf & 1
   while (u < nunits) {
     // the next unit of this CTA: its planes and ids are fetched a whole unit ahead
-    const Unit nxt = decode(d_nxt);
-    const int unn = un + gridDim.x;
-    const int4 d_nn = unn < nunits ? __ldg(udesc + unn) : dzero;           // consumed when this unit is done
+    const Unit nxt = decode(d_nxt), nn = decode(d_nn);
+    const int un3 = unn + gridDim.x;
+    const int4 d_n3 = un3 < nunits ? __ldg(udesc + un3) : dzero;           // consumed when this unit is done
+    const int nb_nxt = nbatch_of(nxt);
     if (un < nunits && tid == 0) fetch_planes(nxt.tile, (kbuf + 1) & 1);   // that buffer's last reader (unit kbuf-1) has retired
     const float k_us = __ldg(tile_scale + cur.tile);      // 2^-(sG+16): planes' 2^sG and the 2^8 of each factor
     const int tx = cur.tile % vp.tiles_x, ty = cur.tile / vp.tiles_x;
     const float x0 = (float)(tx * TILE) + 0.5f, y0 = (float)(ty * TILE) + 0.5f;
     const uint32_t pb = smem_u32(&sP[kbuf & 1][0]);
     const int nbatch = (cur.n + BT_THREADS - 1) / BT_THREADS;
-    for (int bi = 0; bi < nbatch; ++bi, ++step) {
+    for (int bi = 0; bi < nbatch; ++bi) {
       cp_async_wait_b<0>();                                // this step's record (issued after the previous step's barrier)
-      const bool active = bi * BT_THREADS + tid < cur.n;
-      const int cur_id = active ? sId[kbuf & 1][bi * BT_THREADS + tid] : -1;
+      const int cur_id = id_cur;
+      const bool active = cur_id >= 0;
       float4 ra = make_float4(1e18f, -1.0f, 0.0f, 0.0f), rb = ra, col = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) {
-        ra = sRec[step & 1][0][tid];
-        rb = sRec[step & 1][1][tid];
+        ra = sRec[0][tid];
+        rb = sRec[1][tid];
         // clamped colour = hi + lo of the forward's pre-split halves (22 significant bits): red in ra.w, green in
         // rb.w, blue in rb.z, each {hi | lo << 16} -- saves the gather of the record's third float4
         const uint32_t cr = __float_as_uint(ra.w), cg = __float_as_uint(rb.w), cb = __float_as_uint(rb.z);
@@ -869,13 +868,13 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       // the step that issued them -- a full L2 round trip on the critical path of every step.  Issued here they have
       // the MMA round trip, the epilogue and the next step's factor evaluation to land.
       flush_sums();
-      if (bi == 0 && un < nunits) fetch_ids(nxt, (kbuf + 1) & 1);
-      if (bi + 1 < nbatch) {
-        fetch_rec(cur, kbuf & 1, bi + 1, (step + 1) & 1);
-      } else if (un < nunits) {
-        if (nbatch == 1) cp_async_wait_b<0>();             // single-batch unit: the next unit's ids were requested just above
-        fetch_rec(nxt, (kbuf + 1) & 1, 0, (step + 1) & 1);
-      }
+      fetch_rec(id1);                                      // the next step's record, into the slot read at the top
+      id_cur = id1;
+      // id of the step after next: in this unit, the next one, or (single-step next unit) the one after it
+      if (bi + 2 < nbatch) id1 = id_of(cur, bi + 2);
+      else if (un >= nunits) id1 = -1;
+      else if (bi + 2 - nbatch < nb_nxt) id1 = id_of(nxt, bi + 2 - nbatch);
+      else id1 = unn < nunits ? id_of(nn, 0) : -1;
       mbar_wait(&bar_mma, phase);
       phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -900,8 +899,10 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     }
     u = un;
     un = unn;
+    unn = un3;
     cur = nxt;
     d_nxt = d_nn;
+    d_nn = d_n3;
     ++kbuf;
   }
   flush_sums();
