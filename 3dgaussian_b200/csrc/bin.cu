@@ -7,9 +7,8 @@
 
 namespace b2s {
 
-// unit descriptor table (common.cuh: launch_udesc): a unit's class is its number of 128-Gaussian steps
-constexpr int UD_STEP = 128;
-constexpr int UD_NCLS = (SEG + UD_STEP - 1) / UD_STEP;
+// unit descriptor table (common.cuh: launch_udesc): a unit's class is its size in eighths of the largest unit
+constexpr int UD_NCLS = 8;
 
 // Visits the tiles of Gaussian i row-major: the set bits of its mask for rects of at most 8 x 8 tiles
 // (tile_cull_mask), the whole rect otherwise.
@@ -132,7 +131,7 @@ int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect
 // that its background pixels are written).  unit_start[t] = exclusive prefix, unit_start[n_tiles]
 // = number of units; units[u] = (tile, segment).  One block: n_tiles is a few thousand.
 __global__ void __launch_bounds__(1024)
-units_kernel(const int2* __restrict__ ranges, int n_tiles, int unit_cap, int* __restrict__ unit_start,
+units_kernel(const int2* __restrict__ ranges, int n_tiles, int SEG, int unit_cap, int* __restrict__ unit_start,
              int2* __restrict__ units) {
   __shared__ int wtot[32];
   __shared__ int carry_s;
@@ -179,8 +178,8 @@ units_kernel(const int2* __restrict__ ranges, int n_tiles, int unit_cap, int* __
   if (threadIdx.x == 0) unit_start[n_tiles] = carry_s < unit_cap ? carry_s : unit_cap;
 }
 
-int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st) {
-  units_kernel<<<1, 1024, 0, st>>>(ranges, n_tiles, (int)unit_cap, unit_start, units);
+int launch_units(const int2* ranges, int n_tiles, int seg, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st) {
+  units_kernel<<<1, 1024, 0, st>>>(ranges, n_tiles, seg, (int)unit_cap, unit_start, units);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -190,8 +189,9 @@ int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_st
 // chunk of tiles [t*per, (t+1)*per), counts its units per class, one block-wide exclusive scan per class gives it
 // a deterministic slot range inside each class, classes are laid out largest first.
 __global__ void __launch_bounds__(1024)
-udesc_kernel(const int2* __restrict__ ranges, const int* __restrict__ unit_start, int n_tiles, int unit_cap,
+udesc_kernel(const int2* __restrict__ ranges, const int* __restrict__ unit_start, int n_tiles, int SEG, int unit_cap,
              int4* __restrict__ udesc, Counters* __restrict__ counters) {
+  const int UD_STEP = (SEG + UD_NCLS - 1) / UD_NCLS;
   __shared__ int wtot[UD_NCLS][32];
   __shared__ int cls_total[UD_NCLS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -264,9 +264,9 @@ udesc_kernel(const int2* __restrict__ ranges, const int* __restrict__ unit_start
   if (threadIdx.x == 0) counters->n_ne = run;
 }
 
-int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int64_t unit_cap, int4* udesc, Counters* counters,
-                 cudaStream_t st) {
-  udesc_kernel<<<1, 1024, 0, st>>>(ranges, unit_start, n_tiles, (int)unit_cap, udesc, counters);
+int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int seg, int64_t unit_cap, int4* udesc,
+                 Counters* counters, cudaStream_t st) {
+  udesc_kernel<<<1, 1024, 0, st>>>(ranges, unit_start, n_tiles, seg, (int)unit_cap, udesc, counters);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -338,9 +338,10 @@ cs_colscan_kernel(int* __restrict__ table, int nb, int n_tiles, int* __restrict_
 // [t*per, (t+1)*per): one pass to sum its chunk, ONE block-wide scan of the 1024 chunk sums, one pass to
 // write -- two barriers instead of four per 1024 tiles.
 __global__ void __launch_bounds__(1024)
-cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, long long max_pairs, int2* __restrict__ ranges,
+cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long long max_pairs, int2* __restrict__ ranges,
                    Counters* __restrict__ counters, int unit_cap, int* __restrict__ unit_start,
                    int2* __restrict__ units, int4* __restrict__ udesc) {
+  const int UD_STEP = (SEG + UD_NCLS - 1) / UD_NCLS;
   extern __shared__ int ts_smem[];                 // cnt[n_tiles] then ustart[n_tiles]
   int* cnt = ts_smem;
   int* ust = ts_smem + n_tiles;
@@ -519,7 +520,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
-    cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, (long long)max_pairs, ranges, counters, (int)unit_cap,
+    cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, vp.seg, (long long)max_pairs, ranges, counters, (int)unit_cap,
                                            unit_start, units, udesc);
     B2S_LAUNCH_CHECK();
   } else {

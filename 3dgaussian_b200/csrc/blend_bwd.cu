@@ -226,8 +226,8 @@ blend_wsum_bwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
   const int2 ud = units[u];
   const int tile = ud.x;
   const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = min(SEG, rg.y - start);
+  const int start = rg.x + ud.y * vp.seg;
+  const int n = min(vp.seg, rg.y - start);
   if (n <= 0) return;
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
 
@@ -540,8 +540,8 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   const int2 ud = units[u];
   const int tile = ud.x;
   const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = min(SEG, rg.y - start);
+  const int start = rg.x + ud.y * vp.seg;
+  const int n = min(vp.seg, rg.y - start);
   if (n <= 0) return;
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
   const int g = lane >> 2, t = lane & 3;

@@ -92,8 +92,8 @@ blend_wsum_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const
   const int2 ud = units[u];
   const int tile = ud.x;
   const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = max(0, min(SEG, rg.y - start));
+  const int start = rg.x + ud.y * vp.seg;
+  const int n = max(0, min(vp.seg, rg.y - start));
   const int nseg = unit_start[tile + 1] - unit_start[tile];
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
   const int cx = lane & 15, half = lane >> 4;
@@ -245,8 +245,8 @@ blend_wsum_fwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   const int2 ud = units[u];
   const int tile = ud.x;
   const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = max(0, min(SEG, rg.y - start));
+  const int start = rg.x + ud.y * vp.seg;
+  const int n = max(0, min(vp.seg, rg.y - start));
   const int nseg = unit_start[tile + 1] - unit_start[tile];
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
   const int g = lane >> 2, t = lane & 3;
@@ -400,8 +400,8 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
   const int2 ud = units[u];
   const int tile = ud.x;
   const int2 rg = ranges[tile];
-  const int start = rg.x + ud.y * SEG;
-  const int n = max(0, min(SEG, rg.y - start));
+  const int start = rg.x + ud.y * vp.seg;
+  const int n = max(0, min(vp.seg, rg.y - start));
   const int nseg = unit_start[tile + 1] - unit_start[tile];
   const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
   const int g = lane >> 2, t = lane & 3;

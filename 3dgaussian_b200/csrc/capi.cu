@@ -107,6 +107,11 @@ static int make_view(const b2s_params* p, ViewParams* vp) {
   vp->tiles_x = (p->width + TILE - 1) / TILE;
   vp->tiles_y = (p->height + TILE - 1) / TILE;
   vp->n_tiles = vp->tiles_x * vp->tiles_y;
+  {
+    static const int forced = [] { const char* e = getenv("B2S_UNIT_SIZE"); const int v = e ? atoi(e) : 0;
+                                   return (v >= SEG_MIN && (v & (v - 1)) == 0) ? v : 0; }();   // development knob
+    vp->seg = forced ? forced : unit_size(vp->n_tiles);
+  }
   vp->style = p->style;
   vp->sh = p->sh_coeffs > 0 ? p->sh_coeffs : 1;
   vp->act = p->act_flags;
@@ -263,8 +268,8 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   {
     StageTimer t(ctx, ST_RANGES, st);
     rc = launch_ranges(ks, &B.counters->kept, max_pairs, vp.n_tiles, B.ranges, st);
-    if (rc == B2S_OK) rc = launch_units(B.ranges, vp.n_tiles, B.unit_cap, B.unit_start, B.units, st);
-    if (rc == B2S_OK) rc = launch_udesc(B.ranges, B.unit_start, vp.n_tiles, B.unit_cap, B.udesc, B.counters, st);
+    if (rc == B2S_OK) rc = launch_units(B.ranges, vp.n_tiles, vp.seg, B.unit_cap, B.unit_start, B.units, st);
+    if (rc == B2S_OK) rc = launch_udesc(B.ranges, B.unit_start, vp.n_tiles, vp.seg, B.unit_cap, B.udesc, B.counters, st);
   }
   if (rc != B2S_OK) return rc;
   if (keys_sorted != nullptr) *keys_sorted = ks;

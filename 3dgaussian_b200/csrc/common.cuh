@@ -25,6 +25,7 @@ struct ViewParams {
   float fx, fy;     // |P00|, |P11|
   int width, height, tiles_x, tiles_y, n_tiles;
   int style, sh, act, exact_bbox, mode;
+  int seg;          // Gaussians per work unit of the blend kernels (unit_size(): grows with the image)
 };
 
 // One Gaussian after projection.  Every quantity that feeds an integer (bbox, tile rect,
@@ -199,13 +200,14 @@ struct WorkLayout {
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
 // to ~5000 Gaussians; one CTA per tile left the SMs idle a third of the time).
-#ifndef B2S_SEG
-#define B2S_SEG 1024
-#endif
-constexpr int SEG = B2S_SEG;
+// Unit size: long units amortise the per-unit costs of the persistent tcgen05 kernels (accumulator read-back,
+// partial planes, plane fetch) -- 512 -> 4096 takes the C4 forward from 19.8 to 17.1 ms -- but a unit is the grain of
+// the static load balance, so an image needs enough tiles to keep every CTA busy with several of them.
+constexpr int SEG_MIN = 512;
+inline int unit_size(int n_tiles) { return n_tiles >= 4096 ? 4096 : (n_tiles >= 1024 ? 1024 : SEG_MIN); }
 inline int64_t max_units(int width, int height, int64_t max_pairs) {
   const int64_t tiles = (int64_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
-  return (max_pairs > 0 ? max_pairs : 0) / SEG + tiles;   // sum_t max(1, ceil(c_t/SEG)) <= P1/SEG + tiles
+  return (max_pairs > 0 ? max_pairs : 0) / SEG_MIN + tiles;   // sum_t max(1, ceil(c_t/seg)) <= P1/seg + tiles, seg >= SEG_MIN
 }
 constexpr int SORT_KPB = 4096;   // keys per radix block
 constexpr int CS_NB = 296;       // counting-sort blocks: 2 per SM (148 SMs)
@@ -328,13 +330,13 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
                          const unsigned long long* tmask, int* table, int* total,
                          int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
                          int* vals, int stage, cudaStream_t st);
-int launch_units(const int2* ranges, int n_tiles, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
+int launch_units(const int2* ranges, int n_tiles, int seg, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
 // Unit descriptor table of the persistent tcgen05 blend kernels: the NON-EMPTY units as {tile, first pair, pairs,
 // unit index | multi-unit-tile flag << 31}, ordered by their number of 128-Gaussian steps, largest first, so that CTA i
 // taking entries i, i + grid, i + 2 grid, ... gets the same mix of work as every other CTA (static, balanced), and a
 // unit costs ONE 16-byte load instead of the dependent units -> ranges pair.
-int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int64_t unit_cap, int4* udesc, Counters* counters,
-                 cudaStream_t st);
+int launch_udesc(const int2* ranges, const int* unit_start, int n_tiles, int seg, int64_t unit_cap, int4* udesc,
+                 Counters* counters, cudaStream_t st);
 int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
                           int64_t unit_cap, float* partial,
