@@ -633,20 +633,6 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 // `rows*16` B apart), validated by profiles/microbench/umma_probe.cu.
 constexpr int BT_THREADS = 128;
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
-}
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-               : "r"(taddr));
-}
 // one quad: 16 consecutive accumulator columns = [plane][index in quad]
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[4][4]) {
   asm volatile(
