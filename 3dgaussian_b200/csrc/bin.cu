@@ -503,13 +503,16 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
                          const unsigned long long* tmask, int* table, int* total,
                          int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
                          int* vals, int stage, cudaStream_t st) {
-  static bool attr_set = false;
   const size_t smem = (size_t)vp.n_tiles * 4;
-  if (!attr_set) {
+  // function attributes are per device and a process may drive several GPUs: once per device, not once per process
+  static bool attr_set[64] = {};
+  int dev = 0;
+  B2S_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     B2S_CUDA_TRY(cudaFuncSetAttribute(cs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
     B2S_CUDA_TRY(cudaFuncSetAttribute(cs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
     B2S_CUDA_TRY(cudaFuncSetAttribute(cs_tilescan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int nb = counting_sort_blocks(n);
   const int per_block = (n + nb - 1) / nb;

@@ -890,9 +890,15 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
   else if (!depth && !tf32 && !mmasync) {
     // tcgen05: persistent, 4 CTAs per SM, each strides over the work units (4-plane case; depth stays on v5)
-    // (the attribute is per device: set on every launch, a process may drive several GPUs)
-    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
-    B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+    // (the attribute is per device and a process may drive several GPUs: once per device, not once per process)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    B2S_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+      B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     // B2S_FWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
     static const bool direct = [] { const char* e = getenv("B2S_FWD_EX2"); return e != nullptr && e[0] == '1'; }();
     static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= FT_CTAS) ? v : FT_CTAS; }();
