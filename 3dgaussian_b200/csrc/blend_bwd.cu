@@ -623,12 +623,12 @@ blend_wsum_bwd_mma_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 //   U[i][(ch,r)] = sum_c fx_i[c] G_ch[r][c]      V[i][(ch,c)] = sum_r fy_i[r] G_ch[r][c]
 // are two 128 x 64 x 16 products -- one tcgen05.mma each per plane half (hi, lo accumulate in TMEM) -- against
 // the tile's planes, which sit in shared memory as K-major operand matrices for the whole unit.  One thread owns
-// one Gaussian: it evaluates its 16 + 16 factors (32 MUFU.EX2), writes them as one fp16 row of the two A operands,
+// one Gaussian: it evaluates its 16 + 16 factors (by recurrence, 14 MUFU.EX2), writes them as one fp16 row of the two A operands,
 // and after the MMA reads ITS accumulator row (TMEM lane = thread) with tcgen05.ld: all 16 rows and 16 columns
 // of its Gaussian arrive in its own registers, so the FP32 epilogue is thread local -- no quad shuffles, no
 // fragment bookkeeping, and no HMMA issue slots (mma.sync tops out at a quarter of the tcgen05 rate).
 //   CTA = 128 threads = 4 warps (warp w reads TMEM lanes 32w..32w+31), 128 TMEM columns (U: 0..63, V: 64..127),
-//   16 KB of shared memory; 4 CTAs per SM cover each other's MMA round trips.
+//   28 KB of shared memory; 4 CTAs per SM cover each other's MMA round trips.
 // Operand layout: K-major, no swizzle (8-row x 16-byte core matrices; row groups 128 B apart, the two K chunks
 // `rows*16` B apart), validated by profiles/microbench/umma_probe.cu.
 constexpr int BT_THREADS = 128;
@@ -962,7 +962,7 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
                                                                             nullptr, frag, tile_scale);
     B2S_LAUNCH_CHECK();
     if (umma) {
-      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the work units
+      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the unit descriptor table
       static const int cps = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
       const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
       // B2S_BWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)

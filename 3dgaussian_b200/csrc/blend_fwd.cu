@@ -889,7 +889,7 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   if (vp.exact_bbox) { if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
   else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
   else if (!depth && !tf32 && !mmasync) {
-    // tcgen05: persistent, 4 CTAs per SM, each strides over the work units (4-plane case; depth stays on v5)
+    // tcgen05: persistent, 5 CTAs per SM, each strides over the unit descriptor table (4-plane case; depth stays on v5)
     // (the attribute is per device and a process may drive several GPUs: once per device, not once per process)
     static bool attr_set[64] = {};
     int dev = 0;
