@@ -121,7 +121,8 @@ size_t b2s_view_block_bytes(void);
 /* Converts num_views parameter blocks into the kernels' per-view constant blocks
  * (out_host: num_views * b2s_view_block_bytes() bytes of HOST memory; upload it once). */
 int b2s_pack_views(const b2s_params* params, int num_views, void* out_host);
-/* Blend backward of one view: gacc_out (n,12) float = per-Gaussian partial sums (overwritten). */
+/* Blend backward of one view: gacc_out (n,12) float = per-Gaussian partial sums (overwritten), opaque to the caller:
+ * rows {dR, dG, dB, Syy | S, Sx, Sxx, Sy | dZ, colour clamp mask, -, -} consumed by b2s_backward_params. */
 int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* g_rgb,
                        const float* g_alpha, const float* g_depth, const void* state, void* workspace,
                        size_t ws_bytes, float* gacc_out, void* stream);
