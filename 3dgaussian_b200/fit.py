@@ -207,8 +207,11 @@ class FitDriver:
         return out_rgb, out_alpha
 
     # ---- one fit iteration -------------------------------------------------------------------
-    def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor], lane: int = 0):
-        """forward + loss + blend backward of view i on the CURRENT stream with lane `lane`'s buffers."""
+    def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor], lane: int = 0,
+                      ready: Optional[torch.cuda.Event] = None):
+        """forward + loss + blend backward of view i on the CURRENT stream with lane `lane`'s buffers.  `ready`: event
+        after which tgt / mask hold this view's data (host-fed steps): only the loss needs them, so the stream waits
+        for it between the forward and the backward, not in front of the forward."""
         L, ctx, st = capi.lib(), capi.ctx(self.dev.index), _stream()
         pc = C.byref(self.params_c[i])
         rgb, alpha, g_rgb, g_alpha = self.rgb_l[lane], self.alpha_l[lane], self.g_rgb_l[lane], self.g_alpha_l[lane]
@@ -225,10 +228,14 @@ class FitDriver:
                                          self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, None,
                                          None, None, _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
             self.overflow_l[lane] += self._counters_l[lane][3]
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
             capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask), self.w_sil,
                                                 1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), pv,
                                                 _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
             return
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
         capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
                                  self._pp(self.o_opac), self.n, self.max_pairs, _ptr(rgb), _ptr(alpha), None,
                                  _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
@@ -268,7 +275,7 @@ class FitDriver:
 
     def _iterate(self, inputs):
         """One pass over this rank's views: forward + loss + blend backward per view, chain rule, on `lanes`
-        concurrent streams.  inputs(k, stream) -> (target, mask, done_callback) for local view k.
+        concurrent streams.  inputs(k, stream) -> (target, mask, done_callback[, ready_event]) for local view k.
 
         With several lanes the views are cut into `view_groups` groups and pipelined: the caller's stream runs the
         batched preprocess of every group (group g+1's while the lanes blend group g), the lanes wait for their
@@ -287,8 +294,8 @@ class FitDriver:
         if nl == 1:
             self._preprocess_views(0, nv)
             for k in range(nv):
-                tgt, mask, done = inputs(k, main)
-                self._view_fwd_bwd(k, self.views[k], tgt, mask, 0)
+                tgt, mask, done, *rest = inputs(k, main)
+                self._view_fwd_bwd(k, self.views[k], tgt, mask, 0, rest[0] if rest else None)
                 if done is not None:
                     done(main)
             self.loss_dev.copy_(self.loss_l[0])
@@ -315,8 +322,8 @@ class FitDriver:
             for k in range(a, b):
                 lane = k % nl
                 with torch.cuda.stream(streams[lane]):
-                    tgt, mask, done = inputs(k, streams[lane])
-                    self._view_fwd_bwd(k, self.views[k], tgt, mask, lane)
+                    tgt, mask, done, *rest = inputs(k, streams[lane])
+                    self._view_fwd_bwd(k, self.views[k], tgt, mask, lane, rest[0] if rest else None)
                     if done is not None:
                         done(streams[lane])
             for l in used:
@@ -402,9 +409,8 @@ class FitDriver:
             def inputs(k, st):
                 issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
                 slot = k % nslots
-                st.wait_event(self._ev_ready[slot])
                 return (self._stage[slot][0], self._stage[slot][1] if use_mask else None,
-                        lambda s, slot=slot: self._ev_free[slot].record(s))
+                        lambda s, slot=slot: self._ev_free[slot].record(s), self._ev_ready[slot])
 
             self._iterate(inputs)
             self._finish_step()
