@@ -472,8 +472,8 @@ def main():
         if world > 1:
             torch.distributed.all_reduce(dt8, op=torch.distributed.ReduceOp.MAX)
         # Headline = the 8-bit feed: that is what target images ARE (the reference decodes 8-bit JPEG / PNG files,
-        # python/fit_multiview_stub.py:16-34), and at this iteration time the float32 feed measures the PCIe link
-        # (2.1 GB per iteration), not the fit.  The float32 number stays beside it.
+        # python/fit_multiview_stub.py:16-34), and with several ranks pulling 2.1 GB of float32 per iteration the
+        # float32 feed measures the host link, not the fit (8 GPUs: 73 vs 136 iters/s).  It stays beside it.
         f32 = {"value": e2e["value"], "unit": "iters/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
                "api": e2e["api"]}
         e2e = {"value": args.steps / float(dt8.item()), "unit": "iters/s",
