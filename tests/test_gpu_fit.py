@@ -315,3 +315,43 @@ def test_two_gpu_fit_equals_one_gpu(tmp_path):
         loss = d.step()
     assert abs(float(loss.item()) - float(r0["loss"])) <= 1e-6
     assert rel_l2(r0["p"].numpy(), d.p.cpu().numpy()) <= 1e-5
+
+
+_XCHECK = r'''
+import importlib, sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import scenes
+fit = importlib.import_module("3dgaussian_b200.fit")
+dev = torch.device("cuda", 0)
+n, V, W, H, sh = 60000, 2, 1920, 1080, 4
+means, scales, colors, opac = scenes.make_scene(11, n, sh=sh, s_lo=0.01, s_hi=0.06)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+sr = np.log(np.expm1(np.maximum(scales - 1e-3, 1e-4))).astype(np.float32)
+orr = np.log(opac / (1 - opac)).astype(np.float32)
+cams = [tuple(m.reshape(-1).tolist() for m in scenes.orbit_camera(i, V, W, H)) for i in range(V)]
+d = fit.FitDriver(n, sh, W, H, cams, dev)
+d.set_params(t(means), t(sr), t(orr), t(colors)); d.plan()
+g = torch.Generator(device="cpu").manual_seed(3)
+d.set_targets({{i: torch.rand(H, W, 3, generator=g).to(dev) for i in range(V)}},
+              {{i: (torch.rand(H, W, generator=g) > 0.5).float().to(dev) for i in range(V)}})
+loss = float(d.step().item())
+assert not d.check_overflow()
+np.savez({out!r}, loss=np.float64(loss), g=d.g.cpu().numpy())
+'''
+
+
+def test_tcgen05_blend_matches_mma_sync_at_full_hd(tmp_path):
+    """The tcgen05 forward / backward blend kernels against the mma.sync ones (B2S_FWD_MMASYNC / B2S_BWD_MMASYNC,
+    read once per process: two subprocesses) on a 1080p fit step: 8160 tiles, i.e. work units of up to 4096
+    Gaussians, several 128-Gaussian steps per unit, multi-unit tiles, the unit descriptor table."""
+    outs = []
+    for tag, env in (("umma", {}), ("mma", {"B2S_FWD_MMASYNC": "1", "B2S_BWD_MMASYNC": "1"})):
+        out = str(tmp_path / f"{tag}.npz")
+        e = dict(os.environ, **env)
+        r = subprocess.run([sys.executable, "-c", _XCHECK.format(root=ROOT, out=out)], env=e, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out))
+    a, b = outs
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 5e-6 * max(1.0, abs(float(b["loss"])))
+    assert rel_l2(a["g"], b["g"]) <= 1e-3          # the gradient bar of north_star, between two kernel families
