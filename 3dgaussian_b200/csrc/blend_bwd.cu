@@ -774,7 +774,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   else if (un < nunits) id1 = id_of(decode(d_nxt), 0);
   // sums of the previous step waiting for their REDs: Gaussian id (complemented when op == 0: only S is kept), 8 sums
   int pend_id = INT_MIN;
-  float pend[8];
+  float pend[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto flush_sums = [&]() {
     if (pend_id == INT_MIN) return;
     const bool zop = pend_id < 0;
