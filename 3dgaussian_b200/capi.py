@@ -24,6 +24,7 @@ EXPORTS = [
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_fit_backward_blend", "b2s_backward_params",
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
+    "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count",
 ]
 
 
@@ -35,6 +36,7 @@ class Params(C.Structure):
         ("enable_depth_sort", C.c_int32), ("depth_slices", C.c_int32), ("force_cpu", C.c_int32),
         ("style", C.c_int32), ("cutoff_sigma", C.c_float), ("sh_coeffs", C.c_int32),
         ("sort_depth", C.c_int32), ("act_flags", C.c_int32), ("exact_bbox", C.c_int32),
+        ("background_dev", C.c_void_p),
     ]
 
 
@@ -111,6 +113,14 @@ def lib() -> C.CDLL:
                                         vp, vp, vp, vp, C.POINTER(C.c_int), vp, sz, vp]
         L.b2s_launch_count.restype = i64
         L.b2s_launch_count.argtypes = []
+        L.b2s_last_ticket.restype = i64
+        L.b2s_last_ticket.argtypes = [vp]
+        L.b2s_ticket_info.restype = i32
+        L.b2s_ticket_info.argtypes = [vp, i64, C.POINTER(i64)]
+        L.b2s_path_counts.restype = None
+        L.b2s_path_counts.argtypes = [C.POINTER(i64)]
+        L.b2s_sm_count.restype = i32
+        L.b2s_sm_count.argtypes = []
         L.b2s_num_stages.restype = i32
         L.b2s_stage_name.restype = C.c_char_p
         L.b2s_stage_name.argtypes = [i32]
@@ -135,6 +145,23 @@ def timing_read(device_index: int) -> dict:
     return {lib().b2s_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(ns)}
 
 
+def path_counts() -> dict:
+    """Launches so far of the weighted-sum blend kernel families (tests prove with it which path ran)."""
+    out = (C.c_int64 * 4)()
+    lib().b2s_path_counts(out)
+    return {"fwd_tcgen05": int(out[0]), "fwd_other": int(out[1]), "bwd_tcgen05": int(out[2]), "bwd_other": int(out[3])}
+
+
+def ticket_info(device_index: int, ticket: Optional[int] = None) -> tuple:
+    """(pairs needed, pairs kept, overflow flag) of a forward call; waits for that call's binning kernels only."""
+    c = ctx(device_index)
+    if ticket is None:
+        ticket = lib().b2s_last_ticket(c)
+    info = (C.c_int64 * 3)()
+    check(lib().b2s_ticket_info(c, ticket, info))
+    return int(info[0]), int(info[1]), int(info[2])
+
+
 def check(rc: int) -> None:
     if rc != 0:
         raise B2SError(f"libb2splat error {rc}: {lib().b2s_last_error().decode()}")
@@ -154,8 +181,9 @@ def ctx(device_index: int):
 
 
 def make_params(width, height, view, proj, background=(0.0, 0.0, 0.0), mode=MODE_WSUM, style=STYLE_TORCH,
-                cutoff_sigma=5.0, sh_coeffs=1, sort_depth=0, act_flags=0, exact_bbox=0) -> Params:
-    """view/proj: 16 floats row-major (any iterable)."""
+                cutoff_sigma=5.0, sh_coeffs=1, sort_depth=0, act_flags=0, exact_bbox=0, background_dev=None) -> Params:
+    """view/proj: 16 floats row-major (any iterable).  background_dev: optional device address of 3 floats that
+    overrides `background` inside the kernels (the caller keeps that memory alive while the work is queued)."""
     p = Params()
     p.width, p.height = int(width), int(height)
     p.view[:] = [float(x) for x in view]
@@ -170,4 +198,5 @@ def make_params(width, height, view, proj, background=(0.0, 0.0, 0.0), mode=MODE
     p.sort_depth = int(sort_depth)
     p.act_flags = int(act_flags)
     p.exact_bbox = int(exact_bbox)
+    p.background_dev = background_dev
     return p

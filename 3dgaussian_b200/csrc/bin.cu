@@ -37,7 +37,8 @@ __device__ __forceinline__ void for_each_tile(uint2 rc, unsigned long long mask,
 // Level 2 of the scan: one block turns the per-preprocess-block sums into exclusive
 // offsets in place, and publishes the total / overflow counters.
 __global__ void __launch_bounds__(1024)
-scan_bsum_kernel(long long* __restrict__ bsum, int nb, long long max_pairs, Counters* __restrict__ counters) {
+scan_bsum_kernel(long long* __restrict__ bsum, int nb, long long max_pairs, Counters* __restrict__ counters,
+                 Counters* __restrict__ mirror) {
   __shared__ long long wtot[32];
   __shared__ long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -76,6 +77,11 @@ scan_bsum_kernel(long long* __restrict__ bsum, int nb, long long max_pairs, Coun
     counters->needed = total;
     counters->kept = (total <= max_pairs) ? (int)total : 0;   // on overflow nothing is rendered; the caller must look at the flag
     counters->overflow = total > max_pairs ? 1 : 0;
+    if (mirror != nullptr) {
+      mirror->needed = total;
+      mirror->kept = (total <= max_pairs) ? (int)total : 0;
+      mirror->overflow = total > max_pairs ? 1 : 0;
+    }
   }
 }
 
@@ -116,9 +122,9 @@ emit_kernel(int n, int tiles_x, long long max_pairs, const uint2* __restrict__ r
 int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
                const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
-               cudaStream_t st) {
+               Counters* mirror, cudaStream_t st) {
   const int nb = (n + PRE_BLOCK - 1) / PRE_BLOCK;
-  scan_bsum_kernel<<<1, 1024, 0, st>>>(bsum, nb, (long long)max_pairs, counters);
+  scan_bsum_kernel<<<1, 1024, 0, st>>>(bsum, nb, (long long)max_pairs, counters, mirror);
   B2S_LAUNCH_CHECK();
   if (n > 0 && keys != nullptr) {
     emit_kernel<<<nb, PRE_BLOCK, 0, st>>>(n, vp.tiles_x, (long long)max_pairs, rect, tmask, dbits, cnt, bsum, keys, vals);
@@ -339,8 +345,8 @@ cs_colscan_kernel(int* __restrict__ table, int nb, int n_tiles, int* __restrict_
 // write -- two barriers instead of four per 1024 tiles.
 __global__ void __launch_bounds__(1024)
 cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long long max_pairs, int2* __restrict__ ranges,
-                   Counters* __restrict__ counters, int unit_cap, int* __restrict__ unit_start,
-                   int2* __restrict__ units, int4* __restrict__ udesc) {
+                   Counters* __restrict__ counters, Counters* __restrict__ mirror, int unit_cap,
+                   int* __restrict__ unit_start, int2* __restrict__ units, int4* __restrict__ udesc) {
   const int UD_STEP = (SEG + UD_NCLS - 1) / UD_NCLS;
   extern __shared__ int ts_smem[];                 // cnt[n_tiles] then ustart[n_tiles]
   int* cnt = ts_smem;
@@ -471,6 +477,11 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long lon
     counters->kept = kept;
     counters->overflow = ov ? 1 : 0;
     counters->n_ne = ov ? 0 : n_ne;
+    if (mirror != nullptr) {
+      mirror->needed = grand;
+      mirror->kept = kept;
+      mirror->overflow = ov ? 1 : 0;
+    }
     unit_start[n_tiles] = nunits < unit_cap ? nunits : unit_cap;
   }
 }
@@ -496,24 +507,21 @@ cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* _
 bool counting_sort_fits(int n_tiles) { return (size_t)n_tiles * 8 <= CS_MAX_SMEM; }   // tile scan stages 2 ints per tile
 int counting_sort_blocks(int n) {
   int nb = (n + CS_THREADS - 1) / CS_THREADS;
-  return nb < 1 ? 1 : (nb > CS_NB ? CS_NB : nb);
+  const int cap = 2 * sm_count() < CS_NB ? 2 * sm_count() : CS_NB;   // two blocks per SM
+  return nb < 1 ? 1 : (nb > cap ? cap : nb);
 }
 
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, int* table, int* total,
-                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
-                         int* vals, int stage, cudaStream_t st) {
+                         int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
+                         int4* udesc, int* vals, int stage, cudaStream_t st) {
   const size_t smem = (size_t)vp.n_tiles * 4;
-  // function attributes are per device and a process may drive several GPUs: once per device, not once per process
-  static bool attr_set[64] = {};
-  int dev = 0;
-  B2S_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    B2S_CUDA_TRY(cudaFuncSetAttribute(cs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
-    B2S_CUDA_TRY(cudaFuncSetAttribute(cs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
-    B2S_CUDA_TRY(cudaFuncSetAttribute(cs_tilescan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  B2S_CUDA_TRY(per_device_once(ONCE_COUNTING_SORT, [] {
+    cudaError_t e = cudaFuncSetAttribute(cs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_tilescan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM);
+    return e;
+  }));
   const int nb = counting_sort_blocks(n);
   const int per_block = (n + nb - 1) / nb;
   static const int threads = [] { const char* e = getenv("B2S_CS_THREADS"); const int v = e ? atoi(e) : 0;
@@ -523,8 +531,8 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
-    cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, vp.seg, (long long)max_pairs, ranges, counters, (int)unit_cap,
-                                           unit_start, units, udesc);
+    cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, vp.seg, (long long)max_pairs, ranges, counters, mirror,
+                                           (int)unit_cap, unit_start, units, udesc);
     B2S_LAUNCH_CHECK();
   } else {
     cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,

@@ -50,7 +50,7 @@ gbuf_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __r
     const size_t p = (size_t)yi * vp.width + xi;
     const float A0 = acc[p], A1 = acc[hw + p], A2 = acc[2 * hw + p], W = acc[3 * hw + p];
     const float inv = 1.0f / (1.0f + W);
-    const float o0 = (vp.bg[0] + A0) * inv, o1 = (vp.bg[1] + A1) * inv, o2 = (vp.bg[2] + A2) * inv;
+    const float o0 = (view_bg(vp, 0) + A0) * inv, o1 = (view_bg(vp, 1) + A1) * inv, o2 = (view_bg(vp, 2) + A2) * inv;
     g.x = (o0 >= 0.f && o0 <= 1.f) ? g_rgb[3 * p] * inv : 0.f;
     g.y = (o1 >= 0.f && o1 <= 1.f) ? g_rgb[3 * p + 1] * inv : 0.f;
     g.z = (o2 >= 0.f && o2 <= 1.f) ? g_rgb[3 * p + 2] * inv : 0.f;
@@ -114,7 +114,7 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     const size_t p = (size_t)yi * vp.width + xi;
     const float A0 = acc[p], A1 = acc[hw + p], A2 = acc[2 * hw + p], W = acc[3 * hw + p];
     const float inv = 1.0f / (1.0f + W);
-    const float o0 = (vp.bg[0] + A0) * inv, o1 = (vp.bg[1] + A1) * inv, o2 = (vp.bg[2] + A2) * inv;
+    const float o0 = (view_bg(vp, 0) + A0) * inv, o1 = (view_bg(vp, 1) + A1) * inv, o2 = (view_bg(vp, 2) + A2) * inv;
     float gr0, gr1, gr2, ga = 0.f;
     if constexpr (LOSS) {
       const float inv3 = 1.0f / (3.0f * (float)hw), inv1 = 1.0f / (float)hw;
@@ -933,6 +933,7 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
   if (vp.n_tiles <= 0) return B2S_OK;
   const bool depth = g_depth != nullptr;
   if (use_simt_bwd() && fl == nullptr) {   // development cross-check: the FP32-pipe kernel (v3)
+    count_path(PATH_BWD_OTHER);
     if (depth) gbuf_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
     else       gbuf_kernel<false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
     B2S_LAUNCH_CHECK();
@@ -964,7 +965,8 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     if (umma) {
       // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the unit descriptor table
       static const int cps = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
-      const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
+      const int grid = (int)(unit_cap < cps * sm_count() ? unit_cap : cps * sm_count());
+      count_path(PATH_BWD_UMMA);
       // B2S_BWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
       static const bool direct = [] { const char* e = getenv("B2S_BWD_EX2"); return e != nullptr && e[0] == '1'; }();
       if (direct)
@@ -976,6 +978,7 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
       B2S_LAUNCH_CHECK();
       return B2S_OK;
     }
+    count_path(PATH_BWD_OTHER);
     const int blocks = (int)((unit_cap + BM_WARPS - 1) / BM_WARPS);
     const uint4* f4 = reinterpret_cast<const uint4*>(frag);
     static const bool minb4 = [] { const char* e = getenv("B2S_BWD_MINB"); return e != nullptr && e[0] == '4'; }();

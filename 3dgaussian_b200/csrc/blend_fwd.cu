@@ -34,9 +34,9 @@ __device__ __forceinline__ void write_pixel(const ViewParams& vp, size_t p, size
                                             float W, float D, float* out_rgb, float* out_alpha, float* out_depth,
                                             float* acc, uint8_t* out_rgba) {
   const float inv = 1.0f / (1.0f + W);
-  const float o0 = fminf(fmaxf((vp.bg[0] + R) * inv, 0.0f), 1.0f);
-  const float o1 = fminf(fmaxf((vp.bg[1] + G) * inv, 0.0f), 1.0f);
-  const float o2 = fminf(fmaxf((vp.bg[2] + B) * inv, 0.0f), 1.0f);
+  const float o0 = fminf(fmaxf((view_bg(vp, 0) + R) * inv, 0.0f), 1.0f);
+  const float o1 = fminf(fmaxf((view_bg(vp, 1) + G) * inv, 0.0f), 1.0f);
+  const float o2 = fminf(fmaxf((view_bg(vp, 2) + B) * inv, 0.0f), 1.0f);
   if (out_rgb != nullptr) {
     out_rgb[3 * p] = o0; out_rgb[3 * p + 1] = o1; out_rgb[3 * p + 2] = o2;
   }
@@ -886,23 +886,20 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   static const bool simt = [] { const char* e = getenv("B2S_FWD_SIMT"); return e != nullptr && e[0] == '1'; }();
   static const bool mmasync = [] { const char* e = getenv("B2S_FWD_MMASYNC"); return e != nullptr && e[0] == '1'; }();
   static const bool tf32 = [] { const char* e = getenv("B2S_FWD_TF32"); return e != nullptr && e[0] == '1'; }();
-  if (vp.exact_bbox) { if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
-  else if (simt)     { if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
+  if (vp.exact_bbox) { count_path(PATH_FWD_OTHER); if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
+  else if (simt)     { count_path(PATH_FWD_OTHER); if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
   else if (!depth && !tf32 && !mmasync) {
     // tcgen05: persistent, 5 CTAs per SM, each strides over the unit descriptor table (4-plane case; depth stays on v5)
-    // (the attribute is per device and a process may drive several GPUs: once per device, not once per process)
-    static bool attr_set[64] = {};
-    int dev = 0;
-    B2S_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
-      B2S_CUDA_TRY(cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem)));
-      if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
+    B2S_CUDA_TRY(per_device_once(ONCE_FWD_UMMA, [] {
+      cudaError_t e = cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem));
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem));
+      return e;
+    }));
     // B2S_FWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
     static const bool direct = [] { const char* e = getenv("B2S_FWD_EX2"); return e != nullptr && e[0] == '1'; }();
     static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= FT_CTAS) ? v : FT_CTAS; }();
-    const int grid = (int)(unit_cap < cps * 148 ? unit_cap : cps * 148);
+    const int grid = (int)(unit_cap < cps * sm_count() ? unit_cap : cps * sm_count());
+    count_path(PATH_FWD_UMMA);
     if (direct)
       blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
                                                                                    out_rgb, out_alpha, acc, out_rgba);
@@ -910,8 +907,8 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
       blend_wsum_fwd_umma_kernel<true><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
                                                                                   out_rgb, out_alpha, acc, out_rgba);
   }
-  else if (tf32)     { if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
-  else               { if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }
+  else if (tf32)     { count_path(PATH_FWD_OTHER); if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
+  else               { count_path(PATH_FWD_OTHER); if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }
 #undef B2S_FWM
 #undef B2S_FW
   B2S_LAUNCH_CHECK();
@@ -1001,9 +998,9 @@ blend_sorted_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, con
   if (xi >= vp.width || yi >= vp.height) return;
   const size_t p = (size_t)yi * vp.width + xi;
   const float af = fminf(fmaxf(A, 0.0f), 1.0f);
-  const float o0 = fminf(fmaxf(C0 + (1.0f - af) * vp.bg[0], 0.0f), 1.0f);
-  const float o1 = fminf(fmaxf(C1 + (1.0f - af) * vp.bg[1], 0.0f), 1.0f);
-  const float o2 = fminf(fmaxf(C2 + (1.0f - af) * vp.bg[2], 0.0f), 1.0f);
+  const float o0 = fminf(fmaxf(C0 + (1.0f - af) * view_bg(vp, 0), 0.0f), 1.0f);
+  const float o1 = fminf(fmaxf(C1 + (1.0f - af) * view_bg(vp, 1), 0.0f), 1.0f);
+  const float o2 = fminf(fmaxf(C2 + (1.0f - af) * view_bg(vp, 2), 0.0f), 1.0f);
   if (out_rgb != nullptr) {
     out_rgb[3 * p] = o0; out_rgb[3 * p + 1] = o1; out_rgb[3 * p + 2] = o2;
   }

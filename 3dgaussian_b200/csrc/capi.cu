@@ -4,14 +4,21 @@
 #include <math.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 #include <vector>
 #include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
 
+constexpr int B2S_TICKET_RING = 256;
+
 struct b2s_ctx {
   int device;
+  // forward tickets (b2s_ticket_info): pair counters mirrored into pinned host memory + an event behind the binning
+  b2s::Counters* probe = nullptr;                 // B2S_TICKET_RING slots, cudaHostAlloc (mapped)
+  cudaEvent_t probe_ev[B2S_TICKET_RING] = {};
+  long long tickets = 0;                          // tickets issued so far; the last one is tickets - 1
   // grow-only cache used by b2s_render_rgba8_host only
   void* host_dev = nullptr;
   size_t host_dev_bytes = 0;
@@ -53,6 +60,60 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<long long> g_paths[PATH_COUNT];
+void count_path(int which) { if (which >= 0 && which < PATH_COUNT) g_paths[which].fetch_add(1, std::memory_order_relaxed); }
+
+constexpr int MAX_DEVICES = 64;
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = MAX_DEVICES - 1;
+  return dev;
+}
+int sm_count() {
+  static std::atomic<int> cache[MAX_DEVICES];
+  const int dev = current_device_slot();
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    int real = 0;
+    cudaGetDevice(&real);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, real) != cudaSuccess || v <= 0) v = 1;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+std::once_flag& device_once_flag(int slot) {
+  static std::once_flag flags[ONCE_SLOTS][MAX_DEVICES];
+  return flags[slot][current_device_slot()];
+}
+
+// Next ticket of the ctx: the slot of the pinned ring the binning kernels mirror their counters into (nullptr if
+// the ring could not be allocated: tickets then report an error instead of data).
+static Counters* ticket_begin(b2s_ctx* ctx) {
+  if (ctx == nullptr) return nullptr;
+  if (ctx->probe == nullptr) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(Counters) * B2S_TICKET_RING, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    memset(h, 0, sizeof(Counters) * B2S_TICKET_RING);
+    ctx->probe = (Counters*)h;
+  }
+  const int slot = (int)(ctx->tickets % B2S_TICKET_RING);
+  ctx->tickets += 1;
+  return ctx->probe + slot;
+}
+// records the event behind the kernels that wrote the mirror of the ticket just begun
+static void ticket_mark(b2s_ctx* ctx, cudaStream_t st) {
+  if (ctx == nullptr || ctx->probe == nullptr || ctx->tickets <= 0) return;
+  const int slot = (int)((ctx->tickets - 1) % B2S_TICKET_RING);
+  if (ctx->probe_ev[slot] == nullptr && cudaEventCreateWithFlags(&ctx->probe_ev[slot], cudaEventDisableTiming) != cudaSuccess) {
+    ctx->probe_ev[slot] = nullptr;
+    cudaGetLastError();
+    return;
+  }
+  cudaEventRecord(ctx->probe_ev[slot], st);
+}
 
 // inverse of a row-major 4x4 (Gauss-Jordan, double) -> camera centre inv(V)[:3,3]
 static bool camera_centre(const float* v, float* cam) {
@@ -93,6 +154,8 @@ static int make_view(const b2s_params* p, ViewParams* vp) {
   memcpy(vp->view, p->view, sizeof(float) * 16);
   memcpy(vp->proj, p->proj, sizeof(float) * 16);
   memcpy(vp->bg, p->background, sizeof(float) * 3);
+  vp->bg_dev = p->background_dev;
+  vp->pad_ = 0;
   vp->cam[0] = vp->cam[1] = vp->cam[2] = 0.0f;
   if (p->sh_coeffs > 1 && !camera_centre(p->view, vp->cam)) { set_error("view matrix is singular"); return B2S_ERR_INVALID; }
   vp->k = p->cutoff_sigma;
@@ -208,6 +271,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
                        float* dbg, int* dbg_bbox, unsigned long long** keys_sorted,
                        unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
   int rc = B2S_OK;
+  Counters* mirror = ticket_begin(ctx);
   if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
     StageTimer t(ctx, ST_PREPROCESS, st);
     rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
@@ -223,13 +287,14 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     // order inside a tile is irrelevant: group with one counting pass + one scatter pass
     {
       StageTimer t(ctx, ST_BIN, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, mirror, B.unit_cap,
                                 B.unit_start, B.units, B.udesc, B.vals, 0, st);   // also writes the unit descriptor table
     }
     if (rc != B2S_OK) return rc;
+    ticket_mark(ctx, st);
     if (keys_unsorted_copy != nullptr || vals_unsorted_copy != nullptr) {   // dump hook only: the emit order
       Counters* scratch = (Counters*)B.hist;
-      rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, st);
+      rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, nullptr, st);
       if (rc != B2S_OK) return rc;
       if (keys_unsorted_copy != nullptr)
         B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, B.keysA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
@@ -238,7 +303,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     }
     {
       StageTimer t(ctx, ST_SORT, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, nullptr, B.unit_cap,
                                 B.unit_start, B.units, B.udesc, B.vals, 1, st);
     }
     if (rc != B2S_OK) return rc;
@@ -251,9 +316,10 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   int* vB = (passes % 2 == 0) ? B.valsB : B.vals;
   {
     StageTimer t(ctx, ST_BIN, st);
-    rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, st);
+    rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, mirror, st);
   }
   if (rc != B2S_OK) return rc;
+  ticket_mark(ctx, st);
   if (keys_unsorted_copy != nullptr)
     B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, kA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
   if (vals_unsorted_copy != nullptr)
@@ -312,6 +378,8 @@ b2s_ctx* b2s_create(int device) {
 void b2s_destroy(b2s_ctx* ctx) {
   if (ctx == nullptr) return;
   if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
+  if (ctx->probe != nullptr) cudaFreeHost(ctx->probe);
+  for (auto& e : ctx->probe_ev) if (e != nullptr) cudaEventDestroy(e);
   for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto& e : ctx->pool) cudaEventDestroy(e);
   delete ctx;
@@ -341,7 +409,7 @@ int b2s_count_pairs(b2s_ctx* ctx, const b2s_params* p, const float* means, const
   Counters* counters = (Counters*)B.hist;
   rc = launch_preprocess(vp, means, scales, nullptr, opacities, n, nullptr, nullptr, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, st);
   if (rc != B2S_OK) return rc;
-  rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, st);
+  rc = launch_bin(vp, n, 0x7fffffffLL, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, nullptr, nullptr, counters, nullptr, st);
   if (rc != B2S_OK) return rc;
   Counters h;
   B2S_CUDA_TRY(cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -580,6 +648,8 @@ int b2s_render_rgba8_host(b2s_ctx* ctx, const b2s_params* p, const float* means_
   auto ensure = [&](size_t bytes) -> int {
     if (bytes <= ctx->host_dev_bytes) return B2S_OK;
     if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
+  if (ctx->probe != nullptr) cudaFreeHost(ctx->probe);
+  for (auto& e : ctx->probe_ev) if (e != nullptr) cudaEventDestroy(e);
     ctx->host_dev = nullptr;
     ctx->host_dev_bytes = 0;
     B2S_CUDA_TRY(cudaMalloc(&ctx->host_dev, bytes));
@@ -753,7 +823,30 @@ int b2s_densify_prune(b2s_ctx* ctx, const float* means, const float* scales_raw,
   return B2S_OK;
 }
 
+int64_t b2s_last_ticket(b2s_ctx* ctx) { return ctx == nullptr ? -1 : (int64_t)ctx->tickets - 1; }
+
+int b2s_ticket_info(b2s_ctx* ctx, int64_t ticket, int64_t* info_host) {
+  if (ctx == nullptr || info_host == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (ticket < 0 || ticket >= ctx->tickets || ticket + B2S_TICKET_RING < ctx->tickets) {
+    set_error("ticket %lld is not among the last %d of this ctx (issued: %lld)", (long long)ticket, B2S_TICKET_RING, ctx->tickets);
+    return B2S_ERR_INVALID;
+  }
+  const int slot = (int)(ticket % B2S_TICKET_RING);
+  if (ctx->probe == nullptr || ctx->probe_ev[slot] == nullptr) { set_error("ticket ring unavailable (pinned allocation failed)"); return B2S_ERR_CUDA; }
+  B2S_CUDA_TRY(cudaEventSynchronize(ctx->probe_ev[slot]));   // the binning of that call only, not the stream
+  const Counters c = ctx->probe[slot];
+  info_host[0] = c.needed;
+  info_host[1] = c.kept;
+  info_host[2] = c.overflow;
+  return B2S_OK;
+}
+
 int64_t b2s_launch_count(void) { return (int64_t)g_launches.load(); }
+void b2s_path_counts(int64_t out[4]) {
+  if (out == nullptr) return;
+  for (int i = 0; i < PATH_COUNT; ++i) out[i] = (int64_t)g_paths[i].load();
+}
+int b2s_sm_count(void) { return sm_count(); }
 int b2s_num_stages(void) { return ST_COUNT; }
 const char* b2s_stage_name(int stage) {
   static const char* names[ST_COUNT] = {"preprocess", "bin", "sort", "ranges", "blend_fwd", "loss",

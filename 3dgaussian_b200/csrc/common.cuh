@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "b2splat.h"
 
 namespace b2s {
@@ -26,7 +28,15 @@ struct ViewParams {
   int width, height, tiles_x, tiles_y, n_tiles;
   int style, sh, act, exact_bbox, mode;
   int seg;          // Gaussians per work unit of the blend kernels (unit_size(): grows with the image)
+  int pad_;
+  const float* bg_dev;   // optional DEVICE pointer to 3 floats overriding bg[] (b2s_params.background_dev): the
+                         // drop-in receives the background as a device tensor and must not sync to read it
 };
+
+// background colour of the view: the device override when given, else the host-supplied constants
+__device__ __forceinline__ float view_bg(const ViewParams& vp, int c) {
+  return vp.bg_dev != nullptr ? __ldg(vp.bg_dev + c) : vp.bg[c];
+}
 
 // One Gaussian after projection.  Every quantity that feeds an integer (bbox, tile rect,
 // depth key) is computed with explicitly rounded, non-contracted fp32 ops in exactly the
@@ -210,7 +220,7 @@ inline int64_t max_units(int width, int height, int64_t max_pairs) {
   return (max_pairs > 0 ? max_pairs : 0) / SEG_MIN + tiles;   // sum_t max(1, ceil(c_t/seg)) <= P1/seg + tiles, seg >= SEG_MIN
 }
 constexpr int SORT_KPB = 4096;   // keys per radix block
-constexpr int CS_NB = 296;       // counting-sort blocks: 2 per SM (148 SMs)
+constexpr int CS_NB = 296;       // counting-sort blocks: 2 per SM, at most this many (the table is sized for it)
 constexpr size_t CS_MAX_SMEM = 200 * 1024;   // per-block tile histogram (4 B per tile) must fit
 constexpr int PRE_BLOCK = 256;   // Gaussians per preprocess block
 
@@ -297,6 +307,22 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 void count_launch();
+// launches of the weighted-sum blend kernel families (b2s_path_counts)
+enum Path { PATH_FWD_UMMA = 0, PATH_FWD_OTHER, PATH_BWD_UMMA, PATH_BWD_OTHER, PATH_COUNT };
+void count_path(int which);
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device): persistent grids and the
+// counting-sort block count are sized from it, nothing assumes 148
+int sm_count();
+// One-time per-device setup (cudaFuncSetAttribute ...): function attributes are per device and a process may drive
+// several GPUs from several host threads, so the guard is a std::once_flag per (slot, current device).
+enum OnceSlot { ONCE_FWD_UMMA = 0, ONCE_COUNTING_SORT, ONCE_BWD_UMMA, ONCE_SORT, ONCE_SORTED_BLEND, ONCE_SLOTS };
+std::once_flag& device_once_flag(int slot);
+template <class F>
+inline cudaError_t per_device_once(int slot, F f) {
+  cudaError_t e = cudaSuccess;
+  std::call_once(device_once_flag(slot), [&] { e = f(); });
+  return e;
+}
 #define B2S_LAUNCH_CHECK()             \
   do {                                 \
     b2s::count_launch();               \
@@ -313,10 +339,11 @@ int launch_preprocess(const ViewParams& vp, const float* means, const float* sca
                       int* dbg_bbox, cudaStream_t st);
 int launch_preprocess_views(const ViewParams* views_dev, int num_views, int sh, const float* means, const float* scales,
                             const float* colors, const float* opac, int n, char* prepared, cudaStream_t st);
+// mirror: optional second destination of the pair counters (pinned host memory, see b2s_ticket_info)
 int launch_bin(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect, const unsigned long long* tmask,
                const uint32_t* dbits,
                const int* cnt, long long* bsum, unsigned long long* keys, int* vals, Counters* counters,
-               cudaStream_t st);
+               Counters* mirror, cudaStream_t st);
 // sorts (keysA, valsA) on key bits [begin_bit,end_bit); returns via *result_in_B where the result lives
 int launch_sort(unsigned long long* keysA, int* valsA, unsigned long long* keysB, int* valsB, int64_t cap,
                 const int* count_dev, int begin_bit, int end_bit, int* hist, int* hsum, int* result_in_B,
@@ -328,8 +355,8 @@ int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t 
 bool counting_sort_fits(int n_tiles);
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, int* table, int* total,
-                         int2* ranges, Counters* counters, int64_t unit_cap, int* unit_start, int2* units, int4* udesc,
-                         int* vals, int stage, cudaStream_t st);
+                         int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
+                         int4* udesc, int* vals, int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int seg, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
 // Unit descriptor table of the persistent tcgen05 blend kernels: the NON-EMPTY units as {tile, first pair, pairs,
 // unit index | multi-unit-tile flag << 31}, ordered by their number of 128-Gaussian steps, largest first, so that CTA i

@@ -46,7 +46,7 @@ int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, cons
   const int hw = width * height;
   if (hw <= 0) return B2S_OK;
   int blocks = (hw + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   fit_loss_kernel<<<blocks, 256, 0, st>>>(rgb, alpha, tgt, mask, hw, w_sil, scale, g_rgb, g_alpha, loss_accum);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
@@ -114,7 +114,7 @@ int launch_adam(float* params, const float* grads, float* m, float* v, int64_t c
   const float rs = (se > sb) ? reg_scale / (float)(se - sb) : 0.f;
   const float ro = (oe > ob) ? reg_op / (float)(oe - ob) : 0.f;
   long long blocks = (count + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   adam_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, m, v, (long long)count, b1, b2, eps, step_size,
                                             inv_sqrt_bc2, (long long)sb, (long long)se, rs, (long long)ob,
                                             (long long)oe, ro);

@@ -122,33 +122,57 @@ def count_pairs(params: capi.Params, means, scales, opac) -> int:
     return int(total.value)
 
 
+# Pair capacity of the last successful forward per (device, N, W, H, cutoff, sort_depth): the drop-in is called once
+# per view per iteration by the reference's fit loop (python/fit_multiview_stub.py:278-290) and the Gaussians move a
+# little between calls, so the buffers are sized from this cache instead of a count pass + stream sync per call.
+_PAIR_CAP: dict = {}
+
+
+def _capacity_key(dev, n, params):
+    return (dev.index, int(n), int(params.width), int(params.height), round(float(params.cutoff_sigma), 4),
+            int(params.sort_depth))
+
+
 class _RenderFn(torch.autograd.Function):
     """forward -> b2s_forward, backward -> b2s_backward.  Saves the compact per-view state
     (48 B/Gaussian records, sorted ids, tile ranges, 5 floats/pixel), not O(N*H*W)."""
 
     @staticmethod
-    def forward(ctx, means, scales, colors, opacities, params, want_aux):
+    def forward(ctx, means, scales, colors, opacities, params, want_aux, bg_keep):
         dev = means.device
         n = means.shape[0]
         m32, s32, c32, o32 = _f32c(means), _f32c(scales), _f32c(colors), _f32c(opacities)
         L = capi.lib()
         W, H = params.width, params.height
+        key = _capacity_key(dev, n, params)
         with torch.cuda.device(dev):
-            total = count_pairs(params, m32, s32, o32)
-            if total > 0x7FFFFFFF:
-                raise capi.B2SError(f"view needs {total} (Gaussian,tile) pairs; limit is 2^31-1")
-            state_bytes = L.b2s_state_bytes(n, W, H, total)
-            ws_bytes = L.b2s_workspace_bytes(n, W, H, total)
-            state = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
-            alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
-            depth = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
-            capi.check(L.b2s_forward(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(c32),
-                                     _ptr(o32), n, total, _ptr(rgb), _ptr(alpha), _ptr(depth), _ptr(state),
-                                     state_bytes, _ptr(ws), ws_bytes, _stream()))
+            cap = _PAIR_CAP.get(key)
+            if cap is None:         # first call for this shape: one exact count pass (synchronises once)
+                cap = int(count_pairs(params, m32, s32, o32) * 1.25) + 1024
+            for attempt in range(4):
+                if cap > 0x7FFFFFFF:
+                    raise capi.B2SError(f"view needs {cap} (Gaussian,tile) pairs; limit is 2^31-1")
+                state_bytes = L.b2s_state_bytes(n, W, H, cap)
+                ws_bytes = L.b2s_workspace_bytes(n, W, H, cap)
+                state = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+                alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+                depth = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+                capi.check(L.b2s_forward(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(c32),
+                                         _ptr(o32), n, cap, _ptr(rgb), _ptr(alpha), _ptr(depth), _ptr(state),
+                                         state_bytes, _ptr(ws), ws_bytes, _stream()))
+                # waits for this call's binning kernels only; the blend kernels queued behind them keep running
+                needed, _, overflow = capi.ticket_info(dev.index)
+                if not overflow:
+                    break
+                cap = int(needed * 1.5) + 1024      # the Gaussians grew past the cached capacity: render again
+            else:
+                raise capi.B2SError("pair buffers overflowed repeatedly")
+            _PAIR_CAP[key] = cap if needed * 4 > cap else int(needed * 1.5) + 1024
         ctx.params = params
-        ctx.total = total
+        ctx.total = cap
+        ctx.bg_keep = bg_keep          # the device background (params.background_dev) stays alive until backward
         ctx.in_dtypes = (means.dtype, scales.dtype, colors.dtype, opacities.dtype)
         ctx.colors_shape = tuple(colors.shape)
         ctx.save_for_backward(m32, s32, c32, o32, state)
@@ -182,7 +206,7 @@ class _RenderFn(torch.autograd.Function):
                                       _ptr(state), _ptr(ws), ws_bytes, _ptr(gm), _ptr(gs), _ptr(gc), _ptr(go),
                                       0, _stream()))
         dm, ds, dc, do = ctx.in_dtypes
-        return gm.to(dm), gs.to(ds), gc.to(dc), go.to(do), None, None
+        return gm.to(dm), gs.to(ds), gc.to(dc), go.to(do), None, None, None
 
 
 def _default_cutoff(return_aux: bool) -> float:
@@ -229,8 +253,16 @@ def render_gaussians_torch(
     if n > max_gaussians:
         raise ValueError(f"N={n} too large for torch reference renderer. Increase max_gaussians or downsample.")
     sh = _sh_coeffs(colors)
+    bg, bg_dev, bg_keep = [0.0, 0.0, 0.0], None, None
     if background is None:
-        bg = [0.0, 0.0, 0.0]
+        pass
+    elif isinstance(background, torch.Tensor) and background.is_cuda and background.device == dev:
+        # the reference's callers build the background on the device every call (fit_multiview_stub.py:287): the
+        # kernels read it from there (b2s_params.background_dev) -- reading it back would sync the stream per view
+        if background.numel() != 3:
+            raise ValueError("background must be (3,)")
+        bg_keep = background.detach().to(dtype=torch.float32).contiguous()
+        bg_dev = bg_keep.data_ptr()
     elif isinstance(background, torch.Tensor):
         bg = background.detach().to(device="cpu", dtype=torch.float32).reshape(-1).tolist()
     else:
@@ -238,11 +270,11 @@ def render_gaussians_torch(
     view, proj = _camera_host(camera)
     k = _default_cutoff(return_aux) if cutoff_sigma is None else float(cutoff_sigma)
     params = capi.make_params(width, height, view, proj, bg, mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
-                              cutoff_sigma=k, sh_coeffs=sh, sort_depth=int(sort_depth))
+                              cutoff_sigma=k, sh_coeffs=sh, sort_depth=int(sort_depth), background_dev=bg_dev)
     scales = scales.to(dev)
     colors = colors.to(dev)
     opacities = opacities.to(dev)
-    return _RenderFn.apply(means, scales, colors, opacities, params, bool(return_aux))
+    return _RenderFn.apply(means, scales, colors, opacities, params, bool(return_aux), bg_keep)
 
 
 # ------------------------------------------------------------------------------------------

@@ -24,17 +24,17 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-import scenes  # noqa: E402
+synth = importlib.import_module("3dgaussian_b200.synth")     # workload generators (package side, no test-tree import)
+synth_gaussians, to_raw, cameras = synth.synth_gaussians, synth.to_raw, synth.orbit_cameras
 
 METRIC = "fit iters/s (fwd+bwd+Adam, all views)"
-NUM_SMS, LANES_PER_SM = 148, 128
+LANES_PER_SM = 128       # FP32 lanes per SM; the SM count comes from the device (b2s_sm_count)
 
 
 def parse_args():
@@ -66,44 +66,6 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------
-def synth_gaussians(n, sh, seed, device, s_lo=0.004, s_hi=0.02):
-    """SURVEY 8(d) recipe, generated on the device: means U(-0.6,0.6)^3, log-uniform scales,
-    opacity sigmoid(N(0,1)), dc U(0,1), higher SH bands N(0,0.1).  Returns ACTIVATED values."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    means = (torch.rand((n, 3), generator=g, device=device) - 0.5) * 1.2
-    u = torch.rand((n, 3), generator=g, device=device)
-    scales = torch.exp(math.log(s_lo) + u * (math.log(s_hi) - math.log(s_lo)))
-    opac = torch.sigmoid(torch.randn((n,), generator=g, device=device))
-    if sh == 1:
-        colors = torch.rand((n, 3), generator=g, device=device)
-    else:
-        colors = 0.1 * torch.randn((n, sh, 3), generator=g, device=device)
-        colors[:, 0, :] = torch.rand((n, 3), generator=g, device=device)
-    return means, scales, colors, opac
-
-
-def to_raw(scales, opac, colors, sh):
-    """Inverse activations (fit_multiview_stub.py:268-275): softplus^-1(s-1e-3), logit."""
-    s = (scales - 1e-3).clamp_min(1e-6)
-    scales_raw = torch.where(s > 20.0, s, torch.log(torch.expm1(s)))
-    op = opac.clamp(1e-6, 1 - 1e-6)
-    op_raw = torch.log(op / (1 - op))
-    if sh == 1:
-        c = colors.clamp(1e-4, 1 - 1e-4)
-        col_raw = torch.log(c / (1 - c))
-    else:
-        col_raw = colors
-    return scales_raw, op_raw, col_raw
-
-
-def cameras(views, width, height):
-    out = []
-    for i in range(views):
-        v, p = scenes.orbit_camera(i, views, width, height)
-        out.append((v.reshape(-1).tolist(), p.reshape(-1).tolist()))
-    return out
-
-
 def bbox_pairs(means, scales, view, proj, W, H, k):
     """Algorithmic pixel-pair count P2 = sum of clamped k-sigma bbox areas (statistic only)."""
     V = torch.tensor(view, device=means.device).view(4, 4)
@@ -179,18 +141,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_fit_sample(args, n_slice=1024, w=480, h=270, steps=1, warmup=0):
-    """The reference's CPU path for this metric: R1 (oracle port of python/torch_renderer.py)
-    forward + autograd backward + torch Adam on a bounded slice of the same workload -- the
-    first n_slice Gaussians of the seed-1234 set, one orbit view, 480x270 -- on all host
-    threads.  R1 is O(N*H*W), so the full iteration is extrapolated by (Gaussian,pixel) pairs."""
+def _ref_threads():
+    """Host threads of the CPU arm, set explicitly (torchrun exports OMP_NUM_THREADS=1, which silently made the
+    N>=2 reference runs single-threaded in round 1)."""
+    n = int(os.environ.get("B2S_REF_THREADS", "0")) or min(32, os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return n
+
+
+def _reference_renderer():
+    """(render function, fit-loss function, kind).  The UNMODIFIED reference module python/torch_renderer.py when it
+    is staged under oracle/_ref/reference (oracle/Makefile `stage`; it travels with the snapshot) -- kind
+    "reference"; otherwise the oracle port of it (oracle/r1_oracle.py) -- kind "port"."""
     from oracle import r1_oracle as r1
+    ref_py = os.path.join(ROOT, "oracle", "_ref", "reference", "python")
+    if os.path.exists(os.path.join(ref_py, "torch_renderer.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_reference_torch_renderer", os.path.join(ref_py, "torch_renderer.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+
+        def render(means, sc, col, op, tv, tp, w, h):
+            return mod.render_gaussians_torch(means, sc, col, op, mod.Camera(view=tv, proj=tp), w, h,
+                                              max_gaussians=max(10000, means.shape[0]), return_aux=True)
+        return render, r1.fit_loss, "reference"
+    return (lambda means, sc, col, op, tv, tp, w, h: r1.render_r1(means, sc, col, op, tv, tp, w, h, chunk=256)), r1.fit_loss, "port"
+
+
+def cpu_fit_sample(args, n_slice=1024, w=480, h=270, steps=1, warmup=0):
+    """The reference's CPU path for this metric: R1 (python/torch_renderer.py) forward + autograd backward + torch
+    Adam with the fit script's loss (fit_multiview_stub.py:292-311) on a bounded slice of the same workload -- the
+    first n_slice Gaussians of the seed-1234 set, one orbit view, 480x270 -- on the host threads of _ref_threads().
+    R1 is O(N*H*W) (no culling, no tiles): the full iteration (1.3e14 pairs) is extrapolated from the measured
+    (Gaussian,pixel) pair rate.  The reference module supports (N,3)/(N,4,3) colours only (:106), so the slice
+    uses its first 4 SH coefficients when the workload has more."""
+    render, fit_loss, kind = _reference_renderer()
+    threads = _ref_threads()
     dev = torch.device("cpu")
     means, scales, colors, opac = synth_gaussians(n_slice, args.sh, 1234, dev)
-    scales_raw, op_raw, col_raw = to_raw(scales, opac, colors, args.sh)
+    sh = args.sh
+    if kind == "reference" and sh > 4:
+        colors, sh = colors[:, :4, :].contiguous(), 4
+    scales_raw, op_raw, col_raw = to_raw(scales, opac, colors, sh)
     params = [torch.nn.Parameter(t.clone()) for t in (means, scales_raw, op_raw, col_raw)]
     opt = torch.optim.Adam(params, lr=0.02)
-    view, proj = scenes.orbit_camera(0, args.views, w, h)
+    view, proj = synth.orbit_camera(0, args.views, w, h)
     tv, tp = torch.from_numpy(view), torch.from_numpy(proj)
     tgt = torch.rand((h, w, 3), generator=torch.Generator().manual_seed(4321))
     mask = (tgt.mean(dim=2) > 0.06).float()
@@ -200,9 +195,9 @@ def cpu_fit_sample(args, n_slice=1024, w=480, h=270, steps=1, warmup=0):
         opt.zero_grad(set_to_none=True)
         sc = torch.nn.functional.softplus(params[1]) + 1e-3
         op = torch.sigmoid(params[2])
-        col = torch.sigmoid(params[3]) if args.sh == 1 else params[3]
-        rgb, alpha, depth = r1.render_r1(params[0], sc, col, op, tv, tp, w, h, chunk=256)
-        loss = r1.fit_loss(rgb, alpha, depth, tgt, mask, None) + 1e-3 * op.mean() + 1e-3 * sc.mean()
+        col = torch.sigmoid(params[3]) if sh == 1 else params[3]
+        rgb, alpha, depth = render(params[0], sc, col, op, tv, tp, w, h)
+        loss = fit_loss(rgb, alpha, depth, tgt, mask, None) + 1e-3 * op.mean() + 1e-3 * sc.mean()
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -212,10 +207,12 @@ def cpu_fit_sample(args, n_slice=1024, w=480, h=270, steps=1, warmup=0):
     pairs = float(n_slice) * w * h
     rate = pairs / sec                                   # dense (Gaussian,pixel) pairs per second
     full_pairs = float(args.n) * args.width * args.height * args.views
-    return {"sec_per_sample": sec, "pairs_per_s": rate, "iters_per_s_extrapolated": rate / full_pairs,
-            "sample": f"R1 port (oracle/r1_oracle.py) fwd+bwd+Adam, first {n_slice} Gaussians, 1 view, {w}x{h}; "
-                      f"extrapolated to the full iteration by dense pair count N*H*W*V",
-            "cores": torch.get_num_threads()}
+    what = ("the unmodified reference module python/torch_renderer.py (staged copy, oracle/_ref/reference)" if kind == "reference"
+            else "R1 port (oracle/r1_oracle.py)")
+    return {"sec_per_sample": sec, "pairs_per_s": rate, "iters_per_s_extrapolated": rate / full_pairs, "kind": kind,
+            "sample": f"{what}: fwd+bwd+Adam, first {n_slice} Gaussians (SH{sh}), 1 view, {w}x{h}, {threads} threads; "
+                      f"EXTRAPOLATED to the full iteration by dense pair count N*H*W*V (R1 has no culling)",
+            "cores": threads}
 
 
 def run_reference(args, out_fd):
@@ -229,7 +226,7 @@ def run_reference(args, out_fd):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "iters/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+        "cpu_baseline": {"value": val, "unit": "iters/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                          "sec_per_sample": r["sec_per_sample"], "dense_pairs_per_s": r["pairs_per_s"]},
         "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -257,7 +254,7 @@ def render_bench(device, frames=20):
     r = importlib.import_module("3dgaussian_b200.renderer")
     n, W, H = 1_000_000, 960, 540
     means, scales, colors, opac = synth_gaussians(n, 1, 1234, device, 0.004, 0.02)
-    view, proj = scenes.orbit_camera(0, 1, W, H)
+    view, proj = synth.orbit_camera(0, 1, W, H)
     out = {}
     capi = importlib.import_module("3dgaussian_b200.capi")
     for name, ds in (("sorted", 1), ("wsum", 0)):
@@ -283,6 +280,45 @@ def render_bench(device, frames=20):
         out[f"ms_per_frame_{name}_device_resident"] = e0.elapsed_time(e1) / frames
         out[f"tile_pairs_{name}"] = int((mp - 4096) / 1.25)
         del ws, img
+    # per-stage CUDA-event spans of the sorted frame (one more pass of `frames` frames with the brackets on)
+    try:
+        params = capi.make_params(W, H, view.reshape(-1).tolist(), proj.reshape(-1).tolist(), (0.02, 0.02, 0.02),
+                                  mode=capi.MODE_SORTED, style=capi.STYLE_NATIVE, cutoff_sigma=3.0, sh_coeffs=1,
+                                  sort_depth=1, exact_bbox=1)
+        p1s = int(r.count_pairs(params, means, scales, opac))
+        mp = int(p1s * 1.25) + 4096
+        L = capi.lib()
+        ws = torch.empty(L.b2s_workspace_bytes(n, W, H, mp) + L.b2s_state_bytes(n, W, H, mp), dtype=torch.uint8, device=device)
+        img = torch.empty((H, W, 4), dtype=torch.uint8, device=device)
+        kw = dict(enable_depth_sort=1, max_pairs=mp, out=img, workspace=ws)
+        r.render_rgba8(means, scales, colors, opac, view, proj, W, H, (0.02, 0.02, 0.02), **kw)
+        torch.cuda.synchronize()
+        capi.timing_enable(device.index, True)
+        capi.timing_read(device.index)
+        for _ in range(frames):
+            r.render_rgba8(means, scales, colors, opac, view, proj, W, H, (0.02, 0.02, 0.02), **kw)
+        st = capi.timing_read(device.index)
+        capi.timing_enable(device.index, False)
+        out["stages_ms_per_frame_sorted"] = {k: v[0] / frames for k, v in st.items() if v[1] > 0}
+        # roofline of the frame's HBM-bound stage, the 64-bit (tile|depth) radix sort: SURVEY 8(d) B_sort = 24 B per
+        # tile-pair per 8-bit digit pass (12 B read + 12 B written), passes = ceil((tile bits + 32)/8)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        passes = (max(1, math.ceil(math.log2(max(n_tiles, 2)))) + 32 + 7) // 8
+        sort_ms = out["stages_ms_per_frame_sorted"].get("sort")
+        if sort_ms:
+            gbs = p1s * 24.0 * passes / (sort_ms * 1e-3) / 1e9
+            out["roofline"] = {"kernel": "radix sort of the 64-bit tile|depth keys (sort stage)", "bound": "hbm", "achieved": gbs,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                               "note": f"{p1s} tile-pairs x 24 B x {passes} digit passes / {sort_ms:.4f} ms (CUDA-event span of the sort stage)"}
+        del ws, img
+    except Exception as e:  # noqa: BLE001
+        out["stages_error"] = str(e)
     # host-pointer path (gr::render_gaussians signature): H2D of 40 MB + render + D2H of 2 MB per frame
     hm, hs, hc, ho = (t.cpu().numpy() for t in (means, scales, colors, opac))
     bg = np.array([0.02, 0.02, 0.02], np.float32)
@@ -293,6 +329,19 @@ def render_bench(device, frames=20):
     out["ms_per_frame_sorted_host_buffers"] = (time.perf_counter() - t0) / 5 * 1000.0
     try:
         from oracle import cpu as ocpu
+        if ocpu.have_r3ref():
+            # R3: the reference's own CUDA renderer (src/renderer.cu, unmodified, sm_100a build) on the same GPU through its
+            # own host-pointer API (6 blocking H2D copies + D2H per frame, :363-368,:405); viewer parameters
+            # enable_depth_sort=1, depth_slices=32 (src/model_viewer_main.cpp:193-200).  Best of 10 after 2 warm-ups.
+            for mode, key in ((1, "ms_per_frame_reference_cuda_r3_sliced"), (0, "ms_per_frame_reference_cuda_r3_wsum")):
+                best = 1e30
+                for it in range(12):
+                    t0 = time.perf_counter()
+                    ocpu.r3_render(hm, hs, hc, ho, view, proj, W, H, bg, depth_sort=mode, depth_slices=32)
+                    dt = (time.perf_counter() - t0) * 1000.0
+                    if it >= 2:
+                        best = min(best, dt)
+                out[key] = best
         if ocpu.have_r2ref():
             t0 = time.perf_counter()
             ocpu.r2_render(hm, hs, hc, ho, view, proj, W, H, bg, depth_sort=1)
@@ -498,21 +547,44 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    issue_peak = NUM_SMS * LANES_PER_SM * sm_mhz * 1e6          # FP32 lane-instructions / s
+    num_sms = int(capi.lib().b2s_sm_count())
+    issue_peak = num_sms * LANES_PER_SM * sm_mhz * 1e6          # FP32 lane-instructions / s
+    mufu_peak = num_sms * 16 * sm_mhz * 1e6                     # MUFU.EX2 / s
+    smem_peak = num_sms * 128 * sm_mhz * 1e6 / 1e9              # GB/s of shared-memory bandwidth (128 B/clk/SM)
     nv = len(drv.views)
     p1 = float(worst_p1)                                        # worst local view (upper bound per view)
     p2_rank0 = p2
     n, sh, hw = args.n, args.sh, args.width * args.height
     n_tiles = ((args.width + 15) // 16) * ((args.height + 15) // 16)
-    passes = (max(1, math.ceil(math.log2(max(n_tiles, 2)))) + 7) // 8     # tile bits only (sort_depth=0)
-    alg_bytes = {   # per span (= per view; preprocess_bwd and adam: per step), DESIGN.md section 4
-        "preprocess": n * (28 + 12 * sh + 64), "bin": n * 16 + p1 * 12, "sort": passes * p1 * 32, "ranges": p1 * 8,
-        "loss": hw * 48, "preprocess_bwd": n * (48 * nv + 2 * (28 + 12 * sh)),
+    cs_nb = min(296, 2 * num_sms, (n + 1023) // 1024)           # counting-sort blocks (bin.cu: counting_sort_blocks)
+    # Algorithmic bytes per span, DESIGN.md section 4.  A span is one view for bin / sort / blend, one STEP for the
+    # batched preprocess, the chain rule and Adam.  (Round 1 modelled `sort` as a 2-pass radix sort although the timed
+    # kernel is the counting-sort scatter, and `preprocess` as one view of a 64-view launch: VERDICT r1 weak #7.)
+    alg_bytes = {
+        # batched preprocess: parameters read once per step, 65 B (record 48 + clamp mask 1 + rect 8 + tile mask 8) per view
+        "preprocess": n * (28 + 12 * sh) + n * nv * 65,
+        # counting-sort stage 0 (histogram + column scan + tile scan): rect + tile mask per Gaussian, the
+        # [blocks][tiles] table written once, read and rewritten once (it stays in L2)
+        "bin": n * 16 + 3 * cs_nb * n_tiles * 4,
+        # counting-sort stage 1 (scatter): rect + tile mask again, the table once, one 4-byte id per pair
+        "sort": n * 16 + cs_nb * n_tiles * 4 + p1 * 4,
+        "ranges": p1 * 8,
+        "loss": hw * 48,
+        "preprocess_bwd": n * (48 * nv + 2 * (28 + 12 * sh)),
         "adam": (7 + 3 * sh) * n * 28,
     }
+    bound_note = {"bin": "shared-memory atomics (1 per pair) + L2; HBM fraction shown for reference",
+                  "sort": "shared-memory atomics + scattered 4-byte stores; HBM fraction shown for reference",
+                  "preprocess": "instruction issue (~1000 instr per Gaussian*view)"}
     # SURVEY 8(d) per-unit figures of the blend: FP32 lane-instructions (+1 MUFU.EX2) per algorithmic pixel-pair,
     # each FP32 instruction counted as one FMA = 2 flop
-    flop_per_pair = {"blend_fwd": 2 * 11 + 1, "blend_bwd": 2 * 24 + 1}
+    fp32_per_pair = {"blend_fwd": 11, "blend_bwd": 24}
+    flop_per_pair = {k: 2 * v + 1 for k, v in fp32_per_pair.items()}
+    # work the tensor-core formulation ISSUES per (Gaussian,tile) pair: forward one 128x32x16 tcgen05.mma per 16
+    # Gaussians, backward four 128x64x16 per 128 Gaussians -> 8192 flop per pair either way; shared-memory bytes per
+    # pair: operand stores by the threads + operand reads by the tensor core
+    mma_flop_per_p1 = {"blend_fwd": 2 * 128 * 32 * 16 / 16, "blend_bwd": 4 * 2 * 128 * 64 * 16 / 128}
+    smem_bytes_per_p1 = {"blend_fwd": 320 + 320, "blend_bwd": 64 + 128 + 64}
     tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
     tensor_src = ("measured dense bf16, sustained (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks
                   else "nominal 2250 TFLOP/s dense bf16 (B200_PROFILING.md fallback)")
@@ -525,13 +597,26 @@ def main():
         row = {"ms_per_step": sms / args.steps, "spans": spans, "ms_per_span": per_launch_ms}
         if name in alg_bytes:
             gbs = alg_bytes[name] / (per_launch_ms * 1e-3) / 1e9
-            row.update({"bound": "hbm", "achieved_gbs": gbs, "frac": gbs / hbm_peak})
+            row.update({"bound": "hbm", "achieved_gbs": gbs, "frac": gbs / hbm_peak, "alg_bytes_per_span": alg_bytes[name]})
+            if name in bound_note:
+                row["bound_note"] = bound_note[name]
         else:
             pairs_per_span = p2_rank0 / max(nv, 1)
-            tflops = pairs_per_span * flop_per_pair[name] / (per_launch_ms * 1e-3) / 1e12
+            sec = per_launch_ms * 1e-3
+            tflops = pairs_per_span * flop_per_pair[name] / sec / 1e12
+            sol_pairs = min(issue_peak / fp32_per_pair[name], mufu_peak)       # SURVEY 8(d) FP32-issue / MUFU ceiling
             row.update({"bound": "tensor", "achieved_tflops": tflops, "frac": tflops / tensor_peak,
                         "x_fp32_pipe_peak": tflops / fp32_pipe_tflops,
-                        "gpairs_s": pairs_per_span / (per_launch_ms * 1e-3) / 1e9})
+                        "gpairs_s": pairs_per_span / sec / 1e9,
+                        "three_ways": {
+                            "pairs_per_s_over_survey_fp32_sol": (pairs_per_span / sec) / sol_pairs,
+                            "issued_mma_tflops": p1 * mma_flop_per_p1[name] / sec / 1e12,
+                            "issued_mma_over_tensor_peak": p1 * mma_flop_per_p1[name] / sec / 1e12 / tensor_peak,
+                            "smem_gbs": p1 * smem_bytes_per_p1[name] / sec / 1e9,
+                            "smem_over_peak": p1 * smem_bytes_per_p1[name] / sec / 1e9 / smem_peak,
+                            "note": "P2 pixel-pairs/s vs min(FP32 issue/instr per pair, MUFU) of SURVEY 8(d); MMA flop actually issued "
+                                    "(8192 per (Gaussian,tile) pair, P1 = worst view) vs the measured bf16 tensor peak; shared-memory "
+                                    "operand bytes (stores + tensor-core reads) vs SMs x 128 B x clock"}})
         table[name] = row
     roofline = None
     if "blend_bwd" in table:
@@ -543,15 +628,15 @@ def main():
             pass
         roofline = {"kernel": "blend_wsum_bwd_umma_kernel", "bound": "tensor",
                     "achieved": b["achieved_tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": b["frac"], "traffic": traffic,
+                    "frac": b["frac"], "traffic": traffic, "three_ways": b["three_ways"],
                     "note": f"algorithmic work = P2 pixel-pairs/view ({p2_rank0 / max(nv, 1):.3e}) x {flop_per_pair['blend_bwd']} flop "
                             f"(SURVEY 8d: 24 FP32 + 1 MUFU per pair) / mean span of the backward blend stage (gbuf_frag + gacc_init + "
                             f"blend_wsum_bwd_umma_kernel; the tcgen05 kernel is ~87% of it); peak = {tensor_src}. The kernel runs the "
                             f"separable sums as fp16 hi/lo tcgen05.mma 128x64x16 products (one thread per Gaussian, accumulators in "
                             f"TMEM), so the same work is {b['x_fp32_pipe_peak']:.2f}x the FP32-pipe "
-                            f"peak ({fp32_pipe_tflops:.1f} TFLOP/s at {sm_mhz:.0f} MHz); it is bound by the per-step dependent chain "
-                            f"(factor generation -> MMA round trip -> TMEM read-back -> FP32 epilogue) at 4 CTAs/SM, not by MMA rate "
-                            f"(DESIGN.md section 5). "
+                            f"peak ({fp32_pipe_tflops:.1f} TFLOP/s at {sm_mhz:.0f} MHz). `frac` follows the contract (algorithmic flop / "
+                            f"tensor peak); the kernel is NOT tensor-pipe bound -- see three_ways for pairs/s vs the FP32 speed of light, "
+                            f"the MMA flop actually issued and the shared-memory operand traffic (DESIGN.md section 5). "
                             f"tile-pairs P1<={p1:.3e}/view; HBM-bound stages are in roofline_stages vs {hbm_src}",
                     "share_of_step": b["ms_per_step"] / (ms_one_lane or ms_per_step),
                     "timing": "mean CUDA-event span of the kernel over the K steps repeated on one lane right after the "
@@ -561,7 +646,7 @@ def main():
     if not args.no_cpu and world == 1:
         try:
             c = cpu_fit_sample(args)
-            cpu = {"value": c["iters_per_s_extrapolated"], "unit": "iters/s", "cores": c["cores"], "kind": "port",
+            cpu = {"value": c["iters_per_s_extrapolated"], "unit": "iters/s", "cores": c["cores"], "kind": c["kind"],
                    "sample": c["sample"], "sec_per_sample": c["sec_per_sample"], "dense_pairs_per_s": c["pairs_per_s"]}
         except Exception as e:  # noqa: BLE001
             cpu = {"error": str(e)}

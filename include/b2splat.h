@@ -73,6 +73,9 @@ typedef struct b2s_params {
   int32_t sort_depth;        /* 1: radix-sort the full 64-bit tile|depth key; 0: tile bits only (stable) */
   int32_t act_flags;         /* B2S_ACT_* */
   int32_t exact_bbox;        /* 1: a Gaussian only touches pixels inside its bbox (renderer_cpu.cpp:202-203) */
+  const float* background_dev; /* optional DEVICE pointer to 3 floats; when non-NULL it overrides background[] (the
+                                * reference's callers pass the background as a device tensor,
+                                * python/fit_multiview_stub.py:287: reading it back would cost a stream sync per view) */
 } b2s_params;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -221,9 +224,25 @@ int b2s_densify_prune(b2s_ctx* ctx, const float* means, const float* scales_raw,
                       float* out_scales_raw, float* out_opacities_raw, float* out_colors, int* n_new_host,
                       void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- forward tickets: cheap, exact overflow detection ---------------------------------------
+ * Every b2s_forward / b2s_forward_prepared / b2s_render_rgba8 call issued through `ctx` gets a ticket (a running
+ * number, returned by b2s_last_ticket right after the call).  The binning kernels of that call mirror their pair
+ * counters into pinned host memory and an event is recorded right behind them, so b2s_ticket_info waits for THAT
+ * point of the stream only -- the blend kernels queued behind it keep running -- and returns
+ * info_host[0] = pairs needed, [1] = pairs kept, [2] = overflow flag.  The drop-in renderer sizes its pair buffers
+ * from a cached capacity and re-renders the rare view that overflowed, instead of a count pass + full sync per call.
+ * The ring holds the last 256 tickets of a ctx. */
+int64_t b2s_last_ticket(b2s_ctx* ctx);
+int b2s_ticket_info(b2s_ctx* ctx, int64_t ticket, int64_t* info_host);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* number of kernels this library has launched in this process (all contexts) */
 int64_t b2s_launch_count(void);
+/* launches of the four weighted-sum blend kernel families so far: out[0] = forward tcgen05, [1] = forward other
+ * (mma.sync / FP32), [2] = backward tcgen05, [3] = backward other.  Tests use it to prove which path ran. */
+void b2s_path_counts(int64_t out[4]);
+/* SM count the persistent grids are sized from (cudaDevAttrMultiProcessorCount of the current device) */
+int b2s_sm_count(void);
 /* Per-stage CUDA-event timing.  While enabled, every stage launched through `ctx` is
  * bracketed by events on the caller's stream.  b2s_timing_read synchronises on the last
  * event, adds up elapsed milliseconds and launch counts per stage (arrays of

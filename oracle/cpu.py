@@ -4,6 +4,9 @@
   libr2ref.so     <- /root/reference/src/renderer_cpu.cpp + oracle/r2_shim.cpp
                      (the unmodified reference CPU renderer; built in the build
                      container by `make -C oracle`, travels prebuilt in oracle/_ref/)
+  libr3ref.so     <- /root/reference/src/renderer.cu + oracle/r3_shim.cpp, nvcc sm_100a
+                     (the unmodified reference CUDA renderer: the same-box GPU baseline
+                     bench.py times next to the viewer config; needs a GPU to run)
 """
 from __future__ import annotations
 
@@ -59,6 +62,31 @@ def r2ref() -> C.CDLL:
             raise FileNotFoundError("oracle/_ref/libr2ref.so missing and reference tree absent")
         _R2 = C.CDLL(path)
     return _R2
+
+
+_R3: Optional[C.CDLL] = None
+
+
+def have_r3ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libr3ref.so"))
+
+
+def r3_render(means, scales, colors, opac, view, proj, width, height, bg=(0, 0, 0), depth_sort=1, depth_slices=32):
+    """The reference's own gr::render_gaussians_cuda (src/renderer.cu:272-408): host pointers in, RGBA8 out,
+    with its per-frame H2D copies and D2H read-back."""
+    global _R3
+    if _R3 is None:
+        _R3 = C.CDLL(os.path.join(_HERE, "_ref", "libr3ref.so"))
+    means, scales, colors, opac = _f32(means), _f32(scales), _f32(colors), _f32(opac)
+    view, proj, bg = _f32(view).reshape(16), _f32(proj).reshape(16), _f32(bg)
+    out = np.zeros((height, width, 4), np.uint8)
+    FP = C.c_float
+    rc = _R3.r3ref_render(_p(means, FP), _p(scales, FP), _p(colors, FP), _p(opac, FP), C.c_int(means.shape[0]),
+                          C.c_int(width), C.c_int(height), _p(view, FP), _p(proj, FP), _p(bg, FP),
+                          C.c_int(depth_sort), C.c_int(depth_slices), _p(out, C.c_uint8))
+    if rc != 0:
+        raise RuntimeError("reference CUDA renderer threw")
+    return out
 
 
 def have_r2ref() -> bool:

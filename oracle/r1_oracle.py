@@ -106,7 +106,7 @@ def screen_sigmas(scales, proj, z_abs, width: int, height: int):
 
 def render_r1(means, scales, colors, opacities, view, proj, width: int, height: int,
               background: Optional[torch.Tensor] = None, chunk: int = 512,
-              cutoff_sigma: Optional[float] = None, tile: int = 0
+              cutoff_sigma: Optional[float] = None, tile: int = 0, pixels=None
               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Weighted-sum blend (torch_renderer.py:109-203).  Returns (rgb, alpha, depth).
 
@@ -116,22 +116,33 @@ def render_r1(means, scales, colors, opacities, view, proj, width: int, height: 
     renderers' bbox (src/renderer_cpu.cpp:96-102) with k instead of 3 -- snapped
     outwards to `tile`-pixel tiles when tile > 0; used to restate what the
     binned CUDA path evaluates.
+    `pixels` = (ix, iy) integer index tensors (P,) evaluates only those pixels of the
+    width x height image (the crop oracle of the full-size parity tests: the same
+    arithmetic on a subset of the reference's pixel grid) and returns (P,3), (P,), (P,).
     """
     dt, dev = means.dtype, means.device
     if background is None:
         background = torch.zeros(3, dtype=dt, device=dev)
     background = background.to(dt)
     n = means.shape[0]
-    hw = height * width
     px, py, z_abs, valid, _ = project(means, view, proj, width, height)
     col = eval_colors(colors, means, view)
     sx, sy = screen_sigmas(scales, proj, z_abs, width, height)
     op = opacities.clamp_min(0.0)                                        # :175
 
-    ys = torch.arange(height, dtype=dt, device=dev) + 0.5                # :153-155
-    xs = torch.arange(width, dtype=dt, device=dev) + 0.5
-    gx = xs.view(1, 1, width)
-    gy = ys.view(1, height, 1)
+    if pixels is None:
+        ys = torch.arange(height, dtype=dt, device=dev) + 0.5            # :153-155
+        xs = torch.arange(width, dtype=dt, device=dev) + 0.5
+        gx = xs.view(1, 1, width)
+        gy = ys.view(1, height, 1)
+        ix = torch.arange(width, dtype=dt, device=dev).view(1, 1, width)
+        iy = torch.arange(height, dtype=dt, device=dev).view(1, height, 1)
+        hw = height * width
+    else:
+        ix = pixels[0].to(dt).view(1, 1, -1)
+        iy = pixels[1].to(dt).view(1, 1, -1)
+        gx, gy = ix + 0.5, iy + 0.5
+        hw = ix.numel()
 
     acc_c = torch.zeros((hw, 3), dtype=dt, device=dev)
     acc_w = torch.zeros((hw,), dtype=dt, device=dev)
@@ -155,8 +166,6 @@ def render_r1(means, scales, colors, opacities, view, proj, width: int, height: 
                     y0 = torch.floor(y0 / tile) * tile
                     x1 = torch.floor(x1 / tile) * tile + (tile - 1)
                     y1 = torch.floor(y1 / tile) * tile + (tile - 1)
-                ix = torch.arange(width, dtype=dt, device=dev).view(1, 1, width)
-                iy = torch.arange(height, dtype=dt, device=dev).view(1, height, 1)
                 inside = ((ix >= x0.view(-1, 1, 1)) & (ix <= x1.view(-1, 1, 1)) &
                           (iy >= y0.view(-1, 1, 1)) & (iy <= y1.view(-1, 1, 1)))
             keep = keep & inside
@@ -166,11 +175,12 @@ def render_r1(means, scales, colors, opacities, view, proj, width: int, height: 
         acc_c = acc_c + wf.t() @ col[s:e]                                # :189
         acc_d = acc_d + wf.t() @ z_abs[s:e]                              # :190
 
-    wimg = acc_w.view(height, width)
-    rgb = ((background.view(1, 1, 3) + acc_c.view(height, width, 3)) /
+    shape = (height, width) if pixels is None else (hw,)
+    wimg = acc_w.view(*shape)
+    rgb = ((background.view(*([1] * len(shape)), 3) + acc_c.view(*shape, 3)) /
            (1.0 + wimg).unsqueeze(-1)).clamp(0.0, 1.0)                   # :194-196
     alpha = (wimg / (1.0 + wimg)).clamp(0.0, 1.0)                        # :201
-    depth = (acc_d.view(height, width) / (wimg + 1e-6)).clamp_min(0.0)   # :202
+    depth = (acc_d.view(*shape) / (wimg + 1e-6)).clamp_min(0.0)          # :202
     return rgb, alpha, depth
 
 

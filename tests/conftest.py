@@ -31,3 +31,17 @@ def rel_l2(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def report(test: str, **values):
+    """Appends one JSON line of measured parity figures (achieved errors, % exact, ...) to
+    gpurun_out/parity_report.jsonl -- the numbers behind the pass/fail bars, summarised under profiles/."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": test, **{k: (float(v) if isinstance(v, (np.floating, float)) else v)
+                                                  for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass

@@ -1,48 +1,20 @@
-"""Seeded synthetic scenes + numpy camera helpers shared by the tests, the golden
-generator and bench.py.  Camera maths restates the recipe of the reference's
-fit script (/root/reference/python/fit_multiview_stub.py:70-90) and of
-torch_renderer.py:24-54 in numpy float32 so the same matrices can be produced
-on a box without the reference tree."""
+"""Seeded synthetic test scenes.  The camera helpers live in the package (3dgaussian_b200/synth.py, shared with
+bench.py) and are re-exported here for the tests and the golden generator."""
 from __future__ import annotations
 
-import math
+import importlib
+import os
+import sys
 
 import numpy as np
 
-
-def perspective(fovy_deg, aspect, znear, zfar):
-    f = np.float32(1.0) / np.tan(np.float32(fovy_deg) * np.float32(math.pi) / np.float32(180.0) * np.float32(0.5))
-    m = np.zeros((4, 4), np.float32)
-    m[0, 0] = f / np.float32(aspect)
-    m[1, 1] = f
-    m[2, 2] = (zfar + znear) / (znear - zfar)
-    m[2, 3] = (2.0 * zfar * znear) / (znear - zfar)
-    m[3, 2] = -1.0
-    return m
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
 
 
-def look_at(eye, target, up):
-    eye, target, up = (np.asarray(v, np.float32) for v in (eye, target, up))
-    f = target - eye
-    f = f / (np.linalg.norm(f) + np.float32(1e-8))
-    u = up / (np.linalg.norm(up) + np.float32(1e-8))
-    s = np.cross(f, u)
-    s = s / (np.linalg.norm(s) + np.float32(1e-8))
-    u2 = np.cross(s, f)
-    m = np.eye(4, dtype=np.float32)
-    m[0, :3], m[1, :3], m[2, :3] = s, u2, -f
-    t = np.eye(4, dtype=np.float32)
-    t[:3, 3] = -eye
-    return (m @ t).astype(np.float32)
-
-
-def orbit_camera(i, num_views, width, height, radius=2.5, pitch=0.2, fovy=60.0):
-    yaw = (2.0 * math.pi * i) / max(1, num_views)
-    eye = [radius * math.cos(pitch) * math.sin(yaw), radius * math.sin(pitch),
-           radius * math.cos(pitch) * math.cos(yaw)]
-    view = look_at(eye, [0, 0, 0], [0, 1, 0])
-    proj = perspective(fovy, width / height, 0.01, 100.0)
-    return view, proj
+_synth = importlib.import_module("3dgaussian_b200.synth")
+perspective, look_at, orbit_camera = _synth.perspective, _synth.look_at, _synth.orbit_camera
 
 
 def make_scene(seed, n, sh=1, s_lo=0.02, s_hi=0.2, spread=0.6, edge_cases=False):

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import scenes
-from conftest import golden_names, load_golden, rel_l2
+from conftest import golden_names, load_golden, rel_l2, report
 from gpu_util import camera, dev, pkg, to_dev
 from oracle import cpu as ocpu
 from oracle import r1_oracle as r1
@@ -20,6 +20,18 @@ R1 = golden_names("r1_")
 R2 = golden_names("r2_")
 IMG_TOL = 1e-4
 GRAD_TOL = 1e-3
+DEPTH_TOL = 1e-4          # where the pixel carries weight (W >= 1e-2); SURVEY H2: depth = D/(W+1e-6) is ill-conditioned
+                          # where W ~ 0, so the all-pixel figure is reported (parity_report.jsonl), not asserted
+
+
+def _depth_check(test, got, ref_depth, ref_alpha, **tags):
+    """depth <= 1e-4 on pixels with W >= 1e-2 (alpha = W/(1+W) >= 1e-2/1.01); the all-pixel error is recorded."""
+    err = np.abs(got - ref_depth)
+    m = ref_alpha >= 1e-2 / 1.01
+    e_m = float(err[m].max()) if m.any() else 0.0
+    report(test, depth_maxabs_weighted=e_m, depth_maxabs_all=float(err.max()), weighted_px=int(m.sum()), px=int(m.size),
+           **tags)
+    assert e_m <= DEPTH_TOL, (e_m, float(err.max()))
 
 
 def _render(g, return_aux=True, **kw):
@@ -106,8 +118,7 @@ def test_image_matches_reference_golden(name):
     rgb, alpha, depth = _render(g, True)            # aux => k = 7
     assert np.abs(rgb.cpu().numpy() - g["rgb"]).max() <= IMG_TOL
     assert np.abs(alpha.cpu().numpy() - g["alpha"]).max() <= IMG_TOL
-    m = g["alpha"] > 1e-2                           # depth is ill-conditioned where W ~ 0
-    assert np.abs(depth.cpu().numpy() - g["depth"])[m].max() <= 1e-3
+    _depth_check("image_golden", depth.cpu().numpy(), g["depth"], g["alpha"], scene=name)
     rgb5 = _render(g, False)                        # no aux => k = 5
     assert np.abs(rgb5.cpu().numpy() - g["rgb"]).max() <= IMG_TOL
 
@@ -124,8 +135,7 @@ def test_image_matches_oracle_larger(sh):
     rgb, alpha, depth = _render(g, True)
     assert np.abs(rgb.cpu().numpy() - ref[0].numpy()).max() <= IMG_TOL
     assert np.abs(alpha.cpu().numpy() - ref[1].numpy()).max() <= IMG_TOL
-    m = ref[1].numpy() > 1e-2
-    assert np.abs(depth.cpu().numpy() - ref[2].numpy())[m].max() <= 1e-3
+    _depth_check("image_oracle_larger", depth.cpu().numpy(), ref[2].numpy(), ref[1].numpy(), sh=sh)
 
 
 # ---------------------------------------------------------------- gradients -----------------
@@ -188,6 +198,8 @@ def test_rgba8_matches_reference_cpu_renderer(name, depth_sort):
                          enable_depth_sort=depth_sort).cpu().numpy().astype(np.int32)
     assert np.abs(img - want).max() <= 1
     assert (img == want).mean() >= 0.99
+    report("rgba8_golden", scene=name, depth_sort=depth_sort, pct_exact=100.0 * float((img == want).mean()),
+           max_lsb=int(np.abs(img - want).max()))
     # host-pointer entry (the gr::render_gaussians / pybind signature)
     img2 = r.render_gaussians(g["means"], g["scales"], g["colors"], g["opac"], int(g["width"]), int(g["height"]),
                               g["view"], g["proj"], g["bg"], enable_depth_sort=depth_sort).astype(np.int32)
@@ -208,6 +220,8 @@ def test_rgba8_vs_compiled_reference_medium():
         got = r.render_gaussians(means, scales, colors, opac, W, H, view, proj, bg, enable_depth_sort=ds).astype(np.int32)
         assert np.abs(got - want).max() <= 1
         assert (got == want).mean() >= 0.99
+        report("rgba8_vs_libr2ref_50k", depth_sort=ds, pct_exact=100.0 * float((got == want).mean()),
+               max_lsb=int(np.abs(got - want).max()))
 
 
 # ---------------------------------------------------------------- drop-in behaviour ---------
