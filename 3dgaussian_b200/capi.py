@@ -24,7 +24,7 @@ EXPORTS = [
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_fit_backward_blend", "b2s_backward_params",
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
-    "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count",
+    "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded",
 ]
 
 
@@ -36,7 +36,7 @@ class Params(C.Structure):
         ("enable_depth_sort", C.c_int32), ("depth_slices", C.c_int32), ("force_cpu", C.c_int32),
         ("style", C.c_int32), ("cutoff_sigma", C.c_float), ("sh_coeffs", C.c_int32),
         ("sort_depth", C.c_int32), ("act_flags", C.c_int32), ("exact_bbox", C.c_int32),
-        ("background_dev", C.c_void_p),
+        ("background_dev", C.c_void_p), ("keep_depth", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -78,7 +78,7 @@ def lib() -> C.CDLL:
         L.b2s_backward_blend.restype = i32
         L.b2s_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp]
         L.b2s_fit_backward_blend.restype = i32
-        L.b2s_fit_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp, vp]
+        L.b2s_fit_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp, vp]
         L.b2s_prepared_view_bytes.restype = sz
         L.b2s_prepared_view_bytes.argtypes = [i32]
         L.b2s_preprocess_views.restype = i32
@@ -106,6 +106,9 @@ def lib() -> C.CDLL:
         L.b2s_adam_step.restype = i32
         L.b2s_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
                                     i64, i64, C.c_float, i64, i64, C.c_float, vp]
+        L.b2s_adam_step_guarded.restype = i32
+        L.b2s_adam_step_guarded.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            i64, i64, C.c_float, i64, i64, C.c_float, vp, vp, vp]
         L.b2s_densify_workspace_bytes.restype = sz
         L.b2s_densify_workspace_bytes.argtypes = [i32]
         L.b2s_densify_prune.restype = i32
@@ -181,7 +184,8 @@ def ctx(device_index: int):
 
 
 def make_params(width, height, view, proj, background=(0.0, 0.0, 0.0), mode=MODE_WSUM, style=STYLE_TORCH,
-                cutoff_sigma=5.0, sh_coeffs=1, sort_depth=0, act_flags=0, exact_bbox=0, background_dev=None) -> Params:
+                cutoff_sigma=5.0, sh_coeffs=1, sort_depth=0, act_flags=0, exact_bbox=0, background_dev=None,
+                keep_depth=0) -> Params:
     """view/proj: 16 floats row-major (any iterable).  background_dev: optional device address of 3 floats that
     overrides `background` inside the kernels (the caller keeps that memory alive while the work is queued)."""
     p = Params()
@@ -199,4 +203,6 @@ def make_params(width, height, view, proj, background=(0.0, 0.0, 0.0), mode=MODE
     p.act_flags = int(act_flags)
     p.exact_bbox = int(exact_bbox)
     p.background_dev = background_dev
+    p.keep_depth = int(keep_depth)
+    p.reserved_ = 0
     return p

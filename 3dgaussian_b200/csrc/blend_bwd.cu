@@ -93,11 +93,19 @@ gbuf_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __r
 // backward instead (see blend_wsum_bwd_umma_kernel): [U_hi | U_lo | V_hi | V_lo], each N = CH*16 rows x K = 16
 // halves in the canonical no-swizzle layout (8-row x 16-byte core matrices),
 //   U: row n = ch*16 + r, k = c        V: row n = ch*16 + c, k = r.
+// With DEPTH the tcgen05 layout appends the gD plane as four small matrices (16 rows x 16 halves, 512 B each) behind
+// the 8 KB of the four-plane matrices:  UD_hi | UD_lo | VD_hi | VD_lo,  UD: row n = r, k = c;  VD: row n = c, k = r.
+// LOSS + DEPTH adds the fit script's depth term (python/fit_multiview_stub.py:298-303)
+//   w_d * mean | depth / (max depth + 1e-6) - d_gt |
+// whose gradient needs three per-view numbers computed beforehand by depth_stats_kernel (dstats = {max depth M,
+// number of pixels attaining it, sum_p sign_p depth_p}): torch's max() backward hands the gradient of M to the arg-max
+// pixels in equal shares.
 template <bool DEPTH, bool LOSS, bool UMMA>
 __global__ void __launch_bounds__(TILE_PIX)
 gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float* __restrict__ g_rgb,
                  const float* __restrict__ g_alpha, const float* __restrict__ g_depth, const float* __restrict__ tgt,
-                 const float* __restrict__ mask, float w_sil, float scale, float* __restrict__ loss_accum,
+                 const float* __restrict__ mask, const float* __restrict__ depth_gt, const float* __restrict__ dstats,
+                 float w_sil, float w_depth, float scale, float* __restrict__ loss_accum,
                  uint32_t* __restrict__ frag, float* __restrict__ tile_scale) {
   constexpr int CH = DEPTH ? 5 : 4;
   constexpr int NREG = CH * 16;
@@ -142,7 +150,23 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     if (DEPTH) {
       const float D = acc[4 * hw + p];
       const float iw = 1.0f / (W + 1e-6f);
-      const float gdep = (D * iw >= 0.f) ? g_depth[p] : 0.f;
+      float gdep;
+      if constexpr (LOSS) {
+        // d_pred = depth / (M + 1e-6);  dL/ddepth_q = k (s_q / (M+eps) - [q in argmax] / cnt * sum_p s_p depth_p / (M+eps)^2)
+        const float inv1 = 1.0f / (float)hw;
+        const float dep = fmaxf(D / (W + 1e-6f), 0.0f);     // the very expression of depth_max_kernel: dep == M must be exact
+        const float M = dstats[0], cnt = dstats[1], ssum = dstats[2];
+        const float im = 1.0f / (M + 1e-6f);
+        const float dd = dep * im - depth_gt[p];
+        const float sg = (float)((dd > 0.f) - (dd < 0.f));
+        loss = fmaf(w_depth * inv1, fabsf(dd), loss);
+        const float k = scale * w_depth * inv1;
+        gdep = k * sg * im;
+        if (dep == M && cnt > 0.0f) gdep -= k * ssum * im * im / cnt;
+        gdep = (D * iw >= 0.f) ? gdep : 0.f;
+      } else {
+        gdep = (D * iw >= 0.f) ? g_depth[p] : 0.f;
+      }
       v[4] = gdep * iw;
       v[3] = fmaf(-gdep * D, iw * iw, v[3]);
     }
@@ -185,12 +209,17 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     for (int part = 0; part < 2; ++part) {
       const __half val = part ? lo : hi;
       if constexpr (UMMA) {
-        constexpr int NR = CH * 16;                 // operand rows; one matrix = NR x 16 halves
-        // operand row (= TMEM column of the accumulator) = quad * 16 + plane * 4 + index in quad: the epilogue's
-        // unit of work -- 4 rows / columns x 4 planes -- is 16 consecutive columns, ONE tcgen05.ld
-        const int nu = (r >> 2) * 16 + ch * 4 + (r & 3), nv = (c >> 2) * 16 + ch * 4 + (c & 3);
-        sfrag[(0 + part) * NR * 16 + (c >> 3) * NR * 8 + (nu >> 3) * 64 + (nu & 7) * 8 + (c & 7)] = val;   // U: k = c
-        sfrag[(2 + part) * NR * 16 + (r >> 3) * NR * 8 + (nv >> 3) * 64 + (nv & 7) * 8 + (r & 7)] = val;   // V: k = r
+        if (ch < 4) {
+          constexpr int NR = 64;                    // operand rows of the four-plane matrices; one matrix = NR x 16 halves
+          // operand row (= TMEM column of the accumulator) = quad * 16 + plane * 4 + index in quad: the epilogue's
+          // unit of work -- 4 rows / columns x 4 planes -- is 16 consecutive columns, ONE tcgen05.ld
+          const int nu = (r >> 2) * 16 + ch * 4 + (r & 3), nv = (c >> 2) * 16 + ch * 4 + (c & 3);
+          sfrag[(0 + part) * NR * 16 + (c >> 3) * NR * 8 + (nu >> 3) * 64 + (nu & 7) * 8 + (c & 7)] = val;   // U: k = c
+          sfrag[(2 + part) * NR * 16 + (r >> 3) * NR * 8 + (nv >> 3) * 64 + (nv & 7) * 8 + (r & 7)] = val;   // V: k = r
+        } else {                                    // gD: 16-row matrices behind the 4 x 2 KB block
+          sfrag[4096 + (0 + part) * 256 + (c >> 3) * 128 + (r >> 3) * 64 + (r & 7) * 8 + (c & 7)] = val;     // UD: n = r, k = c
+          sfrag[4096 + (2 + part) * 256 + (r >> 3) * 128 + (c >> 3) * 64 + (c & 7) * 8 + (r & 7)] = val;     // VD: n = c, k = r
+        }
       } else {
         {   // B1: N = row r, K = column c
           const int h = r >> 3, g = r & 7, slot = c >> 3, t = (c & 7) >> 1, half = c & 1;
@@ -658,26 +687,51 @@ __device__ __forceinline__ void tmem_wait_quad(float (&q)[4][4]) {
 // TMEM round trip hides behind the FP32 work of quad q (tcgen05.wait::ld waits for ALL outstanding loads, so at most
 // one quad may be in flight when it is issued).  fy_pair(p) / fx_pair(p): factors of rows / columns 2p, 2p+1.
 struct BwdSums {
-  float2 aR, aG, aB, aS, aSy, aSyy, aSx, aSxx;
+  float2 aR, aG, aB, aS, aSy, aSyy, aSx, aSxx, aZ;
 };
-template <class FyPair, class FxPair>
-__device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float dy0, float2 cR, float2 cG, float2 cB,
-                                              FyPair fy_pair, FxPair fx_pair, BwdSums& A) {
+// four consecutive accumulator columns (the gD plane's share of a quad)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_quad5(float (&q)[4][4], float (&d)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+f"(q[0][0]), "+f"(q[0][1]), "+f"(q[0][2]), "+f"(q[0][3]), "+f"(q[1][0]), "+f"(q[1][1]), "+f"(q[1][2]),
+                 "+f"(q[1][3]), "+f"(q[2][0]), "+f"(q[2][1]), "+f"(q[2][2]), "+f"(q[2][3]), "+f"(q[3][0]), "+f"(q[3][1]),
+                 "+f"(q[3][2]), "+f"(q[3][3]), "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               :
+               : "memory");
+}
+// DEPTH: the gD plane's sums U_D (rows) / V_D (columns) sit in a second TMEM region `taddr_d` (16 + 16 columns); they
+// enter T = colour . v + v_W + z v_D and, along the rows, the depth gradient dZ = sum_r fy[r] U_D[r].
+template <bool DEPTH, class FyPair, class FxPair>
+__device__ __forceinline__ void umma_epilogue(uint32_t taddr, uint32_t taddr_d, float dx0, float dy0, float2 cR, float2 cG,
+                                              float2 cB, float2 cZ, FyPair fy_pair, FxPair fx_pair, BwdSums& A) {
   float buf[2][4][4];
-  auto request = [&](int q, float (&dst)[4][4]) { tmem_ld16(taddr + (uint32_t)(q * 16), dst); };
-  A.aR = A.aG = A.aB = A.aS = A.aSy = A.aSyy = A.aSx = A.aSxx = make_float2(0.f, 0.f);
-  request(0, buf[0]);
+  float bd[2][4];
+  auto request = [&](int q, float (&dst)[4][4], float (&dd)[4]) {
+    tmem_ld16(taddr + (uint32_t)(q * 16), dst);
+    if constexpr (DEPTH) tmem_ld4(taddr_d + (uint32_t)(q * 4), dd);
+  };
+  A.aR = A.aG = A.aB = A.aS = A.aSy = A.aSyy = A.aSx = A.aSxx = A.aZ = make_float2(0.f, 0.f);
+  request(0, buf[0], bd[0]);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    tmem_wait_quad(buf[q & 1]);
-    if (q < 7) request(q + 1, buf[(q + 1) & 1]);
+    if constexpr (DEPTH) tmem_wait_quad5(buf[q & 1], bd[q & 1]); else tmem_wait_quad(buf[q & 1]);
+    if (q < 7) request(q + 1, buf[(q + 1) & 1], bd[(q + 1) & 1]);
     float (&b)[4][4] = buf[q & 1];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int i0 = 4 * (q & 3) + 2 * j;                  // row (U) or column (V) of the pair
       const float2 vR = make_float2(b[0][2 * j], b[0][2 * j + 1]), vG = make_float2(b[1][2 * j], b[1][2 * j + 1]),
                    vB = make_float2(b[2][2 * j], b[2][2 * j + 1]), vW = make_float2(b[3][2 * j], b[3][2 * j + 1]);
-      const float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+      float2 T = __ffma2_rn(cR, vR, __ffma2_rn(cG, vG, __ffma2_rn(cB, vB, vW)));
+      if constexpr (DEPTH) {
+        const float2 vD = make_float2(bd[q & 1][2 * j], bd[q & 1][2 * j + 1]);
+        T = __ffma2_rn(cZ, vD, T);
+        if (q < 4) A.aZ = __ffma2_rn(fy_pair(i0 >> 1), vD, A.aZ);
+      }
       if (q < 4) {
         const float2 f = fy_pair(i0 >> 1);
         const float2 dy = make_float2(dy0 + (float)i0, dy0 + (float)(i0 + 1));
@@ -698,20 +752,26 @@ __device__ __forceinline__ void umma_epilogue(uint32_t taddr, float dx0, float d
   }
 }
 
-template <bool RECUR>
-__global__ void __launch_bounds__(BT_THREADS, 4)
+// DEPTH (a depth gradient is present): the gD plane adds four N = 16 products per step into a SECOND TMEM allocation of
+// 32 columns (U_D | V_D) -- 128 + 32 columns per CTA, three CTAs per SM -- read in the epilogue next to each quad; the
+// thread's sums gain dZ, which leaves as a third, scalar RED.
+template <bool RECUR, bool DEPTH>
+__global__ void __launch_bounds__(BT_THREADS, DEPTH ? 3 : 4)
 blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int4* __restrict__ udesc, const Counters* __restrict__ counters,
                            const uint4* __restrict__ planes,
                            const float* __restrict__ tile_scale, float* __restrict__ gacc) {
   constexpr int NR = 64;                                   // operand rows of a plane matrix: 4 planes x 16
-  constexpr uint32_t PLANE_BYTES = 4 * NR * 16 * 2;        // U_hi | U_lo | V_hi | V_lo, 2 KB each
+  constexpr uint32_t PLANE4_BYTES = 4 * NR * 16 * 2;       // U_hi | U_lo | V_hi | V_lo, 2 KB each
+  constexpr uint32_t PLANE_BYTES = PLANE4_BYTES + (DEPTH ? 4 * 16 * 16 * 2 : 0);   // + UD_hi | UD_lo | VD_hi | VD_lo, 512 B each
+  constexpr uint32_t PLANE_STRIDE = GBUF_FRAG_WORDS * 4;   // bytes between tiles in global memory (10 KB: room for both layouts)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 += f16 x f16, K-major
+  constexpr uint32_t IDESC_D = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // N = 16: the gD plane
   __shared__ __align__(128) uint4 sP[2][PLANE_BYTES / 16];       // the planes of the current and of the next unit's tile
   __shared__ __align__(128) uint4 sA[2][128 * 16 * 2 / 16];      // A operands: fx rows, fy rows (4 KB each)
-  __shared__ __align__(16) float4 sRec[2][BT_THREADS];          // x / y record of the next step, one private slot per thread
+  __shared__ __align__(16) float4 sRec[DEPTH ? 3 : 2][BT_THREADS];   // x / y [/ colour + zabs] record of the next step, one private slot per thread
   __shared__ __align__(8) unsigned long long bar_load[2], bar_mma;
-  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t tmem_base_s, tmem_base_d;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int nunits = counters->n_ne;                       // entries of the unit descriptor table (non-empty units, largest first)
   if ((int)blockIdx.x >= nunits) return;                   // block-uniform
@@ -723,12 +783,16 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(128) : "memory");
+    if constexpr (DEPTH)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_d)), "r"(32) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_d = DEPTH ? tmem_base_d : 0u;
+  const uint32_t taddr_d = tmem_d + ((uint32_t)(warp * 32) << 16);
   // this thread's A rows (row tid): K chunk 0 at +0, K chunk 1 at +2048 B
   uint4* rowx = &sA[0][(tid >> 3) * 8 + (tid & 7)];
   uint4* rowy = &sA[1][(tid >> 3) * 8 + (tid & 7)];
@@ -743,7 +807,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   const int4 dzero = make_int4(0, 0, 0, 0);
   auto fetch_planes = [&](int tile, int buf) {             // ONE bulk copy (async proxy), lands on bar_load[buf]
     mbar_expect_tx(&bar_load[buf], PLANE_BYTES);
-    bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_BYTES / 16), PLANE_BYTES, &bar_load[buf]);
+    bulk_g2s(&sP[buf][0], planes + (size_t)tile * (PLANE_STRIDE / 16), PLANE_BYTES, &bar_load[buf]);
   };
   // Staging as in the forward: the Gaussian id of a step is a coalesced load into a REGISTER two steps ahead, the
   // record of a step a cp.async gather into the thread's own slot one step ahead (slots are private: cp.async.wait_group
@@ -757,6 +821,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       const float4* src = rec + 3 * (size_t)id;
       cp_async16_b(&sRec[0][tid], src);                     // two of the record's three float4: the clamped colour
       cp_async16_b(&sRec[1][tid], src + 1);                 // is rebuilt from its fp16 hi | lo halves below
+      if (DEPTH) cp_async16_b(&sRec[DEPTH ? 2 : 0][tid], src + 2);   // zabs rides in the third one
     }
     cp_async_commit_b();
   };
@@ -774,7 +839,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   else if (un < nunits) id1 = id_of(decode(d_nxt), 0);
   // sums of the previous step waiting for their REDs: Gaussian id (complemented when op == 0: only S is kept), 8 sums
   int pend_id = INT_MIN;
-  float pend[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float pend[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto flush_sums = [&]() {
     if (pend_id == INT_MIN) return;
     const bool zop = pend_id < 0;
@@ -782,6 +847,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     if (!zop) {
       red_add_v4(dst, pend[0], pend[1], pend[2], pend[7]);
       red_add_v4(dst + 4, pend[3], pend[4], pend[5], pend[6]);
+      if (DEPTH) atomicAdd(dst + 8, pend[8]);
     } else {
       red_add_v4(dst + 4, pend[3], 0.0f, 0.0f, 0.0f);
     }
@@ -815,6 +881,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         col.x = __half2float(__ushort_as_half((unsigned short)(cr & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cr >> 16)));
         col.y = __half2float(__ushort_as_half((unsigned short)(cg & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cg >> 16)));
         col.z = __half2float(__ushort_as_half((unsigned short)(cb & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(cb >> 16)));
+        if (DEPTH) col.w = sRec[DEPTH ? 2 : 0][tid].w;
       }
       const float lop = ra.z;
       // ---- factors of this thread's Gaussian, scaled by 2^8 (fp16 range), WITHOUT opacity
@@ -846,6 +913,13 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         umma_f16(tmem,      dax, umma_desc_kmajor(pb + 2048,     NR * 16, 128), IDESC, 1);    // U += fx . G_lo
         umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 2 * 2048, NR * 16, 128), IDESC, 0);    // V  = fy . G_hi
         umma_f16(tmem + NR, day, umma_desc_kmajor(pb + 3 * 2048, NR * 16, 128), IDESC, 1);    // V += fy . G_lo
+        if constexpr (DEPTH) {
+          const uint32_t pd = pb + PLANE4_BYTES;
+          umma_f16(tmem_d,      dax, umma_desc_kmajor(pd,            16 * 16, 128), IDESC_D, 0);    // U_D  = fx . gD_hi
+          umma_f16(tmem_d,      dax, umma_desc_kmajor(pd + 512,      16 * 16, 128), IDESC_D, 1);    // U_D += fx . gD_lo
+          umma_f16(tmem_d + 16, day, umma_desc_kmajor(pd + 2 * 512,  16 * 16, 128), IDESC_D, 0);    // V_D  = fy . gD_hi
+          umma_f16(tmem_d + 16, day, umma_desc_kmajor(pd + 3 * 512,  16 * 16, 128), IDESC_D, 1);    // V_D += fy . gD_lo
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_mma)) : "memory");
       }
       // ---- global memory traffic of this thread goes HERE, behind the barrier: fence.proxy.async is a MEMBAR for the
@@ -867,8 +941,8 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 
       // ---- thread-local epilogue: this Gaussian's 16 rows (U) and 16 columns (V), packed f32x2
       BwdSums A;
-      umma_epilogue(taddr, dx0, dy0, bc2(col.x), bc2(col.y), bc2(col.z), [&](int p) { return fy2[p]; },
-                    [&](int p) { return fx2[p]; }, A);
+      umma_epilogue<DEPTH>(taddr, taddr_d, dx0, dy0, bc2(col.x), bc2(col.y), bc2(col.z), bc2(col.w),
+                           [&](int p) { return fy2[p]; }, [&](int p) { return fx2[p]; }, A);
       const float2 aR = A.aR, aG = A.aG, aB = A.aB, aS = A.aS, aSy = A.aSy, aSyy = A.aSyy, aSx = A.aSx, aSxx = A.aSxx;
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next step's barrier
       // the sums of this step are added to gacc after the NEXT barrier (see above)
@@ -881,6 +955,7 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         pend[0] = (aR.x + aR.y) * z; pend[1] = (aG.x + aG.y) * z; pend[2] = (aB.x + aB.y) * z;
         pend[3] = (aS.x + aS.y) * opk; pend[4] = (aSx.x + aSx.y) * z; pend[5] = (aSxx.x + aSxx.y) * z;
         pend[6] = (aSy.x + aSy.y) * z; pend[7] = (aSyy.x + aSyy.y) * z;
+        if (DEPTH) pend[8] = (A.aZ.x + A.aZ.y) * z;
       }
     }
     u = un;
@@ -893,7 +968,44 @@ blend_wsum_bwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   }
   flush_sums();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128) : "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128) : "memory");
+    if constexpr (DEPTH) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(32) : "memory");
+  }
+}
+
+// Per-view statistics of the depth image for the fit script's depth term (python/fit_multiview_stub.py:298-303):
+// stats = {M = max_p depth_p, number of pixels attaining M, sum_p sign(depth_p/(M+1e-6) - d_gt_p) depth_p}, with
+// depth_p = max(D/(W+1e-6), 0) from the saved accumulators.  Two passes (the second needs M); float max through the
+// integer order of non-negative floats.
+__global__ void __launch_bounds__(256)
+depth_max_kernel(const float* __restrict__ acc, int hw, float* __restrict__ stats) {
+  float m = 0.0f;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < hw; p += gridDim.x * 256)
+    m = fmaxf(m, fmaxf(acc[4 * (size_t)hw + p] / (acc[3 * (size_t)hw + p] + 1e-6f), 0.0f));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats), __float_as_int(m));
+}
+__global__ void __launch_bounds__(256)
+depth_sums_kernel(const float* __restrict__ acc, const float* __restrict__ depth_gt, int hw, float* __restrict__ stats) {
+  const float M = stats[0], im = 1.0f / (M + 1e-6f);
+  float cnt = 0.0f, ssum = 0.0f;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < hw; p += gridDim.x * 256) {
+    const float dep = fmaxf(acc[4 * (size_t)hw + p] / (acc[3 * (size_t)hw + p] + 1e-6f), 0.0f);
+    const float dd = dep * im - depth_gt[p];
+    ssum += (float)((dd > 0.f) - (dd < 0.f)) * dep;
+    cnt += (dep == M) ? 1.0f : 0.0f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 1, cnt);
+    atomicAdd(stats + 2, ssum);
+  }
 }
 
 // Clears the per-view backward sums and plants the colour clamp mask of each Gaussian (written by
@@ -931,7 +1043,8 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
                           const float* g_rgb, const float* g_alpha, const float* g_depth, const FitLossArgs* fl,
                           float* gbuf, float* gacc, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
-  const bool depth = g_depth != nullptr;
+  const bool fit_depth = fl != nullptr && fl->depth_gt != nullptr && fl->w_depth != 0.0f;
+  const bool depth = g_depth != nullptr || fit_depth;
   if (use_simt_bwd() && fl == nullptr) {   // development cross-check: the FP32-pipe kernel (v3)
     count_path(PATH_BWD_OTHER);
     if (depth) gbuf_kernel<true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, gbuf);
@@ -940,41 +1053,54 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
     if (depth) blend_wsum_bwd_kernel<true><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
     else       blend_wsum_bwd_kernel<false><<<(int)unit_cap, BB_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, units, gbuf, gacc);
   } else {
-    // gbuf region: [tile][20 uint4][32 lanes] fragments (10 KB per tile), then one scale per tile
+    // gbuf region: [tile][10 KB] plane fragments / operand matrices, then one scale per tile
     uint32_t* frag = reinterpret_cast<uint32_t*>(gbuf);
     float* tile_scale = gbuf + (size_t)vp.n_tiles * GBUF_FRAG_WORDS;
-    // the tcgen05 kernel covers the 4-plane case (no depth gradient); B2S_BWD_MMASYNC=1 keeps the mma.sync kernel
+    // the tcgen05 kernel is the default; B2S_BWD_MMASYNC=1 keeps the mma.sync kernel (development cross-check)
     static const bool mmasync = [] { const char* e = getenv("B2S_BWD_MMASYNC"); return e != nullptr && e[0] == '1'; }();
-    const bool umma = !depth && !mmasync;
-    if (fl != nullptr && umma)
-      gbuf_frag_kernel<false, true, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
-                                                                          fl->scale, fl->loss_accum, frag, tile_scale);
-    else if (fl != nullptr)
-      gbuf_frag_kernel<false, true, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, nullptr, nullptr, nullptr, fl->tgt, fl->mask, fl->w_sil,
-                                                                           fl->scale, fl->loss_accum, frag, tile_scale);
-    else if (depth)
-      gbuf_frag_kernel<true, false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
-                                                                           nullptr, frag, tile_scale);
-    else if (umma)
-      gbuf_frag_kernel<false, false, true><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
-                                                                           nullptr, frag, tile_scale);
-    else
-      gbuf_frag_kernel<false, false, false><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, nullptr, nullptr, 0.f, 0.f,
-                                                                            nullptr, frag, tile_scale);
+    const bool umma = !mmasync;
+    float* dstats = nullptr;
+    if (fit_depth) {
+      // per-view depth statistics (max, arg-max count, signed sum) live behind the per-tile scales
+      dstats = tile_scale + vp.n_tiles;
+      const int hw = vp.width * vp.height;
+      int blocks = (hw + 255) / 256;
+      if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+      B2S_CUDA_TRY(cudaMemsetAsync(dstats, 0, 4 * sizeof(float), st));
+      depth_max_kernel<<<blocks, 256, 0, st>>>(acc, hw, dstats);
+      B2S_LAUNCH_CHECK();
+      depth_sums_kernel<<<blocks, 256, 0, st>>>(acc, fl->depth_gt, hw, dstats);
+      B2S_LAUNCH_CHECK();
+    }
+#define B2S_GBUF(DD, LL, UU)                                                                                              \
+  gbuf_frag_kernel<DD, LL, UU><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, fl ? fl->tgt : nullptr,  \
+                                                                fl ? fl->mask : nullptr, fit_depth ? fl->depth_gt : nullptr, dstats, \
+                                                                fl ? fl->w_sil : 0.f, fit_depth ? fl->w_depth : 0.f,        \
+                                                                fl ? fl->scale : 0.f, fl ? fl->loss_accum : nullptr, frag, tile_scale)
+    if (fl != nullptr) {
+      if (depth) { if (umma) B2S_GBUF(true, true, true); else B2S_GBUF(true, true, false); }
+      else       { if (umma) B2S_GBUF(false, true, true); else B2S_GBUF(false, true, false); }
+    } else {
+      if (depth) { if (umma) B2S_GBUF(true, false, true); else B2S_GBUF(true, false, false); }
+      else       { if (umma) B2S_GBUF(false, false, true); else B2S_GBUF(false, false, false); }
+    }
+#undef B2S_GBUF
     B2S_LAUNCH_CHECK();
     if (umma) {
-      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns), each strides over the unit descriptor table
-      static const int cps = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
+      // persistent: 4 CTAs per SM (TMEM: 4 x 128 columns; 3 x 160 with the gD plane), each strides over the unit descriptor table
+      static const int cps_env = [] { const char* e = getenv("B2S_BWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 0; }();
+      const int cps_max = depth ? 3 : 4;
+      const int cps = (cps_env >= 1 && cps_env <= cps_max) ? cps_env : cps_max;
       const int grid = (int)(unit_cap < cps * sm_count() ? unit_cap : cps * sm_count());
       count_path(PATH_BWD_UMMA);
       // B2S_BWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
       static const bool direct = [] { const char* e = getenv("B2S_BWD_EX2"); return e != nullptr && e[0] == '1'; }();
-      if (direct)
-        blend_wsum_bwd_umma_kernel<false><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,
-                                                                       reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
-      else
-        blend_wsum_bwd_umma_kernel<true><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,
-                                                                      reinterpret_cast<const uint4*>(frag), tile_scale, gacc);
+#define B2S_BWU(RR, DD)                                                                                   \
+  blend_wsum_bwd_umma_kernel<RR, DD><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,          \
+                                                                 reinterpret_cast<const uint4*>(frag), tile_scale, gacc)
+      if (depth) { if (direct) B2S_BWU(false, true); else B2S_BWU(true, true); }
+      else       { if (direct) B2S_BWU(false, false); else B2S_BWU(true, false); }
+#undef B2S_BWU
       B2S_LAUNCH_CHECK();
       return B2S_OK;
     }

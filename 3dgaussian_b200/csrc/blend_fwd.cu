@@ -573,11 +573,16 @@ blend_wsum_fwd_f16_kernel(const ViewParams vp, const float4* __restrict__ rec, c
 constexpr int FT_THREADS = 128;
 constexpr int FT_CTAS = 5;                        // per SM: 44 KB of shared memory, <= 102 registers, 32 TMEM columns each
 constexpr uint32_t FT_SBO = FT_THREADS * 16;      // bytes between MN groups of 8: [group][Gaussian] uint4
-struct FtSmem {
+// DEPTH adds the depth plane D = sum_i z_i fx_i[c] fy_i[r] WITHOUT a fifth operand plane (M = 128 is full): z rides on
+// the other operand, B = [fy_hi | fy_lo | (z fy)_hi | (z fy)_lo] (N = 64), and D is read from the weight plane's rows
+// (A = fx) at the accumulator columns 32..63.  One instruction per 16 Gaussians as before; +8 KB of shared memory
+// (4 CTAs per SM instead of 5) and 64 TMEM columns.
+template <bool DEPTH>
+struct FtSmemT {
   uint4 Ah[8][FT_THREADS];        // A hi: group = plane * 2 + column / 8
   uint4 Al[8][FT_THREADS];
-  uint4 B[4][FT_THREADS];         // fy: hi rows 0-7, hi rows 8-15, lo rows 0-7, lo rows 8-15
-  float4 rec[2][FT_THREADS];      // x / y record of the next step, one private slot per thread
+  uint4 B[DEPTH ? 8 : 4][FT_THREADS];   // fy: hi rows 0-7, hi rows 8-15, lo rows 0-7, lo rows 8-15 [, the same four of z * fy]
+  float4 rec[DEPTH ? 3 : 2][FT_THREADS];   // x / y record [/ colour + zabs] of the next step, one private slot per thread
   unsigned long long bar_mma;
   uint32_t tmem_base;
 };
@@ -604,15 +609,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
 }
 
-template <bool RECUR>
-__global__ void __launch_bounds__(FT_THREADS, FT_CTAS)
+template <bool RECUR, bool DEPTH>
+__global__ void __launch_bounds__(FT_THREADS, DEPTH ? FT_CTAS - 1 : FT_CTAS)
 blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                            const int2* __restrict__ ranges, const int4* __restrict__ udesc,
                            const Counters* __restrict__ counters, float* __restrict__ partial, float* __restrict__ out_rgb,
-                           float* __restrict__ out_alpha, float* __restrict__ acc, uint8_t* __restrict__ out_rgba) {
+                           float* __restrict__ out_alpha, float* __restrict__ out_depth, float* __restrict__ acc,
+                           uint8_t* __restrict__ out_rgba) {
   extern __shared__ __align__(128) unsigned char ft_raw[];
+  using FtSmem = FtSmemT<DEPTH>;
   FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_raw);
-  constexpr uint32_t IDESC = umma_idesc_f16(128, 32, true, true);   // M = [A_hi ; A_lo] rows, N = [B_hi | B_lo] rows
+  constexpr int NCOL = DEPTH ? 64 : 32;                                // accumulator columns = operand B rows
+  constexpr uint32_t IDESC = umma_idesc_f16(128, NCOL, true, true);    // M = [A_hi ; A_lo] rows, N = [B_hi | B_lo (| zB_hi | zB_lo)] rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nunits = counters->n_ne;                       // entries of the unit descriptor table (non-empty units, largest first)
   const size_t hw = (size_t)vp.width * vp.height;
@@ -634,7 +642,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         const int pix = tid + h * FT_THREADS;
         const int xi = (t % vp.tiles_x) * TILE + (pix & 15), yi = (t / vp.tiles_x) * TILE + (pix >> 4);
         if (xi < vp.width && yi < vp.height)
-          write_pixel(vp, (size_t)yi * vp.width + xi, hw, 0.f, 0.f, 0.f, 0.f, 0.f, out_rgb, out_alpha, nullptr, acc, out_rgba);
+          write_pixel(vp, (size_t)yi * vp.width + xi, hw, 0.f, 0.f, 0.f, 0.f, 0.f, out_rgb, out_alpha, out_depth, acc, out_rgba);
       }
     }
   }
@@ -642,7 +650,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 
   if (tid == 0) mbar_init(&sm.bar_mma, 1);
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(32) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm.tmem_base)), "r"(NCOL) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -658,17 +666,18 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
   auto decode = [&](const int4& d) -> Unit { return Unit{d.x, d.y, d.z, d.w}; };
   const int4 dzero = make_int4(0, 0, 0, 0);
   // pixels q = tid, tid + 128 of a unit: outputs (single-unit tile) or the unit's partial planes
-  auto emit = [&](const Unit& q, int pix, float R, float G, float Bc, float W) {
+  auto emit = [&](const Unit& q, int pix, float R, float G, float Bc, float W, float Dz) {
     if (q.uidx >= 0) {
       const int xi = (q.tile % vp.tiles_x) * TILE + (pix & 15), yi = (q.tile / vp.tiles_x) * TILE + (pix >> 4);
       if (xi < vp.width && yi < vp.height)
-        write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, Bc, W, 0.0f, out_rgb, out_alpha, nullptr, acc, out_rgba);
+        write_pixel(vp, (size_t)yi * vp.width + xi, hw, R, G, Bc, W, Dz, out_rgb, out_alpha, out_depth, acc, out_rgba);
     } else {
       float* dst = partial + (size_t)(q.uidx & 0x7fffffff) * 5 * TILE_PIX + pix;
       dst[0] = R;
       dst[TILE_PIX] = G;
       dst[2 * TILE_PIX] = Bc;
       dst[3 * TILE_PIX] = W;
+      if (DEPTH) dst[4 * TILE_PIX] = Dz;
     }
   };
   // Staging.  The Gaussian id of a step is a coalesced load into a REGISTER, requested two steps ahead (by the time
@@ -686,6 +695,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       const float4* src = rec + 3 * (size_t)id;
       cp_async16_b(&sm.rec[0][tid], src);
       cp_async16_b(&sm.rec[1][tid], src + 1);
+      if (DEPTH) cp_async16_b(&sm.rec[DEPTH ? 2 : 0][tid], src + 2);     // {r, g, b, zabs}: the depth plane needs zabs
     }
     cp_async_commit_b();
   };
@@ -722,7 +732,12 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       // padding: q = 0 and log2 op = -1000 make every x factor exactly 0 (and every ratio of the recurrence 1: no
       // 0 * inf), the colour halves are 0; a padded K slot then adds 0 to every accumulator
       float4 ra = make_float4(0.0f, 0.0f, -1000.0f, 0.0f), rb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (act) { ra = sm.rec[0][tid]; rb = sm.rec[1][tid]; }
+      float zabs = 0.0f;
+      if (act) {
+        ra = sm.rec[0][tid];
+        rb = sm.rec[1][tid];
+        if (DEPTH) zabs = sm.rec[DEPTH ? 2 : 0][tid].w;
+      }
       fetch_rec(id1);                                      // next step's record into the slot just read
       act = id1 >= 0;
       // id of the step after next: in this unit, the next one, or (single-step next unit) the one after it
@@ -735,6 +750,14 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       const float dx0 = ra.x - x0, dy0 = rb.x - y0;
       const float lop8 = fminf(ra.z, 7.99f) + 8.0f;        // fx * 2^8 stays inside fp16 (op <= 253)
       uint32_t Fh[8], Fl[8], Yh[8], Yl[8];
+      uint32_t Zh[DEPTH ? 8 : 1], Zl[DEPTH ? 8 : 1];      // z * fy (the depth plane's B rows); fy <= 2^8, so z up to 253 fits fp16
+      const float2 z2 = bcast2(zabs), zcap = bcast2(65000.0f);
+      auto split_z = [&](int j, float2 fyv) {
+        if constexpr (DEPTH) {
+          const float2 t = __fmul2_rn(z2, fyv);
+          split_h2v(make_float2(fminf(t.x, zcap.x), fminf(t.y, zcap.y)), Zh[j], Zl[j]);
+        }
+      };
       if (RECUR) {       // by recurrence from the tile centre: 14 MUFU.EX2 + 26 packed multiplies (common.cuh)
         float2 fx2[8], fy2[8];
         factors16(ra.y, -dx0, lop8, fx2);
@@ -743,6 +766,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
         for (int j = 0; j < 8; ++j) {
           split_h2v(fx2[j], Fh[j], Fl[j]);
           split_h2v(fy2[j], Yh[j], Yl[j]);
+          split_z(j, fy2[j]);
         }
       } else {
 #pragma unroll
@@ -751,8 +775,10 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
           const float2 dx = __fadd2_rn(bcast2(dx0), off), dy = __fadd2_rn(bcast2(dy0), off);
           const float2 ax = __ffma2_rn(__fmul2_rn(bcast2(ra.y), dx), dx, bcast2(lop8));
           const float2 ay = __ffma2_rn(__fmul2_rn(bcast2(rb.y), dy), dy, bcast2(8.0f));
+          const float2 fyv = make_float2(ex2_approx(ay.x), ex2_approx(ay.y));
           split_h2v(make_float2(ex2_approx(ax.x), ex2_approx(ax.y)), Fh[j], Fl[j]);
-          split_h2v(make_float2(ex2_approx(ay.x), ex2_approx(ay.y)), Yh[j], Yl[j]);
+          split_h2v(fyv, Yh[j], Yl[j]);
+          split_z(j, fyv);
         }
       }
       // the previous batch's MMAs read the operand buffers: they must have retired before the stores below
@@ -762,6 +788,12 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
       sm.B[1][tid] = make_uint4(Yh[4], Yh[5], Yh[6], Yh[7]);
       sm.B[2][tid] = make_uint4(Yl[0], Yl[1], Yl[2], Yl[3]);
       sm.B[3][tid] = make_uint4(Yl[4], Yl[5], Yl[6], Yl[7]);
+      if constexpr (DEPTH) {
+        sm.B[4][tid] = make_uint4(Zh[0], Zh[1], Zh[2], Zh[3]);
+        sm.B[5][tid] = make_uint4(Zh[4], Zh[5], Zh[6], Zh[7]);
+        sm.B[6][tid] = make_uint4(Zl[0], Zl[1], Zl[2], Zl[3]);
+        sm.B[7][tid] = make_uint4(Zl[4], Zl[5], Zl[6], Zl[7]);
+      }
       sm.Ah[6][tid] = make_uint4(Fh[0], Fh[1], Fh[2], Fh[3]);      // weight plane: fx itself
       sm.Ah[7][tid] = make_uint4(Fh[4], Fh[5], Fh[6], Fh[7]);
       sm.Al[6][tid] = make_uint4(Fl[0], Fl[1], Fl[2], Fl[3]);
@@ -818,19 +850,39 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
 #pragma unroll
         for (int r = 0; r < 16; ++r) dst[r * TILE] = v[r];
       }
+      // depth plane: the weight plane's rows (operand rows 48..63 hi = warp 1, 112..127 lo = warp 3; lanes 16..31) at the
+      // accumulator columns 32..63 = (z fy)_hi | (z fy)_lo rows
+      float vz[DEPTH ? 32 : 1];
+      float* dstz = sOut + 4 * TILE_PIX + (lane & 15);
+      if constexpr (DEPTH) {
+        if (warp & 1) {                                    // warp uniform: the collective load runs on whole warps
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32u, vz);
+          if (warp == 3 && lane >= 16) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dstz[r * TILE] = vz[r];
+          }
+        }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next unit's first MMA
       __syncthreads();
+      const float us = 1.0f / 65536.0f;                    // the two 2^8 factor scales
       if (warp < 2) {
-        const float us = 1.0f / 65536.0f;                  // the two 2^8 factor scales
 #pragma unroll
         for (int r = 0; r < 16; ++r) dst[r * TILE] = (dst[r * TILE] + v[r] + v[16 + r]) * us;
+      }
+      if constexpr (DEPTH) {
+        if (warp == 1 && lane >= 16) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) dstz[r * TILE] = (dstz[r * TILE] + vz[r] + vz[16 + r]) * us;
+        }
       }
     }
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int pix = tid + h * FT_THREADS;
-      emit(cur, pix, sOut[pix], sOut[TILE_PIX + pix], sOut[2 * TILE_PIX + pix], sOut[3 * TILE_PIX + pix]);
+      emit(cur, pix, sOut[pix], sOut[TILE_PIX + pix], sOut[2 * TILE_PIX + pix], sOut[3 * TILE_PIX + pix],
+           DEPTH ? sOut[4 * TILE_PIX + pix] : 0.0f);
     }
     __syncthreads();                                       // sOut aliases the A operand: reads done before the next stores
     u = un;
@@ -841,7 +893,7 @@ blend_wsum_fwd_umma_kernel(const ViewParams vp, const float4* __restrict__ rec, 
     d_nn = d_n3;
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(32) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(NCOL) : "memory");
 }
 
 // Sums the per-unit partial accumulators of tiles that span several units, in unit order.
@@ -876,7 +928,7 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
   const int blocks = (int)((unit_cap + FW_WARPS - 1) / FW_WARPS);
-  const bool depth = out_depth != nullptr;   // D is only accumulated when the depth image is requested
+  const bool depth = out_depth != nullptr || vp.keep_depth != 0;   // D is accumulated when the depth image (or its gradient) is wanted
 #define B2S_FW(DD, EE)                                                                                              \
   blend_wsum_fwd_kernel<DD, EE><<<blocks, FW_WARPS * 32, 0, st>>>(vp, rec, vals, ranges, unit_start, units, partial, \
                                                                    out_rgb, out_alpha, out_depth, acc, out_rgba)
@@ -888,24 +940,30 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
   static const bool tf32 = [] { const char* e = getenv("B2S_FWD_TF32"); return e != nullptr && e[0] == '1'; }();
   if (vp.exact_bbox) { count_path(PATH_FWD_OTHER); if (depth) B2S_FW(true, true); else B2S_FW(false, true); }
   else if (simt)     { count_path(PATH_FWD_OTHER); if (depth) B2S_FW(true, false); else B2S_FW(false, false); }   // development cross-check (v3)
-  else if (!depth && !tf32 && !mmasync) {
-    // tcgen05: persistent, 5 CTAs per SM, each strides over the unit descriptor table (4-plane case; depth stays on v5)
+  else if (!tf32 && !mmasync) {
+    // tcgen05: persistent, 5 CTAs per SM (4 with the depth plane), each strides over the unit descriptor table
     B2S_CUDA_TRY(per_device_once(ONCE_FWD_UMMA, [] {
-      cudaError_t e = cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem));
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_wsum_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem));
+      cudaError_t e = cudaSuccess;
+      auto set = [&](auto kern, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+      set(blend_wsum_fwd_umma_kernel<true, false>, sizeof(FtSmemT<false>));
+      set(blend_wsum_fwd_umma_kernel<false, false>, sizeof(FtSmemT<false>));
+      set(blend_wsum_fwd_umma_kernel<true, true>, sizeof(FtSmemT<true>));
+      set(blend_wsum_fwd_umma_kernel<false, true>, sizeof(FtSmemT<true>));
       return e;
     }));
     // B2S_FWD_EX2=1: every factor from its own MUFU.EX2 instead of the recurrence (development cross-check)
     static const bool direct = [] { const char* e = getenv("B2S_FWD_EX2"); return e != nullptr && e[0] == '1'; }();
-    static const int cps = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= FT_CTAS) ? v : FT_CTAS; }();
+    static const int cps_env = [] { const char* e = getenv("B2S_FWD_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= FT_CTAS) ? v : 0; }();
+    const int cps_max = depth ? FT_CTAS - 1 : FT_CTAS;
+    const int cps = (cps_env >= 1 && cps_env <= cps_max) ? cps_env : cps_max;
     const int grid = (int)(unit_cap < cps * sm_count() ? unit_cap : cps * sm_count());
     count_path(PATH_FWD_UMMA);
-    if (direct)
-      blend_wsum_fwd_umma_kernel<false><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
-                                                                                   out_rgb, out_alpha, acc, out_rgba);
-    else
-      blend_wsum_fwd_umma_kernel<true><<<grid, FT_THREADS, sizeof(FtSmem), st>>>(vp, rec, vals, ranges, udesc, counters, partial,
-                                                                                  out_rgb, out_alpha, acc, out_rgba);
+#define B2S_FWU(RR, DD)                                                                                                      \
+  blend_wsum_fwd_umma_kernel<RR, DD><<<grid, FT_THREADS, sizeof(FtSmemT<DD>), st>>>(vp, rec, vals, ranges, udesc, counters, partial, \
+                                                                                   out_rgb, out_alpha, out_depth, acc, out_rgba)
+    if (depth) { if (direct) B2S_FWU(false, true); else B2S_FWU(true, true); }
+    else       { if (direct) B2S_FWU(false, false); else B2S_FWU(true, false); }
+#undef B2S_FWU
   }
   else if (tf32)     { count_path(PATH_FWD_OTHER); if (depth) B2S_FWM(blend_wsum_fwd_mma_kernel, true); else B2S_FWM(blend_wsum_fwd_mma_kernel, false); }
   else               { count_path(PATH_FWD_OTHER); if (depth) B2S_FWM(blend_wsum_fwd_f16_kernel, true); else B2S_FWM(blend_wsum_fwd_f16_kernel, false); }

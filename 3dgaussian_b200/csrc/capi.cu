@@ -8,6 +8,7 @@
 #include <vector>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -86,13 +87,21 @@ std::once_flag& device_once_flag(int slot) {
   return flags[slot][current_device_slot()];
 }
 
+// Default: the binning kernels write the mirror straight into mapped pinned memory (no extra stream operation);
+// B2S_TICKET_MODE=copy: a 32-byte stream-ordered device-to-host copy of the counters behind the binning kernels
+static bool ticket_mapped() {
+  static const bool m = [] { const char* e = getenv("B2S_TICKET_MODE"); return !(e != nullptr && e[0] == 'c'); }();
+  return m;
+}
 // Next ticket of the ctx: the slot of the pinned ring the binning kernels mirror their counters into (nullptr if
 // the ring could not be allocated: tickets then report an error instead of data).
 static Counters* ticket_begin(b2s_ctx* ctx) {
   if (ctx == nullptr) return nullptr;
+  static const bool off = [] { const char* e = getenv("B2S_NO_TICKETS"); return e != nullptr && e[0] == '1'; }();
+  if (off) return nullptr;
   if (ctx->probe == nullptr) {
     void* h = nullptr;
-    if (cudaHostAlloc(&h, sizeof(Counters) * B2S_TICKET_RING, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&h, sizeof(Counters) * B2S_TICKET_RING, ticket_mapped() ? cudaHostAllocMapped : cudaHostAllocDefault) != cudaSuccess) {
       cudaGetLastError();
       return nullptr;
     }
@@ -104,9 +113,15 @@ static Counters* ticket_begin(b2s_ctx* ctx) {
   return ctx->probe + slot;
 }
 // records the event behind the kernels that wrote the mirror of the ticket just begun
-static void ticket_mark(b2s_ctx* ctx, cudaStream_t st) {
+static void ticket_mark(b2s_ctx* ctx, const Counters* counters_dev, cudaStream_t st) {
   if (ctx == nullptr || ctx->probe == nullptr || ctx->tickets <= 0) return;
   const int slot = (int)((ctx->tickets - 1) % B2S_TICKET_RING);
+  if (!ticket_mapped() && cudaMemcpyAsync(ctx->probe + slot, counters_dev, sizeof(Counters), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  static const bool noev = [] { const char* e = getenv("B2S_TICKET_NOEVENT"); return e != nullptr && e[0] == '1'; }();
+  if (noev) return;
   if (ctx->probe_ev[slot] == nullptr && cudaEventCreateWithFlags(&ctx->probe_ev[slot], cudaEventDisableTiming) != cudaSuccess) {
     ctx->probe_ev[slot] = nullptr;
     cudaGetLastError();
@@ -155,7 +170,7 @@ static int make_view(const b2s_params* p, ViewParams* vp) {
   memcpy(vp->proj, p->proj, sizeof(float) * 16);
   memcpy(vp->bg, p->background, sizeof(float) * 3);
   vp->bg_dev = p->background_dev;
-  vp->pad_ = 0;
+  vp->keep_depth = p->keep_depth ? 1 : 0;
   vp->cam[0] = vp->cam[1] = vp->cam[2] = 0.0f;
   if (p->sh_coeffs > 1 && !camera_centre(p->view, vp->cam)) { set_error("view matrix is singular"); return B2S_ERR_INVALID; }
   vp->k = p->cutoff_sigma;
@@ -272,6 +287,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
                        unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
   int rc = B2S_OK;
   Counters* mirror = ticket_begin(ctx);
+  if (!ticket_mapped()) mirror = nullptr;       // the counters travel by a stream-ordered copy instead (ticket_mark)
   if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
     StageTimer t(ctx, ST_PREPROCESS, st);
     rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
@@ -291,7 +307,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
                                 B.unit_start, B.units, B.udesc, B.vals, 0, st);   // also writes the unit descriptor table
     }
     if (rc != B2S_OK) return rc;
-    ticket_mark(ctx, st);
+    ticket_mark(ctx, B.counters, st);
     if (keys_unsorted_copy != nullptr || vals_unsorted_copy != nullptr) {   // dump hook only: the emit order
       Counters* scratch = (Counters*)B.hist;
       rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, B.keysA, B.valsB, scratch, nullptr, st);
@@ -319,7 +335,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     rc = launch_bin(vp, n, max_pairs, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, kA, vA, B.counters, mirror, st);
   }
   if (rc != B2S_OK) return rc;
-  ticket_mark(ctx, st);
+  ticket_mark(ctx, B.counters, st);
   if (keys_unsorted_copy != nullptr)
     B2S_CUDA_TRY(cudaMemcpyAsync(keys_unsorted_copy, kA, (size_t)max_pairs * 8, cudaMemcpyDeviceToDevice, st));
   if (vals_unsorted_copy != nullptr)
@@ -539,9 +555,9 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
 }
 
 int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
-                           const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
-                           const void* prepared_view, void* workspace, size_t ws_bytes, float* gacc_out,
-                           void* stream) {
+                           const float* mask, const float* depth_gt, float w_sil, float w_depth, float scale,
+                           float* loss_accum, const void* state, const void* prepared_view, void* workspace,
+                           size_t ws_bytes, float* gacc_out, void* stream) {
   if (ctx == nullptr || tgt == nullptr || loss_accum == nullptr || state == nullptr || workspace == nullptr ||
       gacc_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   ViewParams vp;
@@ -556,7 +572,11 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
   cudaStream_t st = (cudaStream_t)stream;
   Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
   if (prepared_view != nullptr) use_prepared(B, prepared_view, n);
-  const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum};
+  if (depth_gt != nullptr && w_depth != 0.0f && !p->keep_depth) {
+    set_error("the depth term needs the depth plane: run the forward with params.keep_depth = 1");
+    return B2S_ERR_INVALID;
+  }
+  const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum, depth_gt, w_depth};
   StageTimer t(ctx, ST_BLEND_BWD, st);
   if (n > 0) {
     rc = launch_gacc_init(B.cmask, gacc_out, n, st);
@@ -647,9 +667,7 @@ int b2s_render_rgba8_host(b2s_ctx* ctx, const b2s_params* p, const float* means_
   const size_t out_bytes = align_up(pixels * 4);
   auto ensure = [&](size_t bytes) -> int {
     if (bytes <= ctx->host_dev_bytes) return B2S_OK;
-    if (ctx->host_dev != nullptr) cudaFree(ctx->host_dev);
-  if (ctx->probe != nullptr) cudaFreeHost(ctx->probe);
-  for (auto& e : ctx->probe_ev) if (e != nullptr) cudaEventDestroy(e);
+    if (ctx->host_dev != nullptr) B2S_CUDA_TRY(cudaFree(ctx->host_dev));
     ctx->host_dev = nullptr;
     ctx->host_dev_bytes = 0;
     B2S_CUDA_TRY(cudaMalloc(&ctx->host_dev, bytes));
@@ -797,7 +815,18 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
   if (step < 1) { set_error("Adam step is 1-based"); return B2S_ERR_INVALID; }
   StageTimer t(ctx, ST_ADAM, (cudaStream_t)stream);
   return launch_adam(params, grads, m, v, count, step, lr, beta1, beta2, eps, scales_begin, scales_end, reg_scale,
-                     opac_begin, opac_end, reg_opacity, (cudaStream_t)stream);
+                     opac_begin, opac_end, reg_opacity, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int b2s_adam_step_guarded(b2s_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t count, int step,
+                          float lr, float beta1, float beta2, float eps, int64_t scales_begin, int64_t scales_end,
+                          float reg_scale, int64_t opac_begin, int64_t opac_end, float reg_opacity,
+                          const float* skip_flag, int* skipped_count, void* stream) {
+  if (ctx == nullptr || params == nullptr || grads == nullptr || m == nullptr || v == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (step < 1) { set_error("Adam step is 1-based"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_ADAM, (cudaStream_t)stream);
+  return launch_adam(params, grads, m, v, count, step, lr, beta1, beta2, eps, scales_begin, scales_end, reg_scale,
+                     opac_begin, opac_end, reg_opacity, skip_flag, skipped_count, (cudaStream_t)stream);
 }
 
 size_t b2s_densify_workspace_bytes(int n) { return densify_workspace_bytes(n) + 256; }

@@ -28,7 +28,7 @@ struct ViewParams {
   int width, height, tiles_x, tiles_y, n_tiles;
   int style, sh, act, exact_bbox, mode;
   int seg;          // Gaussians per work unit of the blend kernels (unit_size(): grows with the image)
-  int pad_;
+  int keep_depth;   // accumulate the depth plane D in the saved accumulators even without a depth image (fit loop with a depth loss)
   const float* bg_dev;   // optional DEVICE pointer to 3 floats overriding bg[] (b2s_params.background_dev): the
                          // drop-in receives the background as a device tensor and must not sync to read it
 };
@@ -263,7 +263,7 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   L.gacc = o;  o += align_up(nn * GACC_F * 4);
   const size_t tiles = (size_t)((width + TILE - 1) / TILE) * ((height + TILE - 1) / TILE);
   L.partial = o; o += align_up((size_t)max_units(width, height, max_pairs) * 5 * TILE_PIX * 4);
-  L.gbuf = o;  o += align_up(tiles * GBUF_FRAG_WORDS * 4) + align_up(tiles * 4);   // plane fragments + per-tile scale
+  L.gbuf = o;  o += align_up(tiles * GBUF_FRAG_WORDS * 4) + align_up(tiles * 4 + 64);   // plane fragments + per-tile scale + depth statistics
   L.cs_table = o; o += align_up((size_t)CS_NB * tiles * 4);
   L.cs_total = o; o += align_up(tiles * 4);
   L.total = o;
@@ -379,6 +379,8 @@ struct FitLossArgs {
   const float* mask;     // may be null
   float w_sil, scale;
   float* loss_accum;
+  const float* depth_gt; // may be null: the depth term  w_depth * mean|depth/(max depth + 1e-6) - depth_gt|
+  float w_depth;
 };
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,
@@ -403,6 +405,6 @@ int launch_fit_loss(const float* rgb, const float* alpha, const float* tgt, cons
 int launch_u8_to_f32(const uint8_t* src, float* dst, int64_t count, cudaStream_t st);
 int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,
                 float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
-                float reg_op, cudaStream_t st);
+                float reg_op, const float* skip_flag, int* skipped_count, cudaStream_t st);
 
 }  // namespace b2s

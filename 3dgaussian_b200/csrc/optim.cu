@@ -88,7 +88,13 @@ int launch_u8_to_f32(const uint8_t* src, float* dst, int64_t count, cudaStream_t
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long count, float b1, float b2, float eps, float step_size, float inv_sqrt_bc2, long long sb,
-            long long se, float reg_s, long long ob, long long oe, float reg_o) {
+            long long se, float reg_s, long long ob, long long oe, float reg_o, const float* __restrict__ skip_flag,
+            int* __restrict__ skipped_count) {
+  // guard: an iteration whose views overflowed their pair buffers leaves the parameters and moments untouched
+  if (skip_flag != nullptr && *skip_flag != 0.0f) {
+    if (skipped_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(skipped_count, 1);
+    return;
+  }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
     float pi = p[i], gi = g[i];
@@ -105,7 +111,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,
                 float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
-                float reg_op, cudaStream_t st) {
+                float reg_op, const float* skip_flag, int* skipped_count, cudaStream_t st) {
   if (count <= 0) return B2S_OK;
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
@@ -117,7 +123,7 @@ int launch_adam(float* params, const float* grads, float* m, float* v, int64_t c
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   adam_kernel<<<(int)blocks, 256, 0, st>>>(params, grads, m, v, (long long)count, b1, b2, eps, step_size,
                                             inv_sqrt_bc2, (long long)sb, (long long)se, rs, (long long)ob,
-                                            (long long)oe, ro);
+                                            (long long)oe, ro, skip_flag, skipped_count);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

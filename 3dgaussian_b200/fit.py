@@ -4,13 +4,20 @@ python/fit_multiview_stub.py:265-311 without the per-view Python autograd graph)
 One FitDriver per process / GPU.  Parameters, gradients and Adam state are flat fp32
 buffers laid out [means 3N | scales_raw 3N | opacities_raw N | colours C*N]; activations
 (softplus+1e-3, sigmoid; fit_multiview_stub.py:268-275) are applied inside the preprocess
-kernels, the per-view loss (mean|pred-tgt| + w_sil*mean|alpha-mask|, :292-297) and the Adam
-step with the regulariser gradients (:307-311) are fused kernels of libb2splat.
+kernels, the per-view loss (mean|pred-tgt| + w_sil*mean|alpha-mask| + w_depth*mean|depth/max-d_gt|,
+:292-303) and the Adam step with the regulariser gradients (:307-311) are fused kernels of libb2splat.
 
 Multi-GPU (torch.distributed, NCCL): parameters are replicated, view i belongs to rank
 i % world; every rank accumulates the gradients of its views into the flat buffer, ONE
-all-reduce (sum) combines them, then every rank runs the identical Adam step, so the
-replicas stay bit-identical without a broadcast.
+all-reduce (sum) combines them -- the iteration's loss and its pair-buffer overflow count ride in
+the tail of the same buffer -- then every rank runs the identical Adam step, so the replicas
+stay bit-identical without a broadcast.
+
+Overflow safety: the pair buffers are sized from the parameters at plan() time; Gaussians grow
+during a fit.  A view that overflows renders nothing, so its iteration must not reach the
+parameters: the Adam kernel is guarded on the device by the (all-reduced) overflow count
+(b2s_adam_step_guarded), and the host polls a device counter of skipped steps every
+`overflow_check_every` steps, re-plans the buffers and repeats the skipped iterations.
 """
 from __future__ import annotations
 
@@ -32,14 +39,24 @@ class FitDriver:
     def __init__(self, n: int, sh_coeffs: int, width: int, height: int,
                  cameras: Sequence[Tuple[Sequence[float], Sequence[float]]], device: torch.device,
                  lr: float = 0.02, silhouette_weight: float = 0.2, reg_opacity: float = 1e-3,
-                 reg_scale: float = 1e-3, cutoff_sigma: float = 5.0, background=(0.0, 0.0, 0.0),
+                 reg_scale: float = 1e-3, cutoff_sigma: Optional[float] = None, background=(0.0, 0.0, 0.0),
                  rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
                  fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30,
-                 view_groups: int = 1):
+                 view_groups: int = 1, use_depth: bool = False, depth_weight: float = 0.05,
+                 overflow_check_every: int = 8):
+        """use_depth: the fit carries the reference's depth term (fit_multiview_stub.py:298-303, weight
+        `depth_weight`): the forward keeps the depth plane and the cutoff defaults to 7 sigma instead of 5, because
+        depth = D/(W+1e-6) and its gradient amplify the truncated tails."""
         if device.type != "cuda":
             raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
         self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
         self.dev = device
+        self.use_depth, self.w_depth = bool(use_depth), float(depth_weight)
+        if cutoff_sigma is None:
+            cutoff_sigma = 7.0 if self.use_depth else 5.0
+        if self.use_depth and not fused_loss:
+            raise ValueError("the depth term is part of the fused loss path (fused_loss=True)")
+        self.overflow_check_every = max(1, int(overflow_check_every))
         self.lr, self.w_sil = float(lr), float(silhouette_weight)
         self.reg_op, self.reg_scale = float(reg_opacity), float(reg_scale)
         self.rank, self.world, self.pg = rank, world, process_group
@@ -49,10 +66,12 @@ class FitDriver:
         self.params_c = {i: capi.make_params(width, height, cameras[i][0], cameras[i][1], background,
                                              mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
                                              cutoff_sigma=cutoff_sigma, sh_coeffs=self.sh, sort_depth=0,
-                                             act_flags=act) for i in self.views}
+                                             act_flags=act, keep_depth=1 if self.use_depth else 0) for i in self.views}
         self._layout(self.n)
         self.step_no = 0
-        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=device)
+        self.skipped_dev = torch.zeros(1, dtype=torch.int32, device=device)   # Adam steps the device guard skipped
+        self._since_check = 0
+        self._overflowed = False
         # View lanes: lane l owns its own per-view buffers (images, image gradients, state, workspace, loss and
         # overflow accumulators) and a CUDA stream; view k of this rank runs on lane k % lanes, so the small
         # latency-bound kernels of one view (scans, finalize, loss, g-buffer) overlap the blend kernels of another.
@@ -67,8 +86,9 @@ class FitDriver:
         self.alpha_l = [torch.empty((height, width), dtype=torch.float32, device=device) for _ in range(self.lanes)]
         self.g_rgb_l = [torch.empty_like(t) for t in self.rgb_l]
         self.g_alpha_l = [torch.empty_like(t) for t in self.alpha_l]
-        self.loss_l = [torch.zeros(1, dtype=torch.float32, device=device) for _ in range(self.lanes)]
-        self.overflow_l = [torch.zeros(1, dtype=torch.int32, device=device) for _ in range(self.lanes)]
+        # per lane {loss sum, overflow count} of the current iteration; summed into the gradient buffer's tail
+        self.lane_acc = torch.zeros((self.lanes, 2), dtype=torch.float32, device=device)
+        self.loss_l = [self.lane_acc[l, 0:1] for l in range(self.lanes)]
         self.rgb, self.alpha = self.rgb_l[0], self.alpha_l[0]
         self.pair_slack = pair_slack
         self.max_pairs = 0
@@ -77,6 +97,7 @@ class FitDriver:
         self._lane_streams = None
         self.targets: dict = {}
         self.masks: dict = {}
+        self.depths: dict = {}
         # per-view constant blocks for the multi-view chain rule, uploaded once (cameras are fixed)
         L = capi.lib()
         vb = L.b2s_view_block_bytes()
@@ -92,7 +113,9 @@ class FitDriver:
 
     def _layout(self, n: int):
         """Flat fp32 layout [means 3n | scales_raw 3n | opacities_raw n | colours 3K n]; segment starts are
-        padded to 64 floats (256 B): the kernels read colours with 16-byte loads."""
+        padded to 64 floats (256 B): the kernels read colours with 16-byte loads.  The gradient buffer carries a
+        64-float tail behind the parameters' gradients: [0] = this iteration's loss (sum_i loss_i / V), [1] = its
+        pair-buffer overflow count -- one all-reduce moves gradients, loss and the Adam guard together."""
         self.n = int(n)
         c = 3 * self.sh
         al = lambda x: (x + 63) // 64 * 64
@@ -101,8 +124,10 @@ class FitDriver:
         self.o_opac = self.o_scales + al(3 * n)
         self.o_colors = self.o_opac + al(n)
         self.count = self.o_colors + al(c * n)
-        z = lambda: torch.zeros(self.count, dtype=torch.float32, device=self.dev)
-        self.p, self.g, self.m, self.v = z(), z(), z(), z()
+        z = lambda extra=0: torch.zeros(self.count + extra, dtype=torch.float32, device=self.dev)
+        self.p, self.g, self.m, self.v = z(), z(64), z(), z()
+        self.tail = self.g[self.count:self.count + 64]
+        self.loss_dev = self.tail[0:1]
 
     # ---- parameter views -------------------------------------------------------------------
     def _seg(self, buf, off, numel): return buf[off:off + numel]
@@ -164,7 +189,7 @@ class FitDriver:
     # ---- capacity ----------------------------------------------------------------------------
     def plan(self, extra_slack: float = 1.0):
         """Sizes the pair buffers from the current parameters (one count pass per local view;
-        synchronises).  Called once up front and again if a step reports an overflow."""
+        synchronises).  Called once up front and again when the device guard reports an overflow."""
         worst = 0
         with torch.cuda.device(self.dev):
             sc = torch.nn.functional.softplus(self.scales_raw()) + 1e-3
@@ -177,41 +202,55 @@ class FitDriver:
             L = capi.lib()
             self.state_bytes = L.b2s_state_bytes(self.n, self.W, self.H, self.max_pairs)
             self.ws_bytes = L.b2s_workspace_bytes(self.n, self.W, self.H, self.max_pairs)
+            self.state = self.ws = self.state_l = self.ws_l = self.prepared = None      # release before re-allocating
             self.state_l = [torch.empty(self.state_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
             self.ws_l = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev) for _ in range(self.lanes)]
             self._counters_l = [st[:16].view(torch.int32) for st in self.state_l]   # needed(lo,hi), kept, overflow
             self.state, self.ws = self.state_l[0], self.ws_l[0]
-            # batched preprocess: one block per local view (b2s_preprocess_views), if it fits the budget
-            self.prepared = None
+            # batched preprocess: one block per local view (b2s_preprocess_views), if it fits the budget and the
+            # image has few enough tiles for the counting-sort path the prepared views feed (bin.cu: the tile scan
+            # stages 8 B per tile in 200 KB of shared memory); larger images take the per-view radix path
             self.pv_bytes = int(L.b2s_prepared_view_bytes(self.n))
-            if self.batched_preprocess and self.views and self.pv_bytes * len(self.views) <= self.prepared_budget:
+            n_tiles = ((self.W + capi.TILE - 1) // capi.TILE) * ((self.H + capi.TILE - 1) // capi.TILE)
+            if (self.batched_preprocess and self.views and n_tiles * 8 <= 200 * 1024 and
+                    self.pv_bytes * len(self.views) <= self.prepared_budget):
                 self.prepared = torch.empty(self.pv_bytes * len(self.views), dtype=torch.uint8, device=self.dev)
         return worst
 
     # ---- targets -------------------------------------------------------------------------------
-    def set_targets(self, targets: dict, masks: Optional[dict] = None):
-        """Device-resident targets {view index: (H,W,3) float32} (+ masks {(H,W)})."""
-        self.targets, self.masks = dict(targets), dict(masks or {})
+    def set_targets(self, targets: dict, masks: Optional[dict] = None, depths: Optional[dict] = None):
+        """Device-resident targets {view index: (H,W,3) float32} (+ masks {(H,W)}, + normalised depth maps {(H,W)}:
+        the d_gt of fit_multiview_stub.py:298-303, used when the driver was built with use_depth=True)."""
+        if depths and not self.use_depth:
+            raise ValueError("depth maps given to a FitDriver built without use_depth=True (the forward would not keep "
+                             "the depth plane); construct it with use_depth=True")
+        self.targets, self.masks, self.depths = dict(targets), dict(masks or {}), dict(depths or {})
 
     def render_view(self, i: int, out_rgb=None, out_alpha=None):
-        """Forward only (used to synthesise targets)."""
+        """Forward only (used to synthesise targets).  Re-plans and renders again if the view overflowed."""
         if self.state is None:
             self.plan()
         out_rgb = self.rgb if out_rgb is None else out_rgb
         out_alpha = self.alpha if out_alpha is None else out_alpha
         with torch.cuda.device(self.dev):
-            capi.check(capi.lib().b2s_forward(
-                capi.ctx(self.dev.index), C.byref(self.params_c[i]), self._pp(self.o_means), self._pp(self.o_scales),
-                self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, _ptr(out_rgb), _ptr(out_alpha),
-                None, _ptr(self.state), self.state_bytes, _ptr(self.ws), self.ws_bytes, _stream()))
+            for attempt in range(3):
+                capi.check(capi.lib().b2s_forward(
+                    capi.ctx(self.dev.index), C.byref(self.params_c[i]), self._pp(self.o_means), self._pp(self.o_scales),
+                    self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, _ptr(out_rgb), _ptr(out_alpha),
+                    None, _ptr(self.state), self.state_bytes, _ptr(self.ws), self.ws_bytes, _stream()))
+                if not capi.ticket_info(self.dev.index)[2]:
+                    break
+                self.plan(extra_slack=1.5 * (attempt + 1))
+            else:
+                raise capi.B2SError("render_view: pair buffers overflowed repeatedly")
         return out_rgb, out_alpha
 
     # ---- one fit iteration -------------------------------------------------------------------
     def _view_fwd_bwd(self, slot: int, i: int, tgt: torch.Tensor, mask: Optional[torch.Tensor], lane: int = 0,
-                      ready: Optional[torch.cuda.Event] = None):
+                      ready: Optional[torch.cuda.Event] = None, depth: Optional[torch.Tensor] = None):
         """forward + loss + blend backward of view i on the CURRENT stream with lane `lane`'s buffers.  `ready`: event
-        after which tgt / mask hold this view's data (host-fed steps): only the loss needs them, so the stream waits
-        for it between the forward and the backward, not in front of the forward."""
+        after which tgt / mask / depth hold this view's data (host-fed steps): only the loss needs them, so the stream
+        waits for it between the forward and the backward, not in front of the forward."""
         L, ctx, st = capi.lib(), capi.ctx(self.dev.index), _stream()
         pc = C.byref(self.params_c[i])
         rgb, alpha, g_rgb, g_alpha = self.rgb_l[lane], self.alpha_l[lane], self.g_rgb_l[lane], self.g_alpha_l[lane]
@@ -227,10 +266,12 @@ class FitDriver:
                 capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales),
                                          self._pp(self.o_colors), self._pp(self.o_opac), self.n, self.max_pairs, None,
                                          None, None, _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
-            self.overflow_l[lane] += self._counters_l[lane][3]
+            self.lane_acc[lane, 1] += self._counters_l[lane][3]
             if ready is not None:
                 torch.cuda.current_stream().wait_event(ready)
-            capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask), self.w_sil,
+            capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask),
+                                                _ptr(depth) if self.use_depth else None, self.w_sil,
+                                                self.w_depth if (self.use_depth and depth is not None) else 0.0,
                                                 1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), pv,
                                                 _ptr(ws), self.ws_bytes, _ptr(self.gacc[slot]), st))
             return
@@ -239,7 +280,7 @@ class FitDriver:
         capi.check(L.b2s_forward(ctx, pc, self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors),
                                  self._pp(self.o_opac), self.n, self.max_pairs, _ptr(rgb), _ptr(alpha), None,
                                  _ptr(state), self.state_bytes, _ptr(ws), self.ws_bytes, st))
-        self.overflow_l[lane] += self._counters_l[lane][3]
+        self.lane_acc[lane, 1] += self._counters_l[lane][3]
         capi.check(L.b2s_fit_loss(ctx, _ptr(rgb), _ptr(alpha), _ptr(tgt), _ptr(mask), self.W, self.H,
                                   self.w_sil, 1.0 / self.num_views, _ptr(g_rgb),
                                   _ptr(g_alpha) if mask is not None else None, _ptr(self.loss_l[lane]), st))
@@ -275,7 +316,7 @@ class FitDriver:
 
     def _iterate(self, inputs):
         """One pass over this rank's views: forward + loss + blend backward per view, chain rule, on `lanes`
-        concurrent streams.  inputs(k, stream) -> (target, mask, done_callback[, ready_event]) for local view k.
+        concurrent streams.  inputs(k, stream) -> dict(tgt=, mask=, depth=, done=callback, ready=event) for local view k.
 
         With several lanes the views are cut into `view_groups` groups and pipelined: the caller's stream runs the
         batched preprocess of every group (group g+1's while the lanes blend group g), the lanes wait for their
@@ -285,97 +326,125 @@ class FitDriver:
         main = torch.cuda.current_stream()
         nv = len(self.views)
         nl = max(1, min(self.active_lanes, self.lanes))
-        for t in self.loss_l:
-            t.zero_()
+        self.lane_acc.zero_()
         if nv == 0:
             self.g.zero_()
-            self.loss_dev.zero_()
             return
+
+        def one_view(k, lane, stream):
+            q = inputs(k, stream)
+            self._view_fwd_bwd(k, self.views[k], q["tgt"], q.get("mask"), lane, q.get("ready"), q.get("depth"))
+            if q.get("done") is not None:
+                q["done"](stream)
+
         if nl == 1:
             self._preprocess_views(0, nv)
             for k in range(nv):
-                tgt, mask, done, *rest = inputs(k, main)
-                self._view_fwd_bwd(k, self.views[k], tgt, mask, 0, rest[0] if rest else None)
-                if done is not None:
-                    done(main)
-            self.loss_dev.copy_(self.loss_l[0])
+                one_view(k, 0, main)
             self._chain_rule(0, nv, False)
-            return
-        streams = self._streams()
-        tail = self._tail_stream
-        self._step_begin.record(main)
-        for st in streams + [tail]:
-            st.wait_event(self._step_begin)       # after everything queued on the caller's stream (the last Adam)
-        G = max(1, min(self.view_groups, nv // nl))
-        bounds = [(g * nv) // G for g in range(G + 1)]
-        pre_ev = []
-        for g in range(G):                         # every group's preprocess is queued up front on the caller's stream
-            self._preprocess_views(bounds[g], bounds[g + 1])
-            ev = torch.cuda.Event()
-            ev.record(main)
-            pre_ev.append(ev)
-        for g in range(G):
-            a, b = bounds[g], bounds[g + 1]
-            used = sorted({k % nl for k in range(a, b)})
-            for l in used:
-                streams[l].wait_event(pre_ev[g])
-            for k in range(a, b):
-                lane = k % nl
-                with torch.cuda.stream(streams[lane]):
-                    tgt, mask, done, *rest = inputs(k, streams[lane])
-                    self._view_fwd_bwd(k, self.views[k], tgt, mask, lane, rest[0] if rest else None)
-                    if done is not None:
-                        done(streams[lane])
-            for l in used:
+        else:
+            streams = self._streams()
+            tail = self._tail_stream
+            self._step_begin.record(main)
+            for st in streams + [tail]:
+                st.wait_event(self._step_begin)       # after everything queued on the caller's stream (the last Adam)
+            G = max(1, min(self.view_groups, nv // nl))
+            bounds = [(g * nv) // G for g in range(G + 1)]
+            pre_ev = []
+            for g in range(G):                         # every group's preprocess is queued up front on the caller's stream
+                self._preprocess_views(bounds[g], bounds[g + 1])
                 ev = torch.cuda.Event()
-                ev.record(streams[l])
-                tail.wait_event(ev)
-            with torch.cuda.stream(tail):
-                self._chain_rule(a, b, g > 0)
-        self._tail_done.record(tail)
-        main.wait_event(self._tail_done)           # the tail has waited for every lane
-        self.loss_dev.copy_(self.loss_l[0])        # fixed order: deterministic
-        for t in self.loss_l[1:nl]:
-            self.loss_dev += t
+                ev.record(main)
+                pre_ev.append(ev)
+            for g in range(G):
+                a, b = bounds[g], bounds[g + 1]
+                used = sorted({k % nl for k in range(a, b)})
+                for l in used:
+                    streams[l].wait_event(pre_ev[g])
+                for k in range(a, b):
+                    lane = k % nl
+                    with torch.cuda.stream(streams[lane]):
+                        one_view(k, lane, streams[lane])
+                for l in used:
+                    ev = torch.cuda.Event()
+                    ev.record(streams[l])
+                    tail.wait_event(ev)
+                with torch.cuda.stream(tail):
+                    self._chain_rule(a, b, g > 0)
+            self._tail_done.record(tail)
+            main.wait_event(self._tail_done)           # the tail has waited for every lane
+        # loss and overflow count of this rank's views into the gradient buffer's tail (fixed order: deterministic)
+        torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
 
     def _finish_step(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.g, group=self.pg)
-            torch.distributed.all_reduce(self.loss_dev, group=self.pg)
+            torch.distributed.all_reduce(self.g, group=self.pg)     # gradients + loss + overflow count: ONE collective
         self.step_no += 1
-        capi.check(capi.lib().b2s_adam_step(
+        capi.check(capi.lib().b2s_adam_step_guarded(
             capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
             self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_scales + 3 * self.n, self.reg_scale, self.o_opac,
-            self.o_opac + self.n, self.reg_op, _stream()))
+            self.o_opac + self.n, self.reg_op, C.c_void_p(self.tail.data_ptr() + 4), _ptr(self.skipped_dev), _stream()))
+
+    def _device_inputs(self, k, stream):
+        i = self.views[k]
+        return {"tgt": self.targets[i], "mask": self.masks.get(i), "depth": self.depths.get(i)}
+
+    def _resolve_overflow(self) -> int:
+        """Reads the device counter of Adam steps the overflow guard skipped (synchronises).  If there were any, every
+        step since the first one was skipped too (unchanged parameters overflow again), so the host step count is
+        rolled back, the pair buffers are re-planned from the current parameters with more slack, and the skipped
+        iterations are repeated.  Returns the number of iterations that had to be repeated."""
+        self._since_check = 0
+        k = int(self.skipped_dev.item())
+        if k == 0:
+            return 0
+        self._overflowed = True
+        self.skipped_dev.zero_()
+        self.step_no -= k
+        self.plan(extra_slack=1.5)
+        for _ in range(k):
+            self._iterate(self._device_inputs)
+            self._finish_step()
+        if int(self.skipped_dev.item()) != 0:
+            raise capi.B2SError("pair buffers overflowed again right after re-planning")
+        return k
 
     def step(self):
         """fwd + bwd over this rank's views (device-resident targets) + all-reduce + Adam.
-        Returns the device scalar holding sum_i loss_i / V (without the regulariser)."""
+        Returns the device scalar holding sum_i loss_i / V (without the regulariser).  No host synchronisation,
+        except every `overflow_check_every` steps to poll the overflow guard (see the module docstring)."""
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            self._iterate(lambda k, st: (self.targets[self.views[k]], self.masks.get(self.views[k]), None))
+            self._iterate(self._device_inputs)
             self._finish_step()
+            self._since_check += 1
+            if self._since_check >= self.overflow_check_every:
+                self._resolve_overflow()
         return self.loss_dev
 
-    def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None) -> float:
-        """Same iteration fed from PINNED HOST buffers: every view's target (and mask) is copied
+    def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None,
+                       host_depths: Optional[dict] = None) -> float:
+        """Same iteration fed from PINNED HOST buffers: every view's target (and mask, and depth map) is copied
         host->device inside the step (two staging slots per lane on a side stream, so the copy of a later
         view overlaps the kernels of the current ones) and the loss is read back to the host at the end.
-        Targets / masks may be float32 in [0,1] or uint8 (decoded image bytes, converted on the device)."""
+        Targets / masks / depth maps may be float32 in [0,1] or uint8 (decoded image bytes, converted on the device)."""
         if self.state is None:
             self.plan()
+        if host_depths is not None and not self.use_depth:
+            raise ValueError("depth maps given to a FitDriver built without use_depth=True")
         with torch.cuda.device(self.dev):
             nslots = 2 * self.lanes
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.dev)
-                self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha)) for _ in range(nslots)]
+                self._stage = [(torch.empty_like(self.rgb), torch.empty_like(self.alpha), torch.empty_like(self.alpha))
+                               for _ in range(nslots)]
                 self._ev_ready = [torch.cuda.Event() for _ in range(nslots)]
                 self._ev_free = [torch.cuda.Event() for _ in range(nslots)]
                 self._stage_u8 = {}
             use_mask = host_masks is not None
+            use_depth = host_depths is not None
             nv = len(self.views)
-            issued = [0]
 
             def upload(dst, src, slot, which):
                 """host -> stage; 8-bit images cross PCIe as bytes and are converted on the device
@@ -391,30 +460,45 @@ class FitDriver:
                 else:
                     dst.copy_(src, non_blocking=True)
 
-            def issue_upto(k_hi):
-                # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
-                while issued[0] < min(k_hi, nv):
-                    k = issued[0]
+            for attempt in range(3):
+                issued = [0]
+
+                def issue_upto(k_hi):
+                    # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
+                    while issued[0] < min(k_hi, nv):
+                        k = issued[0]
+                        slot = k % nslots
+                        i = self.views[k]
+                        with torch.cuda.stream(self._copy_stream):
+                            if k >= nslots or attempt > 0:
+                                self._copy_stream.wait_event(self._ev_free[slot])
+                            upload(self._stage[slot][0], host_targets[i], slot, 0)
+                            if use_mask:
+                                upload(self._stage[slot][1], host_masks[i], slot, 1)
+                            if use_depth:
+                                upload(self._stage[slot][2], host_depths[i], slot, 2)
+                            self._ev_ready[slot].record(self._copy_stream)
+                        issued[0] += 1
+
+                def inputs(k, st):
+                    issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
                     slot = k % nslots
-                    i = self.views[k]
-                    with torch.cuda.stream(self._copy_stream):
-                        if k >= nslots:
-                            self._copy_stream.wait_event(self._ev_free[slot])
-                        upload(self._stage[slot][0], host_targets[i], slot, 0)
-                        if use_mask:
-                            upload(self._stage[slot][1], host_masks[i], slot, 1)
-                        self._ev_ready[slot].record(self._copy_stream)
-                    issued[0] += 1
+                    return {"tgt": self._stage[slot][0], "mask": self._stage[slot][1] if use_mask else None,
+                            "depth": self._stage[slot][2] if use_depth else None,
+                            "done": lambda s, slot=slot: self._ev_free[slot].record(s), "ready": self._ev_ready[slot]}
 
-            def inputs(k, st):
-                issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
-                slot = k % nslots
-                return (self._stage[slot][0], self._stage[slot][1] if use_mask else None,
-                        lambda s, slot=slot: self._ev_free[slot].record(s), self._ev_ready[slot])
-
-            self._iterate(inputs)
-            self._finish_step()
-            return float(self.loss_dev.item())
+                self._iterate(inputs)
+                self._finish_step()
+                loss, overflow = self.tail[0:2].tolist()     # the step's one device->host read: loss + overflow guard
+                if overflow == 0.0:
+                    self._since_check = 0
+                    return float(loss)
+                # the guard skipped this Adam step: re-plan with more room and run the iteration again
+                self._overflowed = True
+                self.skipped_dev.zero_()
+                self.step_no -= 1
+                self.plan(extra_slack=1.5 * (attempt + 1))
+            raise capi.B2SError("pair buffers overflowed repeatedly")
 
     # ---- densify / prune ----------------------------------------------------------------------
     def densify_prune(self, iteration: int, max_gaussians: int, densify_ratio: float = 0.15,
@@ -497,8 +581,10 @@ class FitDriver:
             self.plan()
 
     def check_overflow(self) -> bool:
-        """True if any view since the last call needed more pairs than the buffers hold."""
-        v = sum(int(t.item()) for t in self.overflow_l)
-        for t in self.overflow_l:
-            t.zero_()
-        return v != 0
+        """True if any iteration since the last call overflowed its pair buffers.  Such iterations never reached the
+        parameters (device guard); by the time this returns they have been repeated with re-planned buffers.
+        Synchronises."""
+        with torch.cuda.device(self.dev):
+            self._resolve_overflow()
+        v, self._overflowed = self._overflowed, False
+        return v

@@ -76,6 +76,9 @@ typedef struct b2s_params {
   const float* background_dev; /* optional DEVICE pointer to 3 floats; when non-NULL it overrides background[] (the
                                 * reference's callers pass the background as a device tensor,
                                 * python/fit_multiview_stub.py:287: reading it back would cost a stream sync per view) */
+  int32_t keep_depth;          /* 1: b2s_forward accumulates the depth plane into `state` even when out_depth is NULL
+                                * (the fit loop's depth loss reads it from there) */
+  int32_t reserved_;
 } b2s_params;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -129,12 +132,15 @@ int b2s_pack_views(const b2s_params* params, int num_views, void* out_host);
 int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* g_rgb,
                        const float* g_alpha, const float* g_depth, const void* state, void* workspace,
                        size_t ws_bytes, float* gacc_out, void* stream);
-/* b2s_fit_loss + b2s_backward_blend in one call (python/fit_multiview_stub.py:292-297 and its backward): the
- * per-view loss  mean|rgb-tgt| + w_sil*mean|alpha-mask|  is evaluated from the accumulators b2s_forward left
- * in `state` and its image gradients, scaled by `scale` (1/V), go straight into the blend backward; no
- * rgb / alpha / gradient images are read or written.  mask may be NULL.  Adds scale*loss to *loss_accum. */
+/* b2s_fit_loss + b2s_backward_blend in one call (python/fit_multiview_stub.py:292-303 and its backward): the
+ * per-view loss  mean|rgb-tgt| + w_sil*mean|alpha-mask| + w_depth*mean|depth/(max depth + 1e-6) - depth_gt|  is
+ * evaluated from the accumulators b2s_forward left in `state` and its image gradients, scaled by `scale` (1/V), go
+ * straight into the blend backward; no rgb / alpha / depth / gradient images are read or written.  mask and
+ * depth_gt may be NULL (term absent); the depth term needs a forward run with params.keep_depth = 1 (and a cutoff of
+ * 7 sigma).  Adds scale*loss to *loss_accum. */
 int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
-                           const float* mask, float w_sil, float scale, float* loss_accum, const void* state,
+                           const float* mask, const float* depth_gt, float w_sil, float w_depth, float scale,
+                           float* loss_accum, const void* state,
                            const void* prepared_view /* NULL unless the forward was b2s_forward_prepared */,
                            void* workspace, size_t ws_bytes, float* gacc_out, void* stream);
 
@@ -209,6 +215,16 @@ int b2s_adam_step(b2s_ctx* ctx, float* params, const float* grads, float* m, flo
                   int step, float lr, float beta1, float beta2, float eps, int64_t scales_begin,
                   int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
                   float reg_opacity, void* stream);
+
+/* The same step, guarded on the device: if *skip_flag != 0 (a float the caller's kernels / collective left on the
+ * device, e.g. the summed pair-buffer overflow count of the iteration's views) NOTHING is updated and
+ * *skipped_count is incremented instead -- an iteration whose views overflowed must not reach the parameters, and the
+ * host need not synchronise every step to guarantee it (FitDriver polls skipped_count now and then, re-plans the
+ * buffers and repeats the skipped iterations).  skip_flag / skipped_count may be NULL (= b2s_adam_step). */
+int b2s_adam_step_guarded(b2s_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t count,
+                          int step, float lr, float beta1, float beta2, float eps, int64_t scales_begin,
+                          int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
+                          float reg_opacity, const float* skip_flag, int* skipped_count, void* stream);
 
 /* Densify / prune (python/fit_multiview_stub.py:140-197): keep sigmoid(op_raw) > prune_opacity (or the
  * 64 most opaque if fewer survive), order preserved; then append min(max_gaussians - n1, int(n1 *

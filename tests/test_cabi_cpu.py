@@ -38,7 +38,7 @@ def test_param_block_layout():
     assert capi.Params.width.offset == 0 and capi.Params.height.offset == 4
     assert capi.Params.view.offset == 8 and capi.Params.proj.offset == 72
     assert capi.Params.background.offset == 136 and capi.Params.enable_depth_sort.offset == 148
-    assert capi.Params.background_dev.offset == 184 and C.sizeof(capi.Params) == 192    # extension tail
+    assert capi.Params.background_dev.offset == 184 and C.sizeof(capi.Params) == 200    # extension tail
 
 
 def test_no_gpu_fails_loudly(built):

@@ -355,3 +355,111 @@ def test_tcgen05_blend_matches_mma_sync_at_full_hd(tmp_path):
     a, b = outs
     assert abs(float(a["loss"]) - float(b["loss"])) <= 5e-6 * max(1.0, abs(float(b["loss"])))
     assert rel_l2(a["g"], b["g"]) <= 1e-3          # the gradient bar of north_star, between two kernel families
+
+
+# ---------------------------------------------------------------- depth term + overflow guard ----
+def _oracle_loss_depth(S, leaves, dt, w_depth=0.05):
+    """_oracle_loss with the reference's depth term (fit_multiview_stub.py:298-303) on top."""
+    t = lambda a: torch.from_numpy(a).to(dt)
+    m, sr, orr, cr = leaves
+    sc = torch.nn.functional.softplus(sr) + 1e-3
+    op = torch.sigmoid(orr)
+    col = torch.sigmoid(cr) if S["sh"] == 1 else cr
+    total = torch.zeros((), dtype=dt)
+    for i in range(S["V"]):
+        rgb, alpha, depth = r1.render_r1(m, sc, col, op, t(S["cams"][i][0]), t(S["cams"][i][1]), S["W"], S["H"])
+        total = total + r1.fit_loss(rgb, alpha, depth, t(S["tgts"][i]), t(S["masks"][i]), t(S["depths"][i]),
+                                    silhouette_weight=0.2, depth_weight=w_depth)
+    return total / S["V"]
+
+
+@pytest.mark.parametrize("sh,lanes", [(1, 1), (4, 2), (16, 1)])
+def test_fit_step_with_depth_term_matches_oracle(sh, lanes):
+    """FitDriver(use_depth=True): 5-plane tcgen05 forward (depth plane kept in the accumulators), the per-view depth
+    statistics (max, arg-max count, signed sum), the depth term fused into the g-buffer kernel and the depth-gradient
+    tcgen05 backward -- loss and all four gradients against autograd of the R1 oracle in float64."""
+    capi = pkg("capi")
+    S = _setup(sh, n=260, V=3, W=48, H=32, seed=9)
+    rng = np.random.RandomState(21)
+    S["depths"] = [rng.rand(S["H"], S["W"]).astype(np.float32) for _ in range(S["V"])]
+    before = capi.path_counts()
+    d = _driver(S, use_depth=True, lanes=lanes)
+    t = lambda a: torch.from_numpy(a).to(dev())
+    d.set_targets({i: t(S["tgts"][i]) for i in d.views}, {i: t(S["masks"][i]) for i in d.views},
+                  {i: t(S["depths"][i]) for i in d.views})
+    loss_dev = d.step()
+    assert not d.check_overflow()
+    after = capi.path_counts()
+    assert after["fwd_tcgen05"] - before["fwd_tcgen05"] >= S["V"] and after["bwd_tcgen05"] - before["bwd_tcgen05"] >= S["V"]
+    assert after["fwd_other"] == before["fwd_other"] and after["bwd_other"] == before["bwd_other"]
+    dt = torch.float64
+    leaves = [torch.from_numpy(S[k]).to(dt).requires_grad_(True) for k in ("means", "scales_raw", "op_raw", "col_raw")]
+    data = _oracle_loss_depth(S, leaves, dt)
+    data.backward()
+    ref_g = torch.cat([l.grad.reshape(-1) for l in leaves]).numpy()
+    assert abs(float(loss_dev.item()) - float(data)) <= 2e-5
+    n = S["n"]
+    got = [v.cpu().numpy() for v in d.grad_views()]
+    rels = {}
+    for name, gv, (a, b) in zip(("means", "scales", "opac", "colors"), got,
+                                ((0, 3 * n), (3 * n, 6 * n), (6 * n, 7 * n), (7 * n, None))):
+        rels[name] = rel_l2(gv, ref_g[a:b])
+    from conftest import report
+    report("fit_step_depth_term", sh=sh, lanes=lanes, loss=float(loss_dev.item()), loss_oracle=float(data), **rels)
+    for name, v in rels.items():
+        assert v <= 1e-3, (name, v)
+
+
+def test_step_from_host_with_depth_maps_equals_device_step():
+    S = _setup(4, n=150, V=3, W=40, H=32)
+    rng = np.random.RandomState(2)
+    S["depths"] = [rng.rand(S["H"], S["W"]).astype(np.float32) for _ in range(S["V"])]
+    t = lambda a: torch.from_numpy(a).to(dev())
+    d1, d2 = _driver(S, use_depth=True), _driver(S, use_depth=True, lanes=2)
+    d1.set_targets({i: t(S["tgts"][i]) for i in d1.views}, {i: t(S["masks"][i]) for i in d1.views},
+                   {i: t(S["depths"][i]) for i in d1.views})
+    host = lambda key: {i: torch.from_numpy(S[key][i]).pin_memory() for i in range(S["V"])}
+    for _ in range(3):
+        l1 = float(d1.step().item())
+        l2 = d2.step_from_host(host("tgts"), host("masks"), host("depths"))
+        assert abs(l1 - l2) <= 2e-6
+    assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
+    with pytest.raises(ValueError):
+        _driver(S).set_targets({}, {}, {0: t(S["depths"][0])})      # depth maps need use_depth=True
+
+
+def test_overflowing_iteration_never_reaches_the_parameters():
+    """Pair buffers sized for small Gaussians, then the scales are blown up: the views overflow, the device guard
+    skips Adam (parameters and moments untouched), the driver re-plans and repeats the iteration."""
+    S = _setup(1, n=400, V=2, W=64, H=48)
+    d = _driver(S, overflow_check_every=1000)          # poll only when asked
+    d.step()
+    assert not d.check_overflow()
+    with torch.no_grad():
+        d.scales_raw().add_(3.0)                       # sigma x ~20: far more (Gaussian,tile) pairs than planned
+    p_before, m_before, step_before = d.p.clone(), d.m.clone(), d.step_no
+    d.step()
+    torch.cuda.synchronize()
+    assert int(d.skipped_dev.item()) == 1
+    assert torch.equal(d.p, p_before) and torch.equal(d.m, m_before)      # the guard held
+    assert d.check_overflow()                          # re-planned, iteration repeated
+    assert d.step_no == step_before + 1 and not torch.equal(d.p, p_before)
+    # the repeated step equals a step of a driver planned for the big Gaussians from the start
+    S2 = dict(S)
+    S2["scales_raw"] = S["scales_raw"].copy()
+    d_ref = _driver(S2)
+    d_ref.step()
+    with torch.no_grad():
+        d_ref.scales_raw().add_(3.0)
+    d_ref.plan()
+    d_ref.step()
+    assert not d_ref.check_overflow()
+    assert rel_l2(d.p.cpu().numpy(), d_ref.p.cpu().numpy()) <= 1e-4
+    # host-fed steps check the guard every step
+    with torch.no_grad():
+        d.scales_raw().add_(1.5)
+    host_t = {i: torch.from_numpy(S["tgts"][i]).pin_memory() for i in range(S["V"])}
+    host_m = {i: torch.from_numpy(S["masks"][i]).pin_memory() for i in range(S["V"])}
+    n_before = d.step_no
+    d.step_from_host(host_t, host_m)
+    assert d.step_no == n_before + 1 and int(d.skipped_dev.item()) == 0

@@ -167,3 +167,40 @@ def test_crop_oracle_at_benchmark_scale():
     assert e_depth <= 1e-4, (e_depth, e_depth_all)
     for k, v in rels.items():
         assert v <= GRAD_TOL, (k, v)
+
+
+@pytest.mark.parametrize("sh", [1, 16])
+def test_tcgen05_depth_plane_and_depth_gradient_match_oracle_on_multi_unit_tiles(sh):
+    """return_aux=True with a loss on rgb + alpha + depth: 5-plane tcgen05 forward (depth rides on the B operand),
+    depth-gradient tcgen05 backward (gD plane in a second TMEM region); k = 7."""
+    r, capi = pkg("renderer"), pkg("capi")
+    n, W, H = 3000, 64, 48
+    means, scales, colors, opac = scenes.make_scene(320 + sh, n, sh=sh, s_lo=0.05, s_hi=0.3, edge_cases=True)
+    view, proj = scenes.orbit_camera(3, 5, W, H)
+    rng = np.random.RandomState(5)
+    g_rgb, g_alpha = rng.randn(H, W, 3).astype(np.float32), rng.randn(H, W).astype(np.float32)
+    g_depth = (0.1 * rng.randn(H, W)).astype(np.float32)
+    t64 = lambda a: torch.from_numpy(a).to(torch.float64)
+    leaves_ref = [t64(a).requires_grad_(True) for a in (means, scales, colors, opac)]
+    rgb_ref, alpha_ref, depth_ref = r1.render_r1(*leaves_ref, t64(view), t64(proj), W, H)
+    ((rgb_ref * t64(g_rgb)).sum() + (alpha_ref * t64(g_alpha)).sum() + (depth_ref * t64(g_depth)).sum()).backward()
+    before = capi.path_counts()
+    m, s, c, o, gd, ga, gz = to_dev(means, scales, colors, opac, g_rgb, g_alpha, g_depth)
+    leaves = [x.requires_grad_(True) for x in (m, s, c, o)]
+    rgb, alpha, depth = r.render_gaussians_torch(*leaves, camera(view, proj), W, H, max_gaussians=n, return_aux=True)
+    ((rgb * gd).sum() + (alpha * ga).sum() + (depth * gz).sum()).backward()
+    torch.cuda.synchronize()
+    d = _paths_delta(before)
+    assert d["fwd_tcgen05"] >= 1 and d["bwd_tcgen05"] >= 1 and d["fwd_other"] == 0 and d["bwd_other"] == 0, d
+    e_rgb = float((rgb.detach().cpu() - rgb_ref.detach()).abs().max())
+    e_alpha = float((alpha.detach().cpu() - alpha_ref.detach()).abs().max())
+    de = (depth.detach().cpu() - depth_ref.detach()).abs().numpy()
+    wm = alpha_ref.detach().numpy() >= 1e-2 / 1.01
+    e_depth = float(de[wm].max())
+    rels = {k: rel_l2(x.grad.cpu().numpy(), y.grad.numpy())
+            for k, x, y in zip(("means", "scales", "colors", "opac"), leaves, leaves_ref)}
+    report("tcgen05_depth_multi_unit", sh=sh, rgb_maxabs=e_rgb, alpha_maxabs=e_alpha, depth_maxabs_weighted=e_depth,
+           depth_maxabs_all=float(de.max()), **{"grad_" + k: v for k, v in rels.items()})
+    assert e_rgb <= IMG_TOL and e_alpha <= IMG_TOL and e_depth <= 1e-4, (e_rgb, e_alpha, e_depth)
+    for k, v in rels.items():
+        assert v <= GRAD_TOL, (k, v)
