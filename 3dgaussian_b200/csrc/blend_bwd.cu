@@ -235,7 +235,8 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     }
   }
   __syncthreads();
-  uint4* out = reinterpret_cast<uint4*>(frag + (size_t)tile * NREG * 32);
+  // tcgen05 layout: tiles are GBUF_FRAG_WORDS apart (10 KB, with or without the gD matrices); mma.sync fragments: packed
+  uint4* out = reinterpret_cast<uint4*>(frag + (size_t)tile * (UMMA ? GBUF_FRAG_WORDS : NREG * 32));
   const uint4* src = reinterpret_cast<const uint4*>(sfrag);
 #pragma unroll
   for (int k = q; k < NREG * 32 / 4; k += TILE_PIX) out[k] = src[k];
@@ -1098,7 +1099,10 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
 #define B2S_BWU(RR, DD)                                                                                   \
   blend_wsum_bwd_umma_kernel<RR, DD><<<grid, BT_THREADS, 0, st>>>(vp, rec, vals, udesc, counters,          \
                                                                  reinterpret_cast<const uint4*>(frag), tile_scale, gacc)
-      if (depth) { if (direct) B2S_BWU(false, true); else B2S_BWU(true, true); }
+      // with a depth gradient every factor comes from its own MUFU.EX2 (see launch_blend_wsum_fwd: the recurrence drops
+      // far tails that depth = D/(W+1e-6) amplifies)
+      static const bool recur_depth = [] { const char* e = getenv("B2S_DEPTH_RECUR"); return e != nullptr && e[0] == '1'; }();
+      if (depth) { if (recur_depth) B2S_BWU(true, true); else B2S_BWU(false, true); }
       else       { if (direct) B2S_BWU(false, false); else B2S_BWU(true, false); }
 #undef B2S_BWU
       B2S_LAUNCH_CHECK();

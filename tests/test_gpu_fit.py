@@ -20,8 +20,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _setup(sh, n=203, V=3, W=48, H=32, seed=5):
-    means, scales, colors, opac = scenes.make_scene(seed, n, sh=sh, s_lo=0.03, s_hi=0.15)
+def _setup(sh, n=203, V=3, W=48, H=32, seed=5, s_lo=0.03, s_hi=0.15):
+    means, scales, colors, opac = scenes.make_scene(seed, n, sh=sh, s_lo=s_lo, s_hi=s_hi)
     rng = np.random.RandomState(seed)
     scales_raw = np.log(np.expm1(np.maximum(scales - 1e-3, 1e-4))).astype(np.float32)
     op_raw = np.log(opac / (1 - opac)).astype(np.float32)
@@ -431,7 +431,7 @@ def test_step_from_host_with_depth_maps_equals_device_step():
 def test_overflowing_iteration_never_reaches_the_parameters():
     """Pair buffers sized for small Gaussians, then the scales are blown up: the views overflow, the device guard
     skips Adam (parameters and moments untouched), the driver re-plans and repeats the iteration."""
-    S = _setup(1, n=400, V=2, W=64, H=48)
+    S = _setup(1, n=3000, V=2, W=160, H=120, s_lo=0.004, s_hi=0.01)     # ~2 of 80 tiles per Gaussian
     d = _driver(S, overflow_check_every=1000)          # poll only when asked
     d.step()
     assert not d.check_overflow()
