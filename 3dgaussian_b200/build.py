@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libb2splat.so")
-SOURCES = ["capi.cu", "preprocess.cu", "bin.cu", "sort.cu", "blend_fwd.cu", "blend_bwd.cu", "optim.cu", "densify.cu"]
+SOURCES = ["capi.cu", "preprocess.cu", "bin.cu", "sort.cu", "segsort.cu", "blend_fwd.cu", "blend_bwd.cu", "optim.cu", "densify.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -293,13 +293,17 @@ constexpr int CS_THREADS = 1024;
 
 __global__ void __launch_bounds__(1024)
 cs_hist_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
-               const unsigned long long* __restrict__ tmask, int* __restrict__ table) {
+               const unsigned long long* __restrict__ tmask, const int* __restrict__ order,
+               const int* __restrict__ slab_start, int* __restrict__ table) {
   extern __shared__ int hist[];
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) hist[t] = 0;
   __syncthreads();
-  const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
+  // order / slab_start: block b walks depth slab b of the Gaussians (segsort.cu); else an equal share in index order
+  const int i0 = order != nullptr ? slab_start[blockIdx.x] : blockIdx.x * per_block;
+  const int i1 = order != nullptr ? slab_start[blockIdx.x + 1] : min(n, i0 + per_block);
   for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) { atomicAdd(&hist[tile], 1); });
+    const int g = order != nullptr ? order[i] : i;
+    for_each_tile(rect[g], tmask[g], tiles_x, [&](int tile) { atomicAdd(&hist[tile], 1); });
   }
   __syncthreads();
   int* dst = table + (size_t)blockIdx.x * n_tiles;
@@ -488,18 +492,21 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long lon
 
 __global__ void __launch_bounds__(1024)
 cs_scatter_kernel(int n, int per_block, int tiles_x, int n_tiles, const uint2* __restrict__ rect,
-                  const unsigned long long* __restrict__ tmask, const int* __restrict__ table, const int2* __restrict__ ranges,
-                  const Counters* __restrict__ counters, int* __restrict__ vals) {
+                  const unsigned long long* __restrict__ tmask, const int* __restrict__ order,
+                  const int* __restrict__ slab_start, const int* __restrict__ table,
+                  const int2* __restrict__ ranges, const Counters* __restrict__ counters, int* __restrict__ vals) {
   extern __shared__ int off[];
   if (counters->overflow) return;
   const int* src = table + (size_t)blockIdx.x * n_tiles;
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) off[t] = ranges[t].x + src[t];
   __syncthreads();
-  const int i0 = blockIdx.x * per_block, i1 = min(n, i0 + per_block);
+  const int i0 = order != nullptr ? slab_start[blockIdx.x] : blockIdx.x * per_block;
+  const int i1 = order != nullptr ? slab_start[blockIdx.x + 1] : min(n, i0 + per_block);
   for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    for_each_tile(rect[i], tmask[i], tiles_x, [&](int tile) {
+    const int g = order != nullptr ? order[i] : i;
+    for_each_tile(rect[g], tmask[g], tiles_x, [&](int tile) {
       const int pos = atomicAdd(&off[tile], 1);
-      vals[pos] = i;
+      vals[pos] = g;
     });
   }
 }
@@ -512,7 +519,7 @@ int counting_sort_blocks(int n) {
 }
 
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
-                         const unsigned long long* tmask, int* table, int* total,
+                         const unsigned long long* tmask, const int* order, const int* slab_start, int* table, int* total,
                          int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
                          int4* udesc, int* vals, int stage, cudaStream_t st) {
   const size_t smem = (size_t)vp.n_tiles * 4;
@@ -527,7 +534,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
   static const int threads = [] { const char* e = getenv("B2S_CS_THREADS"); const int v = e ? atoi(e) : 0;
                                   return (v == 256 || v == 512 || v == 1024) ? v : CS_THREADS; }();
   if (stage == 0) {
-    cs_hist_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table);
+    cs_hist_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, order, slab_start, table);
     B2S_LAUNCH_CHECK();
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
@@ -535,7 +542,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
                                            (int)unit_cap, unit_start, units, udesc);
     B2S_LAUNCH_CHECK();
   } else {
-    cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, table, ranges, counters,
+    cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, order, slab_start, table, ranges, counters,
                                                     vals);
     B2S_LAUNCH_CHECK();
   }

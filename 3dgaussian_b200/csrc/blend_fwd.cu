@@ -984,21 +984,30 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
 }
 
 // ---- depth-sorted "over" compositing -----------------------------------------------------------
-// One CTA per tile, one pixel per thread, per-pixel alpha state in a register, block-wide early
-// termination once every pixel of the tile is saturated.  Order matters, so a tile's list is
-// NOT split into units here.
+// (reference src/renderer_cpu.cpp:196-215: a = clamp01(op exp(e)), skip a < 1e-5, contrib = (1 - A) a, C += contrib c,
+//  A += contrib, inside the Gaussian's 3-sigma pixel bbox)
+// Work unit = (tile, segment of <= SEG consecutive Gaussians of its depth-sorted list), one CTA of 256 threads =
+// one pixel per thread.  "Over" is associative: a segment composited alone from A = 0 yields (C_s, A_s), and
+//   C = C_1 + (1 - A_1) C_2,  A = A_1 + (1 - A_1) A_2
+// so long lists no longer serialise on one CTA (a 960x540 frame of 1 M Gaussians has tiles of > 8000: they were the
+// tail of the old one-CTA-per-tile kernel); finalize_sorted_kernel folds a tile's units in order.  Inside a unit the
+// CTA stops once every pixel is saturated (1 - A < 1e-4 cannot move an 8-bit channel).
+// The weight is separable, a(r,c) = [op 2^(qx dx^2)] [2^(qy dy^2)]: per chunk of 64 Gaussians the 256 threads first
+// evaluate the 64 x (16 + 16) factors (8 MUFU.EX2 each, bbox folded in as zeros) into shared memory, then a
+// pixel-pair costs 2 LDS + FMUL + compare + ~6 FP32 instead of the exponent arithmetic + MUFU + 4 bbox compares.
 constexpr int BS_THREADS = 256;
-constexpr int BS_CHUNK = 128;
+constexpr int BS_CHUNK = 64;
 
-struct StageBuf {
-  float4 a[BS_CHUNK];
-  float4 b[BS_CHUNK];
-  float4 c[BS_CHUNK];
+struct SortedStage {
+  float4 a[BS_CHUNK];   // {px, qx, op, bbox x (min | max << 16)}
+  float4 b[BS_CHUNK];   // {py, qy, 1, bbox y}
+  float4 c[BS_CHUNK];   // {r, g, b, zabs}
 };
 
-__device__ __forceinline__ void stage_chunk(StageBuf& sb, const float4* __restrict__ rec, const int* __restrict__ vals,
-                                            int start, int n, int chunk) {
-  for (int t = threadIdx.x; t < BS_CHUNK; t += BS_THREADS) {
+__device__ __forceinline__ void sorted_stage_chunk(SortedStage& sb, const float4* __restrict__ rec, const int* __restrict__ vals,
+                                                   int start, int n, int chunk) {
+  const int t = threadIdx.x;
+  if (t < BS_CHUNK) {
     const int i = chunk * BS_CHUNK + t;
     if (i < n) {
       const int id = __ldg(vals + start + i);
@@ -1010,54 +1019,164 @@ __device__ __forceinline__ void stage_chunk(StageBuf& sb, const float4* __restri
   }
 }
 
-__global__ void __launch_bounds__(BS_THREADS)
-blend_sorted_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
-                        const int2* __restrict__ ranges, float* __restrict__ out_rgb, float* __restrict__ out_alpha,
-                        uint8_t* __restrict__ out_rgba) {
-  __shared__ __align__(16) StageBuf sb[2];
-  const int tile = blockIdx.x;
-  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
-  const int xi = tx * TILE + (threadIdx.x & 15), yi = ty * TILE + (threadIdx.x >> 4);
-  const float x = xi + 0.5f, y = yi + 0.5f;
-  const int2 rg = ranges[tile];
-  const int n = rg.y - rg.x;
-  const int nchunks = (n + BS_CHUNK - 1) / BS_CHUNK;
-  float C0 = 0.f, C1 = 0.f, C2 = 0.f, A = 0.f;
+constexpr int BS_SEGY = 16;      // grid.y of the second kernel: segment index modulo 16
+constexpr int BS_FIRST = 2;      // segments the first kernel walks in order, with early exit, before anything is split
 
-  if (nchunks > 0) stage_chunk(sb[0], rec, vals, rg.x, n, 0);
-  cp_async_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) stage_chunk(sb[(c + 1) & 1], rec, vals, rg.x, n, c + 1);
+// Two launches.  FIRST: one CTA per tile walks the front BS_FIRST segments of the list in order and stops as soon as
+// every pixel is saturated -- most covered tiles end here after a few hundred Gaussians (the lists hold thousands), and
+// the tile is marked hidden-behind.  REST: the remaining segments of the tiles that did NOT saturate (silhouette tiles,
+// thin coverage), one CTA per segment in parallel; a segment behind a saturating one is skipped (finalize stops folding
+// before it).  Splitting everything from the start would composite the hidden 90 % of the interior lists; walking
+// everything in order left the frame waiting for the longest non-saturating tile.
+template <bool FIRST>
+__global__ void __launch_bounds__(BS_THREADS)
+blend_sorted_units_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
+                          const int2* __restrict__ ranges, const int* __restrict__ unit_start,
+                          float* __restrict__ partial, int* __restrict__ sat_seg, float* __restrict__ out_rgb,
+                          float* __restrict__ out_alpha, uint8_t* __restrict__ out_rgba, Counters* dbg) {
+  __shared__ __align__(16) SortedStage sb[2];
+  __shared__ float sfx[BS_CHUNK][TILE], sfy[BS_CHUNK][TILE];
+  __shared__ int s_flag;
+  const int tile = blockIdx.x;
+  const int u0 = unit_start[tile];
+  const int nseg = unit_start[tile + 1] - u0;
+  if (!FIRST && nseg <= BS_FIRST) return;
+  const int2 rg = ranges[tile];
+  const int L = rg.y - rg.x;
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int col = threadIdx.x & 15, row = threadIdx.x >> 4;
+  const int xi = tx * TILE + col, yi = ty * TILE + row;
+  const bool inside = xi < vp.width && yi < vp.height;
+  // factor phase ownership: thread t evaluates 8 factors of Gaussian t / 4: part 0, 1 = columns 0-7, 8-15; 2, 3 = rows
+  const int fj = threadIdx.x >> 2, fpart = threadIdx.x & 3;
+  const bool faxis_y = fpart >= 2;
+  const int f0 = (fpart & 1) * 8;
+  const int cbase = (faxis_y ? ty : tx) * TILE + f0;
+
+  for (int seg = FIRST ? 0 : BS_FIRST + (int)blockIdx.y; seg < (FIRST ? 1 : nseg); seg += BS_SEGY) {   // block uniform
+    if (!FIRST) {
+      // a segment in front of this one that saturates every pixel on its own makes it invisible: finalize stops
+      // folding before it (the FIRST kernel's verdict is final; among REST segments the race is benign)
+      if (threadIdx.x == 0) s_flag = *(volatile int*)(sat_seg + tile);
+      __syncthreads();                                   // one read for the whole block: the decision must be uniform
+      if (seg > s_flag) return;
+    }
+    const int e0 = seg * vp.seg;
+    const int start = rg.x + e0;
+    const int n = max(0, min(FIRST ? BS_FIRST * vp.seg : vp.seg, L - e0));
+    const int nchunks = (n + BS_CHUNK - 1) / BS_CHUNK;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, A = 0.f;
+    int saturated = 0;
+    __syncthreads();                                     // previous segment's reads of the stage buffers are over
+    if (nchunks > 0) sorted_stage_chunk(sb[0], rec, vals, start, n, 0);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const StageBuf& s = sb[c & 1];
-    const int cnt = min(BS_CHUNK, n - c * BS_CHUNK);
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      const float4 a = s.a[j];
-      const float4 b = s.b[j];
-      const float4 cc = s.c[j];
-      const float dx = x - a.x, dy = y - b.x;     // a = x record, b = y record, cc = colour
-      float al = a.z * ex2_approx(fmaf(b.y * dy, dy, a.y * dx * dx));
-      const int bx = __float_as_int(a.w), by = __float_as_int(b.w);
-      const bool in = (xi >= (bx & 0xffff)) && (xi <= (bx >> 16)) && (yi >= (by & 0xffff)) && (yi <= (by >> 16));
-      if (in && al >= 1e-5f) {
-        al = fminf(al, 1.0f);
-        const float contrib = (1.0f - A) * al;
-        if (contrib > 0.0f) {
-          C0 = fmaf(contrib, cc.x, C0);
-          C1 = fmaf(contrib, cc.y, C1);
-          C2 = fmaf(contrib, cc.z, C2);
-          A += contrib;
+    for (int c = 0; c < nchunks; ++c) {
+      if (c + 1 < nchunks) sorted_stage_chunk(sb[(c + 1) & 1], rec, vals, start, n, c + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();                                   // chunk c staged; every thread has left chunk c-1's blend loop
+      const SortedStage& s = sb[c & 1];
+      const int cnt = min(BS_CHUNK, n - c * BS_CHUNK);
+      if (fj < cnt) {
+        const float4 h = faxis_y ? s.b[fj] : s.a[fj];
+        const int bb = __float_as_int(h.w), lo = bb & 0xffff, hi = bb >> 16;
+        float* dst = (faxis_y ? &sfy[fj][0] : &sfx[fj][0]) + f0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ci = cbase + k;
+          const float d = ((float)ci + 0.5f) - h.x;
+          const float f = h.z * ex2_approx(h.y * d * d);   // h.z = op on the x record, 1 on the y record
+          dst[k] = (ci >= lo && ci <= hi) ? f : 0.0f;
         }
       }
+      __syncthreads();
+      // a warp whose 32 pixels are all saturated (or outside the image) sits the chunk out
+      if (!__all_sync(0xffffffffu, !inside || (1.0f - A) < 5e-5f)) {     // the CTA's own stopping bar, not a looser one
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+          float al = sfx[j][col] * sfy[j][row];
+          if (al >= 1e-5f) {
+            al = fminf(al, 1.0f);
+            const float contrib = (1.0f - A) * al;
+            if (contrib > 0.0f) {
+              const float4 cc = s.c[j];
+              C0 = fmaf(contrib, cc.x, C0);
+              C1 = fmaf(contrib, cc.y, C1);
+              C2 = fmaf(contrib, cc.z, C2);
+              A += contrib;
+            }
+          }
+        }
+      }
+      // every later contribution is scaled by (1-A): below 1e-4 it cannot move an 8-bit channel.  The CTA stops at
+      // 5e-5, the same bar that lets this segment hide the ones behind it: stricter than finalize's 1e-4, so rounding
+      // in its fold cannot leave a hidden segment visible.
+      saturated = __syncthreads_and(!inside || (1.0f - A) < 5e-5f);
+      if (saturated) break;
     }
-    // every later contribution is scaled by (1-A): below 1e-4 it cannot move an 8-bit channel
-    const int done = (1.0f - A) < 1e-4f;
-    if (__syncthreads_and(done)) break;
+    cp_async_wait<0>();
+#ifdef B2S_STATS
+    if (threadIdx.x == 0) {
+      if (!FIRST) { atomicAdd(&dbg->pad_[0], nchunks); atomicAdd(&dbg->pad_[1], 1); }
+      if (FIRST && saturated) atomicAdd(&dbg->pad_[2], 1);
+    }
+#endif
+    if (saturated && threadIdx.x == 0) atomicMin(sat_seg + tile, FIRST ? BS_FIRST - 1 : seg);
+    if (nseg > BS_FIRST) {
+      float* dst = partial + (size_t)(u0 + seg) * 5 * TILE_PIX + threadIdx.x;
+      dst[0] = C0;
+      dst[TILE_PIX] = C1;
+      dst[2 * TILE_PIX] = C2;
+      dst[3 * TILE_PIX] = A;
+      if (FIRST) {                                       // segments 1 .. BS_FIRST-1 are part of this result: identity
+        for (int q = 1; q < BS_FIRST; ++q) {
+          float* z = partial + (size_t)(u0 + q) * 5 * TILE_PIX + threadIdx.x;
+          z[0] = 0.f; z[TILE_PIX] = 0.f; z[2 * TILE_PIX] = 0.f; z[3 * TILE_PIX] = 0.f;
+        }
+      }
+      continue;
+    }
+    // the FIRST kernel saw the whole list: the pixel is final
+    if (!inside) return;
+    const size_t p = (size_t)yi * vp.width + xi;
+    const float af = fminf(fmaxf(A, 0.0f), 1.0f);
+    const float o0 = fminf(fmaxf(C0 + (1.0f - af) * view_bg(vp, 0), 0.0f), 1.0f);
+    const float o1 = fminf(fmaxf(C1 + (1.0f - af) * view_bg(vp, 1), 0.0f), 1.0f);
+    const float o2 = fminf(fmaxf(C2 + (1.0f - af) * view_bg(vp, 2), 0.0f), 1.0f);
+    if (out_rgb != nullptr) {
+      out_rgb[3 * p] = o0; out_rgb[3 * p + 1] = o1; out_rgb[3 * p + 2] = o2;
+    }
+    if (out_alpha != nullptr) out_alpha[p] = af;
+    if (out_rgba != nullptr) {   // renderer_cpu.cpp:252-255
+      uchar4 q;
+      q.x = (unsigned char)(o0 * 255.0f + 0.5f);
+      q.y = (unsigned char)(o1 * 255.0f + 0.5f);
+      q.z = (unsigned char)(o2 * 255.0f + 0.5f);
+      q.w = 255;
+      reinterpret_cast<uchar4*>(out_rgba)[p] = q;
+    }
   }
-  cp_async_wait<0>();
+}
+
+// Folds the units of a multi-unit tile front to back: C = C_1 + (1 - A_1) C_2 + ..., A likewise.
+__global__ void __launch_bounds__(TILE_PIX)
+finalize_sorted_kernel(const ViewParams vp, const int* __restrict__ unit_start, const float* __restrict__ partial,
+                       float* __restrict__ out_rgb, float* __restrict__ out_alpha, uint8_t* __restrict__ out_rgba) {
+  const int tile = blockIdx.x;
+  const int u0 = unit_start[tile], u1 = unit_start[tile + 1];
+  if (u1 - u0 <= BS_FIRST) return;                     // the FIRST blend kernel wrote these pixels itself
+  const int q = threadIdx.x;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f, A = 0.f;
+  for (int u = u0; u < u1; ++u) {
+    const float T = 1.0f - A;
+    if (T < 1e-4f) break;
+    const float* src = partial + (size_t)u * 5 * TILE_PIX + q;
+    C0 = fmaf(T, src[0], C0);
+    C1 = fmaf(T, src[TILE_PIX], C1);
+    C2 = fmaf(T, src[2 * TILE_PIX], C2);
+    A = fmaf(T, src[3 * TILE_PIX], A);
+  }
+  const int xi = (tile % vp.tiles_x) * TILE + (q & 15), yi = (tile / vp.tiles_x) * TILE + (q >> 4);
   if (xi >= vp.width || yi >= vp.height) return;
   const size_t p = (size_t)yi * vp.width + xi;
   const float af = fminf(fmaxf(A, 0.0f), 1.0f);
@@ -1068,20 +1187,28 @@ blend_sorted_fwd_kernel(const ViewParams vp, const float4* __restrict__ rec, con
     out_rgb[3 * p] = o0; out_rgb[3 * p + 1] = o1; out_rgb[3 * p + 2] = o2;
   }
   if (out_alpha != nullptr) out_alpha[p] = af;
-  if (out_rgba != nullptr) {   // renderer_cpu.cpp:252-255
-    uchar4 u;
-    u.x = (unsigned char)(o0 * 255.0f + 0.5f);
-    u.y = (unsigned char)(o1 * 255.0f + 0.5f);
-    u.z = (unsigned char)(o2 * 255.0f + 0.5f);
-    u.w = 255;
-    reinterpret_cast<uchar4*>(out_rgba)[p] = u;
+  if (out_rgba != nullptr) {
+    uchar4 w;
+    w.x = (unsigned char)(o0 * 255.0f + 0.5f);
+    w.y = (unsigned char)(o1 * 255.0f + 0.5f);
+    w.z = (unsigned char)(o2 * 255.0f + 0.5f);
+    w.w = 255;
+    reinterpret_cast<uchar4*>(out_rgba)[p] = w;
   }
 }
 
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                            float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st) {
+                            const int* unit_start, float* partial, int* sat_seg, float* out_rgb, float* out_alpha,
+                            uint8_t* out_rgba, Counters* dbg, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
-  blend_sorted_fwd_kernel<<<vp.n_tiles, BS_THREADS, 0, st>>>(vp, rec, vals, ranges, out_rgb, out_alpha, out_rgba);
+  B2S_CUDA_TRY(cudaMemsetAsync(sat_seg, 0x7f, (size_t)vp.n_tiles * sizeof(int), st));   // "no saturating segment yet"
+  blend_sorted_units_kernel<true><<<vp.n_tiles, BS_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, partial, sat_seg,
+                                                                    out_rgb, out_alpha, out_rgba, dbg);
+  B2S_LAUNCH_CHECK();
+  blend_sorted_units_kernel<false><<<dim3(vp.n_tiles, BS_SEGY), BS_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, partial,
+                                                                                    sat_seg, out_rgb, out_alpha, out_rgba, dbg);
+  B2S_LAUNCH_CHECK();
+  finalize_sorted_kernel<<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, unit_start, partial, out_rgb, out_alpha, out_rgba);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

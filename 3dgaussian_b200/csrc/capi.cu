@@ -227,6 +227,7 @@ struct Bufs {  // resolved pointers into state / workspace
   float* gbuf;
   int* cs_table;
   int* cs_total;
+  int *oorder, *oslab, *osmall;
   int64_t unit_cap;
 };
 
@@ -265,6 +266,9 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.gbuf = (float*)(q + L.gbuf);
     b.cs_table = (int*)(q + L.cs_table);
     b.cs_total = (int*)(q + L.cs_total);
+    b.oorder = (int*)(q + L.oorder);
+    b.oslab = (int*)(q + L.oslab);
+    b.osmall = (int*)(q + L.osmall);
   }
   return b;
 }
@@ -291,19 +295,33 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
   if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
     StageTimer t(ctx, ST_PREPROCESS, st);
     rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
-  } else if (p->sort_depth || !counting_sort_fits(vp.n_tiles)) {
-    set_error("prepared views feed the counting-sort path only (sort_depth = 0, at most %d tiles)", (int)(CS_MAX_SMEM / 8));
+  } else if (!counting_sort_fits(vp.n_tiles)) {
+    set_error("prepared views feed the counting-sort path only (at most %d tiles)", (int)(CS_MAX_SMEM / 8));
     return B2S_ERR_UNSUPPORTED;
   }
   if (rc != B2S_OK) return rc;
   const int begin_bit = p->sort_depth ? 0 : 32;
   const int end_bit = 32 + tile_bits(vp.n_tiles);
   const int passes = sort_passes(begin_bit, end_bit);
-  if (!p->sort_depth && counting_sort_fits(vp.n_tiles)) {
-    // order inside a tile is irrelevant: group with one counting pass + one scatter pass
+  if (counting_sort_fits(vp.n_tiles)) {
+    // group by tile with one counting pass + one scatter pass (the weighted sum needs no order inside a tile).  The
+    // depth order, when asked for, comes from walking the Gaussians in their global depth order and sorting the inside
+    // of the small (block, tile) groups (segsort.cu) instead of a 6-pass radix sort of all the pairs.
+    const int* order = nullptr;
+    const int* slab_start = nullptr;
+    if (p->sort_depth) {
+      if (means == nullptr) { set_error("the depth order needs the per-view preprocess (depth bits)"); return B2S_ERR_UNSUPPORTED; }
+      StageTimer t(ctx, ST_SORT, st);
+      uint32_t* splitters = (uint32_t*)B.osmall;
+      int *count = B.osmall + 1024, *sstart = B.osmall + 2048, *cursor = B.osmall + 3072;
+      rc = launch_depth_slabs(B.dbits, n, counting_sort_blocks(n), splitters, count, sstart, cursor, B.oslab, B.oorder, st);
+      if (rc != B2S_OK) return rc;
+      order = B.oorder;
+      slab_start = sstart;
+    }
     {
       StageTimer t(ctx, ST_BIN, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, mirror, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, order, slab_start, B.cs_table, B.cs_total, B.ranges, B.counters, mirror, B.unit_cap,
                                 B.unit_start, B.units, B.udesc, B.vals, 0, st);   // also writes the unit descriptor table
     }
     if (rc != B2S_OK) return rc;
@@ -319,11 +337,14 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     }
     {
       StageTimer t(ctx, ST_SORT, st);
-      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, B.cs_table, B.cs_total, B.ranges, B.counters, nullptr, B.unit_cap,
+      rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, order, slab_start, B.cs_table, B.cs_total, B.ranges, B.counters, nullptr, B.unit_cap,
                                 B.unit_start, B.units, B.udesc, B.vals, 1, st);
+      if (rc == B2S_OK && p->sort_depth)
+        rc = launch_group_sort(vp, B.cs_table, B.cs_total, B.ranges, counting_sort_blocks(n), B.dbits, B.counters, B.vals, B.keysA,
+                               keys_sorted != nullptr ? B.keysB : nullptr, st);
     }
     if (rc != B2S_OK) return rc;
-    if (keys_sorted != nullptr) *keys_sorted = nullptr;   // this path has no keys
+    if (keys_sorted != nullptr) *keys_sorted = p->sort_depth ? B.keysB : nullptr;   // the grouping alone has no keys
     return B2S_OK;
   }
   unsigned long long* kA = B.keysA;
@@ -450,7 +471,7 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
-    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, out_rgb, out_alpha, nullptr, st);
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, out_rgb, out_alpha, nullptr, B.counters, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, out_rgb,
                                out_alpha, out_depth, B.acc, nullptr, st);
 }
@@ -628,7 +649,7 @@ static int render_rgba8_impl(b2s_ctx* ctx, const ViewParams& vp, const b2s_param
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
-    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, nullptr, nullptr, out_rgba, st);
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, nullptr, nullptr, out_rgba, B.counters, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, nullptr,
                                nullptr, nullptr, nullptr, out_rgba, st);
 }

@@ -205,7 +205,9 @@ struct StateLayout {
   size_t rec, ranges, vals, acc, counters, unit_start, units, udesc, cmask, total;
 };
 struct WorkLayout {
-  size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total, total;
+  size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total;
+  size_t oorder, oslab, osmall;   // depth slabs of the Gaussians (segsort.cu): order[n], slab id[n], splitters / counters
+  size_t total;
 };
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
 // list.  Splitting long lists keeps the units uniform (a 1080p tile of the C4 scene holds up
@@ -266,6 +268,9 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   L.gbuf = o;  o += align_up(tiles * GBUF_FRAG_WORDS * 4) + align_up(tiles * 4 + 64);   // plane fragments + per-tile scale + depth statistics
   L.cs_table = o; o += align_up((size_t)CS_NB * tiles * 4);
   L.cs_total = o; o += align_up(tiles * 4);
+  L.oorder = o; o += align_up(nn * 4);
+  L.oslab = o;  o += align_up(nn * 4);
+  L.osmall = o; o += align_up(4 * 1024 * 4);   // splitters | counts | slab_start | cursor, 1024 words each
   L.total = o;
   return L;
 }
@@ -353,8 +358,10 @@ int launch_ranges(const unsigned long long* keys, const int* count_dev, int64_t 
                   cudaStream_t st);
 // tile-major counting sort (bin.cu): stage 0 = histogram + scans (ranges, units, counters), stage 1 = scatter
 bool counting_sort_fits(int n_tiles);
+int counting_sort_blocks(int n);
+// order / slab_start: optional depth slabs of the Gaussians (segsort.cu): block b walks order[slab_start[b] .. slab_start[b+1])
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
-                         const unsigned long long* tmask, int* table, int* total,
+                         const unsigned long long* tmask, const int* order, const int* slab_start, int* table, int* total,
                          int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
                          int4* udesc, int* vals, int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int seg, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
@@ -369,8 +376,18 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           int64_t unit_cap, float* partial,
                           float* out_rgb, float* out_alpha, float* out_depth, float* acc, uint8_t* out_rgba,
                           cudaStream_t st);
+// sat_seg: n_tiles ints of scratch (first segment of a tile that saturates every pixel on its own)
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                            float* out_rgb, float* out_alpha, uint8_t* out_rgba, cudaStream_t st);
+                            const int* unit_start, float* partial, int* sat_seg, float* out_rgb, float* out_alpha,
+                            uint8_t* out_rgba, Counters* dbg /* -DB2S_STATS builds only */, cudaStream_t st);
+// depth order inside the tiles (segsort.cu): the Gaussians partitioned into nb depth slabs (order[], slab_start[]);
+// after the slab-wise counting sort, launch_group_sort orders the inside of every (block, tile) group.
+// scratch: max_pairs x 8 B; keys_out: optional rebuilt sorted keys (tile << 32 | depth bits) for b2s_dump_bins
+int launch_depth_slabs(const uint32_t* dbits, int n, int nb, uint32_t* splitters, int* count, int* slab_start, int* cursor,
+                       int* slab_id, int* order, cudaStream_t st);
+int launch_group_sort(const ViewParams& vp, const int* table, const int* total, const int2* ranges, int nb,
+                      const uint32_t* dbits, const Counters* counters, int* vals, unsigned long long* scratch,
+                      unsigned long long* keys_out, cudaStream_t st);
 int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st);
 // fl != null: the image gradients are those of the fit loss, evaluated from the saved accumulators inside the
 // g-buffer kernel (g_rgb / g_alpha / g_depth are ignored)
