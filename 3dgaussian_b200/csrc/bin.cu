@@ -350,7 +350,8 @@ cs_colscan_kernel(int* __restrict__ table, int nb, int n_tiles, int* __restrict_
 __global__ void __launch_bounds__(1024)
 cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long long max_pairs, int2* __restrict__ ranges,
                    Counters* __restrict__ counters, Counters* __restrict__ mirror, int unit_cap,
-                   int* __restrict__ unit_start, int2* __restrict__ units, int4* __restrict__ udesc) {
+                   int* __restrict__ unit_start, int2* __restrict__ units, int4* __restrict__ udesc,
+                   int* __restrict__ ne_list) {
   const int UD_STEP = (SEG + UD_NCLS - 1) / UD_NCLS;
   extern __shared__ int ts_smem[];                 // cnt[n_tiles] then ustart[n_tiles]
   int* cnt = ts_smem;
@@ -359,6 +360,8 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long lon
   __shared__ int wunits[32];
   __shared__ long long grand_s;
   __shared__ int wcls[UD_NCLS][32];               // unit descriptor table (launch_udesc): units per step class
+  __shared__ int ne_count_s;
+  if (threadIdx.x == 0) ne_count_s = 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // coalesced fetch of the per-tile totals: every load of the block is in flight at once
   for (int t = threadIdx.x; t < n_tiles; t += 1024) cnt[t] = total[t];
@@ -470,13 +473,16 @@ cs_tilescan_kernel(const int* __restrict__ total, int n_tiles, int SEG, long lon
     const int s0 = cnt[t], s1 = (t + 1 < n_tiles) ? cnt[t + 1] : kept;
     const int c = ov ? 0 : s1 - s0;
     ranges[t] = c > 0 ? make_int2(s0, s1) : make_int2(0, 0);   // empty tiles read (0,0) like the radix path
+    if (ne_list != nullptr && c > 1) ne_list[1 + atomicAdd(&ne_count_s, 1)] = t;   // tiles with something to order
     const int u0 = ust[t];
     unit_start[t] = u0;
     const int v = c > 0 ? (c + SEG - 1) / SEG : 1;
     for (int q = 0; q < v; ++q)
       if (u0 + q < unit_cap) units[u0 + q] = make_int2(t, q);
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    if (ne_list != nullptr) ne_list[0] = ne_count_s;
     counters->needed = grand;
     counters->kept = kept;
     counters->overflow = ov ? 1 : 0;
@@ -521,7 +527,7 @@ int counting_sort_blocks(int n) {
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, const int* order, const int* slab_start, int* table, int* total,
                          int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
-                         int4* udesc, int* vals, int stage, cudaStream_t st) {
+                         int4* udesc, int* ne_list, int* vals, int stage, cudaStream_t st) {
   const size_t smem = (size_t)vp.n_tiles * 4;
   B2S_CUDA_TRY(per_device_once(ONCE_COUNTING_SORT, [] {
     cudaError_t e = cudaFuncSetAttribute(cs_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_MAX_SMEM);
@@ -539,7 +545,7 @@ int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const u
     cs_colscan_kernel<<<(vp.n_tiles + 31) / 32, 256, 0, st>>>(table, nb, vp.n_tiles, total);
     B2S_LAUNCH_CHECK();
     cs_tilescan_kernel<<<1, 1024, 2 * smem, st>>>(total, vp.n_tiles, vp.seg, (long long)max_pairs, ranges, counters, mirror,
-                                           (int)unit_cap, unit_start, units, udesc);
+                                           (int)unit_cap, unit_start, units, udesc, ne_list);
     B2S_LAUNCH_CHECK();
   } else {
     cs_scatter_kernel<<<nb, threads, smem, st>>>(n, per_block, vp.tiles_x, vp.n_tiles, rect, tmask, order, slab_start, table, ranges, counters,

@@ -1019,7 +1019,6 @@ __device__ __forceinline__ void sorted_stage_chunk(SortedStage& sb, const float4
   }
 }
 
-constexpr int BS_SEGY = 16;      // grid.y of the second kernel: segment index modulo 16
 constexpr int BS_FIRST = 2;      // segments the first kernel walks in order, with early exit, before anything is split
 
 // Two launches.  FIRST: one CTA per tile walks the front BS_FIRST segments of the list in order and stops as soon as
@@ -1032,34 +1031,43 @@ template <bool FIRST>
 __global__ void __launch_bounds__(BS_THREADS)
 blend_sorted_units_kernel(const ViewParams vp, const float4* __restrict__ rec, const int* __restrict__ vals,
                           const int2* __restrict__ ranges, const int* __restrict__ unit_start,
-                          float* __restrict__ partial, int* __restrict__ sat_seg, float* __restrict__ out_rgb,
-                          float* __restrict__ out_alpha, uint8_t* __restrict__ out_rgba, Counters* dbg) {
+                          float* __restrict__ partial, int* __restrict__ sat_seg, int2* __restrict__ rest_list,
+                          float* __restrict__ out_rgb, float* __restrict__ out_alpha, uint8_t* __restrict__ out_rgba,
+                          Counters* dbg) {
   __shared__ __align__(16) SortedStage sb[2];
   __shared__ float sfx[BS_CHUNK][TILE], sfy[BS_CHUNK][TILE];
   __shared__ int s_flag;
-  const int tile = blockIdx.x;
-  const int u0 = unit_start[tile];
-  const int nseg = unit_start[tile + 1] - u0;
-  if (!FIRST && nseg <= BS_FIRST) return;
-  const int2 rg = ranges[tile];
-  const int L = rg.y - rg.x;
-  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
-  const int col = threadIdx.x & 15, row = threadIdx.x >> 4;
-  const int xi = tx * TILE + col, yi = ty * TILE + row;
-  const bool inside = xi < vp.width && yi < vp.height;
   // factor phase ownership: thread t evaluates 8 factors of Gaussian t / 4: part 0, 1 = columns 0-7, 8-15; 2, 3 = rows
   const int fj = threadIdx.x >> 2, fpart = threadIdx.x & 3;
   const bool faxis_y = fpart >= 2;
   const int f0 = (fpart & 1) * 8;
+  const int col = threadIdx.x & 15, row = threadIdx.x >> 4;
+  // Work items: FIRST -- one CTA per tile.  REST -- the (tile, segment) pairs the FIRST kernel found still visible,
+  // appended to rest_list ([0].x = count); a persistent grid strides over that list, so no CTA is spent on the empty
+  // and the saturated tiles (a CTA per (tile, segment) of the whole frame cost more in launches than in work: 32 640
+  // CTAs for 56 live segments in the 960x540 viewer frame).
+  const int n_items = FIRST ? 1 : rest_list[0].x;
+  for (int w = FIRST ? 0 : (int)blockIdx.x; w < n_items; w += FIRST ? 1 : (int)gridDim.x) {     // block uniform
+  const int2 item = FIRST ? make_int2((int)blockIdx.x, 0) : rest_list[1 + w];
+  const int tile = item.x, ybase = item.y;
+  const int u0 = unit_start[tile];
+  const int nseg = unit_start[tile + 1] - u0;
+  const int2 rg = ranges[tile];
+  const int L = rg.y - rg.x;
+  const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+  const int xi = tx * TILE + col, yi = ty * TILE + row;
+  const bool inside = xi < vp.width && yi < vp.height;
   const int cbase = (faxis_y ? ty : tx) * TILE + f0;
 
-  for (int seg = FIRST ? 0 : BS_FIRST + (int)blockIdx.y; seg < (FIRST ? 1 : nseg); seg += BS_SEGY) {   // block uniform
+  bool hidden = false;
+  for (int seg = FIRST ? 0 : ybase; seg < (FIRST ? 1 : ybase + 1) && !hidden; ++seg) {   // block uniform: one segment
     if (!FIRST) {
       // a segment in front of this one that saturates every pixel on its own makes it invisible: finalize stops
       // folding before it (the FIRST kernel's verdict is final; among REST segments the race is benign)
+      __syncthreads();                                   // everyone has read the previous value of s_flag
       if (threadIdx.x == 0) s_flag = *(volatile int*)(sat_seg + tile);
       __syncthreads();                                   // one read for the whole block: the decision must be uniform
-      if (seg > s_flag) return;
+      if (seg > s_flag) { hidden = true; continue; }
     }
     const int e0 = seg * vp.seg;
     const int start = rg.x + e0;
@@ -1122,6 +1130,12 @@ blend_sorted_units_kernel(const ViewParams vp, const float4* __restrict__ rec, c
     }
 #endif
     if (saturated && threadIdx.x == 0) atomicMin(sat_seg + tile, FIRST ? BS_FIRST - 1 : seg);
+    if (FIRST && !saturated && nseg > BS_FIRST && threadIdx.x == 0) {
+      // still visible behind the front segments: the rest of the list becomes work items of the second launch
+      const int k = nseg - BS_FIRST;
+      const int at = atomicAdd(&rest_list[0].x, k);
+      for (int q = 0; q < k; ++q) rest_list[1 + at + q] = make_int2(tile, BS_FIRST + q);
+    }
     if (nseg > BS_FIRST) {
       float* dst = partial + (size_t)(u0 + seg) * 5 * TILE_PIX + threadIdx.x;
       dst[0] = C0;
@@ -1137,7 +1151,7 @@ blend_sorted_units_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       continue;
     }
     // the FIRST kernel saw the whole list: the pixel is final
-    if (!inside) return;
+    if (!inside) continue;
     const size_t p = (size_t)yi * vp.width + xi;
     const float af = fminf(fmaxf(A, 0.0f), 1.0f);
     const float o0 = fminf(fmaxf(C0 + (1.0f - af) * view_bg(vp, 0), 0.0f), 1.0f);
@@ -1156,6 +1170,7 @@ blend_sorted_units_kernel(const ViewParams vp, const float4* __restrict__ rec, c
       reinterpret_cast<uchar4*>(out_rgba)[p] = q;
     }
   }
+  }   // work items
 }
 
 // Folds the units of a multi-unit tile front to back: C = C_1 + (1 - A_1) C_2 + ..., A likewise.
@@ -1198,15 +1213,16 @@ finalize_sorted_kernel(const ViewParams vp, const int* __restrict__ unit_start, 
 }
 
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                            const int* unit_start, float* partial, int* sat_seg, float* out_rgb, float* out_alpha,
-                            uint8_t* out_rgba, Counters* dbg, cudaStream_t st) {
+                            const int* unit_start, float* partial, int* sat_seg, int2* rest_list, float* out_rgb,
+                            float* out_alpha, uint8_t* out_rgba, Counters* dbg, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
   B2S_CUDA_TRY(cudaMemsetAsync(sat_seg, 0x7f, (size_t)vp.n_tiles * sizeof(int), st));   // "no saturating segment yet"
+  B2S_CUDA_TRY(cudaMemsetAsync(rest_list, 0, sizeof(int2), st));                         // no live segments yet
   blend_sorted_units_kernel<true><<<vp.n_tiles, BS_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, partial, sat_seg,
-                                                                    out_rgb, out_alpha, out_rgba, dbg);
+                                                                    rest_list, out_rgb, out_alpha, out_rgba, dbg);
   B2S_LAUNCH_CHECK();
-  blend_sorted_units_kernel<false><<<dim3(vp.n_tiles, BS_SEGY), BS_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, partial,
-                                                                                    sat_seg, out_rgb, out_alpha, out_rgba, dbg);
+  blend_sorted_units_kernel<false><<<sm_count() * 6, BS_THREADS, 0, st>>>(vp, rec, vals, ranges, unit_start, partial, sat_seg,
+                                                                         rest_list, out_rgb, out_alpha, out_rgba, dbg);
   B2S_LAUNCH_CHECK();
   finalize_sorted_kernel<<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, unit_start, partial, out_rgb, out_alpha, out_rgba);
   B2S_LAUNCH_CHECK();

@@ -227,7 +227,8 @@ struct Bufs {  // resolved pointers into state / workspace
   float* gbuf;
   int* cs_table;
   int* cs_total;
-  int *oorder, *oslab, *osmall;
+  int *oorder, *oslab, *osmall, *ne_list;
+  int2* rest_list;
   int64_t unit_cap;
 };
 
@@ -269,6 +270,8 @@ static Bufs resolve(void* state, void* ws, int n, int w, int h, int64_t mp) {
     b.oorder = (int*)(q + L.oorder);
     b.oslab = (int*)(q + L.oslab);
     b.osmall = (int*)(q + L.osmall);
+    b.ne_list = (int*)(q + L.ne_list);
+    b.rest_list = (int2*)(q + L.rest_list);
   }
   return b;
 }
@@ -322,7 +325,7 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     {
       StageTimer t(ctx, ST_BIN, st);
       rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, order, slab_start, B.cs_table, B.cs_total, B.ranges, B.counters, mirror, B.unit_cap,
-                                B.unit_start, B.units, B.udesc, B.vals, 0, st);   // also writes the unit descriptor table
+                                B.unit_start, B.units, B.udesc, B.ne_list, B.vals, 0, st);   // also writes the unit descriptor table
     }
     if (rc != B2S_OK) return rc;
     ticket_mark(ctx, B.counters, st);
@@ -338,9 +341,9 @@ static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, 
     {
       StageTimer t(ctx, ST_SORT, st);
       rc = launch_counting_sort(vp, n, max_pairs, B.rect, B.tmask, order, slab_start, B.cs_table, B.cs_total, B.ranges, B.counters, nullptr, B.unit_cap,
-                                B.unit_start, B.units, B.udesc, B.vals, 1, st);
+                                B.unit_start, B.units, B.udesc, B.ne_list, B.vals, 1, st);
       if (rc == B2S_OK && p->sort_depth)
-        rc = launch_group_sort(vp, B.cs_table, B.cs_total, B.ranges, counting_sort_blocks(n), B.dbits, B.counters, B.vals, B.keysA,
+        rc = launch_group_sort(vp, B.cs_table, B.cs_total, B.ranges, B.ne_list, counting_sort_blocks(n), B.dbits, B.counters, B.vals, B.keysA,
                                keys_sorted != nullptr ? B.keysB : nullptr, st);
     }
     if (rc != B2S_OK) return rc;
@@ -471,7 +474,7 @@ int b2s_forward(b2s_ctx* ctx, const b2s_params* p, const float* means, const flo
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
-    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, out_rgb, out_alpha, nullptr, B.counters, st);
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, B.rest_list, out_rgb, out_alpha, nullptr, B.counters, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, out_rgb,
                                out_alpha, out_depth, B.acc, nullptr, st);
 }
@@ -649,7 +652,7 @@ static int render_rgba8_impl(b2s_ctx* ctx, const ViewParams& vp, const b2s_param
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_BLEND_FWD, st);
   if (vp.mode == B2S_MODE_SORTED)
-    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, nullptr, nullptr, out_rgba, B.counters, st);
+    return launch_blend_sorted_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.partial, B.cs_total, B.rest_list, nullptr, nullptr, out_rgba, B.counters, st);
   return launch_blend_wsum_fwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.partial, nullptr,
                                nullptr, nullptr, nullptr, out_rgba, st);
 }

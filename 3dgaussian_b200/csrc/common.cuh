@@ -207,6 +207,7 @@ struct StateLayout {
 struct WorkLayout {
   size_t rect, tmask, dbits, cnt, bsum, keysA, keysB, valsB, hist, hsum, gacc, partial, gbuf, cs_table, cs_total;
   size_t oorder, oslab, osmall;   // depth slabs of the Gaussians (segsort.cu): order[n], slab id[n], splitters / counters
+  size_t ne_list, rest_list;      // compact work lists: non-empty tiles (group sort), live segments (sorted blend)
   size_t total;
 };
 // A work unit of the blend kernels: one tile x one segment of at most SEG Gaussians of its
@@ -271,6 +272,8 @@ inline WorkLayout work_layout(int n, int width, int height, int64_t max_pairs) {
   L.oorder = o; o += align_up(nn * 4);
   L.oslab = o;  o += align_up(nn * 4);
   L.osmall = o; o += align_up(4 * 1024 * 4);   // splitters | counts | slab_start | cursor, 1024 words each
+  L.ne_list = o; o += align_up((tiles + 1) * 4);
+  L.rest_list = o; o += align_up(((size_t)max_units(width, height, max_pairs) + 1) * 8);
   L.total = o;
   return L;
 }
@@ -363,7 +366,8 @@ int counting_sort_blocks(int n);
 int launch_counting_sort(const ViewParams& vp, int n, int64_t max_pairs, const uint2* rect,
                          const unsigned long long* tmask, const int* order, const int* slab_start, int* table, int* total,
                          int2* ranges, Counters* counters, Counters* mirror, int64_t unit_cap, int* unit_start, int2* units,
-                         int4* udesc, int* vals, int stage, cudaStream_t st);
+                         int4* udesc, int* ne_list /* [0] = count, then the non-empty tiles; may be null */, int* vals,
+                         int stage, cudaStream_t st);
 int launch_units(const int2* ranges, int n_tiles, int seg, int64_t unit_cap, int* unit_start, int2* units, cudaStream_t st);
 // Unit descriptor table of the persistent tcgen05 blend kernels: the NON-EMPTY units as {tile, first pair, pairs,
 // unit index | multi-unit-tile flag << 31}, ordered by their number of 128-Gaussian steps, largest first, so that CTA i
@@ -378,14 +382,14 @@ int launch_blend_wsum_fwd(const ViewParams& vp, const float4* rec, const int* va
                           cudaStream_t st);
 // sat_seg: n_tiles ints of scratch (first segment of a tile that saturates every pixel on its own)
 int launch_blend_sorted_fwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
-                            const int* unit_start, float* partial, int* sat_seg, float* out_rgb, float* out_alpha,
-                            uint8_t* out_rgba, Counters* dbg /* -DB2S_STATS builds only */, cudaStream_t st);
+                            const int* unit_start, float* partial, int* sat_seg, int2* rest_list, float* out_rgb,
+                            float* out_alpha, uint8_t* out_rgba, Counters* dbg /* -DB2S_STATS builds only */, cudaStream_t st);
 // depth order inside the tiles (segsort.cu): the Gaussians partitioned into nb depth slabs (order[], slab_start[]);
 // after the slab-wise counting sort, launch_group_sort orders the inside of every (block, tile) group.
 // scratch: max_pairs x 8 B; keys_out: optional rebuilt sorted keys (tile << 32 | depth bits) for b2s_dump_bins
 int launch_depth_slabs(const uint32_t* dbits, int n, int nb, uint32_t* splitters, int* count, int* slab_start, int* cursor,
                        int* slab_id, int* order, cudaStream_t st);
-int launch_group_sort(const ViewParams& vp, const int* table, const int* total, const int2* ranges, int nb,
+int launch_group_sort(const ViewParams& vp, const int* table, const int* total, const int2* ranges, const int* ne_list, int nb,
                       const uint32_t* dbits, const Counters* counters, int* vals, unsigned long long* scratch,
                       unsigned long long* keys_out, cudaStream_t st);
 int launch_gacc_init(const uint8_t* cmask, float* gacc, int n, cudaStream_t st);

@@ -23,6 +23,7 @@ constexpr int GS_WARP_CAP = 512;                   // elements a warp sorts in i
 constexpr int GS_CTA_CAP = GS_WARPS * GS_WARP_CAP;   // elements the CTA sorts at a time (all slabs: 32 KB)
 constexpr int GS_MAX_BIG = 64;                     // oversized groups remembered per tile before the CTA handles them
 constexpr int GS_SPLIT = 16;                       // CTAs per tile (grid.y): each takes a contiguous share of the blocks
+constexpr int GS_MAX_SHARE = (CS_NB + GS_SPLIT - 1) / GS_SPLIT;   // groups per CTA
 
 __device__ __forceinline__ int next_pow2(int x) {
   int p = 1;
@@ -48,6 +49,61 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* s, int P, int t
   }
 }
 
+// Bitonic sort of up to 32 R keys held in registers by one warp: element r * 32 + lane lives in k[r] of `lane`.
+// Stages with a partner distance below 32 exchange through shuffles, the others between the thread's own registers:
+// no shared memory, no barriers -- ~8 instructions per key per stage, against ~20 for the shared-memory version, which
+// matters because the (block, tile) groups are small (a few dozen elements) and there are > 100 000 of them per frame.
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(unsigned long long (&k)[R], int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32 * R; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & dr) == 0) {
+            const bool up = (((r << 5) | lane) & kk) == 0;
+            const unsigned long long a = k[r], b = k[r | dr];
+            if ((a > b) == up) { k[r] = b; k[r | dr] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long mine = k[r];
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool up = (((r << 5) | lane) & kk) == 0;
+          const bool lower = (lane & j) == 0;
+          const bool take_min = lower == up;
+          k[r] = (mine < other) == take_min ? mine : other;
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort_group(int* __restrict__ dst, int m, int lane, const uint32_t* __restrict__ dbits) {
+  unsigned long long k[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * 32 + lane;
+    k[r] = ~0ull;
+    if (i < m) {
+      const int id = dst[i];
+      k[r] = ((unsigned long long)__ldg(dbits + id) << 32) | (unsigned)id;
+    }
+  }
+  warp_sort_regs<R>(k, lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * 32 + lane;
+    if (i < m) dst[i] = (int)(unsigned)(k[r] & 0xffffffffull);
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ void load_keys(unsigned long long* s, int P, int t, const int* __restrict__ src, int len,
                                           const uint32_t* __restrict__ dbits) {
@@ -62,57 +118,89 @@ __device__ __forceinline__ void load_keys(unsigned long long* s, int P, int t, c
   if (NT == 32) __syncwarp(); else __syncthreads();
 }
 
+// One CTA per (tile, share of the blocks).  The share's groups are contiguous in the tile's list, so the CTA stages all
+// of them at once -- ids with coalesced loads, depth words with one gather, the group boundaries from the prefix table --
+// and the memory latency is paid twice per CTA instead of four times per group; the warps then sort the groups out of
+// shared memory (registers + shuffles up to 128 elements, the warp's slab up to 512, the CTA beyond) and the result
+// goes back with coalesced stores.
 __global__ void __launch_bounds__(GS_THREADS)
-group_sort_kernel(const int* __restrict__ table, const int* __restrict__ total, const int2* __restrict__ ranges, int nb,
+group_sort_kernel(const int* __restrict__ table, const int* __restrict__ total, const int2* __restrict__ ranges,
+                  const int* __restrict__ ne_list, int nb,
                   int n_tiles, const uint32_t* __restrict__ dbits, const Counters* __restrict__ counters,
                   int* __restrict__ vals, unsigned long long* __restrict__ scratch) {
-  __shared__ unsigned long long slab[GS_WARPS][GS_WARP_CAP];
+  __shared__ unsigned long long keys[GS_CTA_CAP];          // 32 KB: the share's composite keys (or the CTA-wide sort buffer)
+  __shared__ int bound[GS_MAX_SHARE + 1];
   __shared__ int2 big[GS_MAX_BIG];
   __shared__ int nbig_s;
   if (counters->overflow) return;
-  const int tile = blockIdx.x;
-  const int2 rg = ranges[tile];
-  if (rg.y - rg.x <= 1) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int share = (nb + GS_SPLIT - 1) / GS_SPLIT;        // <= GS_MAX_SHARE (nb <= CS_NB)
+  // persistent grid over the compact list of (non-empty tile, share) items written by the tile scan: a CTA per
+  // (tile, share) of the whole grid spent more time retiring the empty tiles' CTAs than sorting
+  const int n_items = ne_list[0] * GS_SPLIT;
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {     // block uniform
+  __syncthreads();                                          // the previous item's shared state is no longer read
+  const int tile = ne_list[1 + w / GS_SPLIT];
+  const int2 rg = ranges[tile];
+  const int b_lo = min(nb, (w % GS_SPLIT) * share), b_hi = min(nb, b_lo + share);
+  const int ng = b_hi - b_lo;
+  if (ng <= 0) continue;
+  if (threadIdx.x <= ng) {
+    const int b = b_lo + threadIdx.x;
+    bound[threadIdx.x] = (b < nb) ? table[(size_t)b * n_tiles + tile] : total[tile];
+  }
   if (threadIdx.x == 0) nbig_s = 0;
   __syncthreads();
-  // ---- phase 1: a warp per group; this CTA owns blocks [b_lo, b_hi)
-  const int share = (nb + GS_SPLIT - 1) / GS_SPLIT;
-  const int b_lo = min(nb, (int)blockIdx.y * share), b_hi = min(nb, b_lo + share);
-  for (int b = b_lo + warp; b < b_hi; b += GS_WARPS) {
-    const int s0 = table[(size_t)b * n_tiles + tile];
-    const int s1 = (b + 1 < nb) ? table[(size_t)(b + 1) * n_tiles + tile] : total[tile];
-    const int m = s1 - s0;
+  const int s_lo = bound[0], m_all = bound[ng] - s_lo;
+  if (m_all <= 1) continue;
+  int* base = vals + rg.x + s_lo;
+  const bool staged = m_all <= GS_CTA_CAP;
+  if (staged) {
+    for (int i = threadIdx.x; i < m_all; i += GS_THREADS) {
+      const int id = base[i];
+      keys[i] = ((unsigned long long)__ldg(dbits + id) << 32) | (unsigned)id;
+    }
+    __syncthreads();
+  }
+  // ---- phase 1: a warp per group
+  for (int g = warp; g < ng; g += GS_WARPS) {
+    const int o = bound[g] - s_lo, m = bound[g + 1] - bound[g];
     if (m <= 1) continue;
-    if (m > GS_WARP_CAP) {
-      if (lane == 0) {
-        const int q = atomicAdd(&nbig_s, 1);
-        if (q < GS_MAX_BIG) big[q] = make_int2(s0, m);
-      }
+    if (staged && m <= 128) {
+      unsigned long long k[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) k[r] = (r * 32 + lane < m) ? keys[o + r * 32 + lane] : ~0ull;
+      if (m <= 32) { unsigned long long k1[1] = {k[0]}; warp_sort_regs<1>(k1, lane); k[0] = k1[0]; }
+      else if (m <= 64) { unsigned long long k2[2] = {k[0], k[1]}; warp_sort_regs<2>(k2, lane); k[0] = k2[0]; k[1] = k2[1]; }
+      else warp_sort_regs<4>(k, lane);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r * 32 + lane < m) keys[o + r * 32 + lane] = k[r];
       continue;
     }
-    int* dst = vals + rg.x + s0;
-    const int P = next_pow2(m);
-    load_keys<32>(slab[warp], P, lane, dst, m, dbits);
-    bitonic_sort<32>(slab[warp], P, lane);
-    for (int i = lane; i < m; i += 32) dst[i] = (int)(unsigned)(slab[warp][i] & 0xffffffffull);
-    __syncwarp();
+    if (lane == 0) {                                         // larger (or unstaged) groups: the CTA takes them below
+      const int q = atomicAdd(&nbig_s, 1);
+      if (q < GS_MAX_BIG) big[q] = make_int2(bound[g] , m);
+    }
   }
   __syncthreads();
+  if (staged) {
+    for (int i = threadIdx.x; i < m_all; i += GS_THREADS) base[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+    __syncthreads();
+  }
   const int nbig = nbig_s;
-  if (nbig == 0) return;
-  // ---- phase 2: the CTA takes the oversized groups one after the other.  More of them than the list holds (a
-  // degenerate scene): the CTA rescans the blocks itself.
-  unsigned long long* all = &slab[0][0];
-  const int rounds = nbig <= GS_MAX_BIG ? nbig : b_hi - b_lo;
+  if (nbig == 0) continue;
+  // ---- phase 2: the CTA sorts the oversized groups one after the other straight from global memory (the staged keys
+  // are no longer needed).  More of them than the list holds: the CTA rescans its groups.
+  unsigned long long* all = keys;
+  const int rounds = nbig <= GS_MAX_BIG ? nbig : ng;
   for (int rr = 0; rr < rounds; ++rr) {
     int s0, m;
     if (nbig <= GS_MAX_BIG) { s0 = big[rr].x; m = big[rr].y; }
     else {
-      const int r = b_lo + rr;
-      s0 = table[(size_t)r * n_tiles + tile];
-      m = ((r + 1 < nb) ? table[(size_t)(r + 1) * n_tiles + tile] : total[tile]) - s0;
-      if (m <= GS_WARP_CAP) continue;                 // block uniform
+      s0 = bound[rr];
+      m = bound[rr + 1] - bound[rr];
+      if (m <= 1 || (staged && m <= 128)) continue;         // block uniform
     }
     int* dst = vals + rg.x + s0;
     if (m <= GS_CTA_CAP) {
@@ -128,11 +216,11 @@ group_sort_kernel(const int* __restrict__ table, const int* __restrict__ total, 
     const int C = (m + GS_CTA_CAP - 1) / GS_CTA_CAP;
     unsigned long long* out = scratch + rg.x + s0;
     for (int c = 0; c < C; ++c) {
-      const int base = c * GS_CTA_CAP, len = min(GS_CTA_CAP, m - base);
+      const int cb = c * GS_CTA_CAP, len = min(GS_CTA_CAP, m - cb);
       const int P = next_pow2(len);
-      load_keys<GS_THREADS>(all, P, threadIdx.x, dst + base, len, dbits);
+      load_keys<GS_THREADS>(all, P, threadIdx.x, dst + cb, len, dbits);
       bitonic_sort<GS_THREADS>(all, P, threadIdx.x);
-      for (int i = threadIdx.x; i < len; i += GS_THREADS) out[base + i] = all[i];
+      for (int i = threadIdx.x; i < len; i += GS_THREADS) out[cb + i] = all[i];
       __syncthreads();
     }
     __threadfence_block();
@@ -155,10 +243,11 @@ group_sort_kernel(const int* __restrict__ table, const int* __restrict__ total, 
     }
     __syncthreads();
   }
+  }   // work items
 }
 
 // ---- step 1: depth slabs -----------------------------------------------------------------------------------------
-constexpr int SL_SAMPLES = 4096;
+constexpr int SL_SAMPLES = 2048;
 constexpr int SL_MAXB = 512;          // >= CS_NB
 
 // one CTA: sorted sample -> nb-1 splitters; clears the slab counters
@@ -271,11 +360,11 @@ int launch_depth_slabs(const uint32_t* dbits, int n, int nb, uint32_t* splitters
 }
 
 // Step 3 (after the order-indirected counting sort): sort the inside of every (block, tile) group.
-int launch_group_sort(const ViewParams& vp, const int* table, const int* total, const int2* ranges, int nb,
+int launch_group_sort(const ViewParams& vp, const int* table, const int* total, const int2* ranges, const int* ne_list, int nb,
                       const uint32_t* dbits, const Counters* counters, int* vals, unsigned long long* scratch,
                       unsigned long long* keys_out, cudaStream_t st) {
   if (vp.n_tiles <= 0) return B2S_OK;
-  group_sort_kernel<<<dim3(vp.n_tiles, GS_SPLIT), GS_THREADS, 0, st>>>(table, total, ranges, nb, vp.n_tiles, dbits, counters, vals, scratch);
+  group_sort_kernel<<<sm_count() * 7, GS_THREADS, 0, st>>>(table, total, ranges, ne_list, nb, vp.n_tiles, dbits, counters, vals, scratch);
   B2S_LAUNCH_CHECK();
   if (keys_out != nullptr) {
     rebuild_keys_kernel<<<vp.n_tiles, 256, 0, st>>>(ranges, dbits, vals, keys_out);
