@@ -24,7 +24,7 @@ EXPORTS = [
     "b2s_adam_step", "b2s_view_block_bytes", "b2s_pack_views", "b2s_backward_blend", "b2s_fit_backward_blend", "b2s_backward_params",
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
-    "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded",
+    "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded", "b2s_backward_params_range",
 ]
 
 
@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         L.b2s_forward_prepared.argtypes = [vp, PP, vp, i32, i64, vp, vp, vp, vp, sz, vp, sz, vp]
         L.b2s_backward_params.restype = i32
         L.b2s_backward_params.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp]
+        L.b2s_backward_params_range.restype = i32
+        L.b2s_backward_params_range.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
         L.b2s_state_info.restype = i32
         L.b2s_state_info.argtypes = [vp, vp, i32, i32, i32, i64, C.POINTER(i64), vp]
         L.b2s_render_rgba8.restype = i32

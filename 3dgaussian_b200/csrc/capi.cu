@@ -539,7 +539,7 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   }
   if (rc != B2S_OK) return rc;
   StageTimer t(ctx, ST_PREPROCESS_BWD, st);
-  return launch_preprocess_bwd(&vp, nullptr, 1, vp.sh, means, scales, colors, opacities, n, B.gacc, grad_means,
+  return launch_preprocess_bwd(&vp, nullptr, 1, vp.sh, means, scales, colors, opacities, n, 0, n, B.gacc, grad_means,
                                grad_scales, grad_colors, grad_opacities, accumulate, st);
 }
 
@@ -610,17 +610,25 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
                                nullptr, &fl, B.gbuf, gacc_out, st);
 }
 
+int b2s_backward_params_range(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                              const float* scales, const float* colors, const float* opacities, int n, int first, int count,
+                              const float* gacc_all, float* grad_means, float* grad_scales, float* grad_colors,
+                              float* grad_opacities, int accumulate, void* stream) {
+  if (ctx == nullptr || views_dev == nullptr || gacc_all == nullptr || grad_means == nullptr || grad_scales == nullptr ||
+      grad_opacities == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  if (n < 0 || num_views < 0 || first < 0 || count < 0 || (long long)first + count > n) { set_error("bad n, num_views or range"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_PREPROCESS_BWD, (cudaStream_t)stream);
+  return launch_preprocess_bwd(nullptr, (const ViewParams*)views_dev, num_views, sh_coeffs > 0 ? sh_coeffs : 1, means,
+                               scales, colors, opacities, n, first, count, gacc_all, grad_means, grad_scales, grad_colors,
+                               grad_opacities, accumulate, (cudaStream_t)stream);
+}
+
 int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
                         const float* scales, const float* colors, const float* opacities, int n, const float* gacc_all,
                         float* grad_means, float* grad_scales, float* grad_colors, float* grad_opacities,
                         int accumulate, void* stream) {
-  if (ctx == nullptr || views_dev == nullptr || gacc_all == nullptr || grad_means == nullptr || grad_scales == nullptr ||
-      grad_opacities == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
-  if (n < 0 || num_views < 0) { set_error("bad n or num_views"); return B2S_ERR_INVALID; }
-  StageTimer t(ctx, ST_PREPROCESS_BWD, (cudaStream_t)stream);
-  return launch_preprocess_bwd(nullptr, (const ViewParams*)views_dev, num_views, sh_coeffs > 0 ? sh_coeffs : 1, means,
-                               scales, colors, opacities, n, gacc_all, grad_means, grad_scales, grad_colors,
-                               grad_opacities, accumulate, (cudaStream_t)stream);
+  return b2s_backward_params_range(ctx, views_dev, num_views, sh_coeffs, means, scales, colors, opacities, n, 0, n > 0 ? n : 0,
+                                   gacc_all, grad_means, grad_scales, grad_colors, grad_opacities, accumulate, stream);
 }
 
 int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,

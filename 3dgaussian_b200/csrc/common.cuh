@@ -412,8 +412,8 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
 // else views_dev[num_views] in device memory and gacc = num_views x n x 12 floats.
 int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,
                           const float* means, const float* scales, const float* colors, const float* opac, int n,
-                          const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
-                          int accumulate, cudaStream_t st);
+                          int first, int count /* Gaussians [first, first + count) */, const float* gacc, float* g_means,
+                          float* g_scales, float* g_colors, float* g_opac, int accumulate, cudaStream_t st);
 int launch_scan_i32(int* data, int len, int* bs, cudaStream_t st);
 size_t densify_workspace_bytes(int n);
 int launch_densify_prune(const float* means, const float* scales_raw, const float* op_raw, const float* colors, int n,

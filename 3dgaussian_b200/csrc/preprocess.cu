@@ -368,17 +368,19 @@ template <int K, int LPG>
 __global__ void __launch_bounds__(PRE_BLOCK)
 preprocess_bwd_kernel(const ViewParams single, const ViewParams* __restrict__ views, int num_views,
                       const float* __restrict__ means, const float* __restrict__ scales,
-                      const float* __restrict__ colors, const float* __restrict__ opac, int n,
+                      const float* __restrict__ colors, const float* __restrict__ opac, int n, int first, int count,
                       const float4* __restrict__ gacc, float* __restrict__ g_means, float* __restrict__ g_scales,
                       float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
   constexpr int KL = K / LPG;       // SH coefficients per lane
   constexpr int CL = KL * 3;        // colour floats per lane
   static_assert(K % LPG == 0 && (LPG == 1 || (CL % 4) == 0), "lane split must keep 16-byte pieces");
   __shared__ ViewParams sv[BWD_VIEWS_SMEM];
+  // Gaussians [first, first + count) of the n (n is also the per-view stride of gacc): the fit loop folds the views
+  // chunk by chunk so that a chunk's gradients can be all-reduced while the next chunk is computed
   const int gidx = blockIdx.x * PRE_BLOCK + threadIdx.x;
-  const int i = gidx / LPG, sub = gidx % LPG;
-  const bool live = i < n;
-  const int ii = live ? i : 0;
+  const int i = first + gidx / LPG, sub = gidx % LPG;
+  const bool live = gidx / LPG < count;
+  const int ii = live ? i : first;
 
   const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
               mz = __ldg(means + 3 * (size_t)ii + 2);
@@ -613,7 +615,7 @@ __device__ __forceinline__ void sh16_group_accumulate(const ViewParams& vp, floa
 __global__ void __launch_bounds__(PRE_BLOCK)
 preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict__ views, int num_views,
                            const float* __restrict__ means, const float* __restrict__ scales,
-                           const float* __restrict__ colors, const float* __restrict__ opac, int n,
+                           const float* __restrict__ colors, const float* __restrict__ opac, int n, int first, int count,
                            const float4* __restrict__ gacc, float* __restrict__ g_means, float* __restrict__ g_scales,
                            float* __restrict__ g_colors, float* __restrict__ g_opac, int accumulate) {
   static_assert(PRE_BLOCK == 256, "8 warps: 2 x 32 Gaussians x 4 coefficient groups");
@@ -621,9 +623,9 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
   __shared__ float part[3][6][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp & 3, slot = (warp >> 2) * 32 + lane;
-  const int i = blockIdx.x * 64 + slot;
-  const bool live = i < n;
-  const int ii = live ? i : 0;
+  const int i = first + blockIdx.x * 64 + slot;
+  const bool live = (int)blockIdx.x * 64 + slot < count;
+  const int ii = live ? i : first;
 
   const float mx = __ldg(means + 3 * (size_t)ii), my = __ldg(means + 3 * (size_t)ii + 1),
               mz = __ldg(means + 3 * (size_t)ii + 2);
@@ -771,23 +773,23 @@ preprocess_bwd_sh16_kernel(const ViewParams single, const ViewParams* __restrict
 
 int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev, int num_views, int sh,
                           const float* means, const float* scales, const float* colors, const float* opac, int n,
-                          const float* gacc, float* g_means, float* g_scales, float* g_colors, float* g_opac,
-                          int accumulate, cudaStream_t st) {
-  if (n <= 0 || num_views <= 0) return B2S_OK;
+                          int first, int count, const float* gacc, float* g_means, float* g_scales, float* g_colors,
+                          float* g_opac, int accumulate, cudaStream_t st) {
+  if (n <= 0 || num_views <= 0 || count <= 0) return B2S_OK;
   ViewParams one;
   if (single != nullptr) one = *single; else memset(&one, 0, sizeof(one));
 #define B2S_PREB(KK, LL)                                                                                              \
-  preprocess_bwd_kernel<KK, LL><<<(int)(((size_t)n * LL + PRE_BLOCK - 1) / PRE_BLOCK), PRE_BLOCK, 0, st>>>(           \
-      one, views_dev, num_views, means, scales, colors, opac, n, reinterpret_cast<const float4*>(gacc), g_means,      \
-      g_scales, g_colors, g_opac, accumulate)
+  preprocess_bwd_kernel<KK, LL><<<(int)(((size_t)count * LL + PRE_BLOCK - 1) / PRE_BLOCK), PRE_BLOCK, 0, st>>>(       \
+      one, views_dev, num_views, means, scales, colors, opac, n, first, count, reinterpret_cast<const float4*>(gacc),  \
+      g_means, g_scales, g_colors, g_opac, accumulate)
   switch (sh) {
     case 1: B2S_PREB(1, 1); break;
     case 4: B2S_PREB(4, 1); break;
     case 9: B2S_PREB(9, 1); break;
     case 16:
       if (colors != nullptr && g_colors != nullptr) {
-        preprocess_bwd_sh16_kernel<<<(n + 63) / 64, PRE_BLOCK, 0, st>>>(one, views_dev, num_views, means, scales, colors, opac, n,
-                                                                       reinterpret_cast<const float4*>(gacc), g_means, g_scales,
+        preprocess_bwd_sh16_kernel<<<(count + 63) / 64, PRE_BLOCK, 0, st>>>(one, views_dev, num_views, means, scales, colors, opac, n,
+                                                                       first, count, reinterpret_cast<const float4*>(gacc), g_means, g_scales,
                                                                        g_colors, g_opac, accumulate);
       } else {
         B2S_PREB(16, 4);

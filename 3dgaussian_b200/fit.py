@@ -43,7 +43,7 @@ class FitDriver:
                  rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
                  fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30,
                  view_groups: int = 1, use_depth: bool = False, depth_weight: float = 0.05,
-                 overflow_check_every: int = 8):
+                 overflow_check_every: int = 8, grad_chunks: Optional[int] = None):
         """use_depth: the fit carries the reference's depth term (fit_multiview_stub.py:298-303, weight
         `depth_weight`): the forward keeps the depth plane and the cutoff defaults to 7 sigma instead of 5, because
         depth = D/(W+1e-6) and its gradient amplify the truncated tails."""
@@ -57,6 +57,12 @@ class FitDriver:
         if self.use_depth and not fused_loss:
             raise ValueError("the depth term is part of the fused loss path (fused_loss=True)")
         self.overflow_check_every = max(1, int(overflow_check_every))
+        # Tail of a multi-GPU iteration: the chain rule, the gradient all-reduce and Adam run as a 3-stage pipeline over
+        # `grad_chunks` ranges of Gaussians (chain rule of chunk k+1 | NCCL all-reduce of chunk k on a comm stream | Adam
+        # of chunk k-1), instead of three serial full-size steps.  One chunk on a single GPU (nothing to overlap).
+        self.grad_chunks = max(1, int(grad_chunks)) if grad_chunks is not None else (4 if world > 1 else 1)
+        self._force_chunks = grad_chunks is not None and world == 1      # tests: the chunked tail on one GPU
+        self._comm_stream = None
         self.lr, self.w_sil = float(lr), float(silhouette_weight)
         self.reg_op, self.reg_scale = float(reg_opacity), float(reg_scale)
         self.rank, self.world, self.pg = rank, world, process_group
@@ -297,14 +303,31 @@ class FitDriver:
                 self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n,
                 C.c_void_p(self.prepared.data_ptr() + a * self.pv_bytes), _stream()))
 
-    def _chain_rule(self, a: int, b: int, accumulate: bool):
-        """Chain rule over local views [a, b): every Gaussian's gradients summed over the views in registers."""
+    def _chain_rule(self, a: int, b: int, accumulate: bool, first: int = 0, count: Optional[int] = None):
+        """Chain rule over local views [a, b) for the Gaussians [first, first + count): every Gaussian's gradients
+        summed over the views in registers."""
         vb = capi.lib().b2s_view_block_bytes()
-        capi.check(capi.lib().b2s_backward_params(
+        capi.check(capi.lib().b2s_backward_params_range(
             capi.ctx(self.dev.index), C.c_void_p(self.views_dev.data_ptr() + a * vb), b - a, self.sh,
             self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n,
+            first, self.n - first if count is None else count,
             _ptr(self.gacc[a]), self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_colors),
             self._gp(self.o_opac), 1 if accumulate else 0, _stream()))
+
+    def _chunks(self):
+        """[(first, count)] Gaussian ranges of the pipelined tail (one range when there is nothing to overlap)."""
+        c = self.grad_chunks if ((self.world > 1 or self._force_chunks) and self.view_groups == 1) else 1
+        c = max(1, min(c, (self.n + 4095) // 4096))
+        per = ((self.n + c - 1) // c + 63) // 64 * 64
+        return [(i, min(per, self.n - i)) for i in range(0, self.n, per)] or [(0, 0)]
+
+    def _chunk_slices(self, buf, first, count):
+        """The four slices of a flat buffer that belong to the Gaussians [first, first + count)."""
+        k = 3 * self.sh
+        return [buf[self.o_means + 3 * first: self.o_means + 3 * (first + count)],
+                buf[self.o_scales + 3 * first: self.o_scales + 3 * (first + count)],
+                buf[self.o_opac + first: self.o_opac + first + count],
+                buf[self.o_colors + k * first: self.o_colors + k * (first + count)]]
 
     def _streams(self):
         if self._lane_streams is None:
@@ -327,6 +350,7 @@ class FitDriver:
         nv = len(self.views)
         nl = max(1, min(self.active_lanes, self.lanes))
         self.lane_acc.zero_()
+        self._chain_ev = []
         if nv == 0:
             self.g.zero_()
             return
@@ -337,11 +361,19 @@ class FitDriver:
             if q.get("done") is not None:
                 q["done"](stream)
 
+        chunks = self._chunks()
         if nl == 1:
             self._preprocess_views(0, nv)
             for k in range(nv):
                 one_view(k, 0, main)
-            self._chain_rule(0, nv, False)
+            torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
+            for first, count in chunks:
+                self._chain_rule(0, nv, False, first, count)
+                if len(chunks) > 1:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self._chain_ev.append(ev)
+            return
         else:
             streams = self._streams()
             tail = self._tail_stream
@@ -370,16 +402,75 @@ class FitDriver:
                     ev.record(streams[l])
                     tail.wait_event(ev)
                 with torch.cuda.stream(tail):
-                    self._chain_rule(a, b, g > 0)
-            self._tail_done.record(tail)
-            main.wait_event(self._tail_done)           # the tail has waited for every lane
-        # loss and overflow count of this rank's views into the gradient buffer's tail (fixed order: deterministic)
-        torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
+                    if g == G - 1:
+                        # loss and overflow count of this rank's views into the gradient buffer's tail (fixed order:
+                        # deterministic); the tail stream has waited for every lane
+                        torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
+                    if G == 1 and len(chunks) > 1:
+                        for first, count in chunks:         # chunk by chunk: _finish_step pipelines all-reduce and Adam behind
+                            self._chain_rule(a, b, False, first, count)
+                            ev = torch.cuda.Event()
+                            ev.record(tail)
+                            self._chain_ev.append(ev)
+                    else:
+                        self._chain_rule(a, b, g > 0)
+            if not self._chain_ev:
+                self._tail_done.record(tail)
+                main.wait_event(self._tail_done)       # the tail has waited for every lane
+            # (chunked tail: the caller's stream waits for each chunk's all-reduce in _finish_step instead, and that
+            # all-reduce waits for the chunk's chain rule -- nothing is queued behind the whole chain rule)
+
+    def _adam(self, p, g, m, v, reg: Optional[str], frac: float, count_skip: bool):
+        """Guarded Adam over one contiguous slice; reg = 'scales' / 'opac' applies that regulariser to the whole slice
+        (its weight scaled by the slice's share `frac` of the segment, so that the per-element gradient stays
+        reg / segment size)."""
+        nel = p.numel()
+        if nel == 0:
+            return
+        sb = se = ob = oe = 0
+        rs = ro = 0.0
+        if reg == "scales":
+            se, rs = nel, self.reg_scale * frac
+        elif reg == "opac":
+            oe, ro = nel, self.reg_op * frac
+        capi.check(capi.lib().b2s_adam_step_guarded(
+            capi.ctx(self.dev.index), _ptr(p), _ptr(g), _ptr(m), _ptr(v), nel, self.step_no, self.lr, 0.9, 0.999, 1e-8,
+            sb, se, rs, ob, oe, ro, C.c_void_p(self.tail.data_ptr() + 4), _ptr(self.skipped_dev) if count_skip else None,
+            _stream()))
 
     def _finish_step(self):
+        self.step_no += 1
+        chain_ev = getattr(self, "_chain_ev", [])
+        if len(self._chunks()) > 1:      # the same decision on every rank (an idle rank has no events)
+            # 3-stage pipeline over the Gaussian chunks: chain rule (already queued, one event per chunk) | coalesced
+            # all-reduce of the chunk's four slices on the comm stream | Adam on the caller's stream.  Loss and
+            # overflow count (the Adam guard) ride with the first chunk.
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.dev)
+            main, comm = torch.cuda.current_stream(), self._comm_stream
+            chunks = self._chunks()
+            for c, (first, count) in enumerate(chunks):
+                gs = self._chunk_slices(self.g, first, count)
+                with torch.cuda.stream(comm):
+                    if c < len(chain_ev):
+                        comm.wait_event(chain_ev[c])
+                    elif c == 0:
+                        comm.wait_stream(main)          # idle rank (no local views): its zeroed buffer is on the caller's stream
+                    if self.world > 1:
+                        with torch.distributed._coalescing_manager(group=self.pg):
+                            for t in gs + ([self.tail] if c == 0 else []):
+                                torch.distributed.all_reduce(t, group=self.pg)
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                main.wait_event(ev)
+                ps, ms, vs = (self._chunk_slices(b, first, count) for b in (self.p, self.m, self.v))
+                frac = count / max(self.n, 1)
+                for q, reg in enumerate((None, "scales", "opac", None)):
+                    self._adam(ps[q], gs[q], ms[q], vs[q], reg, frac, count_skip=(c == 0 and q == 0))
+            self._chain_ev = []
+            return
         if self.world > 1:
             torch.distributed.all_reduce(self.g, group=self.pg)     # gradients + loss + overflow count: ONE collective
-        self.step_no += 1
         capi.check(capi.lib().b2s_adam_step_guarded(
             capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
             self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_scales + 3 * self.n, self.reg_scale, self.o_opac,

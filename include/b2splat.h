@@ -162,6 +162,14 @@ int b2s_backward_params(b2s_ctx* ctx, const void* views_dev, int num_views, int 
                         const float* gacc_all, float* grad_means, float* grad_scales, float* grad_colors,
                         float* grad_opacities, int accumulate, void* stream);
 
+/* The same for the Gaussians [first, first + count) only (all pointers are the bases of the full arrays): the
+ * multi-GPU fit folds the views chunk by chunk, so that chunk k's gradients cross NVLink (all-reduce) and take their
+ * Adam step while chunk k+1 is still being computed. */
+int b2s_backward_params_range(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,
+                              const float* scales, const float* colors, const float* opacities, int n, int first,
+                              int count, const float* gacc_all, float* grad_means, float* grad_scales,
+                              float* grad_colors, float* grad_opacities, int accumulate, void* stream);
+
 /* info_host[0] = pairs needed, [1] = pairs kept, [2] = overflow flag.  Synchronises. */
 int b2s_state_info(b2s_ctx* ctx, const void* state, int n, int width, int height, int64_t max_pairs,
                    int64_t* info_host, void* stream);
