@@ -57,12 +57,6 @@ class FitDriver:
         if self.use_depth and not fused_loss:
             raise ValueError("the depth term is part of the fused loss path (fused_loss=True)")
         self.overflow_check_every = max(1, int(overflow_check_every))
-        # Tail of a multi-GPU iteration: the chain rule, the gradient all-reduce and Adam run as a 3-stage pipeline over
-        # `grad_chunks` ranges of Gaussians (chain rule of chunk k+1 | NCCL all-reduce of chunk k on a comm stream | Adam
-        # of chunk k-1), instead of three serial full-size steps.  One chunk on a single GPU (nothing to overlap).
-        self.grad_chunks = max(1, int(grad_chunks)) if grad_chunks is not None else (4 if world > 1 else 1)
-        self._force_chunks = grad_chunks is not None and world == 1      # tests: the chunked tail on one GPU
-        self._comm_stream = None
         self.lr, self.w_sil = float(lr), float(silhouette_weight)
         self.reg_op, self.reg_scale = float(reg_opacity), float(reg_scale)
         self.rank, self.world, self.pg = rank, world, process_group
@@ -73,11 +67,21 @@ class FitDriver:
                                              mode=capi.MODE_WSUM, style=capi.STYLE_TORCH,
                                              cutoff_sigma=cutoff_sigma, sh_coeffs=self.sh, sort_depth=0,
                                              act_flags=act, keep_depth=1 if self.use_depth else 0) for i in self.views}
+        # Tail of a multi-GPU iteration: the chain rule, the gradient all-reduce and Adam run as a 3-stage pipeline over
+        # `grad_chunks` ranges of Gaussians (chain rule of chunk k+1 | NCCL all-reduce of chunk k on a comm stream | Adam
+        # of chunk k-1), instead of three serial full-size steps.  One chunk on a single GPU (nothing to overlap).
+        self.view_groups = max(1, int(view_groups))
+        self.grad_chunks = max(1, int(grad_chunks)) if grad_chunks is not None else (4 if world > 1 else 1)
+        self._force_chunks = grad_chunks is not None and world == 1      # tests: the chunked tail on one GPU
+        self._comm_stream = None
         self._layout(self.n)
         self.step_no = 0
         self.skipped_dev = torch.zeros(1, dtype=torch.int32, device=device)   # Adam steps the device guard skipped
+        self._skipped_host = torch.zeros(1, dtype=torch.int32).pin_memory()    # its last polled copy
+        self._poll_event = None                  # pending non-blocking poll
         self._since_check = 0
         self._overflowed = False
+        self.profile = None                      # {name: [events]} when bench.py asks for a per-step timeline
         # View lanes: lane l owns its own per-view buffers (images, image gradients, state, workspace, loss and
         # overflow accumulators) and a CUDA stream; view k of this rank runs on lane k % lanes, so the small
         # latency-bound kernels of one view (scans, finalize, loss, g-buffer) overlap the blend kernels of another.
@@ -86,7 +90,6 @@ class FitDriver:
         self.fused_loss = bool(fused_loss)
         self.batched_preprocess = bool(batched_preprocess) and self.fused_loss
         self.prepared_budget = int(prepared_budget_bytes)
-        self.view_groups = max(1, int(view_groups))
         self.prepared = None
         self.rgb_l = [torch.empty((height, width, 3), dtype=torch.float32, device=device) for _ in range(self.lanes)]
         self.alpha_l = [torch.empty((height, width), dtype=torch.float32, device=device) for _ in range(self.lanes)]
@@ -131,8 +134,26 @@ class FitDriver:
         self.o_colors = self.o_opac + al(n)
         self.count = self.o_colors + al(c * n)
         z = lambda extra=0: torch.zeros(self.count + extra, dtype=torch.float32, device=self.dev)
-        self.p, self.g, self.m, self.v = z(), z(64), z(), z()
-        self.tail = self.g[self.count:self.count + 64]
+        self.p, self.m, self.v = z(), z(), z()
+        chunks = self._chunks()
+        if len(chunks) == 1:
+            # gradients laid out like the parameters, the tail behind them
+            self.g = z(64)
+            self.tail = self.g[self.count:self.count + 64]
+            self._gchunks = None
+        else:
+            # pipelined tail: the gradient buffer is CHUNK-major -- [tail 64 | chunk 0: means, scales, opac, colours |
+            # chunk 1: ... ] -- so that a chunk (chunk 0 together with the tail) crosses NVLink as ONE contiguous
+            # all-reduce; parameters and moments keep the segment-major layout (Adam takes a pointer per slice)
+            self._gchunks, o = [], 64
+            for first, cnt in chunks:
+                segs = []
+                for k in (3, 3, 1, c):
+                    segs.append(o)
+                    o += al(k * cnt)
+                self._gchunks.append(segs + [o])          # four segment offsets + end
+            self.g = torch.zeros(o, dtype=torch.float32, device=self.dev)
+            self.tail = self.g[0:64]
         self.loss_dev = self.tail[0:1]
 
     # ---- parameter views -------------------------------------------------------------------
@@ -145,10 +166,16 @@ class FitDriver:
         return t.view(self.n, 3) if self.sh == 1 else t.view(self.n, self.sh, 3)
 
     def grad_views(self):
-        """(means, scales_raw, opacities_raw, colours) views of the flat gradient buffer."""
+        """(means, scales_raw, opacities_raw, colours) gradients as flat tensors (views of the gradient buffer, or
+        gathered from its chunks when the tail is pipelined)."""
         n = self.n
-        return (self._seg(self.g, self.o_means, 3 * n), self._seg(self.g, self.o_scales, 3 * n),
-                self._seg(self.g, self.o_opac, n), self._seg(self.g, self.o_colors, 3 * self.sh * n))
+        if self._gchunks is None:
+            return (self._seg(self.g, self.o_means, 3 * n), self._seg(self.g, self.o_scales, 3 * n),
+                    self._seg(self.g, self.o_opac, n), self._seg(self.g, self.o_colors, 3 * self.sh * n))
+        out = []
+        for q, k in enumerate((3, 3, 1, 3 * self.sh)):
+            out.append(torch.cat([self.g[segs[q]:segs[q] + k * cnt] for (first, cnt), segs in zip(self._chunks(), self._gchunks)]))
+        return tuple(out)
 
     def set_params(self, means, scales_raw, opacities_raw, colors_raw):
         with torch.no_grad():
@@ -307,12 +334,20 @@ class FitDriver:
         """Chain rule over local views [a, b) for the Gaussians [first, first + count): every Gaussian's gradients
         summed over the views in registers."""
         vb = capi.lib().b2s_view_block_bytes()
+        if self._gchunks is None:
+            gm, gs, go, gc = self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_opac), self._gp(self.o_colors)
+        else:
+            # chunk-major gradient buffer: the kernel indexes by the global Gaussian id, so every pointer is the chunk's
+            # segment moved back by the chunk's first id
+            ci = [f for f, _ in self._chunks()].index(first)
+            segs = self._gchunks[ci]
+            gm, gs = self._gp(segs[0] - 3 * first), self._gp(segs[1] - 3 * first)
+            go, gc = self._gp(segs[2] - first), self._gp(segs[3] - 3 * self.sh * first)
         capi.check(capi.lib().b2s_backward_params_range(
             capi.ctx(self.dev.index), C.c_void_p(self.views_dev.data_ptr() + a * vb), b - a, self.sh,
             self._pp(self.o_means), self._pp(self.o_scales), self._pp(self.o_colors), self._pp(self.o_opac), self.n,
             first, self.n - first if count is None else count,
-            _ptr(self.gacc[a]), self._gp(self.o_means), self._gp(self.o_scales), self._gp(self.o_colors),
-            self._gp(self.o_opac), 1 if accumulate else 0, _stream()))
+            _ptr(self.gacc[a]), gm, gs, gc, go, 1 if accumulate else 0, _stream()))
 
     def _chunks(self):
         """[(first, count)] Gaussian ranges of the pipelined tail (one range when there is nothing to overlap)."""
@@ -349,8 +384,9 @@ class FitDriver:
         main = torch.cuda.current_stream()
         nv = len(self.views)
         nl = max(1, min(self.active_lanes, self.lanes))
+        self._mark("step_begin")
         self.lane_acc.zero_()
-        self._chain_ev = []
+        self._chain_job = None
         if nv == 0:
             self.g.zero_()
             return
@@ -367,12 +403,10 @@ class FitDriver:
             for k in range(nv):
                 one_view(k, 0, main)
             torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
-            for first, count in chunks:
-                self._chain_rule(0, nv, False, first, count)
-                if len(chunks) > 1:
-                    ev = torch.cuda.Event()
-                    ev.record(main)
-                    self._chain_ev.append(ev)
+            if len(chunks) > 1:
+                self._chain_job = (main, 0, nv)          # _finish_step interleaves chain rule, all-reduce and Adam per chunk
+            else:
+                self._chain_rule(0, nv, False)
             return
         else:
             streams = self._streams()
@@ -382,19 +416,31 @@ class FitDriver:
                 st.wait_event(self._step_begin)       # after everything queued on the caller's stream (the last Adam)
             G = max(1, min(self.view_groups, nv // nl))
             bounds = [(g * nv) // G for g in range(G + 1)]
+            # The batched preprocess is cut into two launches, both queued up front on the caller's stream: the first
+            # covers one view per lane, so the lanes start blending after a sliver of the head (2.1 ms of a 42 ms
+            # iteration on one GPU, 0.3 of 6.5 ms on eight) instead of all of it; the second (every other view) runs
+            # beside those blends.  (Eight equal launches measured slower: each re-reads the 220 MB of parameters and
+            # takes SMs from the blends.)  With view_groups > 1 a launch is a view group.
+            PG = G if G > 1 else (2 if nv > nl else 1)
+            pbounds = bounds if G > 1 else ([0, nl, nv] if nv > nl else [0, nv])
             pre_ev = []
-            for g in range(G):                         # every group's preprocess is queued up front on the caller's stream
-                self._preprocess_views(bounds[g], bounds[g + 1])
+            for j in range(PG):
+                self._preprocess_views(pbounds[j], pbounds[j + 1])
                 ev = torch.cuda.Event()
                 ev.record(main)
                 pre_ev.append(ev)
+            self._mark("preprocess_done")
+            pgroup = lambda k: next(j for j in range(PG) if pbounds[j] <= k < pbounds[j + 1])
+            waited = [-1] * nl                         # last preprocess launch each lane has waited for
             for g in range(G):
                 a, b = bounds[g], bounds[g + 1]
                 used = sorted({k % nl for k in range(a, b)})
-                for l in used:
-                    streams[l].wait_event(pre_ev[g])
                 for k in range(a, b):
                     lane = k % nl
+                    j = pgroup(k)
+                    if waited[lane] < j:
+                        streams[lane].wait_event(pre_ev[j])
+                        waited[lane] = j
                     with torch.cuda.stream(streams[lane]):
                         one_view(k, lane, streams[lane])
                 for l in used:
@@ -403,18 +449,16 @@ class FitDriver:
                     tail.wait_event(ev)
                 with torch.cuda.stream(tail):
                     if g == G - 1:
+                        self._mark("views_done", tail)
                         # loss and overflow count of this rank's views into the gradient buffer's tail (fixed order:
                         # deterministic); the tail stream has waited for every lane
                         torch.sum(self.lane_acc[:nl], dim=0, out=self.tail[0:2])
                     if G == 1 and len(chunks) > 1:
-                        for first, count in chunks:         # chunk by chunk: _finish_step pipelines all-reduce and Adam behind
-                            self._chain_rule(a, b, False, first, count)
-                            ev = torch.cuda.Event()
-                            ev.record(tail)
-                            self._chain_ev.append(ev)
+                        self._chain_job = (tail, a, b)      # _finish_step interleaves chain rule, all-reduce and Adam per chunk
                     else:
                         self._chain_rule(a, b, g > 0)
-            if not self._chain_ev:
+            if self._chain_job is None:
+                self._mark("chain_done", tail)
                 self._tail_done.record(tail)
                 main.wait_event(self._tail_done)       # the tail has waited for every lane
             # (chunked tail: the caller's stream waits for each chunk's all-reduce in _finish_step instead, and that
@@ -440,45 +484,79 @@ class FitDriver:
 
     def _finish_step(self):
         self.step_no += 1
-        chain_ev = getattr(self, "_chain_ev", [])
-        if len(self._chunks()) > 1:      # the same decision on every rank (an idle rank has no events)
-            # 3-stage pipeline over the Gaussian chunks: chain rule (already queued, one event per chunk) | coalesced
-            # all-reduce of the chunk's four slices on the comm stream | Adam on the caller's stream.  Loss and
-            # overflow count (the Adam guard) ride with the first chunk.
+        if len(self._chunks()) > 1:      # the same decision on every rank (an idle rank simply has no chain rule to run)
+            # 3-stage pipeline over the Gaussian chunks, queued chunk by chunk so that the GPU sees chunk k's all-reduce
+            # BEFORE chunk k+1's chain rule (kernels that arrive first get the SMs first): chain rule on the tail stream |
+            # ONE contiguous all-reduce per chunk on the comm stream (the gradient buffer is chunk-major; loss and
+            # overflow count -- the Adam guard -- ride with chunk 0) | guarded Adam per slice on the caller's stream.
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=self.dev)
             main, comm = torch.cuda.current_stream(), self._comm_stream
+            job = getattr(self, "_chain_job", None)
             chunks = self._chunks()
             for c, (first, count) in enumerate(chunks):
-                gs = self._chunk_slices(self.g, first, count)
+                segs = self._gchunks[c]
+                gs = [self.g[segs[q]:segs[q] + k * count] for q, k in enumerate((3, 3, 1, 3 * self.sh))]
+                if job is not None:
+                    with torch.cuda.stream(job[0]):
+                        self._chain_rule(job[1], job[2], False, first, count)
+                        chain_ev = torch.cuda.Event()
+                        chain_ev.record(job[0])
+                        self._mark(f"chunk{c}_chain", job[0])
                 with torch.cuda.stream(comm):
-                    if c < len(chain_ev):
-                        comm.wait_event(chain_ev[c])
+                    if job is not None:
+                        comm.wait_event(chain_ev)
                     elif c == 0:
                         comm.wait_stream(main)          # idle rank (no local views): its zeroed buffer is on the caller's stream
                     if self.world > 1:
-                        with torch.distributed._coalescing_manager(group=self.pg):
-                            for t in gs + ([self.tail] if c == 0 else []):
-                                torch.distributed.all_reduce(t, group=self.pg)
+                        torch.distributed.all_reduce(self.g[0 if c == 0 else segs[0]:segs[4]], group=self.pg)
                     ev = torch.cuda.Event()
                     ev.record(comm)
+                    self._mark(f"chunk{c}_ar", comm)
                 main.wait_event(ev)
                 ps, ms, vs = (self._chunk_slices(b, first, count) for b in (self.p, self.m, self.v))
                 frac = count / max(self.n, 1)
                 for q, reg in enumerate((None, "scales", "opac", None)):
                     self._adam(ps[q], gs[q], ms[q], vs[q], reg, frac, count_skip=(c == 0 and q == 0))
-            self._chain_ev = []
+                self._mark(f"chunk{c}_adam")
+            self._chain_job = None
+            self._mark("adam_done")
             return
         if self.world > 1:
             torch.distributed.all_reduce(self.g, group=self.pg)     # gradients + loss + overflow count: ONE collective
+        self._mark("allreduce_done")
         capi.check(capi.lib().b2s_adam_step_guarded(
             capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
             self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_scales + 3 * self.n, self.reg_scale, self.o_opac,
             self.o_opac + self.n, self.reg_op, C.c_void_p(self.tail.data_ptr() + 4), _ptr(self.skipped_dev), _stream()))
+        self._mark("adam_done")
 
     def _device_inputs(self, k, stream):
         i = self.views[k]
         return {"tgt": self.targets[i], "mask": self.masks.get(i), "depth": self.depths.get(i)}
+
+    def _poll_overflow(self):
+        """Non-blocking poll of the guard's skipped-step counter: every `overflow_check_every` steps the counter is
+        copied to pinned host memory behind the step (no wait); a later step looks at the copy once its event has
+        completed.  The host never drains the stream for it -- steps queued behind an overflow are skipped by the same
+        guard (unchanged parameters overflow again), so reacting a few steps late loses nothing."""
+        if self._poll_event is not None and self._poll_event.query():
+            self._poll_event = None
+            if int(self._skipped_host[0]) != 0:
+                self._resolve_overflow()
+                return
+        self._since_check += 1
+        if self._poll_event is None and self._since_check >= self.overflow_check_every:
+            self._since_check = 0
+            self._skipped_host.copy_(self.skipped_dev, non_blocking=True)
+            self._poll_event = torch.cuda.Event()
+            self._poll_event.record()
+
+    def _mark(self, name, stream=None):
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream())
+            self.profile.setdefault(name, []).append(ev)
 
     def _resolve_overflow(self) -> int:
         """Reads the device counter of Adam steps the overflow guard skipped (synchronises).  If there were any, every
@@ -486,6 +564,7 @@ class FitDriver:
         rolled back, the pair buffers are re-planned from the current parameters with more slack, and the skipped
         iterations are repeated.  Returns the number of iterations that had to be repeated."""
         self._since_check = 0
+        self._poll_event = None
         k = int(self.skipped_dev.item())
         if k == 0:
             return 0
@@ -509,9 +588,7 @@ class FitDriver:
         with torch.cuda.device(self.dev):
             self._iterate(self._device_inputs)
             self._finish_step()
-            self._since_check += 1
-            if self._since_check >= self.overflow_check_every:
-                self._resolve_overflow()
+            self._poll_overflow()
         return self.loss_dev
 
     def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None,

@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4, help="concurrent view lanes (CUDA streams) per GPU")
     ap.add_argument("--view-groups", type=int, default=0,
                     help="pipeline the local views in this many groups (preprocess ahead, chain rule behind); 0 = auto")
+    ap.add_argument("--grad-chunks", type=int, default=0,
+                    help="Gaussian chunks of the pipelined multi-GPU tail (chain rule | all-reduce | Adam); 0 = FitDriver default")
+    ap.add_argument("--timeline", action="store_true",
+                    help="record CUDA events at the phase boundaries of every timed step on rank 0 (head / views / tail)")
     ap.add_argument("--no-reorder", action="store_true", help="keep the synthetic Gaussians in generation (random) order")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -386,6 +390,7 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")    # NCCL's stream ahead of the compute streams it overlaps with
         torch.distributed.init_process_group("nccl", device_id=device)
     capi = importlib.import_module("3dgaussian_b200.capi")
     fit = importlib.import_module("3dgaussian_b200.fit")
@@ -418,7 +423,7 @@ def main():
     nv_local = len(fit.local_views(args.views, rank, world))
     view_groups = args.view_groups if args.view_groups > 0 else VIEW_GROUPS_AUTO(nv_local, args.lanes)
     drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes,
-                        view_groups=view_groups)
+                        view_groups=view_groups, grad_chunks=args.grad_chunks if (args.grad_chunks > 0 and world > 1) else None)
     means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device, args.s_lo, args.s_hi)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
@@ -448,6 +453,9 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.timeline and rank == 0:
+        drv.profile = {}
+    t_host0 = time.perf_counter()
     e0.record()
     n_after = []
     for it in range(args.steps):
@@ -456,8 +464,23 @@ def main():
             # fit_multiview_stub.py:318-325: prune / clone on the device, Adam state reset, buffers re-planned
             n_after.append(drv.densify_prune(it + 1, max_gaussians=int(args.n * 1.2), seed=1234, reorder=not args.no_reorder))
     e1.record()
+    host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps     # host time to QUEUE a step (no sync inside)
     barrier()
     ms = e0.elapsed_time(e1)
+    timeline = None
+    if drv.profile:
+        prof, drv.profile = drv.profile, None
+        names = ["step_begin", "preprocess_done", "views_done", "chain_done", "allreduce_done", "adam_done"]
+        have = [nm for nm in names if len(prof.get(nm, [])) == args.steps]
+        timeline = {}
+        for a, b in zip(have[:-1], have[1:]):
+            timeline[f"{a}->{b}"] = float(np.mean([x.elapsed_time(y) for x, y in zip(prof[a], prof[b])]))
+        if "views_done" in prof:      # pipelined tail: when each chunk's stages finish, relative to the end of the views
+            for nm in sorted(k for k in prof if k.startswith("chunk")):
+                if len(prof[nm]) == args.steps:
+                    timeline[f"views_done->{nm}"] = float(np.mean([x.elapsed_time(y) for x, y in zip(prof["views_done"], prof[nm])]))
+        if "step_begin" in have and "adam_done" in have:
+            timeline["step_begin->adam_done"] = float(np.mean([x.elapsed_time(y) for x, y in zip(prof["step_begin"], prof["adam_done"])]))
     clocks = sampler.stop() if sampler else None
     launches = capi.lib().b2s_launch_count() - launches0
     # ---- per-stage CUDA-event spans.  With one lane the stages of the timed steps themselves are bracketed; with
@@ -668,6 +691,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "host_ms_per_step": host_ms_per_step, "timeline_ms": timeline,
         "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "view_groups": view_groups, "cpu_baseline": cpu, "render": render,
         "loss_last": loss_last, "pairs": {"P1_tile_pairs_worst_view": worst_p1, "P2_pixel_pairs_rank0_views": p2_rank0,
                                           "P2_all_ranks": float(p2_all.item())},

@@ -28,6 +28,11 @@ KEYS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
 ]
 
+EXTRA_PATTERNS = ["pipe_tensor", "pipe_tc", "tmem", "utcmma", "utchmma", "l1tex__data_pipe_lsu_wavefronts_mem_shared",
+                  "l1tex__data_bank", "smsp__inst_executed_op_shared", "sm__mio", "lts__t_sectors_op_red",
+                  "lts__t_sectors_op_atom", "l1tex__m_xbar2l1tex", "smsp__warp_issue_stalled_barrier",
+                  "sm__pipe_shared", "idc__", "sm__inst_executed_pipe_uniform"]
+
 
 def launches(path):
     rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("=="))]
@@ -58,6 +63,10 @@ def full(path):
         for k in KEYS:
             if k in idx:
                 print(f"- {k} = {r[idx[k]]} {units[idx[k]]}")
+        # tensor pipe, TMEM and shared-memory pipe: whatever the capture holds under these names
+        for h in hdr:
+            if h not in KEYS and any(p in h for p in EXTRA_PATTERNS) and h in idx and r[idx[h]] not in ("", "n/a"):
+                print(f"- {h} = {r[idx[h]]} {units[idx[h]]}")
         print()
 
 
