@@ -31,7 +31,7 @@ KEYS = [
 EXTRA_PATTERNS = ["pipe_tensor", "pipe_tc", "tmem", "utcmma", "utchmma", "l1tex__data_pipe_lsu_wavefronts_mem_shared",
                   "l1tex__data_bank", "smsp__inst_executed_op_shared", "sm__mio", "lts__t_sectors_op_red",
                   "lts__t_sectors_op_atom", "l1tex__m_xbar2l1tex", "smsp__warp_issue_stalled_barrier",
-                  "sm__pipe_shared", "idc__", "sm__inst_executed_pipe_uniform"]
+                  "sm__pipe_shared", "stalled_membar", "stalled_sleeping", "stalled_no_instruction", "stalled_branch", "stalled_drain", "stalled_imc", "stalled_tex", "stalled_selected"]
 
 
 def launches(path):
@@ -65,7 +65,17 @@ def full(path):
                 print(f"- {k} = {r[idx[k]]} {units[idx[k]]}")
         # tensor pipe, TMEM and shared-memory pipe: whatever the capture holds under these names
         for h in hdr:
-            if h not in KEYS and any(p in h for p in EXTRA_PATTERNS) and h in idx and r[idx[h]] not in ("", "n/a"):
+            v = r[idx[h]] if h in idx else ""
+            if any(t in h for t in (".min", ".max", "peak_sustained", "per_second", "per_cycle")) and "pct_of_peak" not in h:
+                continue
+            if any(t in h for t in (".min.", ".max.")):
+                continue
+            try:
+                if float(v.replace(",", "")) == 0.0:
+                    continue
+            except ValueError:
+                continue
+            if h not in KEYS and any(p in h for p in EXTRA_PATTERNS):
                 print(f"- {h} = {r[idx[h]]} {units[idx[h]]}")
         print()
 
