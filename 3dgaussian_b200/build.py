@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libb2splat.so")
-SOURCES = ["capi.cu", "preprocess.cu", "bin.cu", "sort.cu", "segsort.cu", "blend_fwd.cu", "blend_bwd.cu", "optim.cu", "densify.cu"]
+SOURCES = ["capi.cu", "preprocess.cu", "bin.cu", "sort.cu", "segsort.cu", "blend_fwd.cu", "blend_bwd.cu", "optim.cu", "densify.cu", "splat2d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
@@ -39,7 +39,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(ROOT, "include", "b2splat.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "color.cuh"), os.path.join(ROOT, "include", "b2splat.h")]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = []

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("B2S_LIB_PATH") or os.path.join(_HERE, "csrc", "libb2s
 
 MODE_WSUM, MODE_SORTED = 0, 1
 STYLE_TORCH, STYLE_NATIVE = 0, 1
+BLEND_WSUM, BLEND_OVER = 0, 1      # b2s_forward_ext / b2s_backward_ext (extension modes)
 ACT_SCALES_SOFTPLUS, ACT_OPACITY_SIGMOID, ACT_COLORS_SIGMOID = 1, 2, 4
 TILE = 16
 
@@ -25,6 +26,7 @@ EXPORTS = [
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
     "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded", "b2s_backward_params_range",
+    "b2s_forward_ext", "b2s_backward_ext",
 ]
 
 
@@ -71,6 +73,11 @@ def lib() -> C.CDLL:
         L.b2s_forward.argtypes = [vp, PP, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, vp, sz, vp]
         L.b2s_backward.restype = i32
         L.b2s_backward.argtypes = [vp, PP, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, i32, vp]
+        L.b2s_forward_ext.restype = i32
+        L.b2s_forward_ext.argtypes = [vp, PP, vp, vp, vp, vp, vp, i32, i64, i32, C.c_float, vp, vp, vp, vp, sz, vp, sz, vp]
+        L.b2s_backward_ext.restype = i32
+        L.b2s_backward_ext.argtypes = [vp, PP, vp, vp, vp, vp, vp, i32, i64, i32, C.c_float, vp, vp, vp, vp, vp, sz,
+                                       vp, vp, vp, vp, vp, vp]
         L.b2s_view_block_bytes.restype = sz
         L.b2s_view_block_bytes.argtypes = []
         L.b2s_pack_views.restype = i32

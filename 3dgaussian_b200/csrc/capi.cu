@@ -291,11 +291,13 @@ static void use_prepared(Bufs& b, const void* prepared_view, int n) {
 static int run_binning(b2s_ctx* ctx, const ViewParams& vp, const b2s_params* p, const float* means, const float* scales,
                        const float* colors, const float* opac, int n, int64_t max_pairs, const Bufs& B,
                        float* dbg, int* dbg_bbox, unsigned long long** keys_sorted,
-                       unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st) {
+                       unsigned long long* keys_unsorted_copy, int* vals_unsorted_copy, cudaStream_t st,
+                       bool pre_done = false /* the caller has already written rec / rect / tmask / dbits / cnt / bsum */) {
   int rc = B2S_OK;
   Counters* mirror = ticket_begin(ctx);
   if (!ticket_mapped()) mirror = nullptr;       // the counters travel by a stream-ordered copy instead (ticket_mark)
-  if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
+  if (pre_done) {
+  } else if (means != nullptr) {    // means == NULL: B already points at a view block of b2s_preprocess_views
     StageTimer t(ctx, ST_PREPROCESS, st);
     rc = launch_preprocess(vp, means, scales, colors, opac, n, B.rec, B.cmask, B.rect, B.tmask, B.dbits, B.cnt, B.bsum, dbg, dbg_bbox, st);
   } else if (!counting_sort_fits(vp.n_tiles)) {
@@ -541,6 +543,73 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
   StageTimer t(ctx, ST_PREPROCESS_BWD, st);
   return launch_preprocess_bwd(&vp, nullptr, 1, vp.sh, means, scales, colors, opacities, n, 0, n, B.gacc, grad_means,
                                grad_scales, grad_colors, grad_opacities, accumulate, st);
+}
+
+/* ---- extension modes: rotations + EWA covariance, differentiable "over" compositing (splat2d.cu) ---------------- */
+static int ext_view(const b2s_params* p, int blend, b2s_params* q, ViewParams* vp) {
+  if (p == nullptr) { set_error("params is NULL"); return B2S_ERR_INVALID; }
+  if (blend != B2S_BLEND_WSUM && blend != B2S_BLEND_OVER) { set_error("blend must be B2S_BLEND_WSUM or B2S_BLEND_OVER"); return B2S_ERR_INVALID; }
+  *q = *p;
+  q->enable_depth_sort = B2S_MODE_WSUM;       // the shared front end in its torch-style configuration; the blend is chosen by `blend`
+  q->style = B2S_STYLE_TORCH;
+  q->exact_bbox = 0;
+  q->sort_depth = (blend == B2S_BLEND_OVER) ? 1 : 0;
+  return make_view(q, vp);
+}
+
+int b2s_forward_ext(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* rotations,
+                    const float* colors, const float* opacities, int n, int64_t max_pairs, int blend, float ewa_dilation,
+                    float* out_rgb, float* out_alpha, float* out_depth, void* state, size_t state_bytes,
+                    void* workspace, size_t ws_bytes, void* stream) {
+  if (ctx == nullptr || state == nullptr || workspace == nullptr || means == nullptr || scales == nullptr ||
+      colors == nullptr || opacities == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  b2s_params q;
+  ViewParams vp;
+  int rc = ext_view(p, blend, &q, &vp);
+  if (rc != B2S_OK) return rc;
+  rc = check_sizes(n, p->width, p->height, max_pairs, state_bytes, true, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(state, workspace, n, p->width, p->height, max_pairs);
+  {
+    StageTimer t(ctx, ST_PREPROCESS, st);
+    rc = launch_ext_preprocess(vp, means, scales, rotations, colors, opacities, n, ewa_dilation, B.rec, B.cmask, B.rect, B.tmask,
+                               B.dbits, B.cnt, B.bsum, st);
+  }
+  if (rc != B2S_OK) return rc;
+  rc = run_binning(ctx, vp, &q, means, scales, colors, opacities, n, max_pairs, B, nullptr, nullptr, nullptr, nullptr, nullptr, st, true);
+  if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_BLEND_FWD, st);
+  return launch_blend_ext_fwd(vp, blend == B2S_BLEND_OVER, B.rec, B.vals, B.ranges, out_rgb, out_alpha, out_depth, B.acc, st);
+}
+
+int b2s_backward_ext(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* rotations,
+                     const float* colors, const float* opacities, int n, int64_t max_pairs, int blend, float ewa_dilation,
+                     const float* g_rgb, const float* g_alpha, const float* g_depth, const void* state, void* workspace,
+                     size_t ws_bytes, float* grad_means, float* grad_scales, float* grad_rotations, float* grad_colors,
+                     float* grad_opacities, void* stream) {
+  if (ctx == nullptr || state == nullptr || workspace == nullptr || grad_means == nullptr || grad_scales == nullptr ||
+      grad_colors == nullptr || grad_opacities == nullptr || (rotations != nullptr && grad_rotations == nullptr)) {
+    set_error("NULL argument");
+    return B2S_ERR_INVALID;
+  }
+  b2s_params q;
+  ViewParams vp;
+  int rc = ext_view(p, blend, &q, &vp);
+  if (rc != B2S_OK) return rc;
+  rc = check_sizes(n, p->width, p->height, max_pairs, 0, false, ws_bytes);
+  if (rc != B2S_OK) return rc;
+  if (n == 0) return B2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs B = resolve(const_cast<void*>(state), workspace, n, p->width, p->height, max_pairs);
+  {
+    StageTimer t(ctx, ST_BLEND_BWD, st);
+    rc = launch_blend_ext_bwd(vp, blend == B2S_BLEND_OVER, B.rec, B.vals, B.ranges, B.acc, g_rgb, g_alpha, g_depth, B.gacc, n, st);
+  }
+  if (rc != B2S_OK) return rc;
+  StageTimer t(ctx, ST_PREPROCESS_BWD, st);
+  return launch_ext_bwd(vp, means, scales, rotations, colors, opacities, n, ewa_dilation, B.gacc, B.cmask, grad_means, grad_scales,
+                        grad_rotations, grad_colors, grad_opacities, st);
 }
 
 size_t b2s_view_block_bytes(void) { return sizeof(ViewParams); }

@@ -47,6 +47,7 @@ struct Proj {
   float ax, ay;                 // unclamped sigmas
   int xmin, ymin, xmax, ymax;   // pixel bbox (inclusive)
   bool ok;
+  bool valid;                   // ok before the bbox-on-screen test (extension modes with their own footprint: splat2d.cu)
 };
 
 __device__ __forceinline__ float dot4_lr(const float* m, float a, float b, float c, float d) {
@@ -95,6 +96,7 @@ __device__ __forceinline__ Proj project_gaussian(const ViewParams& vp, float mx,
     ok = ok && (op >= 1e-5f);
     r.wsafe = (w == 0.0f) ? 1.0f : w;
   }
+  r.valid = ok;
   r.w = w;
   r.ndcx = nx;
   r.ndcy = ny;
@@ -414,6 +416,19 @@ int launch_preprocess_bwd(const ViewParams* single, const ViewParams* views_dev,
                           const float* means, const float* scales, const float* colors, const float* opac, int n,
                           int first, int count /* Gaussians [first, first + count) */, const float* gacc, float* g_means,
                           float* g_scales, float* g_colors, float* g_opac, int accumulate, cudaStream_t st);
+// extension modes (splat2d.cu): rotations + EWA covariance, differentiable front-to-back compositing
+int launch_ext_preprocess(const ViewParams& vp, const float* means, const float* scales, const float* rotations /* (N,4) or null */,
+                          const float* colors, const float* opac, int n, float dilation, float4* rec, uint8_t* cmask,
+                          uint2* rect, unsigned long long* tmask, uint32_t* dbits, int* cnt, long long* bsum,
+                          cudaStream_t st);
+int launch_blend_ext_fwd(const ViewParams& vp, int over, const float4* rec, const int* vals, const int2* ranges,
+                         float* out_rgb, float* out_alpha, float* out_depth, float* acc, cudaStream_t st);
+int launch_blend_ext_bwd(const ViewParams& vp, int over, const float4* rec, const int* vals, const int2* ranges,
+                         const float* acc, const float* g_rgb, const float* g_alpha, const float* g_depth, float* gacc,
+                         int n, cudaStream_t st);
+int launch_ext_bwd(const ViewParams& vp, const float* means, const float* scales, const float* rotations,
+                   const float* colors, const float* opac, int n, float dilation, const float* gacc, const uint8_t* cmask,
+                   float* g_means, float* g_scales, float* g_rot, float* g_colors, float* g_opac, cudaStream_t st);
 int launch_scan_i32(int* data, int len, int* bs, cudaStream_t st);
 size_t densify_workspace_bytes(int n);
 int launch_densify_prune(const float* means, const float* scales_raw, const float* op_raw, const float* colors, int n,

@@ -209,6 +209,78 @@ class _RenderFn(torch.autograd.Function):
         return gm.to(dm), gs.to(ds), gc.to(dc), go.to(do), None, None, None
 
 
+class _RenderExtFn(torch.autograd.Function):
+    """Extension modes (absent from the reference): `rotations` + EWA covariance and the
+    differentiable front-to-back compositing.  forward -> b2s_forward_ext, backward -> b2s_backward_ext."""
+
+    @staticmethod
+    def forward(ctx, means, scales, rotations, colors, opacities, params, want_aux, bg_keep, blend, dilation):
+        dev = means.device
+        n = means.shape[0]
+        m32, s32, c32, o32 = _f32c(means), _f32c(scales), _f32c(colors), _f32c(opacities)
+        r32 = None if rotations is None else _f32c(rotations)
+        L = capi.lib()
+        W, H = params.width, params.height
+        with torch.cuda.device(dev):
+            # pair capacity: every Gaussian can touch at most the tiles of the image; start from a bound on the footprint
+            # area and grow on overflow (the ticket reports the exact need)
+            cap = _PAIR_CAP.get(("ext", blend, r32 is not None) + _capacity_key(dev, n, params), 16 * n + 4096)
+            for attempt in range(6):
+                if cap > 0x7FFFFFFF:
+                    raise capi.B2SError(f"view needs {cap} (Gaussian,tile) pairs; limit is 2^31-1")
+                state_bytes = L.b2s_state_bytes(n, W, H, cap)
+                ws_bytes = L.b2s_workspace_bytes(n, W, H, cap)
+                state = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+                alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+                depth = torch.empty((H, W), dtype=torch.float32, device=dev) if want_aux else None
+                capi.check(L.b2s_forward_ext(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(r32), _ptr(c32),
+                                             _ptr(o32), n, cap, blend, float(dilation), _ptr(rgb), _ptr(alpha), _ptr(depth),
+                                             _ptr(state), state_bytes, _ptr(ws), ws_bytes, _stream()))
+                needed, _, overflow = capi.ticket_info(dev.index)
+                if not overflow:
+                    break
+                cap = int(needed * 1.5) + 1024
+            else:
+                raise capi.B2SError("pair buffers overflowed repeatedly")
+            _PAIR_CAP[("ext", blend, r32 is not None) + _capacity_key(dev, n, params)] = int(needed * 1.5) + 1024
+        ctx.params, ctx.total, ctx.bg_keep, ctx.blend, ctx.dilation = params, cap, bg_keep, blend, float(dilation)
+        ctx.in_dtypes = (means.dtype, scales.dtype, None if rotations is None else rotations.dtype, colors.dtype, opacities.dtype)
+        ctx.has_rot = r32 is not None
+        saved = (m32, s32, c32, o32, state) + ((r32,) if r32 is not None else ())
+        ctx.save_for_backward(*saved)
+        ctx.set_materialize_grads(False)
+        if want_aux:
+            return rgb, alpha, depth
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha=None, g_depth=None):
+        saved = ctx.saved_tensors
+        m32, s32, c32, o32, state = saved[:5]
+        r32 = saved[5] if ctx.has_rot else None
+        dev = m32.device
+        n = m32.shape[0]
+        params, total = ctx.params, ctx.total
+        L = capi.lib()
+        W, H = params.width, params.height
+        with torch.cuda.device(dev):
+            g_rgb = None if g_rgb is None else _f32c(g_rgb)
+            g_alpha = None if g_alpha is None else _f32c(g_alpha)
+            g_depth = None if g_depth is None else _f32c(g_depth)
+            ws_bytes = L.b2s_workspace_bytes(n, W, H, total)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gm, gs, gc, go = torch.empty_like(m32), torch.empty_like(s32), torch.empty_like(c32), torch.empty_like(o32)
+            gr = None if r32 is None else torch.empty_like(r32)
+            capi.check(L.b2s_backward_ext(capi.ctx(dev.index), C.byref(params), _ptr(m32), _ptr(s32), _ptr(r32), _ptr(c32),
+                                          _ptr(o32), n, total, ctx.blend, ctx.dilation, _ptr(g_rgb), _ptr(g_alpha),
+                                          _ptr(g_depth), _ptr(state), _ptr(ws), ws_bytes, _ptr(gm), _ptr(gs), _ptr(gr),
+                                          _ptr(gc), _ptr(go), _stream()))
+        dm, ds, dr, dc, do = ctx.in_dtypes
+        return (gm.to(dm), gs.to(ds), None if gr is None else gr.to(dr), gc.to(dc), go.to(do), None, None, None, None, None)
+
+
 def _default_cutoff(return_aux: bool) -> float:
     env = os.environ.get("B2S_CUTOFF_SIGMA")
     if env:
@@ -233,6 +305,9 @@ def render_gaussians_torch(
     *,
     cutoff_sigma: Optional[float] = None,
     sort_depth: bool = False,
+    rotations: Optional[torch.Tensor] = None,   # extension: (N,4) quaternions (w,x,y,z) -> EWA covariance
+    blend: str = "wsum",                        # extension: "wsum" (the reference's blend) or "over" (front to back)
+    ewa_dilation: float = 0.3,
 ):
     """Drop-in for the reference's differentiable renderer (python/torch_renderer.py:109-203).
 
@@ -241,6 +316,12 @@ def render_gaussians_torch(
     raises ValueError, :137-138).  `chunk_size` is accepted and ignored.  Keyword-only
     extras: `cutoff_sigma` (bbox radius in sigmas; default 5, or 7 with return_aux) and
     `sort_depth` (also radix-sort the depth half of the 64-bit keys).
+
+    Extension modes named by the task but ABSENT from the reference (pinned by oracle/ext_oracle.py only):
+    `rotations` (N,4) turns the axis-aligned sigmas (:147-150) into a full 3-D covariance R diag(s^2) R^T projected
+    by EWA (+ `ewa_dilation` px^2 on the diagonal); `blend="over"` composites front to back by camera z with the rule
+    of src/renderer_cpu.cpp:196-215 (default cutoff 3 sigma, exact pixel bbox) and is differentiable; its depth output is
+    the expected depth sum T a z.  Both run per pixel on the FP32 pipe (csrc/splat2d.cu), not on the tensor-core path.
     """
     if means.ndim != 2 or means.shape[1] != 3:
         raise ValueError("means must be (N,3)")
@@ -274,6 +355,16 @@ def render_gaussians_torch(
     scales = scales.to(dev)
     colors = colors.to(dev)
     opacities = opacities.to(dev)
+    if blend not in ("wsum", "over"):
+        raise ValueError("blend must be 'wsum' or 'over'")
+    if rotations is not None or blend == "over":
+        if rotations is not None and (rotations.ndim != 2 or rotations.shape != (n, 4)):
+            raise ValueError("rotations must be (N,4) quaternions (w,x,y,z)")
+        if cutoff_sigma is None and blend == "over":
+            params.cutoff_sigma = float(os.environ.get("B2S_CUTOFF_SIGMA", 3.0))   # renderer_cpu.cpp:96-97
+        return _RenderExtFn.apply(means, scales, None if rotations is None else rotations.to(dev), colors, opacities, params,
+                                  bool(return_aux), bg_keep, capi.BLEND_OVER if blend == "over" else capi.BLEND_WSUM,
+                                  float(ewa_dilation))
     return _RenderFn.apply(means, scales, colors, opacities, params, bool(return_aux), bg_keep)
 
 

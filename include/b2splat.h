@@ -118,6 +118,34 @@ int b2s_backward(b2s_ctx* ctx, const b2s_params* p, const float* means, const fl
                  void* workspace, size_t ws_bytes, float* grad_means, float* grad_scales,
                  float* grad_colors, float* grad_opacities, int accumulate, void* stream);
 
+/* ---- extension modes (named by north_star, ABSENT from the reference: SURVEY.md section 0) ---------------------
+ * The reference has no rotation, no covariance projection and no differentiable sorted compositing
+ * (python/torch_renderer.py:109-121 takes no `rotations`; include/gr/gaussian_types.h:8-22 has no such field;
+ * src/renderer_cpu.cpp:125-217 is not differentiable), so nothing on the reference side binds these two entry points:
+ * they extend b2s_forward / b2s_backward for callers that pass the new keyword arguments of the Python drop-in
+ * (render_gaussians_torch(..., rotations=, blend=)).  Pinned by oracle/ext_oracle.py only.
+ *   rotations: (N,4) quaternions (w,x,y,z), normalised inside, or NULL for the reference's axis-aligned sigmas.
+ *              With rotations the footprint is the EWA projection  cov2 = J W R diag(s^2) R^T W^T J^T + ewa_dilation*I
+ *              (J = exact Jacobian of the reference's pixel projection, W = view[:3,:3]; all three scale columns used).
+ *   blend:     B2S_BLEND_WSUM  out = (bg + sum w c)/(1 + sum w), alpha, depth as b2s_forward;
+ *              B2S_BLEND_OVER  front-to-back by camera z with the rule of src/renderer_cpu.cpp:196-215 (exact
+ *                              cutoff_sigma pixel bbox, a < 1e-5 skipped, contrib = T a, a capped at 0.999999),
+ *                              rgb = C + T bg, alpha = 1 - T, depth = sum T a z (expected depth).
+ * params->style / enable_depth_sort / sort_depth / exact_bbox are ignored (torch-style inputs; order by `blend`).
+ * state / workspace sizes as for b2s_forward.  grad_scales is (N,3) (column 2 is zero without rotations),
+ * grad_rotations (N,4) or NULL when rotations is NULL.  Gradients are overwritten, not accumulated. */
+#define B2S_BLEND_WSUM 0
+#define B2S_BLEND_OVER 1
+int b2s_forward_ext(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* rotations,
+                    const float* colors, const float* opacities, int n, int64_t max_pairs, int blend, float ewa_dilation,
+                    float* out_rgb, float* out_alpha, float* out_depth, void* state, size_t state_bytes,
+                    void* workspace, size_t ws_bytes, void* stream);
+int b2s_backward_ext(b2s_ctx* ctx, const b2s_params* p, const float* means, const float* scales, const float* rotations,
+                     const float* colors, const float* opacities, int n, int64_t max_pairs, int blend, float ewa_dilation,
+                     const float* g_rgb, const float* g_alpha, const float* g_depth, const void* state, void* workspace,
+                     size_t ws_bytes, float* grad_means, float* grad_scales, float* grad_rotations, float* grad_colors,
+                     float* grad_opacities, void* stream);
+
 /* ---- multi-view backward (the fit loop) --------------------------------------------------
  * b2s_backward = b2s_backward_blend (per view) + b2s_backward_params (chain rule).  The fit loop
  * calls the first once per view into slot v of a (num_views, n, 12) float buffer and the second
