@@ -82,7 +82,7 @@ def _check(res):
 @pytest.mark.parametrize("rot,blend", [(False, "over"), (True, "wsum"), (True, "over")])
 def test_extension_modes_match_oracle(rot, blend, sh):
     res = _run(40 + sh, 300, sh, 64, 48, rot, blend)
-    report({"test": "ext_modes", "rot": rot, "blend": blend, "sh": sh, **res})
+    report("ext_modes", rot=rot, blend=blend, sh=sh, **res)
     _check(res)
 
 
@@ -90,7 +90,7 @@ def test_extension_modes_match_oracle(rot, blend, sh):
 def test_extension_modes_edge_cases_and_sh16(rot, blend):
     """negative / zero opacity, negative scales, sigma clamp, off-screen and behind-the-camera Gaussians, colour clamp."""
     res = _run(77, 240, 16, 48, 40, rot, blend, edge_cases=True)
-    report({"test": "ext_edge_sh16", "rot": rot, "blend": blend, **res})
+    report("ext_edge_sh16", rot=rot, blend=blend, **res)
     _check(res)
 
 
@@ -99,7 +99,7 @@ def test_extension_modes_long_lists(rot, blend):
     """tile lists of several hundred Gaussians: several shared-memory chunks per tile, early termination of
     saturated pixels in the forward and the matching start of the reverse walk in the backward."""
     res = _run(91, 2500, 1, 96, 64, rot, blend, s_lo=0.05, s_hi=0.3, with_aux=(blend == "over"))
-    report({"test": "ext_long_lists", "rot": rot, "blend": blend, **res})
+    report("ext_long_lists", rot=rot, blend=blend, **res)
     _check(res)
 
 

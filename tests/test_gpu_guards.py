@@ -1,0 +1,181 @@
+"""Memory-safety checks of the C-ABI entry points with the means this pool leaves us: compute-sanitizer is refused on
+the GPU boxes ("closed on this pool ...", profiles/r02_sanitizer.md), so the three things memcheck / initcheck would
+have told us are tested directly:
+
+  * out-of-bounds writes: the caller-owned `state` and `workspace` buffers sit between two 64 KB canary regions that
+    must come back untouched (and the buffers are given at EXACTLY the size b2s_*_bytes reports);
+  * reads of uninitialised scratch: every call is repeated with state / workspace pre-filled with 0x00 and with 0xFF
+    bytes (0xFFFFFFFF is a NaN as a float and -1 as an index): the outputs must not depend on the fill;
+  * ordering hazards in the hand-rolled mbarrier / TMEM / cp.async pipelines of the tcgen05 forward: with depth-ordered
+    tile lists (sort_depth=True: the list order, hence the fp32 summation order, is fixed) the image of 20 consecutive
+    launches is bit-identical -- the forward has no atomics, so any difference would be a race.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from gpu_util import dev, pkg, to_dev
+
+pytestmark = pytest.mark.gpu
+PAD = 1 << 16
+
+
+class Guarded:
+    def __init__(self, nbytes, fill):
+        self.fill = fill
+        self.buf = torch.full((nbytes + 2 * PAD,), 0x5A, dtype=torch.uint8, device=dev())
+        self.view = self.buf[PAD:PAD + nbytes]
+        self.view.fill_(fill)
+        self.n = nbytes
+
+    def ptr(self):
+        return C.c_void_p(self.view.data_ptr())
+
+    def check(self, what):
+        torch.cuda.synchronize()
+        assert bool((self.buf[:PAD] == 0x5A).all()), f"{what}: bytes BEFORE the buffer were overwritten"
+        assert bool((self.buf[PAD + self.n:] == 0x5A).all()), f"{what}: bytes AFTER the buffer were overwritten"
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _scene(n, sh, W, H, seed=5, **kw):
+    means, scales, colors, opac = scenes.make_scene(seed, n, sh=sh, **kw)
+    view, proj = scenes.orbit_camera(1, 5, W, H)
+    return to_dev(means, scales, colors, opac), view, proj
+
+
+def _diff(a, b):
+    return float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
+
+
+@pytest.mark.parametrize("aux", [False, True])
+@pytest.mark.parametrize("sh", [1, 16])
+def test_forward_backward_stay_inside_their_buffers_and_ignore_their_initial_contents(sh, aux):
+    capi, r = pkg("capi"), pkg("renderer")
+    n, W, H = 3000, 80, 48                                  # lists > 512 per tile: several units, partial planes
+    (m, s, c, o), view, proj = _scene(n, sh, W, H, s_lo=0.05, s_hi=0.3, edge_cases=True)
+    L = capi.lib()
+    params = capi.make_params(W, H, view.reshape(-1).tolist(), proj.reshape(-1).tolist(), (0.1, 0.2, 0.3),
+                              cutoff_sigma=7.0 if aux else 5.0, sh_coeffs=sh)
+    cap = int(r.count_pairs(params, m, s, o))               # exact: not one pair of slack
+    sb, wb = L.b2s_state_bytes(n, W, H, cap), L.b2s_workspace_bytes(n, W, H, cap)
+    g = torch.Generator(device=dev()).manual_seed(1)
+    g_rgb = torch.randn((H, W, 3), generator=g, device=dev())
+    g_alpha = torch.randn((H, W), generator=g, device=dev()) if aux else None
+    g_depth = 0.1 * torch.randn((H, W), generator=g, device=dev()) if aux else None
+    results = []
+    for fill in (0x00, 0xFF):
+        state, ws, ws2 = Guarded(sb, fill), Guarded(wb, fill), Guarded(wb, fill)
+        rgb = torch.empty((H, W, 3), device=dev())
+        alpha = torch.empty((H, W), device=dev()) if aux else None
+        depth = torch.empty((H, W), device=dev()) if aux else None
+        capi.check(L.b2s_forward(capi.ctx(0), C.byref(params), _ptr(m), _ptr(s), _ptr(c), _ptr(o), n, cap, _ptr(rgb),
+                                 _ptr(alpha), _ptr(depth), state.ptr(), sb, ws.ptr(), wb, _stream()))
+        needed, _, overflow = capi.ticket_info(0)
+        assert not overflow and needed <= cap
+        gm, gs, gc, go = (torch.empty_like(t) for t in (m, s, c, o))
+        capi.check(L.b2s_backward(capi.ctx(0), C.byref(params), _ptr(m), _ptr(s), _ptr(c), _ptr(o), n, cap, _ptr(g_rgb),
+                                  _ptr(g_alpha), _ptr(g_depth), state.ptr(), ws2.ptr(), wb, _ptr(gm), _ptr(gs), _ptr(gc),
+                                  _ptr(go), 0, _stream()))
+        for b, what in ((state, "state"), (ws, "forward workspace"), (ws2, "backward workspace")):
+            b.check(what)
+        outs = [rgb] + ([alpha, depth] if aux else []) + [gm, gs, gc, go]
+        assert all(bool(torch.isfinite(t).all()) for t in outs)
+        results.append([t.clone() for t in outs])
+    n_img = 3 if aux else 1
+    for k, (a, b) in enumerate(zip(results[0][:n_img], results[1][:n_img])):
+        # the order of a tile's list is whatever the counting sort's shared-memory atomics produced (a weighted sum does
+        # not care), so two runs differ by fp32 summation order -- and by nothing else
+        tol = 2e-6 if k < 2 else 2e-6 * max(1.0, float(b.abs().max()))
+        assert float((a - b).abs().max()) <= tol
+    for a, b in zip(results[0][n_img:], results[1][n_img:]):
+        assert _diff(a, b) <= 1e-4                          # atomics change the summation order, nothing else
+
+
+@pytest.mark.parametrize("rot,blend", [(False, 1), (True, 0), (True, 1)])
+def test_extension_entry_points_stay_inside_their_buffers(rot, blend):
+    capi = pkg("capi")
+    n, W, H = 1200, 64, 48
+    (m, s, c, o), view, proj = _scene(n, 4, W, H, s_lo=0.05, s_hi=0.3, edge_cases=True)
+    q = torch.randn((n, 4), generator=torch.Generator(device=dev()).manual_seed(2), device=dev()) if rot else None
+    L = capi.lib()
+    params = capi.make_params(W, H, view.reshape(-1).tolist(), proj.reshape(-1).tolist(), (0.1, 0.2, 0.3),
+                              cutoff_sigma=3.0 if blend else 5.0, sh_coeffs=4)
+    cap = 40 * n
+    sb, wb = L.b2s_state_bytes(n, W, H, cap), L.b2s_workspace_bytes(n, W, H, cap)
+    g = torch.Generator(device=dev()).manual_seed(1)
+    g_rgb = torch.randn((H, W, 3), generator=g, device=dev())
+    results = []
+    for fill in (0x00, 0xFF):
+        state, ws, ws2 = Guarded(sb, fill), Guarded(wb, fill), Guarded(wb, fill)
+        rgb, alpha, depth = torch.empty((H, W, 3), device=dev()), torch.empty((H, W), device=dev()), torch.empty((H, W), device=dev())
+        capi.check(L.b2s_forward_ext(capi.ctx(0), C.byref(params), _ptr(m), _ptr(s), _ptr(q), _ptr(c), _ptr(o), n, cap, blend,
+                                     0.3, _ptr(rgb), _ptr(alpha), _ptr(depth), state.ptr(), sb, ws.ptr(), wb, _stream()))
+        _, _, overflow = capi.ticket_info(0)
+        assert not overflow
+        gm, gs, gc, go = (torch.empty_like(t) for t in (m, s, c, o))
+        gq = torch.empty_like(q) if rot else None
+        capi.check(L.b2s_backward_ext(capi.ctx(0), C.byref(params), _ptr(m), _ptr(s), _ptr(q), _ptr(c), _ptr(o), n, cap, blend,
+                                      0.3, _ptr(g_rgb), None, None, state.ptr(), ws2.ptr(), wb, _ptr(gm), _ptr(gs), _ptr(gq),
+                                      _ptr(gc), _ptr(go), _stream()))
+        for b, what in ((state, "state"), (ws, "forward workspace"), (ws2, "backward workspace")):
+            b.check(what)
+        outs = [rgb, alpha, depth, gm, gs, gc, go] + ([gq] if rot else [])
+        assert all(bool(torch.isfinite(t).all()) for t in outs)
+        results.append([t.clone() for t in outs])
+    for k, (a, b) in enumerate(zip(results[0][:3], results[1][:3])):
+        if blend == 1:
+            assert torch.equal(a, b)                        # depth-ordered lists, no atomics in the forward: bit-identical
+        else:
+            assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max()))   # list order = summation order
+    for a, b in zip(results[0][3:], results[1][3:]):
+        assert _diff(a, b) <= 1e-4
+
+
+@pytest.mark.parametrize("ds", [0, 1])
+def test_rgba8_frame_stays_inside_its_workspace(ds):
+    capi, r = pkg("capi"), pkg("renderer")
+    n, W, H = 20000, 160, 96
+    (m, s, c, o), view, proj = _scene(n, 1, W, H, s_lo=0.01, s_hi=0.05)
+    L = capi.lib()
+    params = capi.make_params(W, H, view.reshape(-1).tolist(), proj.reshape(-1).tolist(), (0.02, 0.02, 0.02),
+                              mode=capi.MODE_SORTED if ds else capi.MODE_WSUM, style=capi.STYLE_NATIVE, cutoff_sigma=3.0,
+                              sh_coeffs=1, sort_depth=ds, exact_bbox=1)
+    cap = int(r.count_pairs(params, m, s, o))
+    need = L.b2s_workspace_bytes(n, W, H, cap) + L.b2s_state_bytes(n, W, H, cap)
+    frames = []
+    for fill in (0x00, 0xFF):
+        ws = Guarded(need, fill)
+        img = torch.empty((H, W, 4), dtype=torch.uint8, device=dev())
+        capi.check(L.b2s_render_rgba8(capi.ctx(0), C.byref(params), _ptr(m), _ptr(s), _ptr(c), _ptr(o), n, cap, _ptr(img),
+                                      ws.ptr(), need, _stream()))
+        ws.check("rgba8 workspace")
+        frames.append(img.clone())
+    assert torch.equal(frames[0], frames[1])
+
+
+def test_tcgen05_forward_is_bit_deterministic():
+    """20 launches of the tcgen05 forward (mbarrier / TMEM / cp.async pipeline, per-unit partial planes folded in a fixed
+    order) over depth-ordered lists: any difference between two runs of a kernel without atomics is a race.  (Without
+    sort_depth the list order comes from shared-memory atomics of the counting sort and the sums differ in the last bits.)"""
+    r = pkg("renderer")
+    n, W, H = 6000, 96, 64
+    (m, s, c, o), view, proj = _scene(n, 4, W, H, s_lo=0.05, s_hi=0.3)
+    from gpu_util import camera
+    cam = camera(view, proj)
+    before = pkg("capi").path_counts()
+    first = r.render_gaussians_torch(m, s, c, o, cam, W, H, max_gaussians=n, sort_depth=True).clone()
+    for _ in range(19):
+        assert torch.equal(first, r.render_gaussians_torch(m, s, c, o, cam, W, H, max_gaussians=n, sort_depth=True))
+    after = pkg("capi").path_counts()
+    assert after["fwd_tcgen05"] - before["fwd_tcgen05"] == 20
