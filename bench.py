@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--densify-every", type=int, default=0,
                     help="call FitDriver.densify_prune every K timed steps (BASELINE configs[4]); 0 = never")
     ap.add_argument("--render-only", action="store_true", help="only the render config (BASELINE configs[2]); for profiling")
+    ap.add_argument("--fit-scripts", action="store_true",
+                    help="only BASELINE configs[0] and [1]: the reference's UNCHANGED fit_multiview_stub.py on the B200 path, "
+                         "beside the same script on the box's host cores (the reference's stock CPU configuration)")
     return ap.parse_args()
 
 
@@ -371,6 +374,59 @@ def _claim_stdout():
     return saved
 
 
+def fit_scripts_bench():
+    """BASELINE configs[0] and [1]: the reference's unchanged fit script
+    (python/fit_multiview_stub.py:200-382, staged byte for byte under oracle/_ref/reference) three ways on this box --
+      ours       : through 3dgaussian_b200/run_reference_script.py (drop-in torch_renderer / device_utils -> libb2splat);
+      r1_cuda    : the reference's own torch_renderer.py with torch ops on the same GPU;
+      cpu        : the reference's stock configuration (its device policy picks cpu on Linux) on the host cores, a
+                   bounded number of iterations (config 2 costs tens of seconds per iteration on a CPU).
+    iterations/s come from time stamps around the script's optimizer steps (start-up and image loading excluded)."""
+    import subprocess
+    import tempfile
+    ref = os.path.join(ROOT, "oracle", "_ref", "reference")
+    script = os.path.join(ref, "python", "fit_multiview_stub.py")
+    if not os.path.exists(script):
+        return {"unavailable": "oracle/_ref/reference not staged (make -C oracle where /root/reference exists)"}
+    tex = os.path.join(ref, "assets", "scene_tex")
+    c2 = os.path.join(ROOT, "tests", "golden", "c2_inputs")
+    configs = {
+        "config1": (["--width", "128", "--height", "128"], {"ours": 150, "r1_cuda": 150, "cpu": 12}),
+        "config2": (["--width", "256", "--height", "256", "--use_sh", "--num_gaussians", "1200", "--max_gaussians", "3000",
+                     "--densify_interval", "40", "--prune_interval", "40", "--masks_dir", os.path.join(c2, "masks"),
+                     "--depth_dir", os.path.join(c2, "depth")], {"ours": 300, "r1_cuda": 300, "cpu": 4}),
+    }
+    threads = min(32, os.cpu_count() or 1)
+    out = {"cpu_threads": threads}
+    for name, (cfg_args, iters) in configs.items():
+        row = {}
+        for arm, n_it in iters.items():
+            with tempfile.TemporaryDirectory() as td:
+                tj = os.path.join(td, "timing.json")
+                if arm == "ours":
+                    cmd = [sys.executable, os.path.join(ROOT, "3dgaussian_b200", "run_reference_script.py"), "--seed", "0",
+                           "--timing-json", tj, script]
+                else:
+                    cmd = [sys.executable, os.path.join(ROOT, "tests", "run_reference_on_torch_cuda.py"), "--seed", "0",
+                           "--device", "cuda" if arm == "r1_cuda" else "cpu", "--timing-json", tj, os.path.join(ref, "python")]
+                cmd += ["--targets_dir", tex, "--out_dir", os.path.join(td, "out"), "--iters", str(n_it)] + cfg_args
+                env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+                t0 = time.perf_counter()
+                res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+                wall = time.perf_counter() - t0
+                if res.returncode != 0:
+                    row[arm] = {"error": (res.stderr or res.stdout)[-400:]}
+                    continue
+                tm = json.load(open(tj))
+                loss = [float(x) for x in open(os.path.join(td, "out", "loss.txt")).read().split()]
+                row[arm] = {"iters": n_it, "iters_per_s": tm.get("iters_per_s"), "wall_s": wall, "loss_first": loss[0],
+                            "loss_last": loss[-1]}
+        if "iters_per_s" in row.get("ours", {}) and "iters_per_s" in row.get("cpu", {}) and row["cpu"]["iters_per_s"]:
+            row["speedup_vs_cpu"] = row["ours"]["iters_per_s"] / row["cpu"]["iters_per_s"]
+        out[name] = row
+    return out
+
+
 def _emit(saved_fd, line: dict):
     sys.stdout.flush()
     os.write(saved_fd, (json.dumps(line) + "\n").encode())
@@ -396,6 +452,9 @@ def main():
     fit = importlib.import_module("3dgaussian_b200.fit")
     if args.render_only:
         _emit(out_fd, {"render": render_bench(device)})
+        return
+    if args.fit_scripts:
+        _emit(out_fd, {"fit_scripts": fit_scripts_bench()})
         return
     cams = cameras(args.views, args.width, args.height)
 
