@@ -26,7 +26,7 @@ EXPORTS = [
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
     "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded", "b2s_backward_params_range",
-    "b2s_forward_ext", "b2s_backward_ext",
+    "b2s_forward_ext", "b2s_backward_ext", "b2s_adam_step_multimem", "b2s_reduce_tail_multimem",
 ]
 
 
@@ -118,6 +118,11 @@ def lib() -> C.CDLL:
         L.b2s_adam_step_guarded.restype = i32
         L.b2s_adam_step_guarded.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, C.c_float, C.c_float, C.c_float,
                                             i64, i64, C.c_float, i64, i64, C.c_float, vp, vp, vp]
+        L.b2s_adam_step_multimem.restype = i32
+        L.b2s_adam_step_multimem.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, C.c_float, C.c_float, C.c_float,
+                                             C.c_float, i64, i64, C.c_float, i64, i64, C.c_float, vp, vp, vp]
+        L.b2s_reduce_tail_multimem.restype = i32
+        L.b2s_reduce_tail_multimem.argtypes = [vp, vp, vp, i32, vp]
         L.b2s_densify_workspace_bytes.restype = sz
         L.b2s_densify_workspace_bytes.argtypes = [i32]
         L.b2s_densify_prune.restype = i32

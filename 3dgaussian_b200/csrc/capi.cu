@@ -932,6 +932,23 @@ int b2s_adam_step_guarded(b2s_ctx* ctx, float* params, const float* grads, float
 
 size_t b2s_densify_workspace_bytes(int n) { return densify_workspace_bytes(n) + 256; }
 
+int b2s_adam_step_multimem(b2s_ctx* ctx, float* params_mc, const float* grads_mc, const float* params_local, float* m,
+                           float* v, int64_t count, int rank, int world, int step, float lr, float beta1, float beta2,
+                           float eps, int64_t scales_begin, int64_t scales_end, float reg_scale, int64_t opac_begin,
+                           int64_t opac_end, float reg_opacity, const float* skip_flag, int* skipped_count, void* stream) {
+  if (ctx == nullptr || params_mc == nullptr || grads_mc == nullptr || params_local == nullptr || m == nullptr || v == nullptr ||
+      rank < 0 || rank >= world) { set_error("NULL / bad argument"); return B2S_ERR_INVALID; }
+  StageTimer t(ctx, ST_ADAM, (cudaStream_t)stream);
+  return launch_adam_multimem(params_mc, grads_mc, params_local, m, v, count, rank, world, step, lr, beta1, beta2, eps,
+                              scales_begin, scales_end, reg_scale, opac_begin, opac_end, reg_opacity, skip_flag,
+                              skipped_count, (cudaStream_t)stream);
+}
+
+int b2s_reduce_tail_multimem(b2s_ctx* ctx, const float* tail_mc, float* tail_out, int count, void* stream) {
+  if (ctx == nullptr || tail_mc == nullptr || tail_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
+  return launch_tail_multimem(tail_mc, tail_out, count, (cudaStream_t)stream);
+}
+
 int b2s_densify_prune(b2s_ctx* ctx, const float* means, const float* scales_raw, const float* opacities_raw,
                       const float* colors, int n, int color_floats, int max_gaussians, double densify_ratio,
                       float prune_opacity, uint64_t seed, uint64_t iteration, float* out_means, float* out_scales_raw,

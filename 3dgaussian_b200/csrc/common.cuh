@@ -443,4 +443,10 @@ int launch_adam(float* params, const float* grads, float* m, float* v, int64_t c
                 float b1, float b2, float eps, int64_t sb, int64_t se, float reg_scale, int64_t ob, int64_t oe,
                 float reg_op, const float* skip_flag, int* skipped_count, cudaStream_t st);
 
+int launch_adam_multimem(float* params_mc, const float* grads_mc, const float* params_local, float* m, float* v,
+                         int64_t count, int rank, int world, int step, float lr, float b1, float b2, float eps, int64_t sb,
+                         int64_t se, float reg_scale, int64_t ob, int64_t oe, float reg_op, const float* skip_flag,
+                         int* skipped_count, cudaStream_t st);
+int launch_tail_multimem(const float* tail_mc, float* out, int count, cudaStream_t st);
+
 }  // namespace b2s

@@ -2,6 +2,8 @@
 // Adam step (+ regulariser gradients).  Reference semantics:
 //   python/fit_multiview_stub.py:292-308 (loss), :262,311 (torch.optim.Adam defaults).
 // Both are HBM-bound streaming kernels: loss 24..40 B/pixel, Adam 28 B/element.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -107,6 +109,115 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = pi - step_size * (mi / denom);
   }
+}
+
+// ---- multi-GPU: gradient reduce-scatter + Adam + parameter all-gather in ONE kernel over NVLink multicast (NVLS) -------
+// The gradient buffers of the G ranks and their parameter buffers are symmetric allocations bound to a multicast
+// address each.  Rank r owns the r-th share of every slice: it PULLS the sum of that share from all ranks with
+// multimem.ld_reduce (the NVSwitch adds the G copies and returns one), runs the Adam update of `adam_kernel` on it with
+// its own moments, and PUSHES the new parameters to every rank with multimem.st.  The wire carries what an all-reduce
+// carries (each gradient crosses once into the switch, each parameter once out of it), Adam costs 1/G, the moments of a
+// share live on its owner only, and every replica receives the same bits (one owner per element).  The caller brackets
+// the launches of a chunk with two cross-rank barriers (all gradients written before / all parameters landed after).
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* mc) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];\n" : "=f"(r) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st1(float* mc, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;\n" ::"l"(mc), "f"(v) : "memory");
+}
+
+struct AdamConsts {
+  float b1, b2, eps, step_size, inv_sqrt_bc2, reg_s, reg_o;
+  long long sb, se, ob, oe;
+};
+__device__ __forceinline__ float adam_one(const AdamConsts& c, long long i, float pi, float gi, float& mi, float& vi) {
+  if (i >= c.sb && i < c.se) gi += c.reg_s * sigmoidf_acc(pi);
+  if (i >= c.ob && i < c.oe) { const float s = sigmoidf_acc(pi); gi += c.reg_o * s * (1.0f - s); }
+  mi = c.b1 * mi + (1.0f - c.b1) * gi;
+  vi = c.b2 * vi + (1.0f - c.b2) * gi * gi;
+  const float denom = sqrtf(vi) * c.inv_sqrt_bc2 + c.eps;
+  return pi - c.step_size * (mi / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adam_multimem_kernel(float* __restrict__ p_mc, const float* __restrict__ g_mc, const float* __restrict__ p_loc,
+                     float* __restrict__ m, float* __restrict__ v, long long lo, long long hi, AdamConsts c,
+                     const float* __restrict__ skip_flag, int* __restrict__ skipped_count) {
+  if (skip_flag != nullptr && *skip_flag != 0.0f) {      // the same reduced value on every rank: all skip or none
+    if (skipped_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(skipped_count, 1);
+    return;
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = (hi - lo) / 4;
+  for (long long q = t0; q < n4; q += stride) {
+    const long long i = lo + 4 * q;
+    const float4 g = mc_ld_reduce4(g_mc + i);
+    const float4 pv = *reinterpret_cast<const float4*>(p_loc + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+    float4 pn;
+    pn.x = adam_one(c, i, pv.x, g.x, mv.x, vv.x);
+    pn.y = adam_one(c, i + 1, pv.y, g.y, mv.y, vv.y);
+    pn.z = adam_one(c, i + 2, pv.z, g.z, mv.z, vv.z);
+    pn.w = adam_one(c, i + 3, pv.w, g.w, mv.w, vv.w);
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    mc_st4(p_mc + i, pn);
+  }
+  for (long long i = lo + 4 * n4 + t0; i < hi; i += stride) {     // at most 3 elements at the end of a slice
+    const float g = mc_ld_reduce1(g_mc + i);
+    float mi = m[i], vi = v[i];
+    const float pn = adam_one(c, i, p_loc[i], g, mi, vi);
+    m[i] = mi;
+    v[i] = vi;
+    mc_st1(p_mc + i, pn);
+  }
+}
+
+__global__ void __launch_bounds__(64) tail_multimem_kernel(const float* __restrict__ tail_mc, float* __restrict__ out, int count) {
+  if ((int)threadIdx.x < count) out[threadIdx.x] = mc_ld_reduce1(tail_mc + threadIdx.x);
+}
+
+int launch_adam_multimem(float* params_mc, const float* grads_mc, const float* params_local, float* m, float* v,
+                         int64_t count, int rank, int world, int step, float lr, float b1, float b2, float eps, int64_t sb,
+                         int64_t se, float reg_scale, int64_t ob, int64_t oe, float reg_op, const float* skip_flag,
+                         int* skipped_count, cudaStream_t st) {
+  if (count <= 0 || world <= 0) return B2S_OK;
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  AdamConsts c;
+  c.b1 = b1; c.b2 = b2; c.eps = eps;
+  c.step_size = (float)((double)lr / bc1);
+  c.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  c.reg_s = (se > sb) ? reg_scale / (float)(se - sb) : 0.f;
+  c.reg_o = (oe > ob) ? reg_op / (float)(oe - ob) : 0.f;
+  c.sb = sb; c.se = se; c.ob = ob; c.oe = oe;
+  // this rank's share of the slice: ceil(count / world) rounded up to 4 floats (16-byte multimem accesses)
+  const long long per = (((long long)count + world - 1) / world + 3) / 4 * 4;
+  const long long lo = std::min<long long>((long long)rank * per, count), hi = std::min<long long>(lo + per, count);
+  if (hi <= lo) return B2S_OK;
+  long long blocks = ((hi - lo) / 4 + 255) / 256 + 1;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  adam_multimem_kernel<<<(int)blocks, 256, 0, st>>>(params_mc, grads_mc, params_local, m, v, lo, hi, c, skip_flag, skipped_count);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int launch_tail_multimem(const float* tail_mc, float* out, int count, cudaStream_t st) {
+  if (count <= 0 || count > 64) { set_error("tail of %d floats (1..64)", count); return B2S_ERR_INVALID; }
+  tail_multimem_kernel<<<1, 64, 0, st>>>(tail_mc, out, count);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
 }
 
 int launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, int step, float lr,

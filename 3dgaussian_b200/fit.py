@@ -43,10 +43,15 @@ class FitDriver:
                  rank: int = 0, world: int = 1, process_group=None, pair_slack: float = 1.25, lanes: int = 1,
                  fused_loss: bool = True, batched_preprocess: bool = True, prepared_budget_bytes: int = 32 << 30,
                  view_groups: int = 1, use_depth: bool = False, depth_weight: float = 0.05,
-                 overflow_check_every: int = 8, grad_chunks: Optional[int] = None):
+                 overflow_check_every: int = 8, grad_chunks: Optional[int] = None, comm: Optional[str] = None):
         """use_depth: the fit carries the reference's depth term (fit_multiview_stub.py:298-303, weight
         `depth_weight`): the forward keeps the depth plane and the cutoff defaults to 7 sigma instead of 5, because
-        depth = D/(W+1e-6) and its gradient amplify the truncated tails."""
+        depth = D/(W+1e-6) and its gradient amplify the truncated tails.
+        comm (several GPUs): "multimem" = the tail of the iteration is ONE fused kernel per chunk slice -- gradient
+        reduce-scatter through the NVSwitch (multimem.ld_reduce), Adam on the owned share, parameter all-gather
+        (multimem.st) -- over symmetric-memory buffers (b2s_adam_step_multimem); "nccl" = NCCL all-reduce per chunk +
+        replicated Adam.  Default: multimem when NVLink multicast is available on every rank, else nccl
+        (B2S_COMM overrides)."""
         if device.type != "cuda":
             raise RuntimeError("FitDriver needs a CUDA device (no CPU fallback)")
         self.n, self.sh, self.W, self.H = int(n), int(sh_coeffs), int(width), int(height)
@@ -74,6 +79,12 @@ class FitDriver:
         self.grad_chunks = max(1, int(grad_chunks)) if grad_chunks is not None else (4 if world > 1 else 1)
         self._force_chunks = grad_chunks is not None and world == 1      # tests: the chunked tail on one GPU
         self._comm_stream = None
+        import os as _os
+        self.comm = (comm or _os.environ.get("B2S_COMM") or "multimem").lower()
+        if self.comm not in ("multimem", "nccl"):
+            raise ValueError("comm must be 'multimem' or 'nccl'")
+        self._symm = None                        # (parameter handle, gradient handle) of the symmetric buffers
+        self._moments_sharded = False            # multimem: m / v of a share are current on its owner only
         self._layout(self.n)
         self.step_no = 0
         self.skipped_dev = torch.zeros(1, dtype=torch.int32, device=device)   # Adam steps the device guard skipped
@@ -134,7 +145,10 @@ class FitDriver:
         self.o_colors = self.o_opac + al(n)
         self.count = self.o_colors + al(c * n)
         z = lambda extra=0: torch.zeros(self.count + extra, dtype=torch.float32, device=self.dev)
-        self.p, self.m, self.v = z(), z(), z()
+        self.p = self.g = None                   # release (symmetric) buffers of the previous size first
+        self._symm = None
+        self._moments_sharded = False
+        self.m, self.v = z(), z()
         chunks = self._chunks()
         if len(chunks) == 1:
             # gradients laid out like the parameters, the tail behind them
@@ -152,9 +166,59 @@ class FitDriver:
                     segs.append(o)
                     o += al(k * cnt)
                 self._gchunks.append(segs + [o])          # four segment offsets + end
-            self.g = torch.zeros(o, dtype=torch.float32, device=self.dev)
+            if self.comm == "multimem" and self.world > 1:
+                self._alloc_symmetric(o)
+            if self._symm is None:
+                self.g = torch.zeros(o, dtype=torch.float32, device=self.dev)
             self.tail = self.g[0:64]
-        self.loss_dev = self.tail[0:1]
+        if self.p is None:
+            self.p = z()
+        self.tail_red = torch.zeros(64, dtype=torch.float32, device=self.dev)    # multimem: the reduced tail (local)
+        self.loss_dev = self.tail_red[0:1] if self._symm is not None else self.tail[0:1]
+
+    def _alloc_symmetric(self, g_numel: int):
+        """Parameter and gradient buffers as symmetric allocations bound to an NVLink multicast address (torch
+        symmetric memory does the allocation, the handle exchange and the cross-rank barriers; the kernels on them are
+        ours).  All ranks take the same decision: a failure anywhere falls back to NCCL everywhere."""
+        ok, err = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            p = symm_mem.empty(self.count, dtype=torch.float32, device=self.dev)
+            g = symm_mem.empty(g_numel, dtype=torch.float32, device=self.dev)
+            p.zero_()
+            g.zero_()
+            hp, hg = symm_mem.rendezvous(p, group=grp), symm_mem.rendezvous(g, group=grp)
+            if not getattr(hp, "multicast_ptr", 0) or not getattr(hg, "multicast_ptr", 0):
+                raise RuntimeError("no NVLink multicast address for the symmetric buffers")
+        except Exception as e:  # noqa: BLE001
+            ok, err = 0, e
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+        if int(flag.item()) == 1:
+            self.p, self.g, self._symm = p, g, (hp, hg)
+        else:
+            self.comm_fallback = str(err) if err is not None else "another rank has no multicast support"
+
+    def _sync_moments(self):
+        """multimem mode keeps the Adam moments of a share on its owner only; before anything that reads or permutes
+        the whole m / v (checkpoint, spatial reorder) the owners' values are gathered on every rank."""
+        if not self._moments_sharded or self._symm is None:
+            return
+        rank, world = self._symm[0].rank, self._symm[0].world_size
+        for buf in (self.m, self.v):
+            own = torch.zeros_like(buf)
+            for first, count in self._chunks():
+                for sl_src, sl_dst, k in zip(self._chunk_slices(buf, first, count), self._chunk_slices(own, first, count),
+                                             (3, 3, 1, 3 * self.sh)):
+                    nel = k * count
+                    per = ((nel + world - 1) // world + 3) // 4 * 4
+                    lo = min(rank * per, nel)
+                    hi = min(lo + per, nel)
+                    sl_dst[lo:hi] = sl_src[lo:hi]
+            torch.distributed.all_reduce(own, group=self.pg)
+            buf.copy_(own)
+        self._moments_sharded = False
 
     # ---- parameter views -------------------------------------------------------------------
     def _seg(self, buf, off, numel): return buf[off:off + numel]
@@ -167,7 +231,9 @@ class FitDriver:
 
     def grad_views(self):
         """(means, scales_raw, opacities_raw, colours) gradients as flat tensors (views of the gradient buffer, or
-        gathered from its chunks when the tail is pipelined)."""
+        gathered from its chunks when the tail is pipelined).  With comm="multimem" on several GPUs the buffer holds THIS
+        rank's contribution only: the sum over the ranks is formed inside the NVSwitch on its way into the owner's Adam
+        update and is never written back."""
         n = self.n
         if self._gchunks is None:
             return (self._seg(self.g, self.o_means, 3 * n), self._seg(self.g, self.o_scales, 3 * n),
@@ -197,6 +263,7 @@ class FitDriver:
         n = self.n
         if n <= 1:
             return torch.arange(n, device=self.dev)
+        self._sync_moments()
         with torch.no_grad():
             m = self.means()
             lo, hi = m.min(0).values, m.max(0).values
@@ -495,10 +562,17 @@ class FitDriver:
             # ONE contiguous all-reduce per chunk on the comm stream (the gradient buffer is chunk-major; loss and
             # overflow count -- the Adam guard -- ride with chunk 0) | guarded Adam per slice on the caller's stream.
             if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream(device=self.dev)
+                # HIGH priority: when the exchange + Adam of chunk k become ready, the chain-rule grids of chunks k+1.. are
+                # already resident or pending, and at equal priority the block scheduler drains those first -- the whole
+                # exchange then queued up BEHIND the chain rule instead of beside it (2 GPUs: chunk 0 reduced 0.9 ms after
+                # the last view, its Adam done at 1.67 ms, when the last chain rule ended at 1.60 ms)
+                self._comm_stream = torch.cuda.Stream(device=self.dev, priority=-1)
             main, comm = torch.cuda.current_stream(), self._comm_stream
             job = getattr(self, "_chain_job", None)
             chunks = self._chunks()
+            if self._symm is not None:
+                self._finish_step_multimem(main, comm, job, chunks)
+                return
             for c, (first, count) in enumerate(chunks):
                 segs = self._gchunks[c]
                 gs = [self.g[segs[q]:segs[q] + k * count] for q, k in enumerate((3, 3, 1, 3 * self.sh))]
@@ -515,15 +589,16 @@ class FitDriver:
                         comm.wait_stream(main)          # idle rank (no local views): its zeroed buffer is on the caller's stream
                     if self.world > 1:
                         torch.distributed.all_reduce(self.g[0 if c == 0 else segs[0]:segs[4]], group=self.pg)
+                    self._mark(f"chunk{c}_ar", comm)
+                    # Adam of the chunk on the same high-priority stream, right behind its all-reduce
+                    ps, ms, vs = (self._chunk_slices(b, first, count) for b in (self.p, self.m, self.v))
+                    frac = count / max(self.n, 1)
+                    for q, reg in enumerate((None, "scales", "opac", None)):
+                        self._adam(ps[q], gs[q], ms[q], vs[q], reg, frac, count_skip=(c == 0 and q == 0))
                     ev = torch.cuda.Event()
                     ev.record(comm)
-                    self._mark(f"chunk{c}_ar", comm)
+                    self._mark(f"chunk{c}_adam", comm)
                 main.wait_event(ev)
-                ps, ms, vs = (self._chunk_slices(b, first, count) for b in (self.p, self.m, self.v))
-                frac = count / max(self.n, 1)
-                for q, reg in enumerate((None, "scales", "opac", None)):
-                    self._adam(ps[q], gs[q], ms[q], vs[q], reg, frac, count_skip=(c == 0 and q == 0))
-                self._mark(f"chunk{c}_adam")
             self._chain_job = None
             self._mark("adam_done")
             return
@@ -534,6 +609,60 @@ class FitDriver:
             capi.ctx(self.dev.index), _ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.count, self.step_no,
             self.lr, 0.9, 0.999, 1e-8, self.o_scales, self.o_scales + 3 * self.n, self.reg_scale, self.o_opac,
             self.o_opac + self.n, self.reg_op, C.c_void_p(self.tail.data_ptr() + 4), _ptr(self.skipped_dev), _stream()))
+        self._mark("adam_done")
+
+    def _finish_step_multimem(self, main, comm, job, chunks):
+        """The tail over NVLink multicast: per chunk  chain rule (tail stream) | barrier, fused reduce-scatter + Adam +
+        all-gather of the chunk's four slices, barrier (comm stream).  No NCCL call, no separate Adam pass; the caller's
+        stream waits for the last chunk's second barrier, i.e. for every rank's share of the new parameters."""
+        hp, hg = self._symm
+        L, ctx = capi.lib(), capi.ctx(self.dev.index)
+        mc_p, mc_g = int(hp.multicast_ptr), int(hg.multicast_ptr)
+        rank, world = int(hp.rank), int(hp.world_size)
+        ks = (3, 3, 1, 3 * self.sh)
+        for c, (first, count) in enumerate(chunks):
+            segs = self._gchunks[c]
+            p_offs = (self.o_means + 3 * first, self.o_scales + 3 * first, self.o_opac + first, self.o_colors + 3 * self.sh * first)
+            if job is not None:
+                with torch.cuda.stream(job[0]):
+                    self._chain_rule(job[1], job[2], False, first, count)
+                    chain_ev = torch.cuda.Event()
+                    chain_ev.record(job[0])
+                    self._mark(f"chunk{c}_chain", job[0])
+            with torch.cuda.stream(comm):
+                if job is not None:
+                    comm.wait_event(chain_ev)
+                elif c == 0:
+                    comm.wait_stream(main)              # idle rank (no local views): its zeroed buffer is on the caller's stream
+                hg.barrier(channel=0)                   # every rank's gradients of this chunk are written
+                st = _stream()
+                if c == 0:                              # loss + overflow count (the Adam guard), summed by the switch
+                    capi.check(L.b2s_reduce_tail_multimem(ctx, C.c_void_p(mc_g), _ptr(self.tail_red), 2, st))
+                frac = count / max(self.n, 1)
+                for q, reg in enumerate((None, "scales", "opac", None)):
+                    nel = ks[q] * count
+                    if nel == 0:
+                        continue
+                    se = oe = 0
+                    rs = ro = 0.0
+                    if reg == "scales":
+                        se, rs = nel, self.reg_scale * frac
+                    elif reg == "opac":
+                        oe, ro = nel, self.reg_op * frac
+                    po = 4 * p_offs[q]
+                    capi.check(L.b2s_adam_step_multimem(
+                        ctx, C.c_void_p(mc_p + po), C.c_void_p(mc_g + 4 * segs[q]), C.c_void_p(self.p.data_ptr() + po),
+                        C.c_void_p(self.m.data_ptr() + po), C.c_void_p(self.v.data_ptr() + po), nel, rank, world, self.step_no,
+                        self.lr, 0.9, 0.999, 1e-8, 0, se, rs, 0, oe, ro, C.c_void_p(self.tail_red.data_ptr() + 4),
+                        _ptr(self.skipped_dev) if (c == 0 and q == 0) else None, st))
+                hg.barrier(channel=0)                   # every rank's share of the new parameters has landed everywhere
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                self._mark(f"chunk{c}_ar", comm)
+                self._mark(f"chunk{c}_adam", comm)
+            main.wait_event(ev)
+        self._moments_sharded = True
+        self._chain_job = None
         self._mark("adam_done")
 
     def _device_inputs(self, k, stream):
@@ -675,7 +804,7 @@ class FitDriver:
 
                 self._iterate(inputs)
                 self._finish_step()
-                loss, overflow = self.tail[0:2].tolist()     # the step's one device->host read: loss + overflow guard
+                loss, overflow = (self.tail_red if self._symm is not None else self.tail)[0:2].tolist()     # the step's one device->host read: loss + overflow guard
                 if overflow == 0.0:
                     self._since_check = 0
                     return float(loss)
@@ -731,6 +860,7 @@ class FitDriver:
         model, python/fit_multiview_stub.py:338-354, and cannot resume; `io.save_gaussians_npz` is that file)."""
         import numpy as np
         n = self.n
+        self._sync_moments()
         seg = lambda buf, off, k: buf[off:off + k * n].view(n, k).cpu().numpy()
         arrs = {"format": np.array("b2splat-fit-checkpoint-1"), "n": np.int64(n), "sh_coeffs": np.int64(self.sh),
                 "step": np.int64(self.step_no), "lr": np.float64(self.lr)}

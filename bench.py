@@ -54,6 +54,9 @@ def parse_args():
                     help="pipeline the local views in this many groups (preprocess ahead, chain rule behind); 0 = auto")
     ap.add_argument("--grad-chunks", type=int, default=0,
                     help="Gaussian chunks of the pipelined multi-GPU tail (chain rule | all-reduce | Adam); 0 = FitDriver default")
+    ap.add_argument("--comm", default="", choices=["", "nccl", "multimem"],
+                    help="multi-GPU tail: fused NVLink-multicast reduce-scatter + Adam + all-gather kernel (multimem, the "
+                         "default when available) or NCCL all-reduce + replicated Adam")
     ap.add_argument("--timeline", action="store_true",
                     help="record CUDA events at the phase boundaries of every timed step on rank 0 (head / views / tail)")
     ap.add_argument("--no-reorder", action="store_true", help="keep the synthetic Gaussians in generation (random) order")
@@ -482,7 +485,8 @@ def main():
     nv_local = len(fit.local_views(args.views, rank, world))
     view_groups = args.view_groups if args.view_groups > 0 else VIEW_GROUPS_AUTO(nv_local, args.lanes)
     drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes,
-                        view_groups=view_groups, grad_chunks=args.grad_chunks if (args.grad_chunks > 0 and world > 1) else None)
+                        view_groups=view_groups, grad_chunks=args.grad_chunks if (args.grad_chunks > 0 and world > 1) else None,
+                        comm=args.comm or None)
     means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device, args.s_lo, args.s_hi)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
@@ -758,6 +762,10 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "host_ms_per_step": host_ms_per_step, "timeline_ms": timeline,
+        "comm": ("single GPU" if world == 1 else ("multimem: fused reduce-scatter + Adam + all-gather over NVLink multicast"
+                                                  if drv._symm is not None else
+                                                  "nccl all-reduce + replicated Adam" + (f" (multimem unavailable: {drv.comm_fallback})"
+                                                                                         if getattr(drv, "comm_fallback", None) else ""))),
         "roofline": roofline, "roofline_stages": table, "ms_per_step_one_lane": ms_one_lane, "lanes": args.lanes, "view_groups": view_groups, "cpu_baseline": cpu, "render": render,
         "loss_last": loss_last, "pairs": {"P1_tile_pairs_worst_view": worst_p1, "P2_pixel_pairs_rank0_views": p2_rank0,
                                           "P2_all_ranks": float(p2_all.item())},

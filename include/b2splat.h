@@ -262,6 +262,22 @@ int b2s_adam_step_guarded(b2s_ctx* ctx, float* params, const float* grads, float
                           int64_t scales_end, float reg_scale, int64_t opac_begin, int64_t opac_end,
                           float reg_opacity, const float* skip_flag, int* skipped_count, void* stream);
 
+/* Multi-GPU form of the guarded Adam step: gradient reduce-scatter + Adam + parameter all-gather in ONE kernel over
+ * NVLink multicast (NVLS multimem.ld_reduce / multimem.st).  The reference has no multi-GPU code;
+ * on one GPU this is b2s_adam_step_guarded = torch.optim.Adam of python/fit_multiview_stub.py:262,311.
+ *   params_mc / grads_mc: MULTICAST addresses of this slice in the symmetric parameter / gradient buffers of all `world`
+ *   ranks (every rank passes the same offsets); params_local, m, v: this rank's own memory for the same slice.
+ * Rank r updates the r-th share of the slice (ceil(count/world) rounded up to 4 floats) from the switch-reduced gradient
+ * and multicasts the new parameters; moments of a share are kept by its owner only.  scales_/opac_ ranges are relative to
+ * the slice, as in b2s_adam_step.  The caller separates the chain rule that wrote the gradients, these launches and the
+ * next reader of the parameters by cross-rank barriers.  b2s_reduce_tail_multimem: the first `count` (<= 64) floats at
+ * tail_mc summed over the ranks into tail_out (local) -- the iteration's loss and the overflow count that guards the step. */
+int b2s_adam_step_multimem(b2s_ctx* ctx, float* params_mc, const float* grads_mc, const float* params_local, float* m,
+                           float* v, int64_t count, int rank, int world, int step, float lr, float beta1, float beta2,
+                           float eps, int64_t scales_begin, int64_t scales_end, float reg_scale, int64_t opac_begin,
+                           int64_t opac_end, float reg_opacity, const float* skip_flag, int* skipped_count, void* stream);
+int b2s_reduce_tail_multimem(b2s_ctx* ctx, const float* tail_mc, float* tail_out, int count, void* stream);
+
 /* Densify / prune (python/fit_multiview_stub.py:140-197): keep sigmoid(op_raw) > prune_opacity (or the
  * 64 most opaque if fewer survive), order preserved; then append min(max_gaussians - n1, int(n1 *
  * densify_ratio)) clones of the most opaque survivors with mean + 0.25*scale*N(0,1), op_raw - 0.1.

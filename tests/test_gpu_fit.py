@@ -280,7 +280,7 @@ def test_launcher_binds_reference_module_names(tmp_path):
 
 
 # ---------------------------------------------------------------- multi GPU -----------------
-def _mg_worker(rank, world, port, out):
+def _mg_worker(rank, world, port, out, comm="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -288,8 +288,11 @@ def _mg_worker(rank, world, port, out):
     fit = importlib.import_module("3dgaussian_b200.fit")
     S = _setup(4, n=9000, V=5, W=64, H=48)
     cams = [(v.reshape(-1).tolist(), p.reshape(-1).tolist()) for v, p in S["cams"]]
-    d = fit.FitDriver(S["n"], S["sh"], S["W"], S["H"], cams, torch.device("cuda", rank), rank=rank, world=world, lanes=2)
+    d = fit.FitDriver(S["n"], S["sh"], S["W"], S["H"], cams, torch.device("cuda", rank), rank=rank, world=world, lanes=2,
+                      comm=comm)
     assert len(d._chunks()) == 3          # the pipelined tail: chain rule | coalesced all-reduce | Adam, per chunk
+    if comm == "multimem":                # no silent fallback: the fused NVLink-multicast tail is what must run here
+        assert d._symm is not None, getattr(d, "comm_fallback", "multimem tail not active")
     t = lambda a: torch.from_numpy(a).to(d.dev)
     d.set_params(t(S["means"]), t(S["scales_raw"]), t(S["op_raw"]), t(S["col_raw"]))
     d.plan()
@@ -297,25 +300,32 @@ def _mg_worker(rank, world, port, out):
     for _ in range(3):
         loss = d.step()
     torch.cuda.synchronize()
-    torch.save({"p": d.p.cpu(), "loss": loss.cpu(), "views": d.views}, out.format(rank))
+    d._sync_moments()                     # multimem: the owners' Adam moments gathered on every rank
+    torch.save({"p": d.p.cpu(), "m": d.m.cpu(), "v": d.v.cpu(), "loss": loss.cpu(), "views": d.views}, out.format(rank))
     torch.distributed.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpu_fit_equals_one_gpu(tmp_path):
+@pytest.mark.parametrize("comm", ["nccl", "multimem"])
+def test_two_gpu_fit_equals_one_gpu(tmp_path, comm):
+    """comm="nccl": chunked NCCL all-reduce + replicated Adam; comm="multimem": the fused reduce-scatter + Adam +
+    all-gather kernel over NVLink multicast (b2s_adam_step_multimem).  Either way the replicas must be bit-identical
+    and equal to the one-GPU fit."""
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = str(tmp_path / "rank{}.pt")
-    mp.spawn(_mg_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_mg_worker, args=(2, port, out, comm), nprocs=2, join=True)
     r0, r1_ = torch.load(out.format(0)), torch.load(out.format(1))
     assert r0["views"] == [0, 2, 4] and r1_["views"] == [1, 3]
     assert torch.equal(r0["p"], r1_["p"])                       # replicas stay bit-identical
+    assert torch.equal(r0["m"], r1_["m"]) and torch.equal(r0["v"], r1_["v"])
     S = _setup(4, n=9000, V=5, W=64, H=48)
     d = _driver(S)
     for _ in range(3):
         loss = d.step()
     assert abs(float(loss.item()) - float(r0["loss"])) <= 1e-6
     assert rel_l2(r0["p"].numpy(), d.p.cpu().numpy()) <= 1e-5
+    assert rel_l2(r0["m"].numpy(), d.m.cpu().numpy()) <= 1e-4 and rel_l2(r0["v"].numpy(), d.v.cpu().numpy()) <= 1e-4
 
 
 _XCHECK = r'''
