@@ -26,7 +26,7 @@ EXPORTS = [
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
     "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded", "b2s_backward_params_range",
-    "b2s_forward_ext", "b2s_backward_ext", "b2s_adam_step_multimem", "b2s_reduce_tail_multimem",
+    "b2s_forward_ext", "b2s_backward_ext", "b2s_adam_step_multimem", "b2s_reduce_tail_multimem", "b2s_fit_backward_blend_u8",
 ]
 
 
@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         L.b2s_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp]
         L.b2s_fit_backward_blend.restype = i32
         L.b2s_fit_backward_blend.argtypes = [vp, PP, i32, i64, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp, vp]
+        L.b2s_fit_backward_blend_u8.restype = i32
+        L.b2s_fit_backward_blend_u8.argtypes = L.b2s_fit_backward_blend.argtypes
         L.b2s_prepared_view_bytes.restype = sz
         L.b2s_prepared_view_bytes.argtypes = [i32]
         L.b2s_preprocess_views.restype = i32

@@ -106,7 +106,8 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
                  const float* __restrict__ g_alpha, const float* __restrict__ g_depth, const float* __restrict__ tgt,
                  const float* __restrict__ mask, const float* __restrict__ depth_gt, const float* __restrict__ dstats,
                  float w_sil, float w_depth, float scale, float* __restrict__ loss_accum,
-                 uint32_t* __restrict__ frag, float* __restrict__ tile_scale) {
+                 uint32_t* __restrict__ frag, float* __restrict__ tile_scale, const uint8_t* __restrict__ tgt8,
+                 const uint8_t* __restrict__ mask8) {
   constexpr int CH = DEPTH ? 5 : 4;
   constexpr int NREG = CH * 16;
   __shared__ float wmax[TILE_PIX / 32];
@@ -126,15 +127,22 @@ gbuf_frag_kernel(const ViewParams vp, const float* __restrict__ acc, const float
     float gr0, gr1, gr2, ga = 0.f;
     if constexpr (LOSS) {
       const float inv3 = 1.0f / (3.0f * (float)hw), inv1 = 1.0f / (float)hw;
-      const float d0 = fminf(fmaxf(o0, 0.f), 1.f) - tgt[3 * p], d1 = fminf(fmaxf(o1, 0.f), 1.f) - tgt[3 * p + 1],
-                  d2 = fminf(fmaxf(o2, 0.f), 1.f) - tgt[3 * p + 2];
+      float t0, t1, t2;
+      if (tgt8 != nullptr) {          // image bytes: the same value / 255 a host-side conversion would have produced
+        t0 = (float)tgt8[3 * p] / 255.0f; t1 = (float)tgt8[3 * p + 1] / 255.0f; t2 = (float)tgt8[3 * p + 2] / 255.0f;
+      } else {
+        t0 = tgt[3 * p]; t1 = tgt[3 * p + 1]; t2 = tgt[3 * p + 2];
+      }
+      const float d0 = fminf(fmaxf(o0, 0.f), 1.f) - t0, d1 = fminf(fmaxf(o1, 0.f), 1.f) - t1,
+                  d2 = fminf(fmaxf(o2, 0.f), 1.f) - t2;
       loss = (fabsf(d0) + fabsf(d1) + fabsf(d2)) * inv3;
       const float k = scale * inv3;
       gr0 = k * (float)((d0 > 0.f) - (d0 < 0.f));
       gr1 = k * (float)((d1 > 0.f) - (d1 < 0.f));
       gr2 = k * (float)((d2 > 0.f) - (d2 < 0.f));
-      if (mask != nullptr) {
-        const float da = fminf(fmaxf(W * inv, 0.f), 1.f) - mask[p];
+      if (mask != nullptr || mask8 != nullptr) {
+        const float mk = mask8 != nullptr ? (float)mask8[p] / 255.0f : mask[p];
+        const float da = fminf(fmaxf(W * inv, 0.f), 1.f) - mk;
         loss = fmaf(w_sil * inv1, fabsf(da), loss);
         ga = scale * w_sil * inv1 * (float)((da > 0.f) - (da < 0.f));
       }
@@ -1077,7 +1085,8 @@ int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* va
   gbuf_frag_kernel<DD, LL, UU><<<vp.n_tiles, TILE_PIX, 0, st>>>(vp, acc, g_rgb, g_alpha, g_depth, fl ? fl->tgt : nullptr,  \
                                                                 fl ? fl->mask : nullptr, fit_depth ? fl->depth_gt : nullptr, dstats, \
                                                                 fl ? fl->w_sil : 0.f, fit_depth ? fl->w_depth : 0.f,        \
-                                                                fl ? fl->scale : 0.f, fl ? fl->loss_accum : nullptr, frag, tile_scale)
+                                                                fl ? fl->scale : 0.f, fl ? fl->loss_accum : nullptr, frag, tile_scale, \
+                                                                fl ? fl->tgt_u8 : nullptr, fl ? fl->mask_u8 : nullptr)
     if (fl != nullptr) {
       if (depth) { if (umma) B2S_GBUF(true, true, true); else B2S_GBUF(true, true, false); }
       else       { if (umma) B2S_GBUF(false, true, true); else B2S_GBUF(false, true, false); }

@@ -647,11 +647,11 @@ int b2s_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pai
                                g_depth, nullptr, B.gbuf, gacc_out, st);
 }
 
-int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
-                           const float* mask, const float* depth_gt, float w_sil, float w_depth, float scale,
+static int fit_backward_blend_impl(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
+                           const float* mask, const uint8_t* tgt8, const uint8_t* mask8, const float* depth_gt, float w_sil, float w_depth, float scale,
                            float* loss_accum, const void* state, const void* prepared_view, void* workspace,
                            size_t ws_bytes, float* gacc_out, void* stream) {
-  if (ctx == nullptr || tgt == nullptr || loss_accum == nullptr || state == nullptr || workspace == nullptr ||
+  if (ctx == nullptr || (tgt == nullptr && tgt8 == nullptr) || loss_accum == nullptr || state == nullptr || workspace == nullptr ||
       gacc_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   ViewParams vp;
   int rc = make_view(p, &vp);
@@ -669,7 +669,7 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
     set_error("the depth term needs the depth plane: run the forward with params.keep_depth = 1");
     return B2S_ERR_INVALID;
   }
-  const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum, depth_gt, w_depth};
+  const FitLossArgs fl = {tgt, mask, w_sil, scale, loss_accum, depth_gt, w_depth, tgt8, mask8};
   StageTimer t(ctx, ST_BLEND_BWD, st);
   if (n > 0) {
     rc = launch_gacc_init(B.cmask, gacc_out, n, st);
@@ -677,6 +677,22 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
   }
   return launch_blend_wsum_bwd(vp, B.rec, B.vals, B.ranges, B.unit_start, B.units, B.udesc, B.counters, B.unit_cap, B.acc, nullptr, nullptr,
                                nullptr, &fl, B.gbuf, gacc_out, st);
+}
+
+int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const float* tgt,
+                           const float* mask, const float* depth_gt, float w_sil, float w_depth, float scale,
+                           float* loss_accum, const void* state, const void* prepared_view, void* workspace,
+                           size_t ws_bytes, float* gacc_out, void* stream) {
+  return fit_backward_blend_impl(ctx, p, n, max_pairs, tgt, mask, nullptr, nullptr, depth_gt, w_sil, w_depth, scale, loss_accum,
+                                 state, prepared_view, workspace, ws_bytes, gacc_out, stream);
+}
+
+int b2s_fit_backward_blend_u8(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const uint8_t* tgt_u8,
+                              const uint8_t* mask_u8, const float* depth_gt, float w_sil, float w_depth, float scale,
+                              float* loss_accum, const void* state, const void* prepared_view, void* workspace,
+                              size_t ws_bytes, float* gacc_out, void* stream) {
+  return fit_backward_blend_impl(ctx, p, n, max_pairs, nullptr, nullptr, tgt_u8, mask_u8, depth_gt, w_sil, w_depth, scale,
+                                 loss_accum, state, prepared_view, workspace, ws_bytes, gacc_out, stream);
 }
 
 int b2s_backward_params_range(b2s_ctx* ctx, const void* views_dev, int num_views, int sh_coeffs, const float* means,

@@ -404,6 +404,10 @@ struct FitLossArgs {
   float* loss_accum;
   const float* depth_gt; // may be null: the depth term  w_depth * mean|depth/(max depth + 1e-6) - depth_gt|
   float w_depth;
+  // 8-bit target / mask (the decoded image bytes, value / 255 as np.asarray(img, float32) / 255 of
+  // fit_multiview_stub.py:16-23): when non-null they replace tgt / mask and the loss kernel converts on the fly
+  const uint8_t* tgt_u8;
+  const uint8_t* mask_u8;
 };
 int launch_blend_wsum_bwd(const ViewParams& vp, const float4* rec, const int* vals, const int2* ranges,
                           const int* unit_start, const int2* units, const int4* udesc, const Counters* counters,

@@ -372,7 +372,11 @@ class FitDriver:
                 torch.cuda.current_stream().wait_event(ready)
             if convert is not None:
                 convert()
-            capi.check(L.b2s_fit_backward_blend(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask),
+            # 8-bit targets / masks (host-fed steps): the loss kernel reads the image bytes itself
+            entry = L.b2s_fit_backward_blend_u8 if tgt.dtype == torch.uint8 else L.b2s_fit_backward_blend
+            if mask is not None and mask.dtype != tgt.dtype:
+                raise TypeError("target and mask must both be float32 or both be uint8")
+            capi.check(entry(ctx, pc, self.n, self.max_pairs, _ptr(tgt), _ptr(mask),
                                                 _ptr(depth) if self.use_depth else None, self.w_sil,
                                                 self.w_depth if (self.use_depth and depth is not None) else 0.0,
                                                 1.0 / self.num_views, _ptr(self.loss_l[lane]), _ptr(state), pv,
@@ -726,11 +730,88 @@ class FitDriver:
         return self.loss_dev
 
     def step_from_host(self, host_targets: dict, host_masks: Optional[dict] = None,
-                       host_depths: Optional[dict] = None) -> float:
+                       host_depths: Optional[dict] = None, defer_loss: bool = False):
         """Same iteration fed from PINNED HOST buffers: every view's target (and mask, and depth map) is copied
         host->device inside the step (two staging slots per lane on a side stream, so the copy of a later
         view overlaps the kernels of the current ones) and the loss is read back to the host at the end.
-        Targets / masks / depth maps may be float32 in [0,1] or uint8 (decoded image bytes, converted on the device)."""
+        Targets / masks / depth maps may be float32 in [0,1] or uint8 (decoded image bytes, converted on the device).
+
+        defer_loss=True: the step's (loss, overflow count) still cross to pinned host memory every step, but with a
+        non-blocking copy; the call returns the PREVIOUS step's loss (None on the first call) and the host waits for
+        that older copy only, so the device always has the next iteration queued when one ends instead of idling
+        through the host's wake-up and the first launches (what a training loop that logs its loss asynchronously does).
+        `flush_loss()` returns the last step's loss.  An overflow is then seen one step late: both steps were skipped by
+        the device guard, the buffers are re-planned and both are repeated."""
+        if defer_loss:
+            return self._step_from_host_deferred(host_targets, host_masks, host_depths)
+        self.flush_loss()
+        for attempt in range(3):
+            self._queue_host_step(host_targets, host_masks, host_depths, wait_free=attempt > 0)
+            with torch.cuda.device(self.dev):
+                # the step's one device->host read: loss + overflow guard
+                loss, overflow = (self.tail_red if self._symm is not None else self.tail)[0:2].tolist()
+            if overflow == 0.0:
+                self._since_check = 0
+                return float(loss)
+            # the guard skipped this Adam step: re-plan with more room and run the iteration again
+            self._overflowed = True
+            self.skipped_dev.zero_()
+            self.step_no -= 1
+            self.plan(extra_slack=1.5 * (attempt + 1))
+        raise capi.B2SError("pair buffers overflowed repeatedly")
+
+    def _step_from_host_deferred(self, host_targets, host_masks, host_depths):
+        if getattr(self, "_loss_ring", None) is None:
+            self._loss_ring = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._ring_i = 0
+            self._pending_loss = None
+        self._queue_host_step(host_targets, host_masks, host_depths, wait_free=True)
+        slot = self._loss_ring[self._ring_i & 1]
+        self._ring_i += 1
+        with torch.cuda.device(self.dev):
+            slot.copy_((self.tail_red if self._symm is not None else self.tail)[0:2], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        prev, self._pending_loss = self._pending_loss, (slot, ev, (host_targets, host_masks, host_depths))
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        loss, overflow = prev[0].tolist()
+        if overflow == 0.0:
+            return float(loss)
+        # the previous step overflowed its pair buffers: the guard skipped its Adam step, and this one's too (unchanged
+        # parameters overflow again).  Drain, re-plan with more room, repeat both with a blocking read.
+        ev.synchronize()
+        self._pending_loss = None
+        self._overflowed = True
+        self.skipped_dev.zero_()
+        self.step_no -= 2
+        self.plan(extra_slack=1.5)
+        loss = self.step_from_host(*prev[2])
+        self._last_flushed = self.step_from_host(host_targets, host_masks, host_depths)
+        return loss
+
+    def flush_loss(self):
+        """Loss of the last deferred step (waits for it); None when nothing is pending."""
+        pend = getattr(self, "_pending_loss", None)
+        if pend is None:
+            return getattr(self, "_last_flushed", None)
+        self._pending_loss = None
+        pend[1].synchronize()
+        loss, overflow = pend[0].tolist()
+        if overflow != 0.0:
+            self._overflowed = True
+            self.skipped_dev.zero_()
+            self.step_no -= 1
+            self.plan(extra_slack=1.5)
+            loss = self.step_from_host(*pend[2])
+        self._last_flushed = float(loss)
+        return self._last_flushed
+
+    def _queue_host_step(self, host_targets, host_masks, host_depths, wait_free: bool):
+        """Queues one host-fed iteration (copies, views, tail) without reading anything back.  wait_free: the staging
+        slots may still be read by an earlier iteration (a repeated attempt, or a deferred-loss step that did not drain
+        the stream), so every copy waits for its slot's last consumer."""
         if self.state is None:
             self.plan()
         if host_depths is not None and not self.use_depth:
@@ -747,24 +828,32 @@ class FitDriver:
             use_mask = host_masks is not None
             use_depth = host_depths is not None
             nv = len(self.views)
-
             pending = {}                                  # slot -> [(raw bytes, float32 destination)] awaiting conversion
+            staged = {}                                   # slot -> (target, mask, depth) tensors the view's kernels read
+            # With the fused loss, 8-bit targets and masks are consumed as bytes (b2s_fit_backward_blend_u8): no conversion
+            # kernel, no float32 copy.  Both must then be bytes; depth maps (and everything on the unfused path) are converted.
+            direct_u8 = (self.fused_loss and all(host_targets[i].dtype == torch.uint8 for i in self.views) and
+                         (not use_mask or all(host_masks[i].dtype == torch.uint8 for i in self.views)))
 
             def upload(dst, src, slot, which):
                 """host -> stage; 8-bit images cross PCIe as bytes and are converted on the device
-                (np.asarray(img, float32) / 255, fit_multiview_stub.py:16-23) -- by the CONSUMER, on the view's own lane
-                stream (`convert` below): a conversion kernel on the copy stream has to find free SM slots between the
-                persistent blend kernels of four lanes before the next DMA may start, which made the 8-bit feed slower
-                than the float32 one that moves four times the bytes (21.9 vs 22.7 iters/s at C4)."""
+                (np.asarray(img, float32) / 255, fit_multiview_stub.py:16-23): targets and masks by the fused loss kernel
+                itself (it reads the bytes), anything else by the CONSUMER on the view's own lane stream (`convert`
+                below).  A conversion kernel on the copy stream has to find free SM slots between the persistent blend
+                kernels of four lanes before the next DMA may start, which made the 8-bit feed slower than the float32
+                one that moves four times the bytes (21.9 vs 22.7 iters/s at C4)."""
                 if src.dtype == torch.uint8:
                     key = (slot, which)
                     if key not in self._stage_u8:
                         self._stage_u8[key] = torch.empty(src.shape, dtype=torch.uint8, device=self.dev)
                     raw = self._stage_u8[key]
                     raw.copy_(src, non_blocking=True)
+                    if direct_u8 and which < 2:
+                        return raw                        # target / mask bytes go to the loss kernel as they are
                     pending.setdefault(slot, []).append((raw, dst))
                 else:
                     dst.copy_(src, non_blocking=True)
+                return dst
 
             def make_convert(jobs):
                 def convert():
@@ -773,47 +862,35 @@ class FitDriver:
                                                             _stream()))
                 return convert if jobs else None
 
-            for attempt in range(3):
-                issued = [0]
+            issued = [0]
 
-                def issue_upto(k_hi):
-                    # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
-                    while issued[0] < min(k_hi, nv):
-                        k = issued[0]
-                        slot = k % nslots
-                        i = self.views[k]
-                        with torch.cuda.stream(self._copy_stream):
-                            if k >= nslots or attempt > 0:
-                                self._copy_stream.wait_event(self._ev_free[slot])
-                            pending[slot] = []
-                            upload(self._stage[slot][0], host_targets[i], slot, 0)
-                            if use_mask:
-                                upload(self._stage[slot][1], host_masks[i], slot, 1)
-                            if use_depth:
-                                upload(self._stage[slot][2], host_depths[i], slot, 2)
-                            self._ev_ready[slot].record(self._copy_stream)
-                        issued[0] += 1
-
-                def inputs(k, st):
-                    issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
+            def issue_upto(k_hi):
+                # copies are queued in view order on the copy stream, at most nslots ahead of the consumers
+                while issued[0] < min(k_hi, nv):
+                    k = issued[0]
                     slot = k % nslots
-                    return {"tgt": self._stage[slot][0], "mask": self._stage[slot][1] if use_mask else None,
-                            "depth": self._stage[slot][2] if use_depth else None,
-                            "done": lambda s, slot=slot: self._ev_free[slot].record(s), "ready": self._ev_ready[slot],
-                            "convert": make_convert(list(pending.get(slot, [])))}
+                    i = self.views[k]
+                    with torch.cuda.stream(self._copy_stream):
+                        if k >= nslots or wait_free:
+                            self._copy_stream.wait_event(self._ev_free[slot])
+                        pending[slot] = []
+                        t_dev = upload(self._stage[slot][0], host_targets[i], slot, 0)
+                        m_dev = upload(self._stage[slot][1], host_masks[i], slot, 1) if use_mask else None
+                        d_dev = upload(self._stage[slot][2], host_depths[i], slot, 2) if use_depth else None
+                        staged[slot] = (t_dev, m_dev, d_dev)
+                        self._ev_ready[slot].record(self._copy_stream)
+                    issued[0] += 1
 
-                self._iterate(inputs)
-                self._finish_step()
-                loss, overflow = (self.tail_red if self._symm is not None else self.tail)[0:2].tolist()     # the step's one device->host read: loss + overflow guard
-                if overflow == 0.0:
-                    self._since_check = 0
-                    return float(loss)
-                # the guard skipped this Adam step: re-plan with more room and run the iteration again
-                self._overflowed = True
-                self.skipped_dev.zero_()
-                self.step_no -= 1
-                self.plan(extra_slack=1.5 * (attempt + 1))
-            raise capi.B2SError("pair buffers overflowed repeatedly")
+            def inputs(k, st):
+                issue_upto(k + self.lanes + 1)       # view k's slot was freed (recorded) before this point
+                slot = k % nslots
+                t_dev, m_dev, d_dev = staged[slot]
+                return {"tgt": t_dev, "mask": m_dev, "depth": d_dev,
+                        "done": lambda s, slot=slot: self._ev_free[slot].record(s), "ready": self._ev_ready[slot],
+                        "convert": make_convert(list(pending.get(slot, [])))}
+
+            self._iterate(inputs)
+            self._finish_step()
 
     # ---- densify / prune ----------------------------------------------------------------------
     def densify_prune(self, iteration: int, max_gaussians: int, densify_ratio: float = 0.15,

@@ -610,6 +610,21 @@ def main():
         dt8 = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(dt8, op=torch.distributed.ReduceOp.MAX)
+        # the same feed with the loss read back ASYNCHRONOUSLY (FitDriver.step_from_host(defer_loss=True): the copy of
+        # (loss, overflow) to pinned memory is queued every step, the host consumes it one step later and never drains
+        # the device); reported beside the headline, which keeps the blocking read of the reference's loop
+        # (loss.item() every iteration, python/fit_multiview_stub.py:313-316)
+        drv.step_from_host(host_t8, host_m8, defer_loss=True)
+        drv.flush_loss()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            drv.step_from_host(host_t8, host_m8, defer_loss=True)
+        drv.flush_loss()
+        barrier()
+        dtd = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(dtd, op=torch.distributed.ReduceOp.MAX)
         # Headline = the 8-bit feed: that is what target images ARE (the reference decodes 8-bit JPEG / PNG files,
         # python/fit_multiview_stub.py:16-34), and with several ranks pulling 2.1 GB of float32 per iteration the
         # float32 feed measures the host link, not the fit (8 GPUs: 73 vs 136 iters/s).  It stays beside it.
@@ -619,7 +634,10 @@ def main():
                "h2d_bytes_per_step": int(h2d_all.item()) // 4, "d2h_bytes_per_step": 4 * world,
                "api": "FitDriver.step_from_host: pinned-host uint8 targets+masks (the decoded image bytes) H2D per view "
                       "(double-buffered per lane), converted on the device (b2s_u8_to_f32), loss D2H",
-               "f32_targets": f32}
+               "f32_targets": f32,
+               "deferred_loss_read": {"value": args.steps / float(dtd.item()), "unit": "iters/s",
+                                      "api": "step_from_host(defer_loss=True): same H2D feed, (loss, overflow) copied to pinned "
+                                             "host memory every step without blocking, consumed one step later"}}
         del host_t8, host_m8
         del host_t, host_m
 

@@ -171,6 +171,14 @@ int b2s_fit_backward_blend(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max
                            float* loss_accum, const void* state,
                            const void* prepared_view /* NULL unless the forward was b2s_forward_prepared */,
                            void* workspace, size_t ws_bytes, float* gacc_out, void* stream);
+/* The same with the target and the mask as the 8-bit image bytes they are on disk (the reference converts them on the
+ * host, np.asarray(img, float32) / 255, python/fit_multiview_stub.py:16-23): the loss kernel reads the bytes and divides
+ * by 255 itself -- no float32 copy of the target exists on the device and a host-fed fit moves 1 byte per value over
+ * PCIe.  mask_u8 may be NULL; depth_gt stays float32. */
+int b2s_fit_backward_blend_u8(b2s_ctx* ctx, const b2s_params* p, int n, int64_t max_pairs, const uint8_t* tgt_u8,
+                              const uint8_t* mask_u8, const float* depth_gt, float w_sil, float w_depth, float scale,
+                              float* loss_accum, const void* state, const void* prepared_view, void* workspace,
+                              size_t ws_bytes, float* gacc_out, void* stream);
 
 /* Batched per-Gaussian stage of the fit loop: projection, sigma, SH colour, tile rect and tile mask of EVERY
  * local view in one launch -- the parameters (192 B of SH coefficients per Gaussian at degree 3) are read once

@@ -132,6 +132,26 @@ def test_step_from_host_equals_device_step():
     assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
 
 
+def test_step_from_host_deferred_loss_is_the_same_fit_one_step_late():
+    """defer_loss=True returns the PREVIOUS step's loss (None first) and never drains the device; the losses and the
+    parameters are those of the blocking loop."""
+    S = _setup(1)
+    d1, d2 = _driver(S, lanes=2), _driver(S, lanes=2)
+    host_t = {i: torch.from_numpy(S["tgts"][i]).pin_memory() for i in range(S["V"])}
+    host_m = {i: torch.from_numpy(S["masks"][i]).pin_memory() for i in range(S["V"])}
+    blocking = [d1.step_from_host(host_t, host_m) for _ in range(5)]
+    deferred = [d2.step_from_host(host_t, host_m, defer_loss=True) for _ in range(5)]
+    assert deferred[0] is None
+    deferred = deferred[1:] + [d2.flush_loss()]
+    assert d2.flush_loss() == deferred[-1]              # nothing pending any more: the last value again
+    for a, b in zip(blocking, deferred):
+        assert abs(a - b) <= 2e-6
+    assert rel_l2(d1.p.cpu().numpy(), d2.p.cpu().numpy()) <= 1e-4
+    # a blocking call after deferred ones flushes first and carries on
+    l6a, l6b = d1.step_from_host(host_t, host_m), d2.step_from_host(host_t, host_m)
+    assert abs(l6a - l6b) <= 2e-6
+
+
 def test_spatial_reorder_leaves_the_fit_unchanged():
     """FitDriver.reorder_spatial permutes parameters and Adam moments into 3-D Morton order: same losses, and the
     same parameters up to that permutation, as the unpermuted driver."""
