@@ -69,6 +69,12 @@ def parse_args():
     ap.add_argument("--densify-every", type=int, default=0,
                     help="call FitDriver.densify_prune every K timed steps (BASELINE configs[4]); 0 = never")
     ap.add_argument("--render-only", action="store_true", help="only the render config (BASELINE configs[2]); for profiling")
+    ap.add_argument("--cutoff-sigma", type=float, default=0.0,
+                    help="bbox radius of the fit in sigmas (default: FitDriver's 5; the reference has none). For the record only: "
+                         "the headline is measured at the default")
+    ap.add_argument("--ext", action="store_true",
+                    help="only the extension modes (rotations + EWA covariance, differentiable front-to-back compositing): "
+                         "forward and forward+backward time of one view through render_gaussians_torch")
     ap.add_argument("--fit-scripts", action="store_true",
                     help="only BASELINE configs[0] and [1]: the reference's UNCHANGED fit_multiview_stub.py on the B200 path, "
                          "beside the same script on the box's host cores (the reference's stock CPU configuration)")
@@ -253,7 +259,7 @@ def workload_config(args):
     return {"workload": f"synthetic fit: {args.n} Gaussians SH{args.sh} (N,{args.sh},3), {args.views} orbit views at "
                         f"{args.width}x{args.height}, fwd+bwd+Adam, views sharded over ranks (BASELINE configs[3])",
             "gaussians": args.n, "sh_coeffs": args.sh, "views": args.views, "width": args.width, "height": args.height,
-            "cutoff_sigma": 5.0, "loss": "L1 recon + 0.2*L1 silhouette + 1e-3 reg", "parallelism": "views round-robin over ranks",
+            "cutoff_sigma": (args.cutoff_sigma if args.cutoff_sigma > 0 else 5.0), "loss": "L1 recon + 0.2*L1 silhouette + 1e-3 reg", "parallelism": "views round-robin over ranks",
             "l2_note": "per-step inputs (params 220 MB + targets/masks 2.1 GB at N=1) exceed the 126 MB L2"}
 
 
@@ -377,6 +383,41 @@ def _claim_stdout():
     return saved
 
 
+def ext_bench(device, n=200_000, W=960, H=540, iters=10):
+    """Extension modes (csrc/splat2d.cu; absent from the reference): one view of n Gaussians, SH degree 1 (N,4,3), through
+    the drop-in call with rotations= / blend=.  First correct version of these kernels (one CTA per tile, no work units):
+    the numbers are here so that the gap to the tensor-core path of the reference's Gaussian model is on record."""
+    r = importlib.import_module("3dgaussian_b200.renderer")
+    means, scales, colors, opac = synth_gaussians(n, 4, 99, device, 0.004, 0.02)
+    view, proj = synth.orbit_camera(0, 1, W, H)
+    cam = r.Camera(view=torch.from_numpy(view).to(device), proj=torch.from_numpy(proj).to(device))
+    quat = torch.randn((n, 4), generator=torch.Generator(device=device).manual_seed(1), device=device)
+    g = torch.rand((H, W, 3), generator=torch.Generator(device=device).manual_seed(2), device=device)
+    out = {"config": f"{n} Gaussians (N,4,3), {W}x{H}, one view, through render_gaussians_torch (autograd)"}
+    for name, kw in (("billboard_wsum_tcgen05", {}), ("billboard_over", {"blend": "over"}),
+                     ("ewa_wsum", {"rotations": quat}), ("ewa_over", {"rotations": quat, "blend": "over"})):
+        leaves = [t.clone().requires_grad_(True) for t in (means, scales, colors, opac)]
+        kws = dict(kw)
+        if "rotations" in kws:
+            kws["rotations"] = quat.clone().requires_grad_(True)
+        fwd = lambda: r.render_gaussians_torch(*leaves, cam, W, H, max_gaussians=n, **kws)
+        for _ in range(2):
+            (fwd() * g).sum().backward()
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        with torch.no_grad():
+            for _ in range(iters):
+                fwd()
+        e[1].record()
+        for _ in range(iters):
+            (fwd() * g).sum().backward()
+        e[2].record()
+        torch.cuda.synchronize()
+        out[name] = {"fwd_ms": e[0].elapsed_time(e[1]) / iters, "fwd_bwd_ms": e[1].elapsed_time(e[2]) / iters}
+    return out
+
+
 def fit_scripts_bench():
     """BASELINE configs[0] and [1]: the reference's unchanged fit script
     (python/fit_multiview_stub.py:200-382, staged byte for byte under oracle/_ref/reference) three ways on this box --
@@ -459,6 +500,9 @@ def main():
     if args.fit_scripts:
         _emit(out_fd, {"fit_scripts": fit_scripts_bench()})
         return
+    if args.ext:
+        _emit(out_fd, {"ext": ext_bench(device)})
+        return
     cams = cameras(args.views, args.width, args.height)
 
     def barrier():
@@ -486,7 +530,7 @@ def main():
     view_groups = args.view_groups if args.view_groups > 0 else VIEW_GROUPS_AUTO(nv_local, args.lanes)
     drv = fit.FitDriver(args.n, args.sh, args.width, args.height, cams, device, rank=rank, world=world, lanes=args.lanes,
                         view_groups=view_groups, grad_chunks=args.grad_chunks if (args.grad_chunks > 0 and world > 1) else None,
-                        comm=args.comm or None)
+                        comm=args.comm or None, cutoff_sigma=(args.cutoff_sigma if args.cutoff_sigma > 0 else None))
     means, scales, colors, opac = synth_gaussians(args.n, args.sh, 1234, device, args.s_lo, args.s_hi)
     sr, orr, cr = to_raw(scales, opac, colors, args.sh)
     drv.set_params(means, sr, orr, cr)
