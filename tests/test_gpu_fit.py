@@ -321,7 +321,17 @@ def _mg_worker(rank, world, port, out, comm="nccl"):
         loss = d.step()
     torch.cuda.synchronize()
     d._sync_moments()                     # multimem: the owners' Adam moments gathered on every rank
-    torch.save({"p": d.p.cpu(), "m": d.m.cpu(), "v": d.v.cpu(), "loss": loss.cpu(), "views": d.views}, out.format(rank))
+    res = {"p": d.p.cpu(), "m": d.m.cpu(), "v": d.v.cpu(), "loss": loss.cpu(), "views": d.views}
+    # densify / prune changes the Gaussian count: the flat buffers (symmetric allocations + multicast binding in the
+    # multimem mode) are rebuilt on every rank, identically (Philox jitter), and the fit carries on
+    k = d.densify_prune(3, max_gaussians=12000, seed=0, reorder=True)
+    if comm == "multimem":
+        assert d._symm is not None, getattr(d, "comm_fallback", "multimem tail not active after densify")
+    for _ in range(2):
+        loss2 = d.step()
+    torch.cuda.synchronize()
+    res.update({"n_after": k, "p_after": d.p.cpu(), "loss_after": loss2.cpu()})
+    torch.save(res, out.format(rank))
     torch.distributed.destroy_process_group()
 
 
@@ -339,6 +349,9 @@ def test_two_gpu_fit_equals_one_gpu(tmp_path, comm):
     assert r0["views"] == [0, 2, 4] and r1_["views"] == [1, 3]
     assert torch.equal(r0["p"], r1_["p"])                       # replicas stay bit-identical
     assert torch.equal(r0["m"], r1_["m"]) and torch.equal(r0["v"], r1_["v"])
+    assert r0["n_after"] == r1_["n_after"] and r0["n_after"] > 9000
+    assert torch.equal(r0["p_after"], r1_["p_after"]) and torch.equal(r0["loss_after"], r1_["loss_after"])
+    assert bool(torch.isfinite(r0["p_after"]).all()) and float(r0["loss_after"]) < float(r0["loss"]) * 1.5
     S = _setup(4, n=9000, V=5, W=64, H=48)
     d = _driver(S)
     for _ in range(3):
