@@ -26,7 +26,7 @@ EXPORTS = [
     "b2s_prepared_view_bytes", "b2s_preprocess_views", "b2s_forward_prepared", "b2s_u8_to_f32",
     "b2s_densify_workspace_bytes", "b2s_densify_prune", "b2s_launch_count", "b2s_num_stages", "b2s_stage_name", "b2s_timing_enable", "b2s_timing_read",
     "b2s_last_ticket", "b2s_ticket_info", "b2s_path_counts", "b2s_sm_count", "b2s_adam_step_guarded", "b2s_backward_params_range",
-    "b2s_forward_ext", "b2s_backward_ext", "b2s_adam_step_multimem", "b2s_reduce_tail_multimem", "b2s_fit_backward_blend_u8",
+    "b2s_forward_ext", "b2s_backward_ext", "b2s_adam_step_multimem", "b2s_reduce_tail_multimem", "b2s_fit_backward_blend_u8", "b2s_multimem_share",
 ]
 
 
@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
         L.b2s_adam_step_multimem.restype = i32
         L.b2s_adam_step_multimem.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, C.c_float, C.c_float, C.c_float,
                                              C.c_float, i64, i64, C.c_float, i64, i64, C.c_float, vp, vp, vp]
+        L.b2s_multimem_share.restype = i32
+        L.b2s_multimem_share.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
         L.b2s_reduce_tail_multimem.restype = i32
         L.b2s_reduce_tail_multimem.argtypes = [vp, vp, vp, i32, vp]
         L.b2s_densify_workspace_bytes.restype = sz
@@ -162,6 +164,13 @@ def timing_read(device_index: int) -> dict:
     cnt = (C.c_int64 * ns)()
     check(lib().b2s_timing_read(ctx(device_index), ms, cnt))
     return {lib().b2s_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(ns)}
+
+
+def multimem_share(count: int, rank: int, world: int) -> tuple:
+    """[lo, hi) of a slice of `count` floats owned by `rank` in the fused multi-GPU Adam step (host arithmetic only)."""
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    check(lib().b2s_multimem_share(int(count), int(rank), int(world), C.byref(lo), C.byref(hi)))
+    return int(lo.value), int(hi.value)
 
 
 def path_counts() -> dict:

@@ -960,6 +960,15 @@ int b2s_adam_step_multimem(b2s_ctx* ctx, float* params_mc, const float* grads_mc
                               skipped_count, (cudaStream_t)stream);
 }
 
+int b2s_multimem_share(int64_t count, int rank, int world, int64_t* lo, int64_t* hi) {
+  if (count < 0 || world <= 0 || rank < 0 || rank >= world || lo == nullptr || hi == nullptr) { set_error("bad argument"); return B2S_ERR_INVALID; }
+  long long a, b;
+  multimem_share(count, rank, world, &a, &b);
+  *lo = a;
+  *hi = b;
+  return B2S_OK;
+}
+
 int b2s_reduce_tail_multimem(b2s_ctx* ctx, const float* tail_mc, float* tail_out, int count, void* stream) {
   if (ctx == nullptr || tail_mc == nullptr || tail_out == nullptr) { set_error("NULL argument"); return B2S_ERR_INVALID; }
   return launch_tail_multimem(tail_mc, tail_out, count, (cudaStream_t)stream);

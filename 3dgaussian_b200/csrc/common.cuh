@@ -452,5 +452,6 @@ int launch_adam_multimem(float* params_mc, const float* grads_mc, const float* p
                          int64_t se, float reg_scale, int64_t ob, int64_t oe, float reg_op, const float* skip_flag,
                          int* skipped_count, cudaStream_t st);
 int launch_tail_multimem(const float* tail_mc, float* out, int count, cudaStream_t st);
+void multimem_share(int64_t count, int rank, int world, long long* lo, long long* hi);
 
 }  // namespace b2s

@@ -188,6 +188,14 @@ __global__ void __launch_bounds__(64) tail_multimem_kernel(const float* __restri
   if ((int)threadIdx.x < count) out[threadIdx.x] = mc_ld_reduce1(tail_mc + threadIdx.x);
 }
 
+// rank r's share [lo, hi) of a slice of `count` floats: ceil(count / world) rounded up to 4 floats (16-byte multimem
+// accesses), clipped to the slice -- the shares tile the slice, every boundary but the last is a multiple of 4
+void multimem_share(int64_t count, int rank, int world, long long* lo, long long* hi) {
+  const long long per = (((long long)count + world - 1) / world + 3) / 4 * 4;
+  *lo = std::min<long long>((long long)rank * per, count);
+  *hi = std::min<long long>(*lo + per, count);
+}
+
 int launch_adam_multimem(float* params_mc, const float* grads_mc, const float* params_local, float* m, float* v,
                          int64_t count, int rank, int world, int step, float lr, float b1, float b2, float eps, int64_t sb,
                          int64_t se, float reg_scale, int64_t ob, int64_t oe, float reg_op, const float* skip_flag,
@@ -202,9 +210,8 @@ int launch_adam_multimem(float* params_mc, const float* grads_mc, const float* p
   c.reg_s = (se > sb) ? reg_scale / (float)(se - sb) : 0.f;
   c.reg_o = (oe > ob) ? reg_op / (float)(oe - ob) : 0.f;
   c.sb = sb; c.se = se; c.ob = ob; c.oe = oe;
-  // this rank's share of the slice: ceil(count / world) rounded up to 4 floats (16-byte multimem accesses)
-  const long long per = (((long long)count + world - 1) / world + 3) / 4 * 4;
-  const long long lo = std::min<long long>((long long)rank * per, count), hi = std::min<long long>(lo + per, count);
+  long long lo, hi;
+  multimem_share(count, rank, world, &lo, &hi);
   if (hi <= lo) return B2S_OK;
   long long blocks = ((hi - lo) / 4 + 255) / 256 + 1;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;

@@ -211,10 +211,7 @@ class FitDriver:
             for first, count in self._chunks():
                 for sl_src, sl_dst, k in zip(self._chunk_slices(buf, first, count), self._chunk_slices(own, first, count),
                                              (3, 3, 1, 3 * self.sh)):
-                    nel = k * count
-                    per = ((nel + world - 1) // world + 3) // 4 * 4
-                    lo = min(rank * per, nel)
-                    hi = min(lo + per, nel)
+                    lo, hi = capi.multimem_share(k * count, rank, world)      # the kernel's own partition
                     sl_dst[lo:hi] = sl_src[lo:hi]
             torch.distributed.all_reduce(own, group=self.pg)
             buf.copy_(own)

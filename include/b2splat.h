@@ -285,6 +285,9 @@ int b2s_adam_step_multimem(b2s_ctx* ctx, float* params_mc, const float* grads_mc
                            float eps, int64_t scales_begin, int64_t scales_end, float reg_scale, int64_t opac_begin,
                            int64_t opac_end, float reg_opacity, const float* skip_flag, int* skipped_count, void* stream);
 int b2s_reduce_tail_multimem(b2s_ctx* ctx, const float* tail_mc, float* tail_out, int count, void* stream);
+/* Host helper: the share [lo, hi) of a slice of `count` floats that rank `rank` of `world` updates in b2s_adam_step_multimem
+ * (FitDriver gathers the owners' Adam moments with it; no CUDA call). */
+int b2s_multimem_share(int64_t count, int rank, int world, int64_t* lo, int64_t* hi);
 
 /* Densify / prune (python/fit_multiview_stub.py:140-197): keep sigmoid(op_raw) > prune_opacity (or the
  * 64 most opaque if fewer survive), order preserved; then append min(max_gaussians - n1, int(n1 *

@@ -104,3 +104,19 @@ def test_camera_helpers_match_numpy_restatement():
     eye = torch.tensor([1.0, 0.5, 2.0])
     v = r.look_at(eye, torch.zeros(3), torch.tensor([0.0, 1.0, 0.0])).numpy()
     assert np.allclose(v, scenes.look_at([1.0, 0.5, 2.0], [0, 0, 0], [0, 1, 0]), atol=1e-6)
+
+
+def test_multimem_shares_tile_every_slice():
+    """The partition behind b2s_adam_step_multimem (reduce-scatter + Adam + all-gather over NVLink multicast): for every
+    slice length and world size the ranks' shares are disjoint, in rank order, cover the slice, and every boundary except
+    the slice end is a multiple of 4 floats (16-byte multimem accesses).  Host arithmetic only: no GPU needed."""
+    capi = _capi()
+    for world in (1, 2, 3, 4, 8):
+        for count in (0, 1, 3, 4, 5, 63, 64, 65, 1000, 4099, 3 * 250048, 48 * 250048 + 1):
+            pos = 0
+            for rank in range(world):
+                lo, hi = capi.multimem_share(count, rank, world)
+                assert lo == pos and lo <= hi <= count
+                assert lo % 4 == 0 or lo == count
+                pos = hi
+            assert pos == count
