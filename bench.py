@@ -411,6 +411,45 @@ def render_bench(device, frames=20):
         del ws, img
     except Exception as e:  # noqa: BLE001
         out["stages_error"] = str(e)
+    # the sorted frame as ONE CUDA graph (a viewer replays the same 13 launches with the same buffers every frame: the
+    # launch-bound case graphs are for).  Captured on a side stream after a warm-up; best effort -- a capture failure is
+    # reported, not fatal.
+    try:
+        params = capi.make_params(W, H, view.reshape(-1).tolist(), proj.reshape(-1).tolist(), (0.02, 0.02, 0.02),
+                                  mode=capi.MODE_SORTED, style=capi.STYLE_NATIVE, cutoff_sigma=3.0, sh_coeffs=1,
+                                  sort_depth=1, exact_bbox=1)
+        mp = int(r.count_pairs(params, means, scales, opac) * 1.25) + 4096
+        L = capi.lib()
+        ws = torch.empty(L.b2s_workspace_bytes(n, W, H, mp) + L.b2s_state_bytes(n, W, H, mp), dtype=torch.uint8, device=device)
+        img = torch.empty((H, W, 4), dtype=torch.uint8, device=device)
+        kw = dict(enable_depth_sort=1, max_pairs=mp, out=img, workspace=ws)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                r.render_rgba8(means, scales, colors, opac, view, proj, W, H, (0.02, 0.02, 0.02), **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ref_img = img.clone()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            r.render_rgba8(means, scales, colors, opac, view, proj, W, H, (0.02, 0.02, 0.02), **kw)
+        img.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(img, ref_img))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(frames):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out["ms_per_frame_sorted_cuda_graph"] = e0.elapsed_time(e1) / frames
+        out["cuda_graph_frame_identical"] = same
+        del graph, ws, img
+    except Exception as e:  # noqa: BLE001
+        out["cuda_graph_error"] = str(e)[:300]
+        torch.cuda.synchronize()
     # host-pointer path (gr::render_gaussians signature): H2D of 40 MB + render + D2H of 2 MB per frame
     hm, hs, hc, ho = (t.cpu().numpy() for t in (means, scales, colors, opac))
     bg = np.array([0.02, 0.02, 0.02], np.float32)
