@@ -35,6 +35,29 @@ def local_views(num_views: int, rank: int, world: int) -> List[int]:
     return [i for i in range(num_views) if i % world == rank]
 
 
+def gaussian_chunks(n: int, c: int) -> List[Tuple[int, int]]:
+    """[(first, count)] ranges of the pipelined multi-GPU tail: at most c ranges (fewer for small n: a range holds at least
+    4096 Gaussians), every range but the last a multiple of 64 Gaussians, so that every slice of a chunk starts 256-byte
+    aligned in the parameter buffers."""
+    c = max(1, min(int(c), (n + 4095) // 4096))
+    per = ((n + c - 1) // c + 63) // 64 * 64
+    return [(i, min(per, n - i)) for i in range(0, n, per)] or [(0, 0)]
+
+
+def chunk_major_offsets(chunks, sh: int, tail: int = 64) -> Tuple[List[List[int]], int]:
+    """Layout of the chunk-major gradient buffer [tail | chunk 0: means, scales, opacities, colours | chunk 1: ...] in
+    floats: per chunk the four segment offsets + the chunk's end, segments padded to 64 floats; returns (offsets, total)."""
+    al = lambda x: (x + 63) // 64 * 64
+    out, o = [], tail
+    for first, cnt in chunks:
+        segs = []
+        for k in (3, 3, 1, 3 * sh):
+            segs.append(o)
+            o += al(k * cnt)
+        out.append(segs + [o])
+    return out, o
+
+
 class FitDriver:
     def __init__(self, n: int, sh_coeffs: int, width: int, height: int,
                  cameras: Sequence[Tuple[Sequence[float], Sequence[float]]], device: torch.device,
@@ -159,13 +182,7 @@ class FitDriver:
             # pipelined tail: the gradient buffer is CHUNK-major -- [tail 64 | chunk 0: means, scales, opac, colours |
             # chunk 1: ... ] -- so that a chunk (chunk 0 together with the tail) crosses NVLink as ONE contiguous
             # all-reduce; parameters and moments keep the segment-major layout (Adam takes a pointer per slice)
-            self._gchunks, o = [], 64
-            for first, cnt in chunks:
-                segs = []
-                for k in (3, 3, 1, c):
-                    segs.append(o)
-                    o += al(k * cnt)
-                self._gchunks.append(segs + [o])          # four segment offsets + end
+            self._gchunks, o = chunk_major_offsets(chunks, self.sh)      # per chunk: four segment offsets + end
             if self.comm == "multimem" and self.world > 1:
                 self._alloc_symmetric(o)
             if self._symm is None:
@@ -425,9 +442,7 @@ class FitDriver:
     def _chunks(self):
         """[(first, count)] Gaussian ranges of the pipelined tail (one range when there is nothing to overlap)."""
         c = self.grad_chunks if ((self.world > 1 or self._force_chunks) and self.view_groups == 1) else 1
-        c = max(1, min(c, (self.n + 4095) // 4096))
-        per = ((self.n + c - 1) // c + 63) // 64 * 64
-        return [(i, min(per, self.n - i)) for i in range(0, self.n, per)] or [(0, 0)]
+        return gaussian_chunks(self.n, c)
 
     def _chunk_slices(self, buf, first, count):
         """The four slices of a flat buffer that belong to the Gaussians [first, first + count)."""

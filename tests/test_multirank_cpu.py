@@ -57,6 +57,78 @@ def test_local_views_partition():
     assert fit.local_views(3, 5, 8) == []          # more ranks than views: idle rank
 
 
+def test_chunks_and_chunk_major_layout():
+    """Host arithmetic of the pipelined tail: the Gaussian ranges tile [0, n) with 64-aligned starts, and the chunk-major
+    gradient buffer places every (chunk, segment) slice 64-float aligned, in order, without overlap."""
+    fit = importlib.import_module("3dgaussian_b200.fit")
+    for n in (1, 100, 4096, 9000, 250_001, 1_000_000):
+        for c in (1, 2, 3, 4, 7):
+            ch = fit.gaussian_chunks(n, c)
+            assert ch[0][0] == 0 and sum(k for _, k in ch) == n and len(ch) <= c
+            assert all(f % 64 == 0 for f, _ in ch) and all(a + k == b for (a, k), (b, _) in zip(ch, ch[1:]))
+            for sh in (1, 4, 16):
+                offs, total = fit.chunk_major_offsets(ch, sh)
+                pos = 64
+                for (first, cnt), segs in zip(ch, offs):
+                    for q, k in enumerate((3, 3, 1, 3 * sh)):
+                        assert segs[q] == pos and segs[q] % 64 == 0
+                        pos = segs[q] + (k * cnt + 63) // 64 * 64
+                    assert segs[4] == pos
+                assert total == pos
+
+
+def _owner_worker(rank, world, port, out):
+    """CPU emulation of the fused multi-GPU tail (b2s_adam_step_multimem): every rank holds its own gradient; the owner
+    of a share takes the SUM of that share (on the GPU: multimem.ld_reduce through the NVSwitch; here an all-reduce read on
+    the share only), applies Adam with ITS moments, and the new parameters of all shares are gathered on every rank
+    (multimem.st; here a sum of share-masked buffers)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    capi = importlib.import_module("3dgaussian_b200.capi")
+    count = 1003
+    gen = torch.Generator().manual_seed(7)
+    p0 = torch.randn(count, generator=gen, dtype=torch.float64)
+    grads = [torch.randn(count, generator=gen, dtype=torch.float64) for _ in range(world)]
+    p, m, v = p0.clone(), torch.zeros(count, dtype=torch.float64), torch.zeros(count, dtype=torch.float64)
+    for step in (1, 2, 3):
+        g = grads[rank] * step
+        red = g.clone()
+        dist.all_reduce(red)                                   # what ld_reduce returns for any address
+        lo, hi = capi.multimem_share(count, rank, world)
+        newp = torch.zeros(count, dtype=torch.float64)
+        pn, mn, vn = r1.adam_step(p[lo:hi], red[lo:hi], m[lo:hi], v[lo:hi], step, 0.02)
+        m[lo:hi], v[lo:hi] = mn, vn                            # moments live on the owner only
+        newp[lo:hi] = pn
+        dist.all_reduce(newp)                                  # every share lands on every rank
+        p = newp
+    torch.save({"p": p, "m": m, "v": v, "share": capi.multimem_share(count, rank, world)}, out.format(rank))
+    dist.destroy_process_group()
+
+
+def test_owner_update_scheme_equals_replicated_adam(tmp_path):
+    world, count = 2, 1003
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "own{}.pt")
+    mp.spawn(_owner_worker, args=(world, port, out), nprocs=world, join=True)
+    res = [torch.load(out.format(r)) for r in range(world)]
+    assert torch.equal(res[0]["p"], res[1]["p"])                # replicas identical by construction
+    gen = torch.Generator().manual_seed(7)
+    p = torch.randn(count, generator=gen, dtype=torch.float64)
+    grads = [torch.randn(count, generator=gen, dtype=torch.float64) for _ in range(world)]
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        p, m, v = r1.adam_step(p, sum(grads) * step, m, v, step, 0.02)
+    assert torch.allclose(res[0]["p"], p, rtol=1e-12, atol=1e-14)
+    for r in range(world):                                      # each owner's moments are the replicated ones on its share
+        lo, hi = res[r]["share"]
+        assert torch.allclose(res[r]["m"][lo:hi], m[lo:hi], rtol=1e-12, atol=1e-15)
+        assert torch.allclose(res[r]["v"][lo:hi], v[lo:hi], rtol=1e-12, atol=1e-15)
+
+
 def test_two_rank_allreduce_equals_single_process(tmp_path):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
