@@ -7,11 +7,16 @@ buffers laid out [means 3N | scales_raw 3N | opacities_raw N | colours C*N]; act
 kernels, the per-view loss (mean|pred-tgt| + w_sil*mean|alpha-mask| + w_depth*mean|depth/max-d_gt|,
 :292-303) and the Adam step with the regulariser gradients (:307-311) are fused kernels of libb2splat.
 
-Multi-GPU (torch.distributed, NCCL): parameters are replicated, view i belongs to rank
-i % world; every rank accumulates the gradients of its views into the flat buffer, ONE
-all-reduce (sum) combines them -- the iteration's loss and its pair-buffer overflow count ride in
-the tail of the same buffer -- then every rank runs the identical Adam step, so the replicas
-stay bit-identical without a broadcast.
+Multi-GPU (torch.distributed): parameters are replicated, view i belongs to rank i % world;
+every rank accumulates the gradients of its views into its flat buffer.  Default tail
+(comm="multimem"): the buffers are symmetric-memory allocations bound to an NVLink multicast
+address and ONE fused kernel per parameter slice pulls the sum of the owner's share through the
+NVSwitch (multimem.ld_reduce), applies the guarded Adam step with the owner's moments and
+multicasts the new parameters (multimem.st) -- b2s_adam_step_multimem, pipelined per Gaussian
+chunk behind the chain rule.  Fallback (comm="nccl"): one NCCL all-reduce (sum) per chunk -- the
+iteration's loss and its pair-buffer overflow count ride in the tail of the same buffer -- then
+every rank runs the identical Adam step.  Either way the replicas stay bit-identical without a
+broadcast.
 
 Overflow safety: the pair buffers are sized from the parameters at plan() time; Gaussians grow
 during a fit.  A view that overflows renders nothing, so its iteration must not reach the
