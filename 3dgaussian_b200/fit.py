@@ -40,6 +40,25 @@ def local_views(num_views: int, rank: int, world: int) -> List[int]:
     return [i for i in range(num_views) if i % world == rank]
 
 
+import contextlib
+import os
+
+_NVTX = os.environ.get("B2S_NVTX", "") == "1"
+
+
+@contextlib.contextmanager
+def _nvtx(name: str):
+    """NVTX range around a phase of the iteration when B2S_NVTX=1 (for nsys / ncu --nvtx timelines); free otherwise."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 def gaussian_chunks(n: int, c: int) -> List[Tuple[int, int]]:
     """[(first, count)] ranges of the pipelined multi-GPU tail: at most c ranges (fewer for small n: a range holds at least
     4096 Gaussians), every range but the last a multiple of 64 Gaussians, so that every slice of a chunk starts 256-byte
@@ -486,6 +505,8 @@ class FitDriver:
 
         def one_view(k, lane, stream):
             q = inputs(k, stream)
+            if _NVTX:
+                torch.cuda.nvtx.mark(f"b2s.view {self.views[k]} lane {lane}")
             self._view_fwd_bwd(k, self.views[k], q["tgt"], q.get("mask"), lane, q.get("ready"), q.get("depth"), q.get("convert"))
             if q.get("done") is not None:
                 q["done"](stream)
@@ -741,8 +762,10 @@ class FitDriver:
         if self.state is None:
             self.plan()
         with torch.cuda.device(self.dev):
-            self._iterate(self._device_inputs)
-            self._finish_step()
+            with _nvtx("b2s.views"):            # batched preprocess + forward / loss / blend backward of the local views
+                self._iterate(self._device_inputs)
+            with _nvtx("b2s.tail"):             # chain rule | gradient exchange | Adam
+                self._finish_step()
             self._poll_overflow()
         return self.loss_dev
 
@@ -906,8 +929,10 @@ class FitDriver:
                         "done": lambda s, slot=slot: self._ev_free[slot].record(s), "ready": self._ev_ready[slot],
                         "convert": make_convert(list(pending.get(slot, [])))}
 
-            self._iterate(inputs)
-            self._finish_step()
+            with _nvtx("b2s.views(host-fed)"):
+                self._iterate(inputs)
+            with _nvtx("b2s.tail"):
+                self._finish_step()
 
     # ---- densify / prune ----------------------------------------------------------------------
     def densify_prune(self, iteration: int, max_gaussians: int, densify_ratio: float = 0.15,
